@@ -1,0 +1,165 @@
+"""ctypes binding of oracle/_build/libdpose_oracle.so (the C restatement).
+
+TEST INFRASTRUCTURE ONLY — see oracle/dpose_oracle.h.  `build()` runs oracle/Makefile.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libdpose_oracle.so")
+
+
+class _CostData(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int), ("cols", C.c_int),
+        ("center", C.c_int * 2), ("box", C.c_int * 10),
+        ("cost", C.POINTER(C.c_float)), ("pre_blur", C.POINTER(C.c_float)),
+        ("edt_sq", C.POINTER(C.c_int32)), ("outline", C.POINTER(C.c_uint8)),
+        ("mask", C.POINTER(C.c_uint8)), ("min_outer", C.c_float),
+    ]
+
+
+def build(force=False):
+    src_newer = (not os.path.exists(_SO)) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
+        for f in ("dpose_oracle.c", "dpose_oracle.h"))
+    if force or src_newer:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.oracle_make_footprint.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.oracle_cost_data_create.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.POINTER(_CostData)]
+        L.oracle_cost_data_free.argtypes = [C.POINTER(_CostData)]
+        L.oracle_get_cost.restype = C.c_double
+        L.oracle_get_cost.argtypes = [C.POINTER(_CostData), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.oracle_get_cost_truth.restype = C.c_longdouble
+        L.oracle_get_cost_truth.argtypes = [C.POINTER(_CostData), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.oracle_raytrace.restype = C.c_size_t
+        L.oracle_raytrace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_lethal_cells_within.restype = C.c_size_t
+        L.oracle_lethal_cells_within.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.oracle_get_cost_batch.argtypes = [C.POINTER(_CostData), C.c_void_p, C.c_uint32, C.c_uint32,
+                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.oracle_get_cost_batch_truth.argtypes = [C.POINTER(_CostData), C.c_void_p, C.c_uint32, C.c_uint32,
+                                                  C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        L.oracle_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def make_footprint(xy_m, res):
+    """dpose_costmap.cpp:40-55; xy_m: (n,2) metres -> (n,2) int32 cells."""
+    xy = np.ascontiguousarray(np.asarray(xy_m, dtype=np.float64).reshape(-1, 2))
+    out = np.empty(xy.shape, dtype=np.int32)
+    if lib().oracle_make_footprint(xy.ctypes.data, xy.shape[0], float(res), out.ctypes.data) != 0:
+        raise RuntimeError("resolution must be positive")
+    return out
+
+
+class CostData:
+    """cost_data (dpose_core.cpp:122-139). footprint: (n,2) int cells (x,y)."""
+
+    def __init__(self, footprint, padding):
+        fp = _i32(footprint).reshape(-1, 2)
+        self._cd = _CostData()
+        if lib().oracle_cost_data_create(fp.ctypes.data, fp.shape[0], int(padding), C.byref(self._cd)) != 0:
+            raise RuntimeError("bad footprint")
+        cd = self._cd
+        shape = (cd.rows, cd.cols)
+        n = cd.rows * cd.cols
+        self.rows, self.cols = shape
+        self.cost = np.ctypeslib.as_array(cd.cost, (n,)).reshape(shape).copy()
+        self.pre_blur = np.ctypeslib.as_array(cd.pre_blur, (n,)).reshape(shape).copy()
+        self.edt_sq = np.ctypeslib.as_array(cd.edt_sq, (n,)).reshape(shape).copy()
+        self.outline = np.ctypeslib.as_array(cd.outline, (n,)).reshape(shape).copy()
+        self.mask = np.ctypeslib.as_array(cd.mask, (n,)).reshape(shape).copy()
+        self.center = np.array(list(cd.center), dtype=np.int32)
+        self.box = np.array(list(cd.box), dtype=np.int32).reshape(5, 2)  # rows = ring points (x,y)
+        self.min_outer = float(cd.min_outer)
+
+    def __del__(self):
+        try:
+            lib().oracle_cost_data_free(C.byref(self._cd))
+        except Exception:
+            pass
+
+    def get_cost(self, se2, cells, want_jacobian=True):
+        """pose_gradient::get_cost (dpose_core.cpp:200-260), FD Jacobian."""
+        se2 = np.ascontiguousarray(np.asarray(se2, dtype=np.float64))
+        cells = _i32(cells).reshape(-1, 2)
+        J = np.zeros(3, dtype=np.float64)
+        cost = lib().oracle_get_cost(C.byref(self._cd), se2.ctypes.data, cells.ctypes.data,
+                                     cells.shape[0], J.ctypes.data if want_jacobian else None)
+        return cost, J
+
+    def get_cost_truth(self, se2, cells):
+        se2 = np.ascontiguousarray(np.asarray(se2, dtype=np.float64))
+        cells = _i32(cells).reshape(-1, 2)
+        J = np.zeros(3, dtype=np.longdouble)
+        cost = lib().oracle_get_cost_truth(C.byref(self._cd), se2.ctypes.data, cells.ctypes.data,
+                                           cells.shape[0], J.ctypes.data)
+        return float(cost), J.astype(np.float64)
+
+    def get_cost_batch(self, costmap, poses, want_jacobian=True, shift=False, nthreads=1):
+        m = np.ascontiguousarray(np.asarray(costmap, dtype=np.uint8))
+        p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+        out = np.zeros((p.shape[0], 4), dtype=np.float64)
+        lib().oracle_get_cost_batch(C.byref(self._cd), m.ctypes.data, m.shape[1], m.shape[0],
+                                    p.ctypes.data, p.shape[0], out.ctypes.data,
+                                    int(want_jacobian), int(shift), int(nthreads))
+        return out
+
+    def get_cost_batch_truth(self, costmap, poses, nthreads=1):
+        m = np.ascontiguousarray(np.asarray(costmap, dtype=np.uint8))
+        p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+        out = np.zeros((p.shape[0], 4), dtype=np.float64)
+        lib().oracle_get_cost_batch_truth(C.byref(self._cd), m.ctypes.data, m.shape[1], m.shape[0],
+                                          p.ctypes.data, p.shape[0], out.ctypes.data, int(nthreads))
+        return out
+
+
+def raytrace(begin, end):
+    """dpose_costmap.cpp:57-104."""
+    b, e = _i32(begin), _i32(end)
+    n = int(max(abs(int(e[0]) - int(b[0])), abs(int(e[1]) - int(b[1]))))
+    out = np.empty((max(n, 1), 2), dtype=np.int32)
+    k = lib().oracle_raytrace(b.ctypes.data, e.ctypes.data, out.ctypes.data)
+    return out[:k].copy()
+
+
+def lethal_cells_within(costmap, box):
+    """dpose_costmap.cpp:117-184; box: (5,2) ring (x,y). Returns (n,2) int32, (y,x)-sorted."""
+    m = np.ascontiguousarray(np.asarray(costmap, dtype=np.uint8))
+    b = _i32(box).reshape(10)
+    ptr = C.c_void_p()
+    sy, sx = (m.shape if m.ndim == 2 else (0, 0))
+    n = lib().oracle_lethal_cells_within(m.ctypes.data, sx, sy, b.ctypes.data, C.byref(ptr))
+    if n == 0:
+        return np.empty((0, 2), dtype=np.int32)
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int32)), (n * 2,)).reshape(n, 2).copy()
+    _libc.free(ptr)
+    return arr
+
+
+def max_threads():
+    return lib().oracle_max_threads()

@@ -1,0 +1,662 @@
+/*
+ * dpose_oracle.c — CPU restatement of dpose_core's footprint-cost path (plain C11).
+ *
+ * TEST INFRASTRUCTURE ONLY (see dpose_oracle.h).  Parity pin: the image pipeline is
+ * checked bit-for-bit against OpenCV (cv2 4.13.0, IPP off) by tests/test_oracle_cv2.py
+ * and frozen in tests/golden/; get_cost is checked against the known-answer vectors of
+ * SURVEY.md §8(c) and the reference's own Jacobian self-consistency test.
+ *
+ * The arithmetic of the image pipeline lives in OpenCV imgproc, which is not vendored
+ * by the reference (package.xml: libopencv-dev of ROS noetic).  The rules restated here
+ * (LineIterator, FillEdgeCollection, trueDistTrans, cvtScale, GaussianBlur) are OpenCV's
+ * published algorithms, anchored on the reference's call sites dpose_core.cpp:61-111.
+ */
+#include "dpose_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------- */
+/* make_footprint — dpose_costmap.cpp:40-55                                   */
+/* ------------------------------------------------------------------------- */
+int oracle_make_footprint(const double *xy_m, int n, double res, int32_t *xy_cells) {
+  if (res <= 0) return -1; /* :44-45 throws "resolution must be positive" */
+  for (int i = 0; i < n; ++i) {
+    xy_cells[2 * i + 0] = (int32_t)round(xy_m[2 * i + 0] / res); /* :51 std::round */
+    xy_cells[2 * i + 1] = (int32_t)round(xy_m[2 * i + 1] / res); /* :52 */
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* cv::polylines(img, pts, closed, 0) — call site dpose_core.cpp:73           */
+/* OpenCV drawing.cpp Line(): 8-connected LineIterator with leftToRight=true.  */
+/* ------------------------------------------------------------------------- */
+static void cv_line8(uint8_t *img, int cols, int rows, int x1, int y1, int x2, int y2,
+                     uint8_t color) {
+  int dx = x2 - x1, dy = y2 - y1;
+  int step_x = 1, step_y = 1;
+  if (dx < 0) { /* leftToRight: start from the left end point */
+    dx = -dx;
+    dy = -dy;
+    x1 = x2;
+    y1 = y2;
+  }
+  if (dy < 0) {
+    dy = -dy;
+    step_y = -1;
+  }
+  const int vert = dy > dx;
+  int major = vert ? dy : dx, minor = vert ? dx : dy;
+  int err = major - 2 * minor;
+  int x = x1, y = y1;
+  for (int i = 0; i <= major; ++i) {
+    if (x >= 0 && x < cols && y >= 0 && y < rows) img[(size_t)y * cols + x] = color;
+    /* err < 0 -> take the diagonal step, else the axis step */
+    const int diag = err < 0;
+    err += -2 * minor + (diag ? 2 * major : 0);
+    if (vert) {
+      y += step_y;
+      if (diag) x += step_x;
+    } else {
+      x += step_x;
+      if (diag) y += step_y;
+    }
+  }
+}
+
+static void cv_polylines_closed(uint8_t *img, int cols, int rows, const int32_t *xy, int n,
+                                uint8_t color) {
+  /* PolyLine(): p0 = v[n-1]; for each i: line(p0, v[i]); p0 = v[i] */
+  int px = xy[2 * (n - 1)], py = xy[2 * (n - 1) + 1];
+  for (int i = 0; i < n; ++i) {
+    cv_line8(img, cols, rows, px, py, xy[2 * i], xy[2 * i + 1], color);
+    px = xy[2 * i];
+    py = xy[2 * i + 1];
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* cv::fillPoly(img, {pts}, 0) — call site dpose_core.cpp:94                   */
+/* OpenCV drawing.cpp CollectPolyEdges + FillEdgeCollection (non-AA, shift 0): */
+/* outline via Line(), then even-odd scanline spans from 16.16 edge walking.   */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int y0, y1;
+  int64_t x, dx;
+} poly_edge;
+
+static int cmp_edges(const void *a, const void *b) {
+  const poly_edge *e1 = (const poly_edge *)a, *e2 = (const poly_edge *)b;
+  if (e1->y0 != e2->y0) return e1->y0 < e2->y0 ? -1 : 1;
+  if (e1->x != e2->x) return e1->x < e2->x ? -1 : 1;
+  if (e1->dx != e2->dx) return e1->dx < e2->dx ? -1 : 1;
+  return 0;
+}
+
+static int cmp_i64(const void *a, const void *b) {
+  const int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+static void cv_fillpoly(uint8_t *img, int cols, int rows, const int32_t *xy, int n,
+                        uint8_t color) {
+  enum { XY_SHIFT = 16 };
+  poly_edge *edges = (poly_edge *)malloc(sizeof(poly_edge) * (size_t)(n > 0 ? n : 1));
+  int64_t *xs = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  int total = 0;
+  int y_min = INT_MAX, y_max = INT_MIN;
+  int px = xy[2 * (n - 1)], py = xy[2 * (n - 1) + 1];
+  for (int i = 0; i < n; ++i) {
+    const int qx = xy[2 * i], qy = xy[2 * i + 1];
+    cv_line8(img, cols, rows, px, py, qx, qy, color);
+    if (py != qy) {
+      poly_edge e;
+      e.dx = (((int64_t)qx - px) * (1 << XY_SHIFT)) / ((int64_t)qy - py); /* trunc toward 0 */
+      if (py < qy) {
+        e.y0 = py;
+        e.y1 = qy;
+        e.x = (int64_t)px * (1 << XY_SHIFT);
+      } else {
+        e.y0 = qy;
+        e.y1 = py;
+        e.x = (int64_t)qx * (1 << XY_SHIFT);
+      }
+      edges[total++] = e;
+      if (e.y0 < y_min) y_min = e.y0;
+      if (e.y1 > y_max) y_max = e.y1;
+    }
+    px = qx;
+    py = qy;
+  }
+  if (total >= 2) {
+    qsort(edges, (size_t)total, sizeof(poly_edge), cmp_edges);
+    if (y_max > rows) y_max = rows;
+    for (int y = y_min; y < y_max; ++y) {
+      int na = 0;
+      for (int i = 0; i < total; ++i)
+        if (edges[i].y0 <= y && y < edges[i].y1)
+          xs[na++] = edges[i].x + (int64_t)(y - edges[i].y0) * edges[i].dx;
+      qsort(xs, (size_t)na, sizeof(int64_t), cmp_i64);
+      if (y < 0) continue;
+      for (int i = 0; i + 1 < na; i += 2) {
+        /* left end rounded to nearest, right end floored (cv2 4.13 behaviour,
+         * probed 0 mismatches on random polygons; the outline drawn above hides
+         * the difference to a ceil'ed left end) */
+        int x1 = (int)((xs[i] + (1 << (XY_SHIFT - 1))) >> XY_SHIFT);
+        int x2 = (int)(xs[i + 1] >> XY_SHIFT);
+        if (x1 < cols && x2 >= 0) {
+          if (x1 < 0) x1 = 0;
+          if (x2 >= cols) x2 = cols - 1;
+          for (int x = x1; x <= x2; ++x) img[(size_t)y * cols + x] = color;
+        }
+      }
+    }
+  }
+  free(xs);
+  free(edges);
+}
+
+/* ------------------------------------------------------------------------- */
+/* cv::distanceTransform(DIST_L2, DIST_MASK_PRECISE, CV_32F) — :82-83          */
+/* exact squared Euclidean distance to the nearest zero pixel (definition).    */
+/* ------------------------------------------------------------------------- */
+static void exact_edt_sq(const uint8_t *img, int cols, int rows, int32_t *d2) {
+  /* separable exact EDT (column pass then exhaustive row pass): O(rows*cols*cols) */
+  const int32_t INF = 1 << 29;
+  int32_t *g = (int32_t *)malloc(sizeof(int32_t) * (size_t)rows * cols);
+  for (int x = 0; x < cols; ++x) {
+    int32_t last = -1;
+    for (int y = 0; y < rows; ++y) {
+      if (img[(size_t)y * cols + x] == 0) last = y;
+      g[(size_t)y * cols + x] = last < 0 ? INF : (y - last);
+    }
+    last = -1;
+    for (int y = rows - 1; y >= 0; --y) {
+      if (img[(size_t)y * cols + x] == 0) last = y;
+      if (last >= 0 && (last - y) < g[(size_t)y * cols + x]) g[(size_t)y * cols + x] = last - y;
+    }
+  }
+  for (int y = 0; y < rows; ++y) {
+    const int32_t *gr = g + (size_t)y * cols;
+    for (int x = 0; x < cols; ++x) {
+      int64_t best = (int64_t)INF * 4;
+      for (int i = 0; i < cols; ++i) {
+        if (gr[i] >= INF) continue;
+        const int64_t v = (int64_t)(x - i) * (x - i) + (int64_t)gr[i] * gr[i];
+        if (v < best) best = v;
+      }
+      d2[(size_t)y * cols + x] = best > INT_MAX ? INT_MAX : (int32_t)best;
+    }
+  }
+  free(g);
+}
+
+/* ------------------------------------------------------------------------- */
+/* _get_cost + cost_data::cost_data — dpose_core.cpp:55-139                    */
+/* ------------------------------------------------------------------------- */
+static inline int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+int oracle_cost_data_create(const int32_t *fp_xy, int n, unsigned padding,
+                            oracle_cost_data *out) {
+  memset(out, 0, sizeof(*out));
+  if (n < 1) return -1;
+  const int pad = (int)padding;
+  /* :124-125 center = padding - rowwise min */
+  int minx = INT_MAX, miny = INT_MAX, maxx = INT_MIN, maxy = INT_MIN;
+  for (int i = 0; i < n; ++i) {
+    const int x = fp_xy[2 * i], y = fp_xy[2 * i + 1];
+    if (x < minx) minx = x;
+    if (x > maxx) maxx = x;
+    if (y < miny) miny = y;
+    if (y > maxy) maxy = y;
+  }
+  out->center[0] = pad - minx;
+  out->center[1] = pad - miny;
+  /* :128 shifted footprint */
+  int32_t *fp = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    fp[2 * i] = fp_xy[2 * i] + out->center[0];
+    fp[2 * i + 1] = fp_xy[2 * i + 1] + out->center[1];
+  }
+  /* :61-69 boundingRect (w = dx+1, h = dy+1) + 2*padding */
+  const int cols = (maxx - minx + 1) + 2 * pad;
+  const int rows = (maxy - miny + 1) + 2 * pad;
+  const size_t np = (size_t)rows * cols;
+  out->rows = rows;
+  out->cols = cols;
+  out->outline = (uint8_t *)malloc(np);
+  out->mask = (uint8_t *)malloc(np);
+  out->edt_sq = (int32_t *)malloc(sizeof(int32_t) * np);
+  out->pre_blur = (float *)malloc(sizeof(float) * np);
+  out->cost = (float *)malloc(sizeof(float) * np);
+  /* :72-73 white image, outline drawn with 0 */
+  memset(out->outline, 255, np);
+  cv_polylines_closed(out->outline, cols, rows, fp, n, 0);
+  /* :81-83 exact EDT */
+  exact_edt_sq(out->outline, cols, rows, out->edt_sq);
+  /* :92-94 mask: 0 inside/on the polygon */
+  memset(out->mask, 255, np);
+  cv_fillpoly(out->mask, cols, rows, fp, n, 0);
+  free(fp);
+  /* :100-106 outer = edt where mask != 0, scaled by (float)-0.01; min over image */
+  const float scale = (float)-0.01;
+  float mn = 0.0f; /* inside pixels contribute 0 */
+  int any = 0;
+  for (size_t i = 0; i < np; ++i) {
+    const float d = sqrtf((float)out->edt_sq[i]);
+    float v;
+    if (out->mask[i] != 0) {
+      volatile float o = d * scale; /* volatile: forbid contraction with the subtract */
+      v = o;
+    } else {
+      v = 0.0f;
+    }
+    if (!any || v < mn) {
+      mn = v;
+      any = 1;
+    }
+  }
+  out->min_outer = mn;
+  /* :109-110 edt = (outside ? outer : edt) - min */
+  for (size_t i = 0; i < np; ++i) {
+    const float d = sqrtf((float)out->edt_sq[i]);
+    volatile float o = d * scale;
+    const float v = out->mask[i] != 0 ? (float)o : d;
+    volatile float r = v - mn;
+    out->pre_blur[i] = r;
+  }
+  /* :111 GaussianBlur 3x3, sigma 0 -> [0.25 0.5 0.25] separable, row pass then column
+   * pass, BORDER_REFLECT_101 */
+  float *tmp = (float *)malloc(sizeof(float) * np);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      const float a = out->pre_blur[(size_t)y * cols + reflect101(x - 1, cols)];
+      const float b = out->pre_blur[(size_t)y * cols + x];
+      const float c = out->pre_blur[(size_t)y * cols + reflect101(x + 1, cols)];
+      volatile float s = a + c;
+      volatile float r = s * 0.25f + b * 0.5f; /* both products exact */
+      tmp[(size_t)y * cols + x] = r;
+    }
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      const float a = tmp[(size_t)reflect101(y - 1, rows) * cols + x];
+      const float b = tmp[(size_t)y * cols + x];
+      const float c = tmp[(size_t)reflect101(y + 1, rows) * cols + x];
+      volatile float s = a + c;
+      volatile float r = s * 0.25f + b * 0.5f;
+      out->cost[(size_t)y * cols + x] = r;
+    }
+  free(tmp);
+  /* :138 box = ring(cols, rows) - center */
+  const int bx[5] = {0, cols, cols, 0, 0};
+  const int by[5] = {0, 0, rows, rows, 0};
+  for (int i = 0; i < 5; ++i) {
+    out->box[2 * i] = bx[i] - out->center[0];
+    out->box[2 * i + 1] = by[i] - out->center[1];
+  }
+  return 0;
+}
+
+void oracle_cost_data_free(oracle_cost_data *cd) {
+  free(cd->cost);
+  free(cd->pre_blur);
+  free(cd->edt_sq);
+  free(cd->outline);
+  free(cd->mask);
+  memset(cd, 0, sizeof(*cd));
+}
+
+/* ------------------------------------------------------------------------- */
+/* Eigen::Isometry2d restated — dpose_core.cpp:141-146, 206-219, 227          */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  double r00, r01, r10, r11, t0, t1;
+} iso2;
+
+/* to_eigen: Translation2d(x, y) * Rotation2Dd(yaw) */
+static inline iso2 to_eigen(double x, double y, double yaw) {
+  iso2 m;
+  const double c = cos(yaw), s = sin(yaw);
+  m.r00 = c;
+  m.r01 = -s;
+  m.r10 = s;
+  m.r11 = c;
+  m.t0 = x;
+  m.t1 = y;
+  return m;
+}
+
+/* Transform * Transform: 3x3 coefficient-wise product, terms summed left to right */
+static inline iso2 iso_mul(const iso2 *a, const iso2 *b) {
+  iso2 m;
+  m.r00 = a->r00 * b->r00 + a->r01 * b->r10;
+  m.r01 = a->r00 * b->r01 + a->r01 * b->r11;
+  m.r10 = a->r10 * b->r00 + a->r11 * b->r10;
+  m.r11 = a->r10 * b->r01 + a->r11 * b->r11;
+  m.t0 = (a->r00 * b->t0 + a->r01 * b->t1) + a->t0;
+  m.t1 = (a->r10 * b->t0 + a->r11 * b->t1) + a->t1;
+  return m;
+}
+
+/* Transform<.., Isometry>::inverse(): linear^T, -linear^T * translation */
+static inline iso2 iso_inv(const iso2 *a) {
+  iso2 m;
+  m.r00 = a->r00;
+  m.r01 = a->r10;
+  m.r10 = a->r01;
+  m.r11 = a->r11;
+  m.t0 = -(m.r00 * a->t0 + m.r01 * a->t1);
+  m.t1 = -(m.r10 * a->t0 + m.r11 * a->t1);
+  return m;
+}
+
+static inline void iso_apply(const iso2 *a, double x, double y, double *ox, double *oy) {
+  *ox = (a->r00 * x + a->r01 * y) + a->t0;
+  *oy = (a->r10 * x + a->r11 * y) + a->t1;
+}
+
+/* interpolator — dpose_core.hpp:111-126, dpose_core.cpp:158-198 */
+typedef struct {
+  const float *img;
+  int cols, rows;
+  int upx, upy;
+  double m00, m01, m10, m11; /* m(i,j) = f(x_i, y_j) */
+} interp;
+
+static inline int interp_init(interp *ip, double kx, double ky) {
+  /* :177 round() half away from zero; :178 lower = upper - 1 */
+  const int ux = (int)round(kx), uy = (int)round(ky);
+  const int lx = ux - 1, ly = uy - 1;
+  /* :181 bounds = (cols-1, rows-1) */
+  if (lx < 1 || ly < 1 || ux >= ip->cols - 1 || uy >= ip->rows - 1) return 0;
+  ip->upx = ux;
+  ip->upy = uy;
+  /* :162-165 */
+  ip->m00 = ip->img[(size_t)ly * ip->cols + lx];
+  ip->m01 = ip->img[(size_t)uy * ip->cols + lx];
+  ip->m10 = ip->img[(size_t)ly * ip->cols + ux];
+  ip->m11 = ip->img[(size_t)uy * ip->cols + ux];
+  return 1;
+}
+
+static inline double interp_get(const interp *ip, double kx, double ky) {
+  /* :193-197 c_rel = k - k_upper + 0.5; [1-cx, cx] * m * [1-cy, cy]^T */
+  const double cx = kx - (double)ip->upx + 0.5;
+  const double cy = ky - (double)ip->upy + 0.5;
+  const double x0 = 1 - cx, x1 = cx, y0 = 1 - cy, y1 = cy;
+  const double r0 = x0 * ip->m00 + x1 * ip->m10;
+  const double r1 = x0 * ip->m01 + x1 * ip->m11;
+  return r0 * y0 + r1 * y1;
+}
+
+double oracle_get_cost(const oracle_cost_data *cd, const double se2[3],
+                       const int32_t *cells_xy, size_t n, double J[3]) {
+  const double offset = 1e-6; /* :211 */
+  const iso2 b_to_k = to_eigen(-(double)cd->center[0], -(double)cd->center[1], 0.0);
+  iso2 tr[7];
+  const double dx[7] = {0, -offset, offset, 0, 0, 0, 0};
+  const double dy[7] = {0, 0, 0, -offset, offset, 0, 0};
+  const double dz[7] = {0, 0, 0, 0, 0, -offset, offset};
+  for (int i = 0; i < 7; ++i) {
+    const iso2 m_to_b = to_eigen(se2[0] + dx[i], se2[1] + dy[i], se2[2] + dz[i]);
+    const iso2 m_to_k = iso_mul(&m_to_b, &b_to_k);
+    tr[i] = iso_inv(&m_to_k);
+  }
+  double sum = 0;
+  if (J) J[0] = J[1] = J[2] = 0; /* :224-225 */
+  interp ip;
+  ip.img = cd->cost;
+  ip.cols = cd->cols;
+  ip.rows = cd->rows;
+  for (size_t i = 0; i < n; ++i) {
+    const double px = (double)cells_xy[2 * i], py = (double)cells_xy[2 * i + 1];
+    double kx, ky;
+    iso_apply(&tr[0], px, py, &kx, &ky); /* :234 */
+    if (!interp_init(&ip, kx, ky)) continue; /* :237-238 */
+    sum += interp_get(&ip, kx, ky); /* :241 */
+    if (J) { /* :244-256 */
+      double lo, hi;
+      for (int a = 0; a < 3; ++a) {
+        iso_apply(&tr[1 + 2 * a], px, py, &kx, &ky);
+        lo = interp_get(&ip, kx, ky);
+        iso_apply(&tr[2 + 2 * a], px, py, &kx, &ky);
+        hi = interp_get(&ip, kx, ky);
+        J[a] += (hi - lo) * 5e5;
+      }
+    }
+  }
+  return sum;
+}
+
+long double oracle_get_cost_truth(const oracle_cost_data *cd, const double se2[3],
+                                  const int32_t *cells_xy, size_t n, long double J[3]) {
+  const long double tx = se2[0], ty = se2[1];
+  const long double c = cosl((long double)se2[2]), s = sinl((long double)se2[2]);
+  const long double cx = cd->center[0], cy = cd->center[1];
+  long double sum = 0, jx = 0, jy = 0, jt = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const long double dx = (long double)cells_xy[2 * i] - tx;
+    const long double dy = (long double)cells_xy[2 * i + 1] - ty;
+    /* k = c + R(-theta) (p - t) */
+    const long double ku = cx + c * dx + s * dy;
+    const long double kv = cy - s * dx + c * dy;
+    const int ux = (int)roundl(ku), uy = (int)roundl(kv);
+    const int lx = ux - 1, ly = uy - 1;
+    if (lx < 1 || ly < 1 || ux >= cd->cols - 1 || uy >= cd->rows - 1) continue;
+    const long double m00 = cd->cost[(size_t)ly * cd->cols + lx];
+    const long double m01 = cd->cost[(size_t)uy * cd->cols + lx];
+    const long double m10 = cd->cost[(size_t)ly * cd->cols + ux];
+    const long double m11 = cd->cost[(size_t)uy * cd->cols + ux];
+    const long double rx = ku - ux + 0.5L, ry = kv - uy + 0.5L;
+    sum += (1 - rx) * (1 - ry) * m00 + rx * (1 - ry) * m10 + (1 - rx) * ry * m01 +
+           rx * ry * m11;
+    const long double fu = (m10 - m00) * (1 - ry) + (m11 - m01) * ry;
+    const long double fv = (m01 - m00) * (1 - rx) + (m11 - m10) * rx;
+    jx += -c * fu + s * fv;
+    jy += -s * fu - c * fv;
+    jt += fu * (-s * dx + c * dy) + fv * (-c * dx - s * dy);
+  }
+  if (J) {
+    J[0] = jx;
+    J[1] = jy;
+    J[2] = jt;
+  }
+  return sum;
+}
+
+/* ------------------------------------------------------------------------- */
+/* raytrace / to_rays / lethal_cells_within — dpose_costmap.cpp:57-184         */
+/* ------------------------------------------------------------------------- */
+static inline int sgn(int v) { return (v > 0) - (v < 0); }
+
+size_t oracle_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_xy) {
+  const int draw[2] = {end[0] - begin[0], end[1] - begin[1]};
+  const int dabs[2] = {abs(draw[0]), abs(draw[1])};
+  /* :64-71 Eigen maxCoeff/minCoeff return the FIRST extremum; equal -> minor = 1-major */
+  int major = dabs[1] > dabs[0] ? 1 : 0;
+  int minor = dabs[1] < dabs[0] ? 1 : 0;
+  if (major == minor) minor = 1 - major;
+  const int den = dabs[major], add = dabs[minor];
+  int num = den / 2; /* :76 */
+  int inc_minor[2] = {sgn(draw[0]), sgn(draw[1])};
+  int inc_major[2] = {inc_minor[0], inc_minor[1]};
+  inc_minor[major] = 0; /* :84-85 */
+  inc_major[minor] = 0;
+  int cur[2] = {begin[0], begin[1]};
+  for (int i = 0; i < den; ++i) { /* :92-101 */
+    out_xy[2 * i] = cur[0];
+    out_xy[2 * i + 1] = cur[1];
+    num += add;
+    if (num >= den) {
+      num -= den;
+      cur[0] += inc_minor[0];
+      cur[1] += inc_minor[1];
+    }
+    cur[0] += inc_major[0];
+    cur[1] += inc_major[1];
+  }
+  return (size_t)den;
+}
+
+int oracle_to_rays(const int32_t box[10], int *y_lo, int *y_hi, int32_t **xmin_out,
+                   int32_t **xmax_out) {
+  int lo = INT_MAX, hi = INT_MIN, maxlen = 0;
+  for (int i = 0; i < 5; ++i) {
+    if (box[2 * i + 1] < lo) lo = box[2 * i + 1];
+    if (box[2 * i + 1] > hi) hi = box[2 * i + 1];
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int a = abs(box[2 * i + 2] - box[2 * i]), b = abs(box[2 * i + 3] - box[2 * i + 1]);
+    const int m = a > b ? a : b;
+    if (m > maxlen) maxlen = m;
+  }
+  const int nrows = hi - lo + 1;
+  int32_t *xmin = (int32_t *)malloc(sizeof(int32_t) * (size_t)nrows);
+  int32_t *xmax = (int32_t *)malloc(sizeof(int32_t) * (size_t)nrows);
+  for (int i = 0; i < nrows; ++i) {
+    xmin[i] = INT_MAX;
+    xmax[i] = INT_MIN;
+  }
+  int32_t *ray = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(maxlen + 1));
+  for (int e = 0; e < 4; ++e) { /* :108-113 */
+    const size_t len = oracle_raytrace(&box[2 * e], &box[2 * e + 2], ray);
+    for (size_t i = 0; i < len; ++i) {
+      const int x = ray[2 * i], y = ray[2 * i + 1];
+      if (x < xmin[y - lo]) xmin[y - lo] = x;
+      if (x > xmax[y - lo]) xmax[y - lo] = x;
+    }
+  }
+  free(ray);
+  *y_lo = lo;
+  *y_hi = hi;
+  *xmin_out = xmin;
+  *xmax_out = xmax;
+  return nrows;
+}
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+size_t oracle_lethal_cells_within(const uint8_t *map, uint32_t size_x, uint32_t size_y,
+                                  const int32_t box[10], int32_t **cells_xy) {
+  *cells_xy = NULL;
+  if (size_x == 0 || size_y == 0) return 0; /* :124-125 */
+  int32_t sb[10];
+  for (int i = 0; i < 5; ++i) { /* :121, :128-129 */
+    sb[2 * i] = clampi(box[2 * i], 0, (int)size_x - 1);
+    sb[2 * i + 1] = clampi(box[2 * i + 1], 0, (int)size_y - 1);
+  }
+  int y_lo, y_hi;
+  int32_t *xmin, *xmax;
+  const int nrows = oracle_to_rays(sb, &y_lo, &y_hi, &xmin, &xmax);
+  size_t count = 0;
+  for (int r = 0; r < nrows; ++r) { /* :143-155 count pass */
+    if (xmin[r] > xmax[r]) continue;
+    const uint8_t *row = map + (size_t)(y_lo + r) * size_x;
+    for (int x = xmin[r]; x <= xmax[r]; ++x) count += (row[x] == ORACLE_LETHAL);
+  }
+  if (count) { /* :157-179 write pass */
+    int32_t *cells = (int32_t *)malloc(sizeof(int32_t) * 2 * count);
+    size_t dd = 0;
+    for (int r = 0; r < nrows; ++r) {
+      if (xmin[r] > xmax[r]) continue;
+      const uint8_t *row = map + (size_t)(y_lo + r) * size_x;
+      for (int x = xmin[r]; x <= xmax[r]; ++x)
+        if (row[x] == ORACLE_LETHAL) {
+          cells[2 * dd] = x;
+          cells[2 * dd + 1] = y_lo + r;
+          ++dd;
+        }
+    }
+    *cells_xy = cells;
+  }
+  free(xmin);
+  free(xmax);
+  return count;
+}
+
+/* ------------------------------------------------------------------------- */
+/* batch driver: per pose lethal_cells_within(rotated box) +  */
+/* get_cost.  Box rotation as in test/lethal_cells_within.cpp:82-86.           */
+/* ------------------------------------------------------------------------- */
+static void rotated_box(const oracle_cost_data *cd, const double *pose, int32_t out[10]) {
+  const iso2 rot = to_eigen(pose[0], pose[1], pose[2]);
+  for (int i = 0; i < 5; ++i) {
+    double x, y;
+    iso_apply(&rot, (double)cd->box[2 * i], (double)cd->box[2 * i + 1], &x, &y);
+    out[2 * i] = (int32_t)round(x);
+    out[2 * i + 1] = (int32_t)round(y);
+  }
+}
+
+void oracle_get_cost_batch(const oracle_cost_data *cd, const uint8_t *map, uint32_t size_x,
+                           uint32_t size_y, const double *poses, size_t n, double *out,
+                           int want_jacobian, int shift, int nthreads) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads > 1 ? nthreads : 1)
+#endif
+  for (long long i = 0; i < (long long)n; ++i) {
+    const double *p = poses + 3 * i;
+    int32_t box[10];
+    rotated_box(cd, p, box);
+    int32_t *cells = NULL;
+    const size_t nc = oracle_lethal_cells_within(map, size_x, size_y, box, &cells);
+    double se2[3] = {p[0], p[1], p[2]};
+    if (shift) {
+      const int sx = (int)floor(p[0]), sy = (int)floor(p[1]);
+      se2[0] -= sx;
+      se2[1] -= sy;
+      for (size_t k = 0; k < nc; ++k) {
+        cells[2 * k] -= sx;
+        cells[2 * k + 1] -= sy;
+      }
+    }
+    double J[3] = {0, 0, 0};
+    out[4 * i] = oracle_get_cost(cd, se2, cells, nc, want_jacobian ? J : NULL);
+    out[4 * i + 1] = J[0];
+    out[4 * i + 2] = J[1];
+    out[4 * i + 3] = J[2];
+    free(cells);
+  }
+  (void)nthreads;
+}
+
+void oracle_get_cost_batch_truth(const oracle_cost_data *cd, const uint8_t *map,
+                                 uint32_t size_x, uint32_t size_y, const double *poses,
+                                 size_t n, double *out, int nthreads) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads > 1 ? nthreads : 1)
+#endif
+  for (long long i = 0; i < (long long)n; ++i) {
+    const double *p = poses + 3 * i;
+    int32_t box[10];
+    rotated_box(cd, p, box);
+    int32_t *cells = NULL;
+    const size_t nc = oracle_lethal_cells_within(map, size_x, size_y, box, &cells);
+    long double J[3] = {0, 0, 0};
+    out[4 * i] = (double)oracle_get_cost_truth(cd, p, cells, nc, J);
+    out[4 * i + 1] = (double)J[0];
+    out[4 * i + 2] = (double)J[1];
+    out[4 * i + 3] = (double)J[2];
+    free(cells);
+  }
+  (void)nthreads;
+}

@@ -1,0 +1,103 @@
+/*
+ * dpose_oracle.h — CPU restatement of dpose_core's footprint-cost path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is linked into, imported by or
+ * executed from the product (dpose_b200/, include/).  Only tests/, the smoke check in
+ * __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs may use it,
+ * and there only as the checker / the timed CPU baseline.
+ *
+ * Every function cites the reference file:line it restates (paths relative to the
+ * upstream dorezyuk/dpose tree).  The reference itself cannot be compiled in this
+ * image (Eigen, OpenCV C++, costmap_2d, boost are absent), and the image arithmetic
+ * lives in OpenCV (un-vendored; ROS noetic's libopencv-dev).  The restatement is
+ * therefore pinned against the same OpenCV functions through the cv2 4.13.0 Python
+ * wheel (oracle/py/cv_pipeline.py, tests/golden/make_golden.py) and against the
+ * known-answer vectors of SURVEY.md §8(c).
+ */
+#ifndef DPOSE_ORACLE_H
+#define DPOSE_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* costmap_2d/cost_values.h (external): LETHAL_OBSTACLE = 254 */
+#define ORACLE_LETHAL 254
+
+/* cost_data (dpose_core.hpp:79-102): cost image + center + box, plus the
+ * intermediate images kept for bit-exact checks. */
+typedef struct oracle_cost_data {
+  int rows, cols;       /* cv::Mat size of `cost` */
+  int center[2];        /* cost_data::center (x, y) */
+  int box[10];          /* cost_data::box, Eigen 2x5 column-major: x0,y0,x1,y1,... */
+  float *cost;          /* rows*cols, row-major, final blurred table */
+  float *pre_blur;      /* rows*cols, table before GaussianBlur */
+  int32_t *edt_sq;      /* rows*cols, exact squared distance to the outline */
+  uint8_t *outline;     /* rows*cols, 0 on the polylines outline, 255 else */
+  uint8_t *mask;        /* rows*cols, 0 inside (fillPoly), 255 outside */
+  float min_outer;      /* minMaxIdx(outer) minimum */
+} oracle_cost_data;
+
+/* make_footprint (dpose_costmap.cpp:40-55): metres -> cells, round half away.
+ * returns 0, or -1 if res <= 0 (the reference throws std::runtime_error). */
+int oracle_make_footprint(const double *xy_m, int n, double res, int32_t *xy_cells);
+
+/* cost_data::cost_data + _get_cost (dpose_core.cpp:55-139).
+ * fp_xy: x0,y0,x1,y1... (n vertices).  returns 0 on success, -1 on bad input. */
+int oracle_cost_data_create(const int32_t *fp_xy, int n, unsigned padding,
+                            oracle_cost_data *out);
+void oracle_cost_data_free(oracle_cost_data *cd);
+
+/* pose_gradient::get_cost (dpose_core.cpp:200-260) incl. interpolator
+ * (dpose_core.cpp:158-198): finite-difference Jacobian exactly as the reference.
+ * J may be NULL.  cells_xy: x0,y0,x1,y1,... */
+double oracle_get_cost(const oracle_cost_data *cd, const double se2[3],
+                       const int32_t *cells_xy, size_t n, double J[3]);
+
+/* Same cost, Jacobian by the analytic chain rule on the bilinear patch, evaluated in
+ * long double (adjudication "truth", SURVEY.md §7 hard part 2).  Not in the reference. */
+long double oracle_get_cost_truth(const oracle_cost_data *cd, const double se2[3],
+                                  const int32_t *cells_xy, size_t n, long double J[3]);
+
+/* raytrace (dpose_costmap.cpp:57-104): writes max(|dx|,|dy|) cells (end exclusive)
+ * into out_xy (caller sized) and returns that count. */
+size_t oracle_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_xy);
+
+/* to_rays (dpose_costmap.cpp:106-115) on a closed 5-point ring: per-row [min,max] x.
+ * rows are reported for y in [*y_lo, *y_hi]; xmin/xmax arrays are caller sized
+ * (y_hi-y_lo+1 <= span of the ring) and rows never touched keep xmin>xmax.
+ * returns number of rows spanned. */
+int oracle_to_rays(const int32_t box[10], int *y_lo, int *y_hi, int32_t **xmin,
+                   int32_t **xmax);
+
+/* lethal_cells_within (dpose_costmap.cpp:117-184).  Output order is canonical
+ * (y ascending, x ascending); the reference's order is unordered_map iteration order.
+ * *cells_xy is malloc'ed (free with free()); returns count. */
+size_t oracle_lethal_cells_within(const uint8_t *map, uint32_t size_x, uint32_t size_y,
+                                  const int32_t box[10], int32_t **cells_xy);
+
+/* The natural per-pose use of dpose_core for arbitrary poses:
+ * box = round(R(theta) * get_box() + t); cells = lethal_cells_within(map, box);
+ * get_cost(pose, cells, &J).  out: n x 4 (cost, Jx, Jy, Jtheta).
+ * shift != 0 evaluates on translated-equivalent inputs (pose and cells shifted by
+ * floor(tx), floor(ty)) — the parity protocol of SURVEY.md §7 hard part 2.
+ * nthreads <= 1: single thread (the reference is single-threaded); else OpenMP. */
+void oracle_get_cost_batch(const oracle_cost_data *cd, const uint8_t *map, uint32_t size_x,
+                           uint32_t size_y, const double *poses, size_t n, double *out,
+                           int want_jacobian, int shift, int nthreads);
+
+/* long-double analytic evaluation of the same batch (adjudication). out: n x 4 doubles. */
+void oracle_get_cost_batch_truth(const oracle_cost_data *cd, const uint8_t *map,
+                                 uint32_t size_x, uint32_t size_y, const double *poses,
+                                 size_t n, double *out, int nthreads);
+
+/* number of OpenMP threads available (1 if built without OpenMP) */
+int oracle_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
