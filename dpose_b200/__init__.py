@@ -1,0 +1,11 @@
+"""dpose_b200 — B200-native footprint-cost path of dpose_core.
+
+Python mirror of the reference's dpose_core interface (same names, argument meaning and
+error behaviour) on top of the C ABI in include/dpose_b200.h.  The compute runs in
+hand-written CUDA kernels (dpose_b200/csrc); there is no CPU fallback.
+"""
+from ._lib import DposeError, LIB_PATH  # noqa: F401
+from .core import (Costmap, cell_vector_device, cost_data, device_count, launch_count,  # noqa: F401
+                   lethal_cells_within, make_footprint, pose_gradient, raytrace, to_rectangle)
+
+LETHAL_OBSTACLE = 254

@@ -1,0 +1,284 @@
+"""Python mirror of dpose_core's public interface over the C ABI.
+
+reference surface                         | here
+------------------------------------------|---------------------------------------------
+cost_data(footprint, padding)             | cost_data            (dpose_core.hpp:79-102)
+pose_gradient(footprint, parameter)       | pose_gradient        (dpose_core.hpp:133-167)
+pose_gradient::get_cost(se2, b, e, &J)    | pose_gradient.get_cost(se2, cells, jacobian=True)
+make_footprint(layered_costmap)           | make_footprint(points_m, resolution)
+lethal_cells_within(costmap, box)         | lethal_cells_within(costmap, box)
+raytrace(begin, end)                      | raytrace(begin, end)
+to_rectangle(w, h) / (min, max)           | to_rectangle
+NEW get_cost(poses[])                     | pose_gradient.get_cost_batch(costmap, poses)
+
+Polygons / cell vectors are (n, 2) int32 arrays of (x, y); rectangles are (5, 2) rings.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import DposeError, check, lib, EINVAL
+
+
+def device_count():
+    n = C.c_int(0)
+    lib().dpose_device_count(C.byref(n))
+    return n.value
+
+
+def launch_count():
+    return int(lib().dpose_launch_count())
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def to_rectangle(a, b):
+    """dpose_core.hpp:45-69"""
+    if np.ndim(a) == 0:
+        lo, hi = (0, 0), (int(a), int(b))
+    else:
+        lo, hi = a, b
+    return np.array([[lo[0], lo[1]], [hi[0], lo[1]], [hi[0], hi[1]], [lo[0], hi[1]], [lo[0], lo[1]]],
+                    dtype=np.int32)
+
+
+def make_footprint(points_m, resolution):
+    """dpose_costmap.cpp:40-55.  Raises RuntimeError("resolution must be positive")."""
+    xy = np.ascontiguousarray(np.asarray(points_m, dtype=np.float64).reshape(-1, 2))
+    out = np.empty(xy.shape, dtype=np.int32)
+    rc = lib().dpose_make_footprint(xy.ctypes.data, xy.shape[0], float(resolution), out.ctypes.data)
+    if rc == EINVAL:
+        raise RuntimeError(lib().dpose_last_error().decode())
+    check(rc)
+    return out
+
+
+def raytrace(begin, end):
+    """dpose_costmap.cpp:57-104 (end exclusive)."""
+    b, e = _i32(begin), _i32(end)
+    cap = int(max(abs(int(e[0]) - int(b[0])), abs(int(e[1]) - int(b[1]))))
+    out = np.empty((max(cap, 1), 2), dtype=np.int32)
+    n = C.c_size_t(0)
+    check(lib().dpose_raytrace(b.ctypes.data, e.ctypes.data, out.ctypes.data, cap, C.byref(n)))
+    return out[: n.value].copy()
+
+
+class Costmap:
+    """Device-resident copy of a costmap_2d::Costmap2D char map (uint8, [y, x])."""
+
+    def __init__(self, data=None, device=0, *, device_ptr=None, size_x=None, size_y=None, pitch=None):
+        self._h = C.c_void_p()
+        self.device = int(device)
+        if device_ptr is not None:
+            check(lib().dpose_map_create_from_device(C.c_void_p(int(device_ptr)), size_x, size_y,
+                                                     pitch or size_x, self.device, C.byref(self._h)))
+            self.size_x, self.size_y = int(size_x), int(size_y)
+        else:
+            m = np.ascontiguousarray(np.asarray(data, dtype=np.uint8))
+            if m.ndim != 2:
+                m = m.reshape(0, 0)
+            self.size_y, self.size_x = m.shape
+            check(lib().dpose_map_create(m.ctypes.data, self.size_x, self.size_y, m.strides[0] if m.size else 0,
+                                         self.device, C.byref(self._h)))
+
+    def update(self, window, x0, y0):
+        """re-upload a dirty window (rows [y0, y0+h), columns [x0, x0+w))"""
+        w = np.ascontiguousarray(np.asarray(window, dtype=np.uint8))
+        check(lib().dpose_map_update(self._h, w.ctypes.data, w.strides[0], int(x0), int(y0), w.shape[1], w.shape[0]))
+
+    def close(self):
+        if self._h:
+            lib().dpose_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class cell_vector_device:
+    """A cell_vector kept in device memory (result of lethal_cells_within(..., on_device=True))."""
+
+    def __init__(self, handle, device):
+        self._h = handle
+        self.device = device
+
+    @classmethod
+    def upload(cls, cells, device=0):
+        c = _i32(cells).reshape(-1, 2)
+        h = C.c_void_p()
+        check(lib().dpose_cells_upload(c.ctypes.data, c.shape[0], int(device), C.byref(h)))
+        return cls(h, int(device))
+
+    def __len__(self):
+        n = C.c_size_t(0)
+        check(lib().dpose_cells_size(self._h, C.byref(n)))
+        return n.value
+
+    def numpy(self):
+        out = np.empty((len(self), 2), dtype=np.int32)
+        check(lib().dpose_cells_download(self._h, out.ctypes.data))
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().dpose_cells_destroy(self._h)
+        except Exception:
+            pass
+
+
+def lethal_cells_within(costmap, box, on_device=False):
+    """dpose_costmap.cpp:117-184.  costmap: Costmap (or a uint8 array, uploaded on the fly).
+    Returns (n, 2) int32 cells, y ascending then x ascending."""
+    own = None
+    if not isinstance(costmap, Costmap):
+        own = costmap = Costmap(costmap)
+    b = _i32(box).reshape(10)
+    try:
+        if on_device:
+            h = C.c_void_p()
+            check(lib().dpose_lethal_cells_within_device(costmap._h, b.ctypes.data, C.byref(h)))
+            return cell_vector_device(h, costmap.device)
+        ptr, n = C.c_void_p(), C.c_size_t(0)
+        check(lib().dpose_lethal_cells_within(costmap._h, b.ctypes.data, C.byref(ptr), C.byref(n)))
+        if n.value == 0:
+            return np.empty((0, 2), dtype=np.int32)
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int32)), (n.value * 2,)).reshape(-1, 2).copy()
+        lib().dpose_free(ptr)
+        return arr
+    finally:
+        if own is not None:
+            own.close()
+
+
+class cost_data:
+    """dpose_core.hpp:79-102 — cost matrix, center cell and bounding box of a footprint."""
+
+    def __init__(self, footprint, padding, device=0):
+        fp = _i32(footprint).reshape(-1, 2)
+        self._h = C.c_void_p()
+        self.device = int(device)
+        # the reference's cost_data accepts any polygon; the <3-vertex check lives in
+        # pose_gradient (dpose_core.cpp:152-153).  The C ABI enforces it for both.
+        rc = lib().dpose_pg_create(fp.ctypes.data, fp.shape[0], int(padding), self.device, C.byref(self._h))
+        if rc == EINVAL:
+            raise RuntimeError(lib().dpose_last_error().decode())
+        check(rc)
+        cost, rows, cols = C.c_void_p(), C.c_int(0), C.c_int(0)
+        center = np.zeros(2, np.int32)
+        box = np.zeros(10, np.int32)
+        check(lib().dpose_pg_table(self._h, C.byref(cost), C.byref(rows), C.byref(cols), center.ctypes.data,
+                                   box.ctypes.data))
+        self.rows, self.cols = rows.value, cols.value
+        n = self.rows * self.cols
+        self._cost = np.ctypeslib.as_array(C.cast(cost, C.POINTER(C.c_float)), (n,)).reshape(self.rows, self.cols).copy()
+        self._center = center
+        self._box = box.reshape(5, 2)
+
+    def get_data(self):
+        return self._cost
+
+    def get_center(self):
+        return self._center
+
+    def get_box(self):
+        return self._box
+
+    def stages(self):
+        """(edt_sq int32, outline uint8, mask uint8, pre_blur float32) for bit-exact checks"""
+        ptrs = [C.c_void_p() for _ in range(4)]
+        check(lib().dpose_pg_stages(self._h, *[C.byref(p) for p in ptrs]))
+        n, shape = self.rows * self.cols, (self.rows, self.cols)
+        types = (C.c_int32, C.c_uint8, C.c_uint8, C.c_float)
+        return tuple(np.ctypeslib.as_array(C.cast(p, C.POINTER(t)), (n,)).reshape(shape).copy()
+                     for p, t in zip(ptrs, types))
+
+    def precompute_us(self):
+        us = C.c_float(0)
+        check(lib().dpose_pg_precompute_us(self._h, C.byref(us)))
+        return us.value
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().dpose_pg_destroy(self._h)
+        except Exception:
+            pass
+
+
+class pose_gradient:
+    """dpose_core.hpp:133-167."""
+
+    class parameter:
+        def __init__(self, padding=2):
+            self.padding = int(padding)
+
+    def __init__(self, footprint, param=None, device=0):
+        param = param or pose_gradient.parameter()
+        if isinstance(param, int):
+            param = pose_gradient.parameter(param)
+        fp = _i32(footprint).reshape(-1, 2)
+        if fp.shape[0] < 3:  # dpose_core.cpp:152-153
+            raise RuntimeError("footprint must contain at least three points")
+        self._data = cost_data(fp, param.padding, device)
+        self.device = int(device)
+
+    def get_data(self):
+        return self._data
+
+    def get_cost(self, se2, cells, jacobian=True):
+        """cost (and J if jacobian) of one pose over an explicit cell list (dpose_core.cpp:200-260).
+        cells: (n, 2) int32 array or a cell_vector_device.  Returns (cost, J) with J = None when
+        jacobian is False."""
+        p = np.ascontiguousarray(np.asarray(se2, dtype=np.float64).reshape(3))
+        cost = C.c_double(0.0)
+        J = np.zeros(3, dtype=np.float64)
+        Jp = J.ctypes.data if jacobian else None
+        if isinstance(cells, cell_vector_device):
+            check(lib().dpose_pg_get_cost_cells_device(self._data._h, p.ctypes.data, cells._h, C.byref(cost), Jp))
+        else:
+            c = _i32(cells).reshape(-1, 2)
+            check(lib().dpose_pg_get_cost_cells(self._data._h, p.ctypes.data, c.ctypes.data, c.shape[0],
+                                                C.byref(cost), Jp))
+        return cost.value, (J if jacobian else None)
+
+    def get_cost_batch(self, costmap, poses, jacobian=True, out=None):
+        """NEW: (n, 3) float64 poses -> (n, 4) float64 [cost, Jx, Jy, Jtheta] over all lethal cells
+        of `costmap`.  Host buffers; H2D and D2H are part of the call."""
+        p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+        if out is None:
+            out = np.empty((p.shape[0], 4), dtype=np.float64)
+        assert out.flags.c_contiguous and out.dtype == np.float64 and out.shape == (p.shape[0], 4)
+        check(lib().dpose_pg_get_cost_batch(self._data._h, costmap._h, p.ctypes.data, p.shape[0],
+                                            out.ctypes.data, int(bool(jacobian))))
+        return out
+
+    def get_cost_batch_device(self, costmap, d_poses, n, d_out, jacobian=True, stream=0):
+        """device pointers (ints), asynchronous on `stream` (a cudaStream_t as int)."""
+        check(lib().dpose_pg_get_cost_batch_device(self._data._h, costmap._h, C.c_void_p(int(d_poses)), int(n),
+                                                   C.c_void_p(int(d_out)), int(bool(jacobian)),
+                                                   C.c_void_p(int(stream))))
+
+    def window_bytes(self, costmap, poses):
+        p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+        b = C.c_uint64(0)
+        check(lib().dpose_pg_window_bytes(self._data._h, costmap._h, p.ctypes.data, p.shape[0], C.byref(b)))
+        return int(b.value)
+
+
+def get_cost_batch_multi(pgs, maps, poses, jacobian=True, out=None):
+    """pose batch sharded contiguously over len(pgs) GPUs (one pose_gradient + Costmap per device)."""
+    p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+    if out is None:
+        out = np.empty((p.shape[0], 4), dtype=np.float64)
+    n = len(pgs)
+    pg_arr = (C.c_void_p * n)(*[pg._data._h for pg in pgs])
+    map_arr = (C.c_void_p * n)(*[m._h for m in maps])
+    check(lib().dpose_pg_get_cost_batch_multi(pg_arr, map_arr, n, p.ctypes.data, p.shape[0], out.ctypes.data,
+                                              int(bool(jacobian))))
+    return out

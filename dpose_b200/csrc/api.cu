@@ -1,0 +1,448 @@
+// api.cu — the extern "C" surface of libdpose_b200.so (include/dpose_b200.h): argument
+// validation, handle lifetime, host<->device staging and the multi-GPU shard driver.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <thread>
+
+#include "common.cuh"
+
+namespace dpose {
+
+std::atomic<uint64_t> g_launches{0};
+
+std::string &last_error() {
+  thread_local std::string e;
+  return e;
+}
+
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+static int check_device(int device) {
+  int n = 0;
+  const cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(DPOSE_ENODEV, "no CUDA device available (%s); libdpose_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(DPOSE_EINVAL, "device %d out of range [0, %d)", device, n);
+  return DPOSE_OK;
+}
+
+}  // namespace dpose
+
+using namespace dpose;
+
+extern "C" {
+
+const char *dpose_last_error(void) { return last_error().c_str(); }
+
+int dpose_device_count(int *n) {
+  if (!n) return fail(DPOSE_EINVAL, "n is NULL");
+  *n = 0;
+  const cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) {
+    *n = 0;
+    return fail(DPOSE_ENODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  return DPOSE_OK;
+}
+
+uint64_t dpose_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dpose_host_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return fail(DPOSE_EINVAL, "ptr is NULL");
+  DPOSE_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+  return DPOSE_OK;
+}
+
+void dpose_host_free(void *ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+void dpose_free(void *ptr) { std::free(ptr); }
+
+// ---- footprint ----------------------------------------------------------------------------
+int dpose_make_footprint(const double *xy_m, int n, double resolution, int32_t *xy_cells) {
+  if (!(resolution > 0)) return fail(DPOSE_EINVAL, "resolution must be positive");
+  if (n < 0 || (n > 0 && (!xy_m || !xy_cells))) return fail(DPOSE_EINVAL, "bad footprint buffer");
+  for (int i = 0; i < 2 * n; ++i) xy_cells[i] = (int32_t)std::round(xy_m[i] / resolution);
+  return DPOSE_OK;
+}
+
+// ---- pose_gradient / cost_data ----------------------------------------------------------------
+int dpose_pg_create(const int32_t *fp, int n, uint32_t padding, int device, dpose_pg **out) {
+  if (!out) return fail(DPOSE_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (n < 3 || !fp) return fail(DPOSE_EINVAL, "footprint must contain at least three points");
+  if (n > 4096) return fail(DPOSE_EINVAL, "footprint has %d vertices; at most 4096 supported", n);
+  if (padding > 4096) return fail(DPOSE_EINVAL, "padding %u too large", padding);
+  DPOSE_TRY(check_device(device));
+  long long minx = LLONG_MAX, miny = LLONG_MAX, maxx = LLONG_MIN, maxy = LLONG_MIN;
+  for (int i = 0; i < n; ++i) {
+    minx = std::min<long long>(minx, fp[2 * i]);
+    maxx = std::max<long long>(maxx, fp[2 * i]);
+    miny = std::min<long long>(miny, fp[2 * i + 1]);
+    maxy = std::max<long long>(maxy, fp[2 * i + 1]);
+  }
+  const long long cols = maxx - minx + 1 + 2ll * padding, rows = maxy - miny + 1 + 2ll * padding;
+  if (cols > 16384 || rows > 16384 || cols * rows > (1ll << 26))
+    return fail(DPOSE_EINVAL, "cost table %lld x %lld too large", rows, cols);
+  dpose_pg *pg = new (std::nothrow) dpose_pg();
+  if (!pg) return fail(DPOSE_ENOMEM, "out of host memory");
+  pg->device = device;
+  pg->padding = padding;
+  pg->rows = (int)rows;
+  pg->cols = (int)cols;
+  // dpose_core.cpp:124-125 center = padding - rowwise min; :138 box = ring(cols, rows) - center
+  pg->center[0] = (int32_t)((long long)padding - minx);
+  pg->center[1] = (int32_t)((long long)padding - miny);
+  const int bx[5] = {0, pg->cols, pg->cols, 0, 0}, by[5] = {0, 0, pg->rows, pg->rows, 0};
+  for (int i = 0; i < 5; ++i) {
+    pg->box[2 * i] = bx[i] - pg->center[0];
+    pg->box[2 * i + 1] = by[i] - pg->center[1];
+  }
+  const double a = pg->cols - 3, b = pg->rows - 3;
+  pg->win_max = (int)std::floor(std::sqrt(a * a + b * b)) + 2;
+  std::vector<int32_t> shifted(2 * (size_t)n);  // :128
+  for (int i = 0; i < n; ++i) {
+    shifted[2 * i] = fp[2 * i] + pg->center[0];
+    shifted[2 * i + 1] = fp[2 * i + 1] + pg->center[1];
+  }
+  int rc;
+  {
+    DeviceGuard guard(device);
+    rc = guard.ok ? precompute_run(pg, shifted.data(), n) : fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", device);
+  }
+  if (rc != DPOSE_OK) {
+    dpose_pg_destroy(pg);
+    return rc;
+  }
+  *out = pg;
+  return DPOSE_OK;
+}
+
+void dpose_pg_destroy(dpose_pg *pg) {
+  if (!pg) return;
+  {
+    DeviceGuard guard(pg->device);
+    cudaFree(pg->d_cost);
+    cudaFree(pg->d_coef);
+  }
+  delete pg;
+}
+
+int dpose_pg_table(const dpose_pg *pg, const float **cost, int *rows, int *cols, int32_t center[2],
+                   int32_t box[10]) {
+  if (!pg) return fail(DPOSE_EINVAL, "pg is NULL");
+  if (cost) *cost = pg->h_cost.data();
+  if (rows) *rows = pg->rows;
+  if (cols) *cols = pg->cols;
+  if (center) std::memcpy(center, pg->center, sizeof(pg->center));
+  if (box) std::memcpy(box, pg->box, sizeof(pg->box));
+  return DPOSE_OK;
+}
+
+int dpose_pg_stages(const dpose_pg *pg, const int32_t **edt_sq, const uint8_t **outline,
+                    const uint8_t **mask, const float **pre_blur) {
+  if (!pg) return fail(DPOSE_EINVAL, "pg is NULL");
+  if (edt_sq) *edt_sq = pg->h_edt_sq.data();
+  if (outline) *outline = pg->h_outline.data();
+  if (mask) *mask = pg->h_mask.data();
+  if (pre_blur) *pre_blur = pg->h_pre_blur.data();
+  return DPOSE_OK;
+}
+
+int dpose_pg_precompute_us(const dpose_pg *pg, float *us) {
+  if (!pg || !us) return fail(DPOSE_EINVAL, "NULL argument");
+  *us = pg->precompute_us;
+  return DPOSE_OK;
+}
+
+// ---- costmap ------------------------------------------------------------------------------------
+static int map_create_impl(const uint8_t *data, uint32_t size_x, uint32_t size_y, size_t pitch,
+                           int device, cudaMemcpyKind kind, dpose_map **out) {
+  if (!out) return fail(DPOSE_EINVAL, "out is NULL");
+  *out = nullptr;
+  if ((size_x && size_y && !data) || pitch < size_x) return fail(DPOSE_EINVAL, "bad costmap buffer / pitch");
+  if (size_x > (1u << 30) || size_y > (1u << 30)) return fail(DPOSE_EINVAL, "costmap too large");
+  DPOSE_TRY(check_device(device));
+  dpose_map *m = new (std::nothrow) dpose_map();
+  if (!m) return fail(DPOSE_ENOMEM, "out of host memory");
+  m->device = device;
+  m->size_x = size_x;
+  m->size_y = size_y;
+  m->pitch = ((size_t)size_x + 15) & ~(size_t)15;
+  auto body = [&]() -> int {
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", device);
+    if (size_x == 0 || size_y == 0) return DPOSE_OK;
+    DPOSE_CUDA(cudaMalloc(&m->d_data, m->pitch * size_y));
+    if (m->pitch != size_x) DPOSE_CUDA(cudaMemset(m->d_data, 0, m->pitch * size_y));
+    DPOSE_CUDA(cudaMemcpy2D(m->d_data, m->pitch, data, pitch, size_x, size_y, kind));
+    return DPOSE_OK;
+  };
+  const int rc = body();
+  if (rc != DPOSE_OK) {
+    dpose_map_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return DPOSE_OK;
+}
+
+int dpose_map_create(const uint8_t *data, uint32_t size_x, uint32_t size_y, size_t pitch, int device,
+                     dpose_map **out) {
+  return map_create_impl(data, size_x, size_y, pitch, device, cudaMemcpyHostToDevice, out);
+}
+
+int dpose_map_create_from_device(const uint8_t *d_data, uint32_t size_x, uint32_t size_y, size_t pitch,
+                                 int device, dpose_map **out) {
+  return map_create_impl(d_data, size_x, size_y, pitch, device, cudaMemcpyDeviceToDevice, out);
+}
+
+int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t x0, uint32_t y0,
+                     uint32_t w, uint32_t h) {
+  if (!map || !data) return fail(DPOSE_EINVAL, "NULL argument");
+  if ((uint64_t)x0 + w > map->size_x || (uint64_t)y0 + h > map->size_y || pitch < w)
+    return fail(DPOSE_EINVAL, "update window outside the map");
+  if (w == 0 || h == 0) return DPOSE_OK;
+  DeviceGuard guard(map->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", map->device);
+  DPOSE_CUDA(cudaMemcpy2D(map->d_data + (size_t)y0 * map->pitch + x0, map->pitch, data, pitch, w, h,
+                          cudaMemcpyHostToDevice));
+  return DPOSE_OK;
+}
+
+int dpose_map_size(const dpose_map *map, uint32_t *size_x, uint32_t *size_y) {
+  if (!map) return fail(DPOSE_EINVAL, "map is NULL");
+  if (size_x) *size_x = map->size_x;
+  if (size_y) *size_y = map->size_y;
+  return DPOSE_OK;
+}
+
+void dpose_map_destroy(dpose_map *map) {
+  if (!map) return;
+  {
+    DeviceGuard guard(map->device);
+    map_release_cache(map);
+    cudaFree(map->d_data);
+  }
+  delete map;
+}
+
+// ---- lethal cells -----------------------------------------------------------------------------------
+int dpose_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_xy, size_t cap, size_t *n) {
+  if (!begin || !end || !n || (cap && !out_xy)) return fail(DPOSE_EINVAL, "NULL argument");
+  *n = host_raytrace(begin, end, out_xy, cap);
+  return DPOSE_OK;
+}
+
+int dpose_lethal_cells_within_device(const dpose_map *map, const int32_t box[10], dpose_cells **out) {
+  if (!map || !box || !out) return fail(DPOSE_EINVAL, "NULL argument");
+  *out = nullptr;
+  DPOSE_TRY(check_device(map->device));
+  dpose_cells *c = new (std::nothrow) dpose_cells();
+  if (!c) return fail(DPOSE_ENOMEM, "out of host memory");
+  c->device = map->device;
+  const int rc = lethal_extract(map, box, &c->d_xy, &c->n);
+  if (rc != DPOSE_OK) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return DPOSE_OK;
+}
+
+int dpose_lethal_cells_within(const dpose_map *map, const int32_t box[10], int32_t **cells_xy, size_t *n) {
+  if (!cells_xy || !n) return fail(DPOSE_EINVAL, "NULL argument");
+  *cells_xy = nullptr;
+  *n = 0;
+  dpose_cells *c = nullptr;
+  DPOSE_TRY(dpose_lethal_cells_within_device(map, box, &c));
+  int rc = DPOSE_OK;
+  if (c->n) {
+    int32_t *h = (int32_t *)std::malloc(sizeof(int32_t) * 2 * c->n);
+    if (!h)
+      rc = fail(DPOSE_ENOMEM, "out of host memory");
+    else if ((rc = dpose_cells_download(c, h)) == DPOSE_OK) {
+      *cells_xy = h;
+      *n = c->n;
+    } else
+      std::free(h);
+  }
+  dpose_cells_destroy(c);
+  return rc;
+}
+
+int dpose_cells_upload(const int32_t *cells_xy, size_t n, int device, dpose_cells **out) {
+  if (!out || (n && !cells_xy)) return fail(DPOSE_EINVAL, "NULL argument");
+  *out = nullptr;
+  DPOSE_TRY(check_device(device));
+  dpose_cells *c = new (std::nothrow) dpose_cells();
+  if (!c) return fail(DPOSE_ENOMEM, "out of host memory");
+  c->device = device;
+  c->n = n;
+  auto body = [&]() -> int {
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", device);
+    if (!n) return DPOSE_OK;
+    DPOSE_CUDA(cudaMalloc(&c->d_xy, sizeof(int2) * n));
+    DPOSE_CUDA(cudaMemcpy(c->d_xy, cells_xy, sizeof(int2) * n, cudaMemcpyHostToDevice));
+    return DPOSE_OK;
+  };
+  const int rc = body();
+  if (rc != DPOSE_OK) {
+    dpose_cells_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return DPOSE_OK;
+}
+
+int dpose_cells_size(const dpose_cells *cells, size_t *n) {
+  if (!cells || !n) return fail(DPOSE_EINVAL, "NULL argument");
+  *n = cells->n;
+  return DPOSE_OK;
+}
+
+int dpose_cells_download(const dpose_cells *cells, int32_t *cells_xy) {
+  if (!cells || (cells->n && !cells_xy)) return fail(DPOSE_EINVAL, "NULL argument");
+  if (!cells->n) return DPOSE_OK;
+  DeviceGuard guard(cells->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", cells->device);
+  DPOSE_CUDA(cudaMemcpy(cells_xy, cells->d_xy, sizeof(int2) * cells->n, cudaMemcpyDeviceToHost));
+  return DPOSE_OK;
+}
+
+void dpose_cells_destroy(dpose_cells *cells) {
+  if (!cells) return;
+  {
+    DeviceGuard guard(cells->device);
+    cudaFree(cells->d_xy);
+  }
+  delete cells;
+}
+
+// ---- get_cost -----------------------------------------------------------------------------------------
+int dpose_pg_get_cost_cells(const dpose_pg *pg, const double se2[3], const int32_t *cells_xy, size_t n,
+                            double *cost, double *J) {
+  if (!pg || !se2 || !cost || (n && !cells_xy)) return fail(DPOSE_EINVAL, "NULL argument");
+  return get_cost_cells_host(pg, se2, cells_xy, n, cost, J);
+}
+
+int dpose_pg_get_cost_cells_device(const dpose_pg *pg, const double se2[3], const dpose_cells *cells,
+                                   double *cost, double *J) {
+  if (!pg || !se2 || !cost || !cells) return fail(DPOSE_EINVAL, "NULL argument");
+  if (cells->device != pg->device) return fail(DPOSE_EINVAL, "cells and pose_gradient live on different devices");
+  return get_cost_cells(pg, se2, cells->d_xy, cells->n, cost, J);
+}
+
+int dpose_pg_get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses,
+                                   size_t n, double *d_out, int want_jacobian, void *stream) {
+  if (!pg || !map || (n && (!d_poses || !d_out))) return fail(DPOSE_EINVAL, "NULL argument");
+  return get_cost_batch_device(pg, map, d_poses, n, d_out, want_jacobian, (cudaStream_t)stream);
+}
+
+// host buffers: H2D / kernel / D2H chunks on three streams, double-buffered device staging
+int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n,
+                            double *out, int want_jacobian) {
+  if (!pg || !map || (n && (!poses || !out))) return fail(DPOSE_EINVAL, "NULL argument");
+  if (n == 0) return DPOSE_OK;
+  DPOSE_TRY(check_device(pg->device));
+  DeviceGuard guard(pg->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
+  constexpr int kBuf = 3;
+  const size_t chunk = std::min<size_t>(n, (size_t)1 << 19);
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t in_done[kBuf] = {}, k_done[kBuf] = {}, out_done[kBuf] = {};
+  double *d_p[kBuf] = {}, *d_o[kBuf] = {};
+  auto body = [&]() -> int {
+    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < kBuf; ++b) {
+      DPOSE_CUDA(cudaMalloc(&d_p[b], sizeof(double) * 3 * chunk));
+      DPOSE_CUDA(cudaMalloc(&d_o[b], sizeof(double) * 4 * chunk));
+      DPOSE_CUDA(cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming));
+      DPOSE_CUDA(cudaEventCreateWithFlags(&k_done[b], cudaEventDisableTiming));
+      DPOSE_CUDA(cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming));
+    }
+    size_t it = 0;
+    for (size_t off = 0; off < n; off += chunk, ++it) {
+      const int b = (int)(it % kBuf);
+      const size_t m = std::min(chunk, n - off);
+      if (it >= kBuf) {  // buffer reuse: its previous D2H must be complete
+        DPOSE_CUDA(cudaStreamWaitEvent(s_in, out_done[b], 0));
+      }
+      DPOSE_CUDA(cudaMemcpyAsync(d_p[b], poses + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, s_in));
+      DPOSE_CUDA(cudaEventRecord(in_done[b], s_in));
+      DPOSE_CUDA(cudaStreamWaitEvent(s_k, in_done[b], 0));
+      DPOSE_TRY(get_cost_batch_device(pg, map, d_p[b], m, d_o[b], want_jacobian, s_k));
+      DPOSE_CUDA(cudaEventRecord(k_done[b], s_k));
+      DPOSE_CUDA(cudaStreamWaitEvent(s_out, k_done[b], 0));
+      DPOSE_CUDA(cudaMemcpyAsync(out + 4 * off, d_o[b], sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s_out));
+      DPOSE_CUDA(cudaEventRecord(out_done[b], s_out));
+    }
+    DPOSE_CUDA(cudaStreamSynchronize(s_out));
+    DPOSE_CUDA(cudaStreamSynchronize(s_k));
+    DPOSE_CUDA(cudaStreamSynchronize(s_in));
+    return DPOSE_OK;
+  };
+  const int rc = body();
+  if (rc != DPOSE_OK) cudaDeviceSynchronize();
+  for (int b = 0; b < kBuf; ++b) {
+    cudaFree(d_p[b]);
+    cudaFree(d_o[b]);
+    if (in_done[b]) cudaEventDestroy(in_done[b]);
+    if (k_done[b]) cudaEventDestroy(k_done[b]);
+    if (out_done[b]) cudaEventDestroy(out_done[b]);
+  }
+  if (s_in) cudaStreamDestroy(s_in);
+  if (s_k) cudaStreamDestroy(s_k);
+  if (s_out) cudaStreamDestroy(s_out);
+  return rc;
+}
+
+int dpose_pg_get_cost_batch_multi(dpose_pg *const *pgs, dpose_map *const *maps, int ndev,
+                                  const double *poses, size_t n, double *out, int want_jacobian) {
+  if (!pgs || !maps || ndev < 1 || (n && (!poses || !out))) return fail(DPOSE_EINVAL, "bad argument");
+  for (int d = 0; d < ndev; ++d)
+    if (!pgs[d] || !maps[d]) return fail(DPOSE_EINVAL, "NULL handle for shard %d", d);
+  if (ndev == 1) return dpose_pg_get_cost_batch(pgs[0], maps[0], poses, n, out, want_jacobian);
+  // contiguous shards, one host thread per device, no collective
+  std::vector<int> rcs((size_t)ndev, DPOSE_OK);
+  std::vector<std::string> errs((size_t)ndev);
+  std::vector<std::thread> th;
+  const size_t per = (n + ndev - 1) / ndev;
+  for (int d = 0; d < ndev; ++d) {
+    const size_t lo = std::min(n, per * d), hi = std::min(n, per * (d + 1));
+    th.emplace_back([&, d, lo, hi]() {
+      rcs[d] = dpose_pg_get_cost_batch(pgs[d], maps[d], poses + 3 * lo, hi - lo, out + 4 * lo, want_jacobian);
+      if (rcs[d] != DPOSE_OK) errs[d] = last_error();
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int d = 0; d < ndev; ++d)
+    if (rcs[d] != DPOSE_OK) return fail(rcs[d], "shard %d: %s", d, errs[d].c_str());
+  return DPOSE_OK;
+}
+
+int dpose_pg_window_bytes(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n,
+                          uint64_t *bytes) {
+  if (!pg || !map || !bytes || (n && !poses)) return fail(DPOSE_EINVAL, "NULL argument");
+  *bytes = window_bytes_host(pg, map, poses, n);
+  return DPOSE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+// common.cuh — handle layouts, error plumbing and launch accounting shared by the
+// translation units of libdpose_b200.so.  Not part of the public surface.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/dpose_b200.h"
+
+namespace dpose {
+
+constexpr uint8_t kLethal = 254;  // costmap_2d::LETHAL_OBSTACLE
+
+// ---- error plumbing -----------------------------------------------------------------
+std::string &last_error();
+int fail(int code, const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define DPOSE_CUDA(expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess)                                                            \
+      return ::dpose::fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver \
+                               ? DPOSE_ENODEV                                         \
+                               : DPOSE_ECUDA,                                         \
+                           "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,              \
+                           cudaGetErrorString(_e));                                   \
+  } while (0)
+
+#define DPOSE_TRY(expr)          \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != DPOSE_OK) return _rc; \
+  } while (0)
+
+// counts the launch and reports launch-configuration errors
+#define DPOSE_LAUNCHED()                          \
+  do {                                            \
+    ::dpose::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    DPOSE_CUDA(cudaGetLastError());               \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// per-patch bilinear coefficients, indexed by k_upper = (ux, uy):
+//   f(cx, cy) = a00 + a10*cx + a01*cy + a11*cx*cy,   c_rel in [0,1)^2
+// a00 = T(uy-1,ux-1), a10 = T(uy-1,ux)-a00, a01 = T(uy,ux-1)-a00,
+// a11 = T(uy,ux) - T(uy-1,ux) - T(uy,ux-1) + a00  (all exact in FP64)
+struct __align__(32) PatchCoef {
+  double a00, a10, a01, a11;
+};
+
+}  // namespace dpose
+
+// ---- handles --------------------------------------------------------------------------
+struct dpose_pg {
+  int device = 0;
+  int rows = 0, cols = 0;
+  int32_t center[2] = {0, 0};
+  int32_t box[10] = {0};
+  uint32_t padding = 0;
+  // device
+  float *d_cost = nullptr;          // rows*cols
+  dpose::PatchCoef *d_coef = nullptr;  // rows*cols, valid for 2<=ux<=cols-2, 2<=uy<=rows-2
+  // host copies
+  std::vector<float> h_cost, h_pre_blur;
+  std::vector<int32_t> h_edt_sq;
+  std::vector<uint8_t> h_outline, h_mask;
+  float precompute_us = 0.f;
+  // batched kernel geometry: side of the largest window (cells) any pose can touch
+  int win_max = 0;
+};
+
+struct dpose_map {
+  int device = 0;
+  uint32_t size_x = 0, size_y = 0;
+  size_t pitch = 0;  // bytes, multiple of 16
+  uint8_t *d_data = nullptr;
+  // TMA descriptor cache (get_cost.cu), keyed by box dims
+  void *tma_cache = nullptr;
+};
+
+struct dpose_cells {
+  int device = 0;
+  size_t n = 0;
+  int2 *d_xy = nullptr;
+};
+
+namespace dpose {
+// precompute.cu
+int precompute_run(dpose_pg *pg, const int32_t *shifted_fp_xy, int n);
+// lethal.cu
+int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, size_t *n);
+size_t host_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_xy, size_t cap);
+// get_cost.cu
+int get_cost_cells(const dpose_pg *pg, const double se2[3], const int2 *d_cells, size_t n,
+                   double *cost, double *J);
+int get_cost_cells_host(const dpose_pg *pg, const double se2[3], const int32_t *cells_xy, size_t n,
+                        double *cost, double *J);
+uint64_t window_bytes_host(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n);
+int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses,
+                          size_t n, double *d_out, int want_jacobian, cudaStream_t stream);
+void map_release_cache(dpose_map *map);
+// host window geometry shared by the kernel launch code and dpose_pg_window_bytes
+struct WindowRect {
+  int x0, y0, x1, y1;  // inclusive cell range, already clipped; empty if x1 < x0
+};
+}  // namespace dpose

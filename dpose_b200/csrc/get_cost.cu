@@ -1,0 +1,317 @@
+// get_cost.cu — pose_gradient::get_cost on the GPU (replaces dpose_core.cpp:158-260).
+//
+// Math (all FP64; table values are float32 promoted exactly, as in the reference):
+//   k = C + R(-theta) (p - t)                      map cell p -> kernel frame   (:206-209,:227,:234)
+//   k_upper = round(k) (half away), valid iff 2 <= k_upper <= (cols-2, rows-2)   (:177-182)
+//   c_rel = k - k_upper + 0.5; f = a00 + a10 cx + a01 cy + a11 cx cy              (:193-197)
+// The reference's Jacobian is a central difference (h = 1e-6) of f along x, y, theta on the
+// SAME patch (:244-256); f is bilinear, so that difference equals the analytic patch
+// derivative up to round-off / O(h^2).  With a = k_u - C_x, b = k_v - C_y,
+// f_u = a10 + a11 cy, f_v = a01 + a11 cx:
+//   J_x = -c Sum f_u + s Sum f_v,  J_y = -s Sum f_u - c Sum f_v,  J_theta = Sum (f_u b - f_v a)
+//
+// Two kernels:
+//   k_cost_cells  : one pose, explicit cell list (the reference's call shape); grid-strided,
+//                   fixed-order block reduction, last CTA folds the CTA partials in index order.
+//   k_cost_batch* : many poses against the whole costmap; one warp per pose scans the pose's
+//                   window (axis-aligned bounding box of the valid kernel region, clipped to
+//                   the map), evaluates every lethal cell in it and reduces cost/Su/Sv/Stheta
+//                   with __shfl_xor_sync in a fixed order.
+#include <cmath>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dpose {
+
+// ---- shared geometry (host + device) ---------------------------------------------------
+struct TableGeom {
+  int rows, cols;
+  double cx, cy;  // center
+};
+
+// axis-aligned bounding box (inclusive integer cells) of the valid kernel region
+// [1.5, cols-1.5) x [1.5, rows-1.5) mapped into the map by p = t + R(theta)(k - C)
+__host__ __device__ inline WindowRect pose_window(const TableGeom &g, double tx, double ty, double c,
+                                                  double s, int size_x, int size_y) {
+  const double au0 = 1.5 - g.cx, au1 = (double)g.cols - 1.5 - g.cx;
+  const double av0 = 1.5 - g.cy, av1 = (double)g.rows - 1.5 - g.cy;
+  const double xa = c * au0, xb = c * au1, xc = -s * av0, xd = -s * av1;
+  const double ya = s * au0, yb = s * au1, yc = c * av0, yd = c * av1;
+  const double eps = 1e-7;
+  const double xmin = tx + fmin(xa, xb) + fmin(xc, xd) - eps, xmax = tx + fmax(xa, xb) + fmax(xc, xd) + eps;
+  const double ymin = ty + fmin(ya, yb) + fmin(yc, yd) - eps, ymax = ty + fmax(ya, yb) + fmax(yc, yd) + eps;
+  WindowRect w;
+  w.x0 = w.y0 = 0;
+  w.x1 = w.y1 = -1;  // empty; also the answer for NaN poses and windows off the map
+  if (!(xmax >= 0.0) || !(ymax >= 0.0) || !(xmin <= (double)size_x - 1.0) || !(ymin <= (double)size_y - 1.0))
+    return w;
+  // clamped in floating point, so the int casts cannot overflow
+  w.x0 = (int)ceil(fmax(xmin, 0.0));
+  w.y0 = (int)ceil(fmax(ymin, 0.0));
+  w.x1 = (int)floor(fmin(xmax, (double)size_x - 1.0));
+  w.y1 = (int)floor(fmin(ymax, (double)size_y - 1.0));
+  return w;
+}
+
+namespace {
+
+struct Accum {
+  double f, su, sv, st;
+};
+
+// one lethal cell with offset (dx, dy) = p - t; adds its contribution
+template <bool kJac>
+__device__ __forceinline__ void eval_cell(const PatchCoef *__restrict__ coef, int rows, int cols,
+                                          double cx, double cy, double c, double s, double dx,
+                                          double dy, Accum &acc) {
+  const double a = fma(c, dx, s * dy);   // k_u - C_x
+  const double b = fma(c, dy, -s * dx);  // k_v - C_y
+  const double ku = cx + a, kv = cy + b;
+  const double ru = round(ku), rv = round(kv);  // half away from zero == std::round (:177)
+  // |k| beyond any table -> reject before the int cast can saturate oddly
+  if (!(fabs(ru) < 1e9) || !(fabs(rv) < 1e9)) return;
+  const int ux = (int)ru, uy = (int)rv;
+  if (ux < 2 || uy < 2 || ux > cols - 2 || uy > rows - 2) return;  // :181-182
+  const double rx = (ku - ru) + 0.5, ry = (kv - rv) + 0.5;         // :193
+  const PatchCoef p = coef[uy * cols + ux];
+  const double fv = fma(p.a11, rx, p.a01);
+  acc.f += fma(ry, fv, fma(p.a10, rx, p.a00));
+  if (kJac) {
+    const double fu = fma(p.a11, ry, p.a10);
+    acc.su += fu;
+    acc.sv += fv;
+    acc.st += fma(fu, b, -fv * a);
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__device__ __forceinline__ void finish(const Accum &t, double c, double s, double *out) {
+  out[0] = t.f;
+  out[1] = -c * t.su + s * t.sv;
+  out[2] = -s * t.su - c * t.sv;
+  out[3] = t.st;
+}
+
+// ---- single pose, explicit cell list ------------------------------------------------------
+constexpr int kCellThreads = 256;
+
+template <bool kJac>
+__global__ void __launch_bounds__(kCellThreads)
+    k_cost_cells(const PatchCoef *__restrict__ coef, TableGeom g, double tx, double ty, double th,
+                 const int2 *__restrict__ cells, size_t n, double *partials, unsigned *ticket,
+                 double *out) {
+  __shared__ double s_part[kCellThreads / 32][4];
+  __shared__ bool s_last;
+  double s, c;
+  sincos(th, &s, &c);
+  Accum acc = {0.0, 0.0, 0.0, 0.0};
+  const size_t stride = (size_t)gridDim.x * kCellThreads;
+  for (size_t i = (size_t)blockIdx.x * kCellThreads + threadIdx.x; i < n; i += stride) {
+    const int2 p = cells[i];
+    eval_cell<kJac>(coef, g.rows, g.cols, g.cx, g.cy, c, s, (double)p.x - tx, (double)p.y - ty, acc);
+  }
+  acc.f = warp_sum(acc.f);
+  acc.su = warp_sum(acc.su);
+  acc.sv = warp_sum(acc.sv);
+  acc.st = warp_sum(acc.st);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_part[warp][0] = acc.f;
+    s_part[warp][1] = acc.su;
+    s_part[warp][2] = acc.sv;
+    s_part[warp][3] = acc.st;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int w = 0; w < kCellThreads / 32; ++w) v += s_part[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    Accum t = {0.0, 0.0, 0.0, 0.0};
+    const volatile double *vp = partials;
+    for (unsigned b = 0; b < gridDim.x; ++b) {  // CTA index order: deterministic
+      t.f += vp[4 * b];
+      t.su += vp[4 * b + 1];
+      t.sv += vp[4 * b + 2];
+      t.st += vp[4 * b + 3];
+    }
+    finish(t, c, s, out);
+    *ticket = 0u;
+  }
+}
+
+// ---- pose batch, generic window scan (any table size) ----------------------------------------
+constexpr int kBatchWarps = 8;
+
+struct BatchArgs {
+  const PatchCoef *coef;
+  TableGeom g;
+  const uint8_t *map;
+  size_t pitch;
+  int size_x, size_y;
+  const double *poses;
+  double *out;
+  size_t n;
+};
+
+template <bool kJac>
+__global__ void __launch_bounds__(kBatchWarps * 32) k_cost_batch_generic(BatchArgs a) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps_total = (size_t)gridDim.x * kBatchWarps;
+  for (size_t i = (size_t)blockIdx.x * kBatchWarps + (threadIdx.x >> 5); i < a.n; i += warps_total) {
+    const double tx = a.poses[3 * i], ty = a.poses[3 * i + 1], th = a.poses[3 * i + 2];
+    double s, c;
+    sincos(th, &s, &c);
+    const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y);
+    Accum acc = {0.0, 0.0, 0.0, 0.0};
+    for (int y = w.y0; y <= w.y1; ++y) {
+      const uint8_t *row = a.map + (size_t)y * a.pitch;
+      const double dy = (double)y - ty;
+      for (int x = w.x0 + lane; x <= w.x1; x += 32)
+        if (__ldg(row + x) == kLethal)
+          eval_cell<kJac>(a.coef, a.g.rows, a.g.cols, a.g.cx, a.g.cy, c, s, (double)x - tx, dy, acc);
+    }
+    acc.f = warp_sum(acc.f);
+    if (kJac) {
+      acc.su = warp_sum(acc.su);
+      acc.sv = warp_sum(acc.sv);
+      acc.st = warp_sum(acc.st);
+    }
+    if (lane == 0) finish(acc, c, s, a.out + 4 * i);
+  }
+}
+
+struct CellScratch {
+  std::mutex mu;
+  int device = -1;
+  int2 *d_cells = nullptr;
+  size_t cap = 0;
+  double *d_partials = nullptr;  // kMaxCellCtas * 4
+  unsigned *d_ticket = nullptr;
+  double *d_out = nullptr;  // 4
+};
+constexpr int kMaxCellCtas = 592;  // 4 per SM
+
+}  // namespace
+
+// per-device scratch for the single-pose entry points (grow-only, mutex-protected)
+static CellScratch g_scratch[64];
+
+static int ensure_scratch(CellScratch &sc, int device, size_t ncells) {
+  if (!sc.d_partials) {
+    DPOSE_CUDA(cudaMalloc(&sc.d_partials, sizeof(double) * 4 * kMaxCellCtas));
+    DPOSE_CUDA(cudaMalloc(&sc.d_ticket, sizeof(unsigned)));
+    DPOSE_CUDA(cudaMemset(sc.d_ticket, 0, sizeof(unsigned)));
+    DPOSE_CUDA(cudaMalloc(&sc.d_out, sizeof(double) * 4));
+    sc.device = device;
+  }
+  if (ncells > sc.cap) {
+    cudaFree(sc.d_cells);
+    sc.d_cells = nullptr;
+    sc.cap = 0;
+    const size_t cap = ncells + ncells / 2 + 1024;
+    DPOSE_CUDA(cudaMalloc(&sc.d_cells, sizeof(int2) * cap));
+    sc.cap = cap;
+  }
+  return DPOSE_OK;
+}
+
+// d_cells == nullptr && h_cells != nullptr: upload first
+static int cost_cells_impl(const dpose_pg *pg, const double se2[3], const int2 *d_cells,
+                           const int32_t *h_cells, size_t n, double *cost, double *J) {
+  if (pg->device < 0 || pg->device >= 64) return fail(DPOSE_EINVAL, "device index out of range");
+  DeviceGuard guard(pg->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
+  CellScratch &sc = g_scratch[pg->device];
+  std::lock_guard<std::mutex> lock(sc.mu);
+  DPOSE_TRY(ensure_scratch(sc, pg->device, h_cells ? n : 0));
+  if (h_cells && n) {
+    DPOSE_CUDA(cudaMemcpy(sc.d_cells, h_cells, sizeof(int2) * n, cudaMemcpyHostToDevice));
+    d_cells = sc.d_cells;
+  }
+  const TableGeom g = {pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
+  int grid = (int)((n + 4 * kCellThreads - 1) / (4 * kCellThreads));
+  grid = grid < 1 ? 1 : (grid > kMaxCellCtas ? kMaxCellCtas : grid);
+  if (J)
+    k_cost_cells<true><<<grid, kCellThreads>>>(pg->d_coef, g, se2[0], se2[1], se2[2], d_cells, n,
+                                               sc.d_partials, sc.d_ticket, sc.d_out);
+  else
+    k_cost_cells<false><<<grid, kCellThreads>>>(pg->d_coef, g, se2[0], se2[1], se2[2], d_cells, n,
+                                                sc.d_partials, sc.d_ticket, sc.d_out);
+  DPOSE_LAUNCHED();
+  double h[4];
+  DPOSE_CUDA(cudaMemcpy(h, sc.d_out, sizeof(h), cudaMemcpyDeviceToHost));
+  *cost = h[0];
+  if (J) {
+    J[0] = h[1];
+    J[1] = h[2];
+    J[2] = h[3];
+  }
+  return DPOSE_OK;
+}
+
+int get_cost_cells(const dpose_pg *pg, const double se2[3], const int2 *d_cells, size_t n,
+                   double *cost, double *J) {
+  return cost_cells_impl(pg, se2, d_cells, nullptr, n, cost, J);
+}
+
+int get_cost_cells_host(const dpose_pg *pg, const double se2[3], const int32_t *cells_xy, size_t n,
+                        double *cost, double *J) {
+  return cost_cells_impl(pg, se2, nullptr, cells_xy, n, cost, J);
+}
+
+int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
+                          double *d_out, int want_jacobian, cudaStream_t stream) {
+  if (n == 0) return DPOSE_OK;
+  if (pg->device != map->device) return fail(DPOSE_EINVAL, "pose_gradient and map live on different devices");
+  DeviceGuard guard(pg->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
+  BatchArgs a;
+  a.coef = pg->d_coef;
+  a.g = TableGeom{pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
+  a.map = map->d_data;
+  a.pitch = map->pitch;
+  a.size_x = (int)map->size_x;
+  a.size_y = (int)map->size_y;
+  a.poses = d_poses;
+  a.out = d_out;
+  a.n = n;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
+  size_t want = (n + kBatchWarps - 1) / kBatchWarps;
+  const size_t cap = (size_t)sms * 8 * 4;  // a few waves of resident CTAs, grid-strided
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (want_jacobian)
+    k_cost_batch_generic<true><<<grid, kBatchWarps * 32, 0, stream>>>(a);
+  else
+    k_cost_batch_generic<false><<<grid, kBatchWarps * 32, 0, stream>>>(a);
+  DPOSE_LAUNCHED();
+  return DPOSE_OK;
+}
+
+void map_release_cache(dpose_map *) {}
+
+uint64_t window_bytes_host(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n) {
+  const TableGeom g = {pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double c = std::cos(poses[3 * i + 2]), s = std::sin(poses[3 * i + 2]);
+    const WindowRect w = pose_window(g, poses[3 * i], poses[3 * i + 1], c, s, (int)map->size_x, (int)map->size_y);
+    if (w.x1 >= w.x0 && w.y1 >= w.y0) total += (uint64_t)(w.x1 - w.x0 + 1) * (uint64_t)(w.y1 - w.y0 + 1);
+  }
+  return total;
+}
+
+}  // namespace dpose

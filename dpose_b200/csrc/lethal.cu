@@ -1,0 +1,305 @@
+// lethal.cu — lethal-cell extraction (replaces lethal_cells_within, dpose_costmap.cpp:117-184).
+//
+// Host: clamp the ring into the map, trace its four edges (integer Bresenham, ROS
+// raytraceLine-compatible) into per-row [xmin, xmax] intervals (to_rays, :106-115).
+// Device: stream compaction over the uint8 grid, two sweeps like the reference
+// (:143-155 count, :167-179 write) with an exclusive scan between them:
+//   k_count : one warp per 512-byte row tile, one aligned 16-byte load per lane, byte
+//             compare against 254 -> 16-bit lane mask -> popc -> per-tile count
+//   k_scan  : two-level exclusive scan of the tile counts
+//   k_write : same tiling; warp prefix over the lane counts, each lane emits its (x, y)
+// Output order is row-major (y ascending, x ascending) and deterministic.
+// HBM traffic: 2 x box bytes read + 8 B per lethal cell written.
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace dpose {
+
+// ---- host geometry ---------------------------------------------------------------------
+// Integer Bresenham from begin to end (end exclusive), max(|dx|,|dy|) cells; error term
+// starts at den/2 and the minor axis steps when it reaches den — the stepping rule of
+// ROS' raytraceLine that dpose_costmap.cpp:57-104 follows.
+template <typename Visit>
+static size_t trace_line(int bx, int by, int ex, int ey, Visit &&visit) {
+  const int ddx = ex - bx, ddy = ey - by;
+  const int ax = std::abs(ddx), ay = std::abs(ddy);
+  const bool y_major = ay > ax;  // ties: x is the major axis (first maximum)
+  const int den = y_major ? ay : ax, add = y_major ? ax : ay;
+  const int sx = (ddx > 0) - (ddx < 0), sy = (ddy > 0) - (ddy < 0);
+  int err = den / 2, x = bx, y = by;
+  for (int i = 0; i < den; ++i) {
+    visit(x, y);
+    err += add;
+    const bool step_minor = err >= den;
+    if (step_minor) err -= den;
+    if (y_major) {
+      y += sy;
+      if (step_minor) x += sx;
+    } else {
+      x += sx;
+      if (step_minor) y += sy;
+    }
+  }
+  return (size_t)den;
+}
+
+size_t host_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_xy, size_t cap) {
+  size_t k = 0;
+  return trace_line(begin[0], begin[1], end[0], end[1], [&](int x, int y) {
+    if (k < cap) {
+      out_xy[2 * k] = x;
+      out_xy[2 * k + 1] = y;
+    }
+    ++k;
+  });
+}
+
+namespace {
+
+constexpr int kTileBytes = 512;  // one warp x 16 B
+constexpr int kWarpsPerCta = 8;
+constexpr int kScanChunk = 2048;  // tiles per scan CTA (512 threads x 4)
+
+struct RowSpan {
+  int xmin, xmax;
+};
+
+struct LethalArgs {
+  const uint8_t *map;
+  size_t pitch;
+  const RowSpan *spans;  // nrows
+  int y_lo, nrows;
+  int x_base;   // 16-byte aligned
+  int tiles_x;  // tiles per row
+  long long n_tiles;
+};
+
+// 16 bytes -> bit i set iff byte i == 254 and x_first + i in [xmin, xmax]
+__device__ __forceinline__ unsigned lethal_mask16(const uint4 v, int x_first, int xmin, int xmax) {
+  const unsigned k = 0xFEFEFEFEu;
+  unsigned m = 0;
+  const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned eq = __vcmpeq4(w[i], k) & 0x01010101u;  // bit 0/8/16/24
+    m |= (((eq * 0x00204081u) >> 21) & 0xFu) << (4 * i);
+  }
+  // clip to the row interval
+  const int lo = xmin - x_first, hi = xmax - x_first;  // valid bit range [lo, hi]
+  if (hi < 0 || lo > 15) return 0u;
+  const unsigned lo_mask = lo <= 0 ? 0xFFFFu : (0xFFFFu << lo) & 0xFFFFu;
+  const unsigned hi_mask = hi >= 15 ? 0xFFFFu : (0xFFFFu >> (15 - hi));
+  return m & lo_mask & hi_mask;
+}
+
+__device__ __forceinline__ unsigned tile_lane_mask(const LethalArgs &a, long long tile, int lane,
+                                                   int *x_first, int *y) {
+  const int r = (int)(tile / a.tiles_x), j = (int)(tile - (long long)r * a.tiles_x);
+  const RowSpan s = a.spans[r];
+  const int x0 = a.x_base + j * kTileBytes + lane * 16;
+  *x_first = x0;
+  *y = a.y_lo + r;
+  if (s.xmin > s.xmax || x0 > s.xmax || x0 + 15 < s.xmin) return 0u;
+  // x0 is 16-byte aligned and < size_x <= pitch, pitch % 16 == 0: the load stays in the row
+  const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.map + (size_t)(a.y_lo + r) * a.pitch + x0));
+  return lethal_mask16(v, x0, s.xmin, s.xmax);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_count(LethalArgs a, unsigned *tile_count) {
+  const int lane = threadIdx.x & 31;
+  const long long tile = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (tile >= a.n_tiles) return;
+  int xf, y;
+  unsigned c = __popc(tile_lane_mask(a, tile, lane, &xf, &y));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if (lane == 0) tile_count[tile] = c;
+}
+
+// level 1: each CTA turns kScanChunk counts into exclusive prefixes + one chunk total
+__global__ void __launch_bounds__(512) k_scan_chunks(const unsigned *tile_count, unsigned *tile_prefix,
+                                                     unsigned long long *chunk_total, long long n_tiles) {
+  __shared__ unsigned warp_sum[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long base = (long long)blockIdx.x * kScanChunk + tid * 4;
+  unsigned v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = base + i < n_tiles ? tile_count[base + i] : 0u;
+  const unsigned mine = v[0] + v[1] + v[2] + v[3];
+  unsigned inc = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += t;
+  }
+  if (lane == 31) warp_sum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < 16 ? warp_sum[lane] : 0u;
+    unsigned winc = w;
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, winc, off);
+      if (lane >= off) winc += t;
+    }
+    if (lane < 16) warp_sum[lane] = winc - w;  // exclusive
+    if (lane == 15) chunk_total[blockIdx.x] = winc;
+  }
+  __syncthreads();
+  unsigned ex = warp_sum[warp] + inc - mine;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (base + i < n_tiles) tile_prefix[base + i] = ex;
+    ex += v[i];
+  }
+}
+
+// level 2: exclusive scan of the chunk totals (one CTA, sequential over 1024-wide slabs)
+__global__ void __launch_bounds__(1024) k_scan_totals(unsigned long long *chunk_total, int n_chunks,
+                                                      unsigned long long *grand_total) {
+  __shared__ unsigned long long warp_sum[32];
+  __shared__ unsigned long long carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0ull;
+  __syncthreads();
+  for (int base = 0; base < n_chunks; base += 1024) {
+    const int i = base + tid;
+    const unsigned long long mine = i < n_chunks ? chunk_total[i] : 0ull;
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += t;
+    }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long w = warp_sum[lane];
+      unsigned long long winc = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, off);
+        if (lane >= off) winc += t;
+      }
+      warp_sum[lane] = winc - w;
+    }
+    __syncthreads();
+    const unsigned long long ex = carry + warp_sum[warp] + inc - mine;
+    if (i < n_chunks) chunk_total[i] = ex;
+    __syncthreads();
+    if (tid == 1023) carry = ex + mine;
+    __syncthreads();
+  }
+  if (tid == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+    k_write(LethalArgs a, const unsigned *tile_prefix, const unsigned long long *chunk_offset, int2 *out) {
+  const int lane = threadIdx.x & 31;
+  const long long tile = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (tile >= a.n_tiles) return;
+  int xf, y;
+  unsigned m = tile_lane_mask(a, tile, lane, &xf, &y);
+  const unsigned c = __popc(m);
+  unsigned inc = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += t;
+  }
+  unsigned long long dst = chunk_offset[tile / kScanChunk] + tile_prefix[tile] + (inc - c);
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    out[dst++] = make_int2(xf + b, y);
+  }
+}
+
+}  // namespace
+
+int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, size_t *n) {
+  *d_cells = nullptr;
+  *n = 0;
+  if (map->size_x == 0 || map->size_y == 0) return DPOSE_OK;  // dpose_costmap.cpp:124-125
+  // clamp the ring into the map (:121, :128-129)
+  int32_t ring[10];
+  for (int i = 0; i < 5; ++i) {
+    ring[2 * i] = std::min(std::max(box[2 * i], 0), (int)map->size_x - 1);
+    ring[2 * i + 1] = std::min(std::max(box[2 * i + 1], 0), (int)map->size_y - 1);
+  }
+  int y_lo = INT_MAX, y_hi = INT_MIN;
+  for (int i = 0; i < 5; ++i) {
+    y_lo = std::min(y_lo, ring[2 * i + 1]);
+    y_hi = std::max(y_hi, ring[2 * i + 1]);
+  }
+  const int nrows = y_hi - y_lo + 1;
+  std::vector<RowSpan> spans((size_t)nrows, RowSpan{INT_MAX, INT_MIN});
+  for (int e = 0; e < 4; ++e)  // to_rays (:106-115)
+    trace_line(ring[2 * e], ring[2 * e + 1], ring[2 * e + 2], ring[2 * e + 3], [&](int x, int y) {
+      RowSpan &s = spans[(size_t)(y - y_lo)];
+      s.xmin = std::min(s.xmin, x);
+      s.xmax = std::max(s.xmax, x);
+    });
+  int gx_min = INT_MAX, gx_max = INT_MIN;
+  for (const RowSpan &s : spans)
+    if (s.xmin <= s.xmax) {
+      gx_min = std::min(gx_min, s.xmin);
+      gx_max = std::max(gx_max, s.xmax);
+    }
+  if (gx_min > gx_max) return DPOSE_OK;  // degenerate ring (all four edges empty)
+
+  DeviceGuard guard(map->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", map->device);
+  LethalArgs a;
+  a.map = map->d_data;
+  a.pitch = map->pitch;
+  a.y_lo = y_lo;
+  a.nrows = nrows;
+  a.x_base = gx_min & ~15;
+  a.tiles_x = (gx_max - a.x_base) / kTileBytes + 1;
+  a.n_tiles = (long long)nrows * a.tiles_x;
+  const int n_chunks = (int)((a.n_tiles + kScanChunk - 1) / kScanChunk);
+
+  RowSpan *d_spans = nullptr;
+  unsigned *d_count = nullptr, *d_prefix = nullptr;
+  unsigned long long *d_chunk = nullptr;  // n_chunks + 1 (last = grand total)
+  int2 *d_out = nullptr;
+  auto body = [&]() -> int {
+    DPOSE_CUDA(cudaMalloc(&d_spans, sizeof(RowSpan) * nrows));
+    DPOSE_CUDA(cudaMalloc(&d_count, sizeof(unsigned) * a.n_tiles));
+    DPOSE_CUDA(cudaMalloc(&d_prefix, sizeof(unsigned) * a.n_tiles));
+    DPOSE_CUDA(cudaMalloc(&d_chunk, sizeof(unsigned long long) * (n_chunks + 1)));
+    DPOSE_CUDA(cudaMemcpy(d_spans, spans.data(), sizeof(RowSpan) * nrows, cudaMemcpyHostToDevice));
+    a.spans = d_spans;
+    const unsigned grid = (unsigned)((a.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta);
+    k_count<<<grid, kWarpsPerCta * 32>>>(a, d_count);
+    DPOSE_LAUNCHED();
+    k_scan_chunks<<<n_chunks, 512>>>(d_count, d_prefix, d_chunk, a.n_tiles);
+    DPOSE_LAUNCHED();
+    k_scan_totals<<<1, 1024>>>(d_chunk, n_chunks, d_chunk + n_chunks);
+    DPOSE_LAUNCHED();
+    unsigned long long total = 0;
+    DPOSE_CUDA(cudaMemcpy(&total, d_chunk + n_chunks, sizeof(total), cudaMemcpyDeviceToHost));
+    if (total == 0) return DPOSE_OK;  // :157-158
+    DPOSE_CUDA(cudaMalloc(&d_out, sizeof(int2) * total));
+    k_write<<<grid, kWarpsPerCta * 32>>>(a, d_prefix, d_chunk, d_out);
+    DPOSE_LAUNCHED();
+    DPOSE_CUDA(cudaDeviceSynchronize());
+    *d_cells = d_out;
+    *n = (size_t)total;
+    d_out = nullptr;
+    return DPOSE_OK;
+  };
+  const int rc = body();
+  cudaFree(d_spans);
+  cudaFree(d_count);
+  cudaFree(d_prefix);
+  cudaFree(d_chunk);
+  cudaFree(d_out);
+  return rc;
+}
+
+}  // namespace dpose

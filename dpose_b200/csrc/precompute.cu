@@ -1,0 +1,327 @@
+// precompute.cu — cost_data precompute on the GPU (replaces _get_cost, dpose_core.cpp:55-114).
+//
+// One fused, single-CTA kernel (the images are a few KB: 17x25 ... ~200x200 pixels, so the
+// work is latency-bound; one launch beats a chain of ten).  Phases, separated by
+// __syncthreads():
+//   1. outline raster  : one thread per polygon edge, 8-connected Bresenham drawn left to
+//                        right (the rule of cv::polylines / cv::fillPoly's outline)
+//   2. even-odd fill   : one warp per scanline, 16.16 fixed-point edge crossings,
+//                        ballot-compacted and rank-sorted inside the warp
+//   3. exact EDT       : column pass (one thread per column, two sweeps), then a row pass
+//                        where each warp owns 32 output pixels and scans the row's parabolas
+//                        g(i)^2 + (x-i)^2 tile by tile, broadcasting candidates with
+//                        __shfl_sync and skipping tiles that cannot beat the current best.
+//                        All integer -> squared distances are exact (bit-exact gate).
+//   4. cost shaping    : sqrt, outside *= -0.01f, global min (warp shuffles + one smem
+//                        atomic), shift, separable [1 2 1]/4 blur with REFLECT_101 borders.
+//                        Every float op uses an explicit round-to-nearest intrinsic so the
+//                        compiler cannot contract it; the table is bit-identical to OpenCV's.
+//   5. patch tables    : FP64 bilinear coefficients per interpolation patch (the
+//                        reference-consistent form of "gradient tables").
+#include "common.cuh"
+
+namespace dpose {
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kWarps = kThreads / 32;
+constexpr int kInfG = 1 << 20;   // "no outline pixel in this column"
+constexpr int kBigD2 = 1 << 29;  // its square stand-in; (x-i)^2 < 2^30 keeps sums in int32
+
+struct PrecomputeArgs {
+  const int2 *fp;  // shifted footprint vertices
+  int n;
+  int rows, cols;
+  uint8_t *outline, *mask;
+  int *g;              // column-pass distances
+  int *d2;             // squared EDT
+  float *pre, *tmp, *cost;
+  PatchCoef *coef;
+  long long *scratch;  // kWarps * 2 * n crossings
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  if (i < 0) return -i;
+  if (i >= n) return 2 * (n - 1) - i;
+  return i;
+}
+
+// cv::Line, 8-connected, left-to-right LineIterator: err = major - 2*minor, diagonal step when err < 0
+__device__ void draw_edge(uint8_t *a, uint8_t *b, int cols, int rows, int x1, int y1, int x2,
+                          int y2) {
+  int dx = x2 - x1, dy = y2 - y1, sy = 1;
+  if (dx < 0) {
+    dx = -dx;
+    dy = -dy;
+    x1 = x2;
+    y1 = y2;
+  }
+  if (dy < 0) {
+    dy = -dy;
+    sy = -1;
+  }
+  const bool vert = dy > dx;
+  const int major = vert ? dy : dx, minor = vert ? dx : dy;
+  int err = major - 2 * minor;
+  int x = x1, y = y1;
+  for (int i = 0; i <= major; ++i) {
+    if (x >= 0 && x < cols && y >= 0 && y < rows) {
+      a[y * cols + x] = 0;
+      b[y * cols + x] = 0;
+    }
+    const bool diag = err < 0;
+    err += -2 * minor + (diag ? 2 * major : 0);
+    if (vert) {
+      y += sy;
+      if (diag) x += 1;
+    } else {
+      x += 1;
+      if (diag) y += sy;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows = p.rows, cols = p.cols, np = rows * cols, n = p.n;
+  __shared__ unsigned s_maxmag;
+
+  // ---- phase 0: white images ---------------------------------------------------------
+  for (int i = tid; i < np; i += kThreads) {
+    p.outline[i] = 255;
+    p.mask[i] = 255;
+  }
+  if (tid == 0) s_maxmag = 0u;
+  __syncthreads();
+
+  // ---- phase 1: outline (polylines == fillPoly's outline) ------------------------------
+  for (int e = tid; e < n; e += kThreads) {
+    const int2 a = p.fp[e == 0 ? n - 1 : e - 1], b = p.fp[e];
+    draw_edge(p.outline, p.mask, cols, rows, a.x, a.y, b.x, b.y);
+  }
+  __syncthreads();
+
+  // ---- phase 2: even-odd scanline fill into mask ---------------------------------------
+  {
+    long long *xs = p.scratch + (size_t)warp * 2 * n, *sorted = xs + n;
+    for (int y = warp; y < rows; y += kWarps) {
+      int na = 0;
+      for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        bool active = false;
+        long long x = 0;
+        if (e < n) {
+          const int2 a = p.fp[e == 0 ? n - 1 : e - 1], b = p.fp[e];
+          if (a.y != b.y) {
+            const long long dx = ((long long)(b.x - a.x) * 65536) / (long long)(b.y - a.y);
+            const int y0 = a.y < b.y ? a.y : b.y, y1 = a.y < b.y ? b.y : a.y;
+            const long long xstart = (long long)(a.y < b.y ? a.x : b.x) * 65536;
+            active = y0 <= y && y < y1;
+            x = xstart + (long long)(y - y0) * dx;
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (active) xs[na + __popc(m & ((1u << lane) - 1u))] = x;
+        na += __popc(m);
+      }
+      __syncwarp();
+      for (int i = lane; i < na; i += 32) {
+        const long long v = xs[i];
+        int rank = 0;
+        for (int j = 0; j < na; ++j) {
+          const long long w = xs[j];
+          rank += (w < v) || (w == v && j < i);
+        }
+        sorted[rank] = v;
+      }
+      __syncwarp();
+      for (int k = 0; k + 1 < na; k += 2) {
+        int x1 = (int)((sorted[k] + 32768) >> 16);  // left end rounded, right end floored
+        int x2 = (int)(sorted[k + 1] >> 16);
+        if (x1 < cols && x2 >= 0) {
+          x1 = x1 < 0 ? 0 : x1;
+          x2 = x2 >= cols ? cols - 1 : x2;
+          for (int x = x1 + lane; x <= x2; x += 32) p.mask[y * cols + x] = 0;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3a: EDT column pass ---------------------------------------------------------
+  for (int x = tid; x < cols; x += kThreads) {
+    int last = -1;
+    for (int y = 0; y < rows; ++y) {
+      if (p.outline[y * cols + x] == 0) last = y;
+      p.g[y * cols + x] = last < 0 ? kInfG : y - last;
+    }
+    last = -1;
+    for (int y = rows - 1; y >= 0; --y) {
+      if (p.outline[y * cols + x] == 0) last = y;
+      if (last >= 0 && last - y < p.g[y * cols + x]) p.g[y * cols + x] = last - y;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3b: EDT row pass, warp-shuffle scan over the row's parabolas ----------------
+  {
+    const int segs = (cols + 31) / 32;
+    for (int item = warp; item < rows * segs; item += kWarps) {
+      const int y = item / segs, s = item - y * segs;
+      const int x = s * 32 + lane;
+      const int *gr = p.g + y * cols;
+      int best = 0x7fffffff;
+      for (int t = 0; t < segs; ++t) {
+        // smallest |x - i| between this segment and tile t
+        const int sep = t > s ? t - s : s - t;
+        const int gap = sep > 0 ? (sep - 1) * 32 + 1 : 0;
+        if (__all_sync(0xffffffffu, best <= gap * gap)) continue;
+        const int i = t * 32 + lane;
+        const int gi = i < cols ? gr[i] : kInfG;
+        const int g2 = gi >= kInfG ? kBigD2 : gi * gi;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const int cand = __shfl_sync(0xffffffffu, g2, j);
+          const int dxi = x - (t * 32 + j);
+          best = min(best, dxi * dxi + cand);
+        }
+      }
+      if (x < cols) p.d2[y * cols + x] = best;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 4a: min over the scaled outside part (all values <= 0) ------------------------
+  {
+    unsigned mag = 0u;
+    for (int i = tid; i < np; i += kThreads) {
+      const float d = __fsqrt_rn(__int2float_rn(p.d2[i]));
+      const float o = p.mask[i] != 0 ? __fmul_rn(d, -0.01f) : 0.0f;
+      mag = max(mag, __float_as_uint(o) & 0x7fffffffu);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mag = max(mag, __shfl_xor_sync(0xffffffffu, mag, off));
+    if (lane == 0) atomicMax(&s_maxmag, mag);
+  }
+  __syncthreads();
+  const float mn = -__uint_as_float(s_maxmag);
+
+  // ---- phase 4b: shift ----------------------------------------------------------------------
+  for (int i = tid; i < np; i += kThreads) {
+    const float d = __fsqrt_rn(__int2float_rn(p.d2[i]));
+    const float v = p.mask[i] != 0 ? __fmul_rn(d, -0.01f) : d;
+    p.pre[i] = __fsub_rn(v, mn);
+  }
+  __syncthreads();
+
+  // ---- phase 4c: blur rows then columns ([0.25 0.5 0.25], BORDER_REFLECT_101) -----------------
+  for (int i = tid; i < np; i += kThreads) {
+    const int y = i / cols, x = i - y * cols;
+    const float a = p.pre[y * cols + reflect101(x - 1, cols)];
+    const float b = p.pre[i];
+    const float c = p.pre[y * cols + reflect101(x + 1, cols)];
+    p.tmp[i] = __fadd_rn(__fmul_rn(__fadd_rn(a, c), 0.25f), __fmul_rn(b, 0.5f));
+  }
+  __syncthreads();
+  for (int i = tid; i < np; i += kThreads) {
+    const int y = i / cols, x = i - y * cols;
+    const float a = p.tmp[reflect101(y - 1, rows) * cols + x];
+    const float b = p.tmp[i];
+    const float c = p.tmp[reflect101(y + 1, rows) * cols + x];
+    p.cost[i] = __fadd_rn(__fmul_rn(__fadd_rn(a, c), 0.25f), __fmul_rn(b, 0.5f));
+  }
+  __syncthreads();
+
+  // ---- phase 5: per-patch FP64 coefficients, indexed by k_upper ---------------------------------
+  for (int i = tid; i < np; i += kThreads) {
+    const int uy = i / cols, ux = i - uy * cols;
+    PatchCoef c = {0.0, 0.0, 0.0, 0.0};
+    if (ux >= 2 && uy >= 2 && ux <= cols - 2 && uy <= rows - 2) {
+      const double m00 = p.cost[(uy - 1) * cols + ux - 1], m10 = p.cost[(uy - 1) * cols + ux];
+      const double m01 = p.cost[uy * cols + ux - 1], m11 = p.cost[uy * cols + ux];
+      c.a00 = m00;
+      c.a10 = m10 - m00;
+      c.a01 = m01 - m00;
+      c.a11 = (m11 - m10) - (m01 - m00);
+    }
+    p.coef[i] = c;
+  }
+}
+
+}  // namespace
+
+int precompute_run(dpose_pg *pg, const int32_t *fp_xy, int n) {
+  const int rows = pg->rows, cols = pg->cols;
+  const size_t np = (size_t)rows * cols;
+  int2 *d_fp = nullptr;
+  uint8_t *d_outline = nullptr, *d_mask = nullptr;
+  int *d_g = nullptr, *d_d2 = nullptr;
+  float *d_pre = nullptr, *d_tmp = nullptr;
+  long long *d_scratch = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = DPOSE_OK;
+  auto body = [&]() -> int {
+    DPOSE_CUDA(cudaMalloc(&d_fp, sizeof(int2) * n));
+    DPOSE_CUDA(cudaMalloc(&d_outline, np));
+    DPOSE_CUDA(cudaMalloc(&d_mask, np));
+    DPOSE_CUDA(cudaMalloc(&d_g, sizeof(int) * np));
+    DPOSE_CUDA(cudaMalloc(&d_d2, sizeof(int) * np));
+    DPOSE_CUDA(cudaMalloc(&d_pre, sizeof(float) * np));
+    DPOSE_CUDA(cudaMalloc(&d_tmp, sizeof(float) * np));
+    DPOSE_CUDA(cudaMalloc(&d_scratch, sizeof(long long) * kWarps * 2 * (size_t)n));
+    DPOSE_CUDA(cudaMalloc(&pg->d_cost, sizeof(float) * np));
+    DPOSE_CUDA(cudaMalloc(&pg->d_coef, sizeof(PatchCoef) * np));
+    DPOSE_CUDA(cudaMemcpy(d_fp, fp_xy, sizeof(int2) * n, cudaMemcpyHostToDevice));
+    DPOSE_CUDA(cudaEventCreate(&e0));
+    DPOSE_CUDA(cudaEventCreate(&e1));
+    PrecomputeArgs a;
+    a.fp = d_fp;
+    a.n = n;
+    a.rows = rows;
+    a.cols = cols;
+    a.outline = d_outline;
+    a.mask = d_mask;
+    a.g = d_g;
+    a.d2 = d_d2;
+    a.pre = d_pre;
+    a.tmp = d_tmp;
+    a.cost = pg->d_cost;
+    a.coef = pg->d_coef;
+    a.scratch = d_scratch;
+    DPOSE_CUDA(cudaEventRecord(e0));
+    k_precompute<<<1, kThreads>>>(a);
+    DPOSE_LAUNCHED();
+    DPOSE_CUDA(cudaEventRecord(e1));
+    DPOSE_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    DPOSE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    pg->precompute_us = ms * 1000.f;
+    pg->h_cost.resize(np);
+    pg->h_pre_blur.resize(np);
+    pg->h_edt_sq.resize(np);
+    pg->h_outline.resize(np);
+    pg->h_mask.resize(np);
+    DPOSE_CUDA(cudaMemcpy(pg->h_cost.data(), pg->d_cost, sizeof(float) * np, cudaMemcpyDeviceToHost));
+    DPOSE_CUDA(cudaMemcpy(pg->h_pre_blur.data(), d_pre, sizeof(float) * np, cudaMemcpyDeviceToHost));
+    DPOSE_CUDA(cudaMemcpy(pg->h_edt_sq.data(), d_d2, sizeof(int) * np, cudaMemcpyDeviceToHost));
+    DPOSE_CUDA(cudaMemcpy(pg->h_outline.data(), d_outline, np, cudaMemcpyDeviceToHost));
+    DPOSE_CUDA(cudaMemcpy(pg->h_mask.data(), d_mask, np, cudaMemcpyDeviceToHost));
+    return DPOSE_OK;
+  };
+  rc = body();
+  cudaFree(d_fp);
+  cudaFree(d_outline);
+  cudaFree(d_mask);
+  cudaFree(d_g);
+  cudaFree(d_d2);
+  cudaFree(d_pre);
+  cudaFree(d_tmp);
+  cudaFree(d_scratch);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  return rc;
+}
+
+}  // namespace dpose

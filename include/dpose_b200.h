@@ -1,0 +1,147 @@
+/*
+ * dpose_b200.h — C ABI of the B200-native footprint-cost path of dpose_core.
+ *
+ * Plain C, opaque handles, caller-owned buffers, int status codes; no exceptions, no
+ * torch / Eigen / OpenCV types.  This is the boundary a maintainer of dorezyuk/dpose
+ * binds instead of the CPU bodies cited per entry point (paths relative to the upstream
+ * tree).  the headers under include/dpose_core/ are the reference-compatible C++ surface on top of it.
+ *
+ * Conventions
+ *  - cells and polygons are int32 pairs "x0,y0,x1,y1,..." (Eigen::Matrix<int,2,N>
+ *    column-major, dpose_core.hpp:72-76); rectangles are the closed 5-point ring
+ *    (dpose_core.hpp:39-69), 10 int32.
+ *  - poses are (x, y, theta) float64 in CELL units / radians (dpose_core.hpp:141-142).
+ *  - costmaps are uint8, row-major, index = y * pitch + x (costmap_2d::Costmap2D::getIndex);
+ *    only the value 254 (costmap_2d::LETHAL_OBSTACLE) is lethal.
+ *  - every function returns DPOSE_OK (0) or an error code; dpose_last_error() gives the
+ *    thread-local message.  There is no CPU fallback: without a CUDA device every
+ *    compute entry point fails with DPOSE_ENODEV / DPOSE_ECUDA.
+ */
+#ifndef DPOSE_B200_H
+#define DPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPOSE_OK 0
+#define DPOSE_EINVAL 1 /* bad argument (e.g. footprint with < 3 vertices) */
+#define DPOSE_ECUDA 2  /* CUDA runtime / driver error */
+#define DPOSE_ENOMEM 3
+#define DPOSE_ENODEV 4 /* no usable CUDA device */
+
+typedef struct dpose_pg dpose_pg;       /* pose_gradient + its cost_data on one device */
+typedef struct dpose_map dpose_map;     /* device-resident costmap */
+typedef struct dpose_cells dpose_cells; /* device-resident cell_vector */
+
+const char *dpose_last_error(void);
+int dpose_device_count(int *n);
+/* number of CUDA kernels this library has launched in the calling process */
+uint64_t dpose_launch_count(void);
+
+/* pinned host memory for the host-buffer entry points (optional, pageable works) */
+int dpose_host_alloc(void **ptr, size_t bytes);
+void dpose_host_free(void *ptr);
+/* frees buffers this library returned (dpose_lethal_cells_within) */
+void dpose_free(void *ptr);
+
+/* ---- footprint --------------------------------------------------------------------
+ * replaces make_footprint (dpose_costmap.cpp:40-55): cells = round(metres / resolution).
+ * DPOSE_EINVAL if resolution <= 0 (reference: std::runtime_error). Host arithmetic. */
+int dpose_make_footprint(const double *xy_m, int n, double resolution, int32_t *xy_cells);
+
+/* ---- cost_data / pose_gradient ------------------------------------------------------
+ * replaces pose_gradient::pose_gradient (dpose_core.cpp:148-156) and cost_data::cost_data
+ * + _get_cost (dpose_core.cpp:55-139): outline raster, even-odd fill, exact EDT,
+ * scale/shift, 3x3 Gaussian blur and the per-patch bilinear coefficient tables, all on
+ * `device`.  DPOSE_EINVAL if n < 3 (reference: "footprint must contain at least three
+ * points").  */
+int dpose_pg_create(const int32_t *footprint_xy, int n, uint32_t padding, int device,
+                    dpose_pg **out);
+void dpose_pg_destroy(dpose_pg *pg);
+/* replaces cost_data::get_data / get_center / get_box (dpose_core.hpp:83-96).
+ * *cost points at a host copy (rows*cols float32, row-major) owned by the handle. */
+int dpose_pg_table(const dpose_pg *pg, const float **cost, int *rows, int *cols,
+                   int32_t center[2], int32_t box[10]);
+/* intermediate images for bit-exact checks (host copies owned by the handle):
+ * squared EDT (int32), polylines outline and fillPoly mask (uint8, 0 = drawn),
+ * table before the blur (float32).  Any out pointer may be NULL. */
+int dpose_pg_stages(const dpose_pg *pg, const int32_t **edt_sq, const uint8_t **outline,
+                    const uint8_t **mask, const float **pre_blur);
+/* device time of the last precompute (all kernels), microseconds */
+int dpose_pg_precompute_us(const dpose_pg *pg, float *us);
+
+/* ---- costmap ------------------------------------------------------------------------
+ * device copy of a costmap_2d::Costmap2D char map (getCharMap(), getSizeInCellsX/Y()).
+ * The copy is pitch-padded to 16 B for TMA.  `pitch` is the host row stride in bytes. */
+int dpose_map_create(const uint8_t *data, uint32_t size_x, uint32_t size_y, size_t pitch,
+                     int device, dpose_map **out);
+/* same, from a buffer already in device memory on `device` (device-to-device copy) */
+int dpose_map_create_from_device(const uint8_t *d_data, uint32_t size_x, uint32_t size_y,
+                                 size_t pitch, int device, dpose_map **out);
+/* re-uploads a dirty window [x0,x0+w) x [y0,y0+h); data points at the window's first
+ * byte in a host buffer with row stride `pitch`.  The caller serialises it against
+ * concurrent use of the map (the reference holds Costmap2D::getMutex(),
+ * dpose_costmap.cpp:138). */
+int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t x0,
+                     uint32_t y0, uint32_t w, uint32_t h);
+int dpose_map_size(const dpose_map *map, uint32_t *size_x, uint32_t *size_y);
+void dpose_map_destroy(dpose_map *map);
+
+/* ---- lethal cells --------------------------------------------------------------------
+ * replaces raytrace (dpose_costmap.cpp:57-104); host arithmetic; writes at most `cap`
+ * cells and reports max(|dx|,|dy|) in *n. */
+int dpose_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_xy, size_t cap,
+                   size_t *n);
+/* replaces lethal_cells_within (dpose_costmap.cpp:117-184): clamps the ring into the map,
+ * builds the per-row intervals (to_rays, :106-115) and stream-compacts the cells equal to
+ * 254 on the GPU.  Order: y ascending, x ascending.  *cells_xy is allocated by the
+ * library (dpose_free). */
+int dpose_lethal_cells_within(const dpose_map *map, const int32_t box[10], int32_t **cells_xy,
+                              size_t *n);
+/* same, result stays on the device */
+int dpose_lethal_cells_within_device(const dpose_map *map, const int32_t box[10],
+                                     dpose_cells **out);
+int dpose_cells_upload(const int32_t *cells_xy, size_t n, int device, dpose_cells **out);
+int dpose_cells_size(const dpose_cells *cells, size_t *n);
+int dpose_cells_download(const dpose_cells *cells, int32_t *cells_xy);
+void dpose_cells_destroy(dpose_cells *cells);
+
+/* ---- get_cost ------------------------------------------------------------------------
+ * replaces pose_gradient::get_cost(se2, begin, end, J) (dpose_core.cpp:200-260).
+ * J (3 doubles: d/dx, d/dy, d/dtheta) may be NULL.  Cells outside the kernel are
+ * skipped (:237-238); n == 0 gives cost 0, J 0. */
+int dpose_pg_get_cost_cells(const dpose_pg *pg, const double se2[3], const int32_t *cells_xy,
+                            size_t n, double *cost, double *J);
+int dpose_pg_get_cost_cells_device(const dpose_pg *pg, const double se2[3],
+                                   const dpose_cells *cells, double *cost, double *J);
+
+/* NEW batched entry point: for every pose i the cost over ALL lethal cells of `map`
+ * (equivalently: the cells of lethal_cells_within(map, rotated get_box()) for poses whose
+ * box lies inside the map) and its Jacobian.  out: n x 4 doubles (cost, Jx, Jy, Jtheta);
+ * with want_jacobian == 0 the three J entries are written as 0.
+ * Host-buffer version: chunks H2D / kernel / D2H on three streams. */
+int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const double *poses,
+                            size_t n, double *out, int want_jacobian);
+/* device-buffer version, asynchronous on `stream` (a cudaStream_t, NULL = default) */
+int dpose_pg_get_cost_batch_device(const dpose_pg *pg, const dpose_map *map,
+                                   const double *d_poses, size_t n, double *d_out,
+                                   int want_jacobian, void *stream);
+/* pose batch sharded contiguously over ndev devices (pgs[i] / maps[i] live on device i's
+ * GPU; map and table replicated; no collective), one host thread per device. */
+int dpose_pg_get_cost_batch_multi(dpose_pg *const *pgs, dpose_map *const *maps, int ndev,
+                                  const double *poses, size_t n, double *out,
+                                  int want_jacobian);
+/* algorithmic window bytes of a pose batch: sum over poses of the
+ * number of map cells inside the axis-aligned bounding box of the valid kernel region,
+ * clipped to the map.  Host arithmetic. */
+int dpose_pg_window_bytes(const dpose_pg *pg, const dpose_map *map, const double *poses,
+                          size_t n, uint64_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPOSE_B200_H */

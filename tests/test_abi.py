@@ -1,0 +1,79 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads without a GPU, exports
+every symbol include/dpose_b200.h declares, validates arguments like the reference, and
+refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fixtures as fx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from dpose_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "dpose_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dpose_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = ctypes.CDLL(built)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    from dpose_b200 import _lib
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+def test_host_side_functions_match_oracle(built):
+    import dpose_b200 as dp
+    from oracle import capi
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        b, e = rng.integers(-50, 50, 2), rng.integers(-50, 50, 2)
+        assert np.array_equal(dp.raytrace(b, e), capi.raytrace(b, e))
+    assert np.array_equal(dp.make_footprint(fx.RECT_M, 0.05), fx.RECT)
+    assert np.array_equal(dp.make_footprint(fx.LSHAPE_M, 0.05), capi.make_footprint(fx.LSHAPE_M, 0.05))
+    assert np.array_equal(dp.to_rectangle(3, 4), fx.to_rectangle(3, 4))
+    assert np.array_equal(dp.to_rectangle((1, 2), (3, 4)), fx.to_rectangle((1, 2), (3, 4)))
+
+
+def test_error_contract(built):
+    import dpose_b200 as dp
+    with pytest.raises(RuntimeError, match="resolution must be positive"):  # dpose_costmap.cpp:44-45
+        dp.make_footprint(fx.RECT_M, 0.0)
+    with pytest.raises(RuntimeError, match="resolution must be positive"):
+        dp.make_footprint(fx.RECT_M, -1.0)
+    for n in (0, 1, 2):  # dpose_core/test/pose_gradient.cpp:9-17
+        with pytest.raises(RuntimeError, match="at least three points"):
+            dp.pose_gradient(np.zeros((n, 2), np.int32), dp.pose_gradient.parameter())
+
+
+def test_no_cpu_fallback(built):
+    import dpose_b200 as dp
+    if dp.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(dp.DposeError) as ei:
+        dp.cost_data(fx.RECT, 2)
+    assert ei.value.code == 4  # DPOSE_ENODEV
+    with pytest.raises(dp.DposeError):
+        dp.Costmap(np.zeros((8, 8), np.uint8))
+
+
+def test_product_does_not_reference_oracle():
+    """the product path must never route through oracle/"""
+    bad = []
+    for base in ("dpose_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    txt = open(os.path.join(dirpath, f), errors="replace").read()
+                    if re.search(r"(from|import)\s+oracle|oracle/|dpose_oracle", txt):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -1,0 +1,353 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle, the cv2-generated goldens and the reference's own unit tests restated.
+
+Bars (BASELINE.json north_star): squared EDT and lethal-cell lists bit-exact (tables too);
+cost and Jacobian within |gpu - ref| <= 1e-6 + 1e-5 |ref|.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dp():
+    import dpose_b200
+    assert dpose_b200.device_count() > 0, "no CUDA device: GPU tests cannot run (no CPU fallback)"
+    return dpose_b200
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from oracle import capi
+    return capi
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+# ------------------------------------------------------------- precompute ----
+@pytest.mark.parametrize("name", list(fx.FOOTPRINTS))
+def test_tables_bit_exact_vs_cv2_golden(dp, golden_tables, name):
+    fp, pad = fx.FOOTPRINTS[name]
+    cd = dp.cost_data(fp, pad)
+    g = golden_tables
+    d2, outline, mask, pre = cd.stages()
+    assert np.array_equal(outline, g[name + ".outline"])
+    assert np.array_equal(mask, g[name + ".mask"])
+    assert np.array_equal(d2, g[name + ".edt_sq"])  # squared EDT bit-exact
+    assert np.array_equal(bits(pre), bits(g[name + ".pre_blur"]))
+    assert np.array_equal(bits(cd.get_data()), bits(g[name + ".cost"]))
+    assert np.array_equal(cd.get_center(), g[name + ".center"])
+    assert np.array_equal(cd.get_box(), g[name + ".box"])
+
+
+def test_tables_bit_exact_vs_oracle_random_polygons(dp, capi):
+    rng = np.random.default_rng(77)
+    checked = 0
+    for _ in range(120):
+        n = int(rng.integers(3, 41))
+        r = int(rng.integers(3, 90))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        rad = rng.uniform(0.2, 1.0, n) * r
+        pts = np.stack([np.round(rad * np.cos(ang)), np.round(rad * np.sin(ang))], 1).astype(np.int32)
+        if rng.random() < 0.3:
+            rng.shuffle(pts)
+        pts += rng.integers(-30, 30, 2).astype(np.int32)
+        pad = int(rng.integers(0, 12))
+        o = capi.CostData(pts, pad)
+        cd = dp.cost_data(pts, pad)
+        d2, outline, mask, pre = cd.stages()
+        assert np.array_equal(outline, o.outline)
+        assert np.array_equal(mask, o.mask)
+        assert np.array_equal(d2, o.edt_sq)
+        assert np.array_equal(bits(pre), bits(o.pre_blur))
+        assert np.array_equal(bits(cd.get_data()), bits(o.cost))
+        assert np.array_equal(cd.get_center(), o.center) and np.array_equal(cd.get_box(), o.box)
+        checked += 1
+    assert checked == 120
+
+
+def test_large_table_exact(dp, capi):
+    # a table larger than any fixture: exercises multi-tile EDT row scans
+    fp = np.array([[150, 0], [40, 90], [-120, 60], [-160, -10], [-20, -100], [90, -70]], np.int32)
+    o = capi.CostData(fp, 7)
+    cd = dp.cost_data(fp, 7)
+    d2, outline, mask, pre = cd.stages()
+    assert np.array_equal(d2, o.edt_sq) and np.array_equal(mask, o.mask)
+    assert np.array_equal(bits(cd.get_data()), bits(o.cost))
+
+
+@pytest.mark.parametrize("shift", [(10, 0), (4, 5), (-4, -5), (0, -9)])
+def test_translated_triangle(dp, shift):  # dpose_core/test/cost_data.cpp:23-62
+    o = dp.cost_data(fx.TRIANGLE, 0)
+    t = dp.cost_data(fx.TRIANGLE + np.array(shift, dtype=np.int32), 0)
+    assert o.get_data().shape == t.get_data().shape
+    assert np.array_equal(o.get_box() + np.array(shift), t.get_box())
+    assert np.array_equal(o.get_center() - np.array(shift), t.get_center())
+    assert np.array_equal(bits(o.get_data()), bits(t.get_data()))  # stronger than the reference's "lazy compare"
+
+
+@pytest.mark.parametrize("pad", [1, 5, 10])
+def test_padded_triangle(dp, pad):  # dpose_core/test/cost_data.cpp:68-115
+    o, p = dp.cost_data(fx.TRIANGLE, 0), dp.cost_data(fx.TRIANGLE, pad)
+    assert (o.rows + 2 * pad, o.cols + 2 * pad) == (p.rows, p.cols)
+    assert np.array_equal(o.get_box().min(0) - pad, p.get_box().min(0))
+    assert np.array_equal(o.get_box().max(0) + pad, p.get_box().max(0))
+    assert np.array_equal(o.get_center() + pad, p.get_center())
+
+
+@pytest.mark.parametrize("angle", [round(0.1 * i, 1) for i in range(1, 30)])
+def test_rotated_triangle(dp, angle):  # dpose_core/test/cost_data.cpp:121-154
+    pad = 5
+    c, s = math.cos(angle), math.sin(angle)
+    tri = fx.round_half_away(fx.TRIANGLE.astype(np.float64) @ np.array([[c, -s], [s, c]]).T)
+    d = dp.cost_data(tri, pad)
+    diff = tri.max(0) - tri.min(0)
+    assert d.cols == diff[0] + 1 + 2 * pad and d.rows == diff[1] + 1 + 2 * pad
+    assert np.array_equal(tri.min(0) - pad, d.get_box().min(0))
+    assert np.array_equal(tri.max(0) + 1 + pad, d.get_box().max(0))
+
+
+# --------------------------------------------------------------- get_cost ----
+def test_get_cost_cells_vs_golden_and_oracle(dp, capi, golden_get_cost):
+    g = golden_get_cost
+    pgs, ocs = {}, {}
+    for i in range(int(g["n"])):
+        name = str(g[f"{i}.table"])
+        if name not in pgs:
+            fp, pad = fx.FOOTPRINTS[name]
+            pgs[name] = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+            ocs[name] = capi.CostData(fp, pad)
+        pose, cells = g[f"{i}.pose"], g[f"{i}.cells"]
+        cost, J = pgs[name].get_cost(pose, cells)
+        assert fx.tol_ok(cost, g[f"{i}.cost"]), (i, cost, g[f"{i}.cost"])
+        assert np.all(fx.tol_ok(J, g[f"{i}.J"])), (i, J, g[f"{i}.J"])
+        oc, oJ = ocs[name].get_cost(pose, cells)
+        assert fx.tol_ok(cost, oc) and np.all(fx.tol_ok(J, oJ))
+        # far tighter against the analytic long-double evaluation
+        tc, tJ = ocs[name].get_cost_truth(pose, cells)
+        assert abs(cost - tc) <= 1e-10 * max(1.0, abs(tc))
+        assert np.all(np.abs(J - tJ) <= 1e-9 * np.maximum(1.0, np.abs(tJ)))
+        # without Jacobian: same cost
+        c2, J2 = pgs[name].get_cost(pose, cells, jacobian=False)
+        assert c2 == cost and J2 is None
+        # device-resident cell vector
+        c3, J3 = pgs[name].get_cost(pose, dp.cell_vector_device.upload(cells))
+        assert c3 == cost and np.array_equal(J3, J)
+
+
+@pytest.mark.parametrize("theta", [round(0.1 * i, 1) for i in range(1, 15)])
+def test_jacobian_self_consistency(dp, theta):  # dpose_core/test/jacobian_data.cpp:43-78 (+theta)
+    pg = dp.pose_gradient(fx.SHIP, dp.pose_gradient.parameter(10))
+    cells = np.array([[x, y] for x in range(20) for y in range(20)], np.int32)
+    _, J = pg.get_cost([0, 0, theta], cells)
+    for a in range(3):
+        off = np.zeros(3)
+        off[a] = 1e-6
+        lo, _ = pg.get_cost(np.array([0, 0, theta]) - off, cells, jacobian=False)
+        hi, _ = pg.get_cost(np.array([0, 0, theta]) + off, cells, jacobian=False)
+        diff = (hi - lo) / 2e-6
+        assert abs((diff - J[a]) / (diff if diff else 1.0)) <= 1e-3
+
+
+def test_get_cost_edge_cases(dp):
+    pg = dp.pose_gradient(fx.RECT)
+    c, J = pg.get_cost([0, 0, 0], np.empty((0, 2), np.int32))
+    assert c == 0 and np.all(J == 0)
+    c, J = pg.get_cost([0, 0, 0.3], np.array([[500, 500], [-400, 3], [2 ** 31 - 1, -2 ** 31]]))
+    assert c == 0 and np.all(J == 0)
+    # rounding tie: k = 2.5 selects k_upper = 3 (std::round), value T(2, 2) (dpose_core.cpp:177)
+    c, _ = pg.get_cost([0.5, 0.5, 0.0], np.array([[-9, -5]], np.int32))
+    assert c == float(pg.get_data().get_data()[2, 2])
+    # a big list: multi-CTA reduction path, deterministic
+    rng = np.random.default_rng(3)
+    cells = rng.integers(-14, 15, size=(300000, 2)).astype(np.int32)
+    r1, r2 = pg.get_cost([0.2, -0.3, 0.4], cells), pg.get_cost([0.2, -0.3, 0.4], cells)
+    assert r1[0] == r2[0] and np.array_equal(r1[1], r2[1])
+
+
+# ------------------------------------------------------------ lethal cells ----
+def test_lethal_reference_tests(dp):  # dpose_core/test/lethal_cells_within.cpp:29-57
+    m = np.zeros((200, 200), np.uint8)
+    m[100, 100] = fx.LETHAL
+    assert dp.lethal_cells_within(m, fx.to_rectangle((99, 99), (101, 101))).tolist() == [[100, 100]]
+    m = np.zeros((200, 200), np.uint8)
+    m[100, 0:200:20] = fx.LETHAL
+    assert len(dp.lethal_cells_within(m, fx.to_rectangle((80, 99), (121, 101)))) == 3
+    m = np.zeros((50, 50), np.uint8)
+    m[10, 10], m[10, 11], m[10, 12] = 253, 254, 255
+    assert dp.lethal_cells_within(m, fx.to_rectangle((0, 0), (49, 49))).tolist() == [[11, 10]]
+    assert len(dp.lethal_cells_within(np.zeros((200, 200), np.uint8), fx.to_rectangle(198, 198))) == 0
+    assert len(dp.lethal_cells_within(np.zeros((0, 0), np.uint8), fx.to_rectangle(5, 5))) == 0
+
+
+def test_lethal_goldens_bit_exact(dp, golden_lethal):
+    g = golden_lethal
+    maps = {"bern200": dp.Costmap(fx.bernoulli_map(200, 200, 0.10, 0)),
+            "full200": dp.Costmap(np.full((200, 200), fx.LETHAL, np.uint8))}
+    for i in range(int(g["n"])):
+        cells = dp.lethal_cells_within(maps[str(g[f"{i}.map"])], g[f"{i}.ring"])
+        assert np.array_equal(cells, g[f"{i}.cells"]), i
+
+
+def test_lethal_random_boxes_vs_oracle(dp, capi):
+    rng = np.random.default_rng(9)
+    m = fx.bernoulli_map(1777, 1234, 0.10, 21)  # width not a multiple of 16: pitch padding
+    cm = dp.Costmap(m)
+    for k in range(60):
+        w, h = rng.integers(1, 900, 2)
+        ring = fx.rotated_ring(fx.to_rectangle((-w // 2, -h // 2), (w // 2, h // 2)),
+                               (rng.uniform(-100, 1900), rng.uniform(-100, 1400), rng.uniform(0, 6.3)))
+        got = dp.lethal_cells_within(cm, ring)
+        ref = capi.lethal_cells_within(m, ring)
+        assert np.array_equal(got, ref), (k, ring.tolist(), len(got), len(ref))
+    # device-resident result equals the host one
+    ring = fx.to_rectangle((3, 5), (1500, 1100))
+    dev = dp.lethal_cells_within(cm, ring, on_device=True)
+    assert np.array_equal(dev.numpy(), capi.lethal_cells_within(m, ring))
+
+
+def test_lethal_perf_bench_workload(dp, capi):  # dpose_core/perf/dpose_core.cpp:73-90
+    m = np.zeros((200, 200), np.uint8)
+    m.reshape(-1)[::2] = fx.LETHAL
+    got = dp.lethal_cells_within(m, fx.to_rectangle(198, 198))
+    assert np.array_equal(got, capi.lethal_cells_within(m, fx.to_rectangle(198, 198)))
+
+
+def test_map_update_window(dp, capi):
+    m = fx.bernoulli_map(300, 200, 0.10, 4)
+    cm = dp.Costmap(m)
+    patch = fx.bernoulli_map(37, 21, 0.5, 5)
+    m2 = m.copy()
+    m2[50:71, 100:137] = patch
+    cm.update(patch, 100, 50)
+    ring = fx.to_rectangle((0, 0), (299, 199))
+    assert np.array_equal(dp.lethal_cells_within(cm, ring), capi.lethal_cells_within(m2, ring))
+
+
+# ---------------------------------------------------------- batched get_cost ----
+@pytest.mark.parametrize("name", ["rect_pad2", "star40_pad2", "lshape_pad2"])
+def test_batch_vs_all_cells_golden(dp, golden_batch, name):
+    m = fx.bernoulli_map(256, 192, 0.10, int(golden_batch["map_seed"]))
+    fp, pad = fx.FOOTPRINTS[name]
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+    cm = dp.Costmap(m)
+    out = pg.get_cost_batch(cm, golden_batch[name + ".poses"])
+    assert np.all(fx.tol_ok(out, golden_batch[name + ".out"]))
+    # equals the list-based GPU path over all lethal cells of the map
+    ys, xs = np.nonzero(m == fx.LETHAL)
+    cells = np.stack([xs, ys], 1).astype(np.int32)
+    for p, o in zip(golden_batch[name + ".poses"][:6], out[:6]):
+        c, J = pg.get_cost(p, cells)
+        assert fx.tol_ok(o[0], c, rel=1e-12, abs_=1e-12) and np.all(fx.tol_ok(o[1:], J, rel=1e-11, abs_=1e-11))
+
+
+@pytest.mark.parametrize("name,n", [("rect_pad2", 20000), ("star40_pad2", 4000), ("ship_pad10", 500)])
+def test_batch_config2_vs_oracle(dp, capi, name, n):
+    """BASELINE config 2 shape (2000x2000, 10 % lethal), subsampled to what the oracle does in
+    seconds: 100 % of poses inside tolerance against the literal reference restatement."""
+    m = fx.bernoulli_map(2000, 2000, 0.10, 1)
+    poses = fx.random_poses(n, 2000, 2000, 2, margin=100.0 if name == "ship_pad10" else 32.0)
+    fp, pad = fx.FOOTPRINTS[name]
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+    cm = dp.Costmap(m)
+    out = pg.get_cost_batch(cm, poses)
+    oc = capi.CostData(fp, pad)
+    ref = oc.get_cost_batch(m, poses, nthreads=capi.max_threads())
+    ok = fx.tol_ok(out, ref)
+    assert ok.all(), (np.argwhere(~ok)[:5], out[~ok.all(1)][:3], ref[~ok.all(1)][:3])
+    truth = oc.get_cost_batch_truth(m, poses, nthreads=capi.max_threads())
+    assert np.all(np.abs(out - truth) <= 1e-9 * np.maximum(1.0, np.abs(truth)))
+    assert (ref[:, 0] > 0).mean() > 0.9  # the workload is not trivially empty
+    # determinism and the no-Jacobian variant
+    out2 = pg.get_cost_batch(cm, poses)
+    assert np.array_equal(out, out2)
+    out3 = pg.get_cost_batch(cm, poses, jacobian=False)
+    assert np.array_equal(out3[:, 0], out[:, 0]) and np.all(out3[:, 1:] == 0)
+
+
+def test_batch_large_coordinates_protocol(dp, capi):
+    """10000-cell coordinates: the reference's FD round-off reaches the tolerance,
+    so the gate is against the reference on translated-equivalent inputs; the literal pass rate is
+    informational and every literal failure is adjudicated against long double."""
+    size = 10000
+    rng = np.random.default_rng(4)
+    m = np.zeros((size, size), np.uint8)
+    # lethal only inside a band to keep host generation cheap
+    band = (rng.random((600, size)) < 0.10)
+    m[4700:5300][band] = fx.LETHAL
+    n = 3000
+    poses = np.stack([rng.uniform(32, size - 32, n), rng.uniform(4750, 5250, n), rng.uniform(-math.pi, math.pi, n)], 1)
+    pg = dp.pose_gradient(fx.RECT)
+    cm = dp.Costmap(m)
+    out = pg.get_cost_batch(cm, poses)
+    oc = capi.CostData(fx.RECT, 2)
+    shifted = oc.get_cost_batch(m, poses, shift=True, nthreads=capi.max_threads())
+    assert fx.tol_ok(out, shifted).all()
+    literal = oc.get_cost_batch(m, poses, nthreads=capi.max_threads())
+    truth = oc.get_cost_batch_truth(m, poses, nthreads=capi.max_threads())
+    bad = ~fx.tol_ok(out, literal)
+    assert bad.mean() < 0.02
+    # where the literal reference disagrees, the GPU is the one next to the truth
+    assert np.all(np.abs(out[bad] - truth[bad]) <= 0.01 * np.abs(literal[bad] - truth[bad]) + 1e-12)
+
+
+def test_batch_border_and_degenerate_poses(dp):
+    m = fx.bernoulli_map(64, 48, 0.3, 8)
+    pg = dp.pose_gradient(fx.RECT)
+    cm = dp.Costmap(m)
+    ys, xs = np.nonzero(m == fx.LETHAL)
+    cells = np.stack([xs, ys], 1).astype(np.int32)
+    poses = np.array([[0, 0, 0.1], [63.9, 47.9, 2.0], [-5.0, 20.0, -1.0], [70.0, 20.0, 0.5], [32, -8, 3.0],
+                      [1e6, 1e6, 0.0], [-1e7, 5, 1.0], [31.5, 23.5, 0.0], [31.5, 23.5, math.pi / 2]])
+    out = pg.get_cost_batch(cm, poses)
+    for p, o in zip(poses, out):
+        c, J = pg.get_cost(p, cells)
+        assert fx.tol_ok(o[0], c, rel=1e-12, abs_=1e-12) and np.all(fx.tol_ok(o[1:], J, rel=1e-11, abs_=1e-11)), p
+    assert np.all(out[5] == 0) and np.all(out[6] == 0)
+    assert len(pg.get_cost_batch(cm, np.empty((0, 3)))) == 0
+    full = dp.Costmap(np.full((64, 48), fx.LETHAL, np.uint8))  # every window cell lethal
+    yy, xx = np.mgrid[0:64, 0:48]
+    allc = np.stack([xx.ravel(), yy.ravel()], 1).astype(np.int32)
+    o = pg.get_cost_batch(full, poses[:5])
+    for p, r in zip(poses[:5], o):
+        c, J = pg.get_cost(p, allc)
+        assert fx.tol_ok(r[0], c, rel=1e-12, abs_=1e-12) and np.all(fx.tol_ok(r[1:], J, rel=1e-10, abs_=1e-10))
+
+
+def test_batch_device_pointer_entry(dp):
+    torch = pytest.importorskip("torch")
+    m = fx.bernoulli_map(512, 512, 0.10, 1)
+    poses = fx.random_poses(5000, 512, 512, 2)
+    pg = dp.pose_gradient(fx.RECT)
+    cm = dp.Costmap(m)
+    ref = pg.get_cost_batch(cm, poses)
+    d_p = torch.from_numpy(poses).cuda()
+    d_o = torch.empty((len(poses), 4), dtype=torch.float64, device="cuda")
+    pg.get_cost_batch_device(cm, d_p.data_ptr(), len(poses), d_o.data_ptr(),
+                             stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_o.cpu().numpy(), ref)
+    # map built from a device buffer
+    cm2 = dp.Costmap(device_ptr=torch.from_numpy(m).cuda().data_ptr(), size_x=512, size_y=512)
+    assert np.array_equal(pg.get_cost_batch(cm2, poses), ref)
+    assert pg.window_bytes(cm, poses) > 400 * len(poses)
+
+
+def test_batch_multi_gpu_shards(dp):
+    from dpose_b200.core import get_cost_batch_multi
+    n = min(dp.device_count(), 8)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    m = fx.bernoulli_map(512, 512, 0.10, 1)
+    poses = fx.random_poses(10001, 512, 512, 2)
+    pgs = [dp.pose_gradient(fx.RECT, device=d) for d in range(n)]
+    maps = [dp.Costmap(m, device=d) for d in range(n)]
+    ref = pgs[0].get_cost_batch(maps[0], poses)
+    assert np.array_equal(get_cost_batch_multi(pgs, maps, poses), ref)
