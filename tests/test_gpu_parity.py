@@ -259,11 +259,22 @@ def test_batch_config2_vs_oracle(dp, capi, name, n):
     cm = dp.Costmap(m)
     out = pg.get_cost_batch(cm, poses)
     oc = capi.CostData(fp, pad)
-    ref = oc.get_cost_batch(m, poses, nthreads=capi.max_threads())
-    ok = fx.tol_ok(out, ref)
-    assert ok.all(), (np.argwhere(~ok)[:5], out[~ok.all(1)][:3], ref[~ok.all(1)][:3])
-    truth = oc.get_cost_batch_truth(m, poses, nthreads=capi.max_threads())
+    nt = capi.max_threads()
+    # gate: 100 % against the reference evaluated on translated-equivalent inputs
+    shifted = oc.get_cost_batch(m, poses, shift=True, nthreads=nt)
+    ok = fx.tol_ok(out, shifted)
+    assert ok.all(), (np.argwhere(~ok)[:5], out[~ok.all(1)][:3], shifted[~ok.all(1)][:3])
+    # against the long-double analytic evaluation: 4 orders of magnitude inside the tolerance
+    truth = oc.get_cost_batch_truth(m, poses, nthreads=nt)
     assert np.all(np.abs(out - truth) <= 1e-9 * np.maximum(1.0, np.abs(truth)))
+    # literal reference (finite differences at coordinates ~1e3): its own round-off occasionally
+    # reaches the tolerance on a near-zero J_theta of a many-cell table; every such element must be
+    # the reference's deviation from the truth, not ours
+    ref = oc.get_cost_batch(m, poses, nthreads=nt)
+    bad = ~fx.tol_ok(out, ref)
+    assert bad.mean() < 1e-3, bad.mean()
+    assert np.all(np.abs(out[bad] - truth[bad]) <= 0.01 * np.abs(ref[bad] - truth[bad]) + 1e-12)
+    assert fx.tol_ok(out[:, 0], ref[:, 0]).all()  # the cost itself never needs the protocol
     assert (ref[:, 0] > 0).mean() > 0.9  # the workload is not trivially empty
     # determinism and the no-Jacobian variant
     out2 = pg.get_cost_batch(cm, poses)
