@@ -20,39 +20,9 @@
 #include <cmath>
 #include <mutex>
 
-#include "common.cuh"
+#include "cost_math.cuh"
 
 namespace dpose {
-
-// ---- shared geometry (host + device) ---------------------------------------------------
-struct TableGeom {
-  int rows, cols;
-  double cx, cy;  // center
-};
-
-// axis-aligned bounding box (inclusive integer cells) of the valid kernel region
-// [1.5, cols-1.5) x [1.5, rows-1.5) mapped into the map by p = t + R(theta)(k - C)
-__host__ __device__ inline WindowRect pose_window(const TableGeom &g, double tx, double ty, double c,
-                                                  double s, int size_x, int size_y) {
-  const double au0 = 1.5 - g.cx, au1 = (double)g.cols - 1.5 - g.cx;
-  const double av0 = 1.5 - g.cy, av1 = (double)g.rows - 1.5 - g.cy;
-  const double xa = c * au0, xb = c * au1, xc = -s * av0, xd = -s * av1;
-  const double ya = s * au0, yb = s * au1, yc = c * av0, yd = c * av1;
-  const double eps = 1e-7;
-  const double xmin = tx + fmin(xa, xb) + fmin(xc, xd) - eps, xmax = tx + fmax(xa, xb) + fmax(xc, xd) + eps;
-  const double ymin = ty + fmin(ya, yb) + fmin(yc, yd) - eps, ymax = ty + fmax(ya, yb) + fmax(yc, yd) + eps;
-  WindowRect w;
-  w.x0 = w.y0 = 0;
-  w.x1 = w.y1 = -1;  // empty; also the answer for NaN poses and windows off the map
-  if (!(xmax >= 0.0) || !(ymax >= 0.0) || !(xmin <= (double)size_x - 1.0) || !(ymin <= (double)size_y - 1.0))
-    return w;
-  // clamped in floating point, so the int casts cannot overflow
-  w.x0 = (int)ceil(fmax(xmin, 0.0));
-  w.y0 = (int)ceil(fmax(ymin, 0.0));
-  w.x1 = (int)floor(fmin(xmax, (double)size_x - 1.0));
-  w.y1 = (int)floor(fmin(ymax, (double)size_y - 1.0));
-  return w;
-}
 
 namespace {
 
@@ -154,17 +124,6 @@ __global__ void __launch_bounds__(kCellThreads)
 
 // ---- pose batch, generic window scan (any table size) ----------------------------------------
 constexpr int kBatchWarps = 8;
-
-struct BatchArgs {
-  const PatchCoef *coef;
-  TableGeom g;
-  const uint8_t *map;
-  size_t pitch;
-  int size_x, size_y;
-  const double *poses;
-  double *out;
-  size_t n;
-};
 
 template <bool kJac>
 __global__ void __launch_bounds__(kBatchWarps * 32) k_cost_batch_generic(BatchArgs a) {
@@ -272,25 +231,10 @@ int get_cost_cells_host(const dpose_pg *pg, const double se2[3], const int32_t *
   return cost_cells_impl(pg, se2, nullptr, cells_xy, n, cost, J);
 }
 
-int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
-                          double *d_out, int want_jacobian, cudaStream_t stream) {
-  if (n == 0) return DPOSE_OK;
-  if (pg->device != map->device) return fail(DPOSE_EINVAL, "pose_gradient and map live on different devices");
-  DeviceGuard guard(pg->device);
-  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
-  BatchArgs a;
-  a.coef = pg->d_coef;
-  a.g = TableGeom{pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
-  a.map = map->d_data;
-  a.pitch = map->pitch;
-  a.size_x = (int)map->size_x;
-  a.size_y = (int)map->size_y;
-  a.poses = d_poses;
-  a.out = d_out;
-  a.n = n;
+int launch_batch_generic(const BatchArgs &a, int want_jacobian, int device, cudaStream_t stream) {
   int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
-  size_t want = (n + kBatchWarps - 1) / kBatchWarps;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t want = (a.n + kBatchWarps - 1) / kBatchWarps;
   const size_t cap = (size_t)sms * 8 * 4;  // a few waves of resident CTAs, grid-strided
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   if (want_jacobian)
@@ -300,8 +244,6 @@ int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double
   DPOSE_LAUNCHED();
   return DPOSE_OK;
 }
-
-void map_release_cache(dpose_map *) {}
 
 uint64_t window_bytes_host(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n) {
   const TableGeom g = {pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
