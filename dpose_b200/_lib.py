@@ -30,6 +30,8 @@ SYMBOLS = {
     "dpose_map_create": (_i, [_vp, _u32, _u32, _sz, _i, _pp]),
     "dpose_map_create_from_device": (_i, [_vp, _u32, _u32, _sz, _i, _pp]),
     "dpose_map_update": (_i, [_vp, _vp, _sz, _u32, _u32, _u32, _u32]),
+    "dpose_map_set_volatile": (_i, [_vp, _i]),
+    "dpose_map_device_ptr": (_i, [_vp, _pp, C.POINTER(_sz)]),
     "dpose_map_size": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
     "dpose_map_destroy": (None, [_vp]),
     "dpose_raytrace": (_i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),

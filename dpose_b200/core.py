@@ -83,6 +83,11 @@ class Costmap:
             check(lib().dpose_map_create(m.ctypes.data, self.size_x, self.size_y, m.strides[0] if m.size else 0,
                                          self.device, C.byref(self._h)))
 
+    def set_volatile(self, flag=True):
+        """rebuild the derived lethal bit plane inside every batched call (the device bytes may
+        change behind the library's back); bench.py times with this ON"""
+        check(lib().dpose_map_set_volatile(self._h, int(bool(flag))))
+
     def update(self, window, x0, y0):
         """re-upload a dirty window (rows [y0, y0+h), columns [x0, x0+w))"""
         w = np.ascontiguousarray(np.asarray(window, dtype=np.uint8))

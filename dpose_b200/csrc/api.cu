@@ -190,6 +190,9 @@ static int map_create_impl(const uint8_t *data, uint32_t size_x, uint32_t size_y
     DPOSE_CUDA(cudaMalloc(&m->d_data, m->pitch * size_y));
     if (m->pitch != size_x) DPOSE_CUDA(cudaMemset(m->d_data, 0, m->pitch * size_y));
     DPOSE_CUDA(cudaMemcpy2D(m->d_data, m->pitch, data, pitch, size_x, size_y, kind));
+    m->bits_pitch = (((size_t)size_x + 127) / 128) * 16;
+    DPOSE_CUDA(cudaMalloc(&m->d_bits, m->bits_pitch * size_y));
+    m->bits_dirty = true;
     return DPOSE_OK;
   };
   const int rc = body();
@@ -221,6 +224,21 @@ int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", map->device);
   DPOSE_CUDA(cudaMemcpy2D(map->d_data + (size_t)y0 * map->pitch + x0, map->pitch, data, pitch, w, h,
                           cudaMemcpyHostToDevice));
+  map->bits_dirty = true;
+  return DPOSE_OK;
+}
+
+int dpose_map_set_volatile(dpose_map *map, int is_volatile) {
+  if (!map) return fail(DPOSE_EINVAL, "map is NULL");
+  map->is_volatile = is_volatile != 0;
+  map->bits_dirty = true;
+  return DPOSE_OK;
+}
+
+int dpose_map_device_ptr(const dpose_map *map, uint8_t **d_data, size_t *pitch) {
+  if (!map || !d_data || !pitch) return fail(DPOSE_EINVAL, "NULL argument");
+  *d_data = map->d_data;
+  *pitch = map->pitch;
   return DPOSE_OK;
 }
 
@@ -237,6 +255,8 @@ void dpose_map_destroy(dpose_map *map) {
     DeviceGuard guard(map->device);
     map_release_cache(map);
     cudaFree(map->d_data);
+    cudaFree(map->d_bits);
+    if (map->bits_ready) cudaEventDestroy(map->bits_ready);
   }
   delete map;
 }

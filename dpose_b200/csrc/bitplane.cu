@@ -1,0 +1,52 @@
+// bitplane.cu — packs the uint8 costmap into a 1-bit-per-cell lethal plane.
+//
+// The batched get_cost kernel only ever asks "is this cell 254?", so it reads the costmap through
+// this plane: 8x fewer bytes per window, and a 10000x10000 map shrinks from 100 MB (thrashes the
+// 126 MB L2 under random window access: 46 % hit rate measured) to 12.5 MB (L2-resident).
+// One thread per output word: two aligned 16-byte loads -> 32 bits.  HBM-bound streaming pass:
+// size_x*size_y bytes read + 1/8 of that written (~20 us for 100 MB); it runs on the caller's stream
+// in front of the batch kernel whenever the map changed (or on every call for volatile maps).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dpose {
+namespace {
+
+__device__ __forceinline__ unsigned lethal_bits16(const uint4 v) {
+  const unsigned k = 0xFEFEFEFEu;
+  const unsigned e0 = __vcmpeq4(v.x, k) & 0x01010101u, e1 = __vcmpeq4(v.y, k) & 0x01010101u;
+  const unsigned e2 = __vcmpeq4(v.z, k) & 0x01010101u, e3 = __vcmpeq4(v.w, k) & 0x01010101u;
+  const unsigned n0 = (e0 * 0x00204081u) >> 21 & 0xFu, n1 = (e1 * 0x00204081u) >> 21 & 0xFu;
+  const unsigned n2 = (e2 * 0x00204081u) >> 21 & 0xFu, n3 = (e3 * 0x00204081u) >> 21 & 0xFu;
+  return n0 | (n1 << 4) | (n2 << 8) | (n3 << 12);
+}
+
+__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t *__restrict__ map, size_t pitch, uint32_t size_y,
+                                                   uint32_t *__restrict__ bits, uint32_t words_per_row) {
+  const size_t total = (size_t)size_y * words_per_row;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t y = (uint32_t)(i / words_per_row), w = (uint32_t)(i - (size_t)y * words_per_row);
+    const size_t x = (size_t)w * 32;
+    unsigned out = 0u;
+    const uint8_t *row = map + (size_t)y * pitch;
+    // pitch % 16 == 0 and the pad bytes of the device copy are zero
+    if (x < pitch) out = lethal_bits16(__ldg(reinterpret_cast<const uint4 *>(row + x)));
+    if (x + 16 < pitch) out |= lethal_bits16(__ldg(reinterpret_cast<const uint4 *>(row + x + 16))) << 16;
+    bits[i] = out;
+  }
+}
+
+}  // namespace
+
+int bitplane_build(const dpose_map *map, cudaStream_t stream) {
+  if (!map->d_bits || map->size_x == 0 || map->size_y == 0) return DPOSE_OK;
+  const uint32_t words_per_row = (uint32_t)(map->bits_pitch / 4);
+  const size_t total = (size_t)map->size_y * words_per_row;
+  const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+  k_pack_bits<<<grid, 256, 0, stream>>>(map->d_data, map->pitch, map->size_y, map->d_bits, words_per_row);
+  DPOSE_LAUNCHED();
+  return DPOSE_OK;
+}
+
+}  // namespace dpose

@@ -92,7 +92,15 @@ struct dpose_map {
   uint32_t size_x = 0, size_y = 0;
   size_t pitch = 0;  // bytes, multiple of 16
   uint8_t *d_data = nullptr;
-  // TMA descriptor cache (get_cost.cu), keyed by box dims
+  // lethal bit plane (bitplane.cu): bit x of row y = (cell == 254); rows padded to 16 bytes.
+  // Rebuilt from d_data when `bits_dirty` (after create / update) or on every batch call when the
+  // map is marked volatile (its bytes may change behind the library's back).
+  uint32_t *d_bits = nullptr;
+  size_t bits_pitch = 0;  // bytes per bit-plane row, multiple of 16
+  bool bits_dirty = true;
+  bool is_volatile = false;
+  cudaEvent_t bits_ready = nullptr;  // recorded after a rebuild; other streams wait on it
+  // TMA descriptor cache (get_cost_batch.cu), keyed by box dims
   void *tma_cache = nullptr;
 };
 
@@ -117,6 +125,8 @@ uint64_t window_bytes_host(const dpose_pg *pg, const dpose_map *map, const doubl
 int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses,
                           size_t n, double *d_out, int want_jacobian, cudaStream_t stream);
 void map_release_cache(dpose_map *map);
+// bitplane.cu: (re)build the lethal bit plane on `stream`
+int bitplane_build(const dpose_map *map, cudaStream_t stream);
 // host window geometry shared by the kernel launch code and dpose_pg_window_bytes
 struct WindowRect {
   int x0, y0, x1, y1;  // inclusive cell range, already clipped; empty if x1 < x0

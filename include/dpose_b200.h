@@ -88,6 +88,13 @@ int dpose_map_create_from_device(const uint8_t *d_data, uint32_t size_x, uint32_
  * dpose_costmap.cpp:138). */
 int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t x0,
                      uint32_t y0, uint32_t w, uint32_t h);
+/* The batched kernel reads the map through a derived 1-bit-per-cell lethal plane that the
+ * library rebuilds (one streaming pass on the call's stream) after create / update.  Mark the map
+ * volatile if its device bytes can change without dpose_map_update (see dpose_map_device_ptr):
+ * the plane is then rebuilt inside every batched call. */
+int dpose_map_set_volatile(dpose_map *map, int is_volatile);
+/* the device copy itself (row stride *pitch), e.g. to let a GPU costmap layer write into it */
+int dpose_map_device_ptr(const dpose_map *map, uint8_t **d_data, size_t *pitch);
 int dpose_map_size(const dpose_map *map, uint32_t *size_x, uint32_t *size_y);
 void dpose_map_destroy(dpose_map *map);
 

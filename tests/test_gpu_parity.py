@@ -336,6 +336,25 @@ def test_batch_border_and_degenerate_poses(dp):
         assert fx.tol_ok(r[0], c, rel=1e-12, abs_=1e-12) and np.all(fx.tol_ok(r[1:], J, rel=1e-10, abs_=1e-10))
 
 
+def test_batch_sees_map_updates(dp):
+    """the batched kernel reads a derived bit plane: it must follow dpose_map_update and the volatile mode"""
+    m = fx.bernoulli_map(300, 200, 0.10, 4)
+    poses = fx.random_poses(3000, 300, 200, 6, margin=0.0)
+    pg = dp.pose_gradient(fx.RECT)
+    cm = dp.Costmap(m)
+    before = pg.get_cost_batch(cm, poses)
+    patch = fx.bernoulli_map(120, 90, 0.6, 5)
+    m2 = m.copy()
+    m2[50:140, 100:220] = patch
+    cm.update(patch, 100, 50)
+    after = pg.get_cost_batch(cm, poses)
+    fresh = pg.get_cost_batch(dp.Costmap(m2), poses)
+    assert np.array_equal(after, fresh) and not np.array_equal(after, before)
+    cm.set_volatile(True)
+    assert np.array_equal(pg.get_cost_batch(cm, poses), fresh)
+    assert np.array_equal(pg.get_cost_batch(cm, poses), fresh)
+
+
 def test_batch_device_pointer_entry(dp):
     torch = pytest.importorskip("torch")
     m = fx.bernoulli_map(512, 512, 0.10, 1)
