@@ -22,9 +22,10 @@
 //                  positive k that can be valid) and c_rel in one go; bounds test; one 32-byte
 //                  patch-coefficient read from the shared-memory copy of the table; f, f_u, f_v by
 //                  FMA; per-lane accumulation
-//       - reduce : lanes park their 4 partial sums in shared memory; every 4 poses the warp sums
-//                  them column-wise in a fixed order (2 lanes per output: 16 adds each + one
-//                  __shfl_xor_sync) and writes 4 poses x 4 doubles = 128 contiguous bytes.
+//       - reduce : cost, Su, Sv, Stheta are reduced across the warp with __shfl_xor_sync in a fixed,
+//                  transposed tree (payload halves at xor 16 and xor 8), so the result is
+//                  deterministic and independent of where the pose sits in the batch; 4 lanes write
+//                  the pose's 32-byte result (one full sector).
 // Tensor cores are not used: there is no dense contraction anywhere on this path.
 //
 // Algorithmic bytes per pose: 24 (pose) + 32 (result) + |window| map bytes.
@@ -39,10 +40,9 @@ namespace dpose {
 namespace {
 
 constexpr int kWarps = 8;        // warps per CTA
-constexpr int kQueueCap = 512;   // queue entries per warp (u16 each)
-constexpr int kPartPitch = 33;   // doubles per (pose, component) row of the partial-sum block
-constexpr int kPartPoses = 4;    // poses reduced together
+constexpr int kQueueCap = 256;   // queue entries per warp (u16 each); denser windows take the slow path
 constexpr int kMaxStages = 8;
+constexpr int kMinCtasPerSm = 4; // 32 resident warps per SM: the kernel is issue-latency bound
 
 struct __align__(16) PoseParam {
   double c, s, ku0, kv0;  // rotation; kernel coordinates (+0.5) of the window origin (x0, y0)
@@ -113,8 +113,9 @@ struct Acc4 {
 // c_rel = k - round(k) + 0.5 (dpose_core.cpp:193), so floor(k + 0.5) is k_upper (:177, std::round
 // for every k that can pass the bounds test) and (k + 0.5) - floor(k + 0.5) is c_rel.
 template <bool kJac, bool kSmemCoef>
-__device__ __forceinline__ void eval_entry(const PatchCoef *__restrict__ coef, int cols, unsigned cols_m4,
-                                           unsigned rows_m4, const PoseParam &P, int xr, int yr, Acc4 &acc) {
+__device__ __forceinline__ void eval_entry(const PatchCoef *__restrict__ coef, uint32_t coef_u32, int cols,
+                                           unsigned cols_m4, unsigned rows_m4, const PoseParam &P, int xr, int yr,
+                                           Acc4 &acc) {
   const double X = (double)xr, Y = (double)yr;
   const double ku = fma(P.c, X, fma(P.s, Y, P.ku0));
   const double kv = fma(P.c, Y, fma(-P.s, X, P.kv0));
@@ -124,8 +125,10 @@ __device__ __forceinline__ void eval_entry(const PatchCoef *__restrict__ coef, i
   if ((unsigned)(ux - 2) <= cols_m4 && (unsigned)(uy - 2) <= rows_m4) {  // :181-182
     const double rx = ku - (tu - M), ry = kv - (tv - M);                 // c_rel in [0, 1)
     PatchCoef p;
-    if (kSmemCoef) {
-      p = coef[uy * cols + ux];
+    if (kSmemCoef) {  // 32-bit shared address: no generic -> shared conversion per load
+      const uint32_t addr = coef_u32 + (uint32_t)(uy * cols + ux) * 32u;
+      asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p.a00), "=d"(p.a10) : "r"(addr));
+      asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(p.a01), "=d"(p.a11) : "r"(addr));
     } else {
       const double2 *g = reinterpret_cast<const double2 *>(coef + uy * cols + ux);
       const double2 lo = __ldg(g), hi = __ldg(g + 1);
@@ -145,18 +148,17 @@ __device__ __forceinline__ void eval_entry(const PatchCoef *__restrict__ coef, i
 
 // kSmall: every window fits 32 x 32 (no row / column chunk loops)
 template <bool kJac, bool kSmemCoef, bool kSmall>
-__global__ void __launch_bounds__(kWarps * 32, 2) k_cost_batch_tma(const __grid_constant__ CUtensorMap tmap, FastArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, kMinCtasPerSm) k_cost_batch_tma(const __grid_constant__ CUtensorMap tmap, FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // ---- shared memory carve-up -----------------------------------------------------------------
   PatchCoef *s_coef = reinterpret_cast<PatchCoef *>(smem);
   unsigned char *wbase = smem + a.coef_bytes + (size_t)warp * a.per_warp_bytes;
-  unsigned char *s_win = wbase;                                                             // stages * stage_bytes
-  double *s_part = reinterpret_cast<double *>(s_win + a.stages * a.stage_bytes);             // 4*4*33 doubles
-  PoseParam *s_param = reinterpret_cast<PoseParam *>(s_part + kPartPoses * 4 * kPartPitch);  // 32
-  unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_param + 32);                // kQueueCap
-  unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_queue + kQueueCap);   // stages
+  unsigned char *s_win = wbase;                                                            // stages * stage_bytes
+  PoseParam *s_param = reinterpret_cast<PoseParam *>(s_win + a.stages * a.stage_bytes);     // 32
+  unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_param + 32);               // kQueueCap
+  unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_queue + kQueueCap);  // stages
 
   if (kSmemCoef) {
     const int n4 = a.g.rows * a.g.cols * 2;  // uint4 per table
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_cost_batch_tma(const __grid_
   __syncthreads();
 
   const PatchCoef *coef = kSmemCoef ? s_coef : a.coef;
+  const uint32_t coef_u32 = smem_u32(s_coef);
   const int cols = a.g.cols;
   const unsigned cols_m4 = (unsigned)(a.g.cols - 4), rows_m4 = (unsigned)(a.g.rows - 4);
   const float hi_u = (float)a.g.cols - 1.0f, hi_v = (float)a.g.rows - 1.0f;  // k + 0.5 < dim - 1
@@ -264,14 +267,20 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_cost_batch_tma(const __grid_
           xlo = (int)ceilf(lo);
           xhi = (int)floorf(hi);
         }
-        const unsigned *roww = reinterpret_cast<const unsigned *>(win + row * box_wb);
+        const unsigned char *rowp = win + row * box_wb;
         for (int cb = 0; cb < (kSmall ? 1 : W); cb += 32) {
           // -- scan: the 32 window bits [cb, cb + 32) of this lane's row -----------------------------------
+          // one LDS.128 of the 16-byte piece holding the field (conflict-free across the quarter-warp
+          // for row pitches of 16 * odd bytes, 2-way for 32) instead of two same-column LDS.32 (8-way)
           unsigned mask = 0u;
           const int lo = max(xlo - cb, 0), hi = min(xhi - cb, 31);
           if (lo <= hi) {
-            const int bo = o + cb;
-            const unsigned w0 = roww[bo >> 5], w1 = roww[(bo >> 5) + 1];  // box rows keep a spare word
+            const int bo = o + cb, wsel = (bo >> 5) & 3;  // warp-uniform
+            const uint4 v = *reinterpret_cast<const uint4 *>(rowp + ((bo >> 7) << 4));
+            unsigned nx = 0u;  // first word of the next piece, only needed when the field straddles it
+            if (wsel == 3 && (bo & 31) + hi >= 32) nx = *reinterpret_cast<const unsigned *>(rowp + ((bo >> 7) << 4) + 16);
+            const unsigned a0 = (wsel & 2) ? v.z : v.x, a1 = (wsel & 2) ? v.w : v.y, a2 = (wsel & 2) ? nx : v.z;
+            const unsigned w0 = (wsel & 1) ? a1 : a0, w1 = (wsel & 1) ? a2 : a1;
             mask = __funnelshift_r(w0, w1, bo & 31);
             mask &= (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
           }
@@ -288,22 +297,25 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_cost_batch_tma(const __grid_
           if (total <= kQueueCap) {
             unsigned short *dst = s_queue + (inc - mine);
             const unsigned base = (unsigned)((row << 8) | cb);
+#pragma unroll 1
             while (mask) {
               const int b = __ffs((int)mask) - 1;
               mask &= mask - 1;
               *dst++ = (unsigned short)(base + b);
             }
             __syncwarp();
+#pragma unroll 1
             for (int e = lane; e < total; e += 32) {
               const unsigned en = s_queue[e];
-              eval_entry<kJac, kSmemCoef>(coef, cols, cols_m4, rows_m4, P, (int)(en & 255u), (int)(en >> 8), acc);
+              eval_entry<kJac, kSmemCoef>(coef, coef_u32, cols, cols_m4, rows_m4, P, (int)(en & 255u), (int)(en >> 8),
+                                          acc);
             }
             __syncwarp();
           } else {  // dense maps: each lane walks its own bits (correct, not fast)
             while (mask) {
               const int b = __ffs((int)mask) - 1;
               mask &= mask - 1;
-              eval_entry<kJac, kSmemCoef>(coef, cols, cols_m4, rows_m4, P, cb + b, row, acc);
+              eval_entry<kJac, kSmemCoef>(coef, coef_u32, cols, cols_m4, rows_m4, P, cb + b, row, acc);
             }
           }
         }
@@ -318,46 +330,34 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_cost_batch_tma(const __grid_
         if (++ist == stages) ist = 0;
       }
 
-      // ---- park the partial sums; every 4 poses reduce them in a fixed order ---------------------------------
-      {
-        double *pp = s_part + (q & (kPartPoses - 1)) * 4 * kPartPitch + lane;
-        pp[0] = acc.f;
-        if (kJac) {
-          pp[kPartPitch] = acc.su;
-          pp[2 * kPartPitch] = acc.sv;
-          pp[3 * kPartPitch] = acc.st;
+      // ---- reduce the 4 per-lane sums with a fixed xor-shuffle tree, transposed so that every level
+      //      halves the payload: after xor 16 a lane carries 2 of the 4 sums, after xor 8 one; lanes
+      //      0-7 end with cost, 8-15 with Su, 16-23 with Sv, 24-31 with Stheta -----------------------------
+      if (kJac) {
+        const bool b4 = lane & 16, b3 = lane & 8;
+        double k0 = b4 ? acc.sv : acc.f, k1 = b4 ? acc.st : acc.su;  // kept
+        const double g0 = b4 ? acc.f : acc.sv, g1 = b4 ? acc.su : acc.st;  // given to lane ^ 16
+        k0 += __shfl_xor_sync(0xffffffffu, g0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, g1, 16);
+        double k = b3 ? k1 : k0;
+        k += __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+        k += __shfl_xor_sync(0xffffffffu, k, 4);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        const double su = __shfl_sync(0xffffffffu, k, 8), sv = __shfl_sync(0xffffffffu, k, 16);
+        if ((lane & 7) == 0) {
+          const int comp = lane >> 3;
+          double o_val = k;  // comp 0: cost
+          if (comp == 1) o_val = -P.c * su + P.s * sv;
+          if (comp == 2) o_val = -P.s * su - P.c * sv;
+          if (comp == 3) o_val = k - (a.g.cy + 0.5) * su + (a.g.cx + 0.5) * sv;
+          a.out[4 * (pose0 + q) + comp] = o_val;
         }
-      }
-      if ((q & (kPartPoses - 1)) == kPartPoses - 1 || q == cnt - 1) {
-        __syncwarp();
-        const int qb = q & ~(kPartPoses - 1);  // first pose of this block
-        // lane = half * 16 + r: the 16 lanes of a half-warp read 16 different rows of pitch 33
-        // doubles -> 16 different bank pairs, no conflict
-        const int r = lane & 15, half = lane >> 4;  // r = pose_in_block * 4 + component
-        const int pj = r >> 2, comp = r & 3;
-        double v = 0.0;
-        if (kJac || comp == 0) {
-          const double *src = s_part + r * kPartPitch + half * 16;
+      } else {
+        double k = acc.f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v += src[i];
-        }
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        // gather the pose's Su / Sv (components 1, 2) for the rotation into map axes
-        const double su = __shfl_sync(0xffffffffu, v, pj * 4 + 1);
-        const double sv = __shfl_sync(0xffffffffu, v, pj * 4 + 2);
-        if (half == 0 && qb + pj <= q) {
-          const PoseParam Q = s_param[qb + pj];
-          double o_val = v;  // comp 0: cost
-          if (kJac) {
-            if (comp == 1) o_val = -Q.c * su + Q.s * sv;
-            if (comp == 2) o_val = -Q.s * su - Q.c * sv;
-            if (comp == 3) o_val = v - (a.g.cy + 0.5) * su + (a.g.cx + 0.5) * sv;
-          } else if (comp != 0) {
-            o_val = 0.0;
-          }
-          a.out[4 * (pose0 + qb + pj) + comp] = o_val;
-        }
-        __syncwarp();
+        for (int off = 16; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+        if (lane < 4) a.out[4 * (pose0 + q) + lane] = lane == 0 ? k : 0.0;
       }
     }
     __syncwarp();  // s_param is rewritten by the next group's phase A
@@ -480,21 +480,20 @@ int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double
     a.stage_bytes = (box_wb * box_h + 127) & ~127;
     const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols;
     a.coef_bytes = table_bytes <= 64 * 1024 ? (int)((table_bytes + 127) & ~(size_t)127) : 0;
-    const int fixed = (int)(sizeof(double) * kPartPoses * 4 * kPartPitch + sizeof(PoseParam) * 32 +
-                            sizeof(unsigned short) * kQueueCap + 8 * kMaxStages);
-    // ring depth: aim for 2 resident CTAs per SM (16 warps) with >= 3 windows in flight per warp;
-    // big tables fall back to 1 CTA per SM, and to the generic kernel if even 2 stages do not fit
+    const int fixed = (int)(sizeof(PoseParam) * 32 + sizeof(unsigned short) * kQueueCap + 8 * kMaxStages);
+    // ring depth: aim for kMinCtasPerSm resident CTAs per SM with >= 3 windows in flight per warp;
+    // bigger tables get fewer CTAs per SM, and the generic kernel if even 2 stages do not fit
     auto stages_for = [&](size_t cta_budget) {
       const long long per_warp = ((long long)cta_budget - a.coef_bytes) / kWarps - fixed - 128;
       const long long st = per_warp / a.stage_bytes;
       return (int)(st > kMaxStages ? kMaxStages : st);
     };
     const size_t sm_smem = 227 * 1024;
-    int stages = stages_for(sm_smem / 2 - 1024);
-    ctas_per_sm = 2;
-    if (stages < 3) {
-      stages = stages_for(std::min<size_t>((size_t)smem_optin, sm_smem - 1024));
-      ctas_per_sm = 1;
+    int stages = 0;
+    for (ctas_per_sm = kMinCtasPerSm; ctas_per_sm >= 1; --ctas_per_sm) {
+      const size_t budget = std::min<size_t>((size_t)smem_optin, sm_smem / ctas_per_sm - 1024);
+      stages = stages_for(budget);
+      if (stages >= 3 || ctas_per_sm == 1) break;
     }
     if (stages < 2) fast = false;
     a.stages = stages;
