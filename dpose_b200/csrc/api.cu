@@ -138,6 +138,7 @@ void dpose_pg_destroy(dpose_pg *pg) {
     DeviceGuard guard(pg->device);
     cudaFree(pg->d_cost);
     cudaFree(pg->d_coef);
+    cudaFree(pg->d_coef_image);
   }
   delete pg;
 }
@@ -193,6 +194,10 @@ static int map_create_impl(const uint8_t *data, uint32_t size_x, uint32_t size_y
     m->bits_pitch = (((size_t)size_x + 127) / 128) * 16;
     DPOSE_CUDA(cudaMalloc(&m->d_bits, m->bits_pitch * size_y));
     m->bits_dirty = true;
+    m->tiles_ntx = (size_x + 31) / 32 + 1;
+    m->tiles_nty = (size_y + 7) / 8;
+    DPOSE_CUDA(cudaMalloc(&m->d_tiles, (size_t)m->tiles_ntx * m->tiles_nty * 32));
+    m->tiles_dirty = true;
     return DPOSE_OK;
   };
   const int rc = body();
@@ -225,6 +230,7 @@ int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t
   DPOSE_CUDA(cudaMemcpy2D(map->d_data + (size_t)y0 * map->pitch + x0, map->pitch, data, pitch, w, h,
                           cudaMemcpyHostToDevice));
   map->bits_dirty = true;
+  map->tiles_dirty = true;
   return DPOSE_OK;
 }
 
@@ -232,6 +238,7 @@ int dpose_map_set_volatile(dpose_map *map, int is_volatile) {
   if (!map) return fail(DPOSE_EINVAL, "map is NULL");
   map->is_volatile = is_volatile != 0;
   map->bits_dirty = true;
+  map->tiles_dirty = true;
   return DPOSE_OK;
 }
 
@@ -256,7 +263,9 @@ void dpose_map_destroy(dpose_map *map) {
     map_release_cache(map);
     cudaFree(map->d_data);
     cudaFree(map->d_bits);
+    cudaFree(map->d_tiles);
     if (map->bits_ready) cudaEventDestroy(map->bits_ready);
+    if (map->tiles_ready) cudaEventDestroy(map->tiles_ready);
   }
   delete map;
 }

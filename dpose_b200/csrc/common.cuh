@@ -85,6 +85,10 @@ struct dpose_pg {
   float precompute_us = 0.f;
   // batched kernel geometry: side of the largest window (cells) any pose can touch
   int win_max = 0;
+  // replicated, bank-interleaved copy of d_coef for the thread-per-pose kernel (get_cost_batch_tile.cu),
+  // built on first use: R = 1 << coef_image_shift replicas
+  void *d_coef_image = nullptr;
+  int coef_image_shift = -1;
 };
 
 struct dpose_map {
@@ -102,6 +106,12 @@ struct dpose_map {
   cudaEvent_t bits_ready = nullptr;  // recorded after a rebuild; other streams wait on it
   // TMA descriptor cache (get_cost_batch.cu), keyed by box dims
   void *tma_cache = nullptr;
+  // the same lethal bits in 32 x 8 cell tiles of 32 bytes (get_cost_batch_tile.cu): word
+  // ((ty * tiles_ntx + tx) * 8 + (y & 7)), bit x & 31; tiles_ntx includes one zero pad tile per tile row
+  uint32_t *d_tiles = nullptr;
+  uint32_t tiles_ntx = 0, tiles_nty = 0;
+  bool tiles_dirty = true;
+  cudaEvent_t tiles_ready = nullptr;
 };
 
 struct dpose_cells {
@@ -127,6 +137,11 @@ int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double
 void map_release_cache(dpose_map *map);
 // bitplane.cu: (re)build the lethal bit plane on `stream`
 int bitplane_build(const dpose_map *map, cudaStream_t stream);
+// get_cost_batch_tile.cu: tile plane build and the thread-per-pose batch kernel; *handled = false
+// when the table does not fit its shared-memory layout (the caller then uses the TMA / generic kernel)
+int tileplane_build(const dpose_map *map, cudaStream_t stream);
+int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
+                        double *d_out, int want_jacobian, cudaStream_t stream, bool *handled);
 // host window geometry shared by the kernel launch code and dpose_pg_window_bytes
 struct WindowRect {
   int x0, y0, x1, y1;  // inclusive cell range, already clipped; empty if x1 < x0

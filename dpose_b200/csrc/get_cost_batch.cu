@@ -32,6 +32,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "cost_math.cuh"
@@ -454,6 +456,20 @@ int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
   const TableGeom g = {pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
 
+  // kernel choice: the thread-per-pose tile kernel unless DPOSE_BATCH_KERNEL asks for the warp-per-pose
+  // TMA kernel ("tma") or the generic window scan ("generic") — kept for A/B measurements and as the
+  // fallbacks for tables that do not fit the tile kernel's shared-memory layout
+  static const int forced = []() {
+    const char *e = std::getenv("DPOSE_BATCH_KERNEL");
+    if (!e) return 0;
+    return !std::strcmp(e, "tma") ? 1 : !std::strcmp(e, "generic") ? 2 : 0;
+  }();
+  if (forced == 0 && map->size_x > 0 && map->size_y > 0) {
+    bool handled = false;
+    DPOSE_TRY(get_cost_batch_tile(pg, map, d_poses, n, d_out, want_jacobian, stream, &handled));
+    if (handled) return DPOSE_OK;
+  }
+
   // TMA box over the bit plane: the window's W <= win_max bits start at bit offset o in [0, 128) of
   // the 16-byte aligned box row; one spare word keeps the funnel shift's second load inside the row
   const int win = pg->win_max;
@@ -463,7 +479,7 @@ int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pg->device);
 
-  bool fast = map->size_x > 0 && map->size_y > 0 && win <= 256 && box_wb <= 256 && pg->rows >= 4 && pg->cols >= 4;
+  bool fast = forced != 2 && map->size_x > 0 && map->size_y > 0 && win <= 256 && box_wb <= 256 && pg->rows >= 4 && pg->cols >= 4;
   FastArgs a;
   size_t smem_bytes = 0;
   int ctas_per_sm = 2;
