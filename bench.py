@@ -242,8 +242,8 @@ def main():
 
     pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad), device=local_rank)
     cmap = dp.Costmap(device_ptr=d_map.data_ptr(), size_x=side, size_y=side, pitch=side, device=local_rank)
-    # every timed step consumes the raw uint8 costmap: the derived lethal bit plane is rebuilt inside
-    # each batched call (k_pack_bits in front of k_cost_batch_tma), never cached across steps
+    # every timed step consumes the raw uint8 costmap: the derived lethal tile plane is rebuilt inside
+    # each batched call (k_pack_tiles in front of k_cost_batch_tile), never cached across steps
     cmap.set_volatile(True)
     stream = torch.cuda.current_stream()
 
@@ -326,7 +326,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_pack_bits + k_cost_batch_tma (one step)",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_pack_tiles + k_cost_batch_tile (one step)",
                 "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_pose": algo_bytes / n_poses,
                 "avg_launch_ms": avg_launch_s * 1e3}
 

@@ -48,10 +48,11 @@ def build(force=False, verbose=False):
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
     procs = []
     objs = []
+    extra = os.environ.get("DPOSE_NVCC_EXTRA", "").split()  # e.g. -DDPOSE_TILE_CVT=0 for A/B builds
     for s in SOURCES:
         o = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc] + ccbin + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + extra + \
               ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:

@@ -123,7 +123,6 @@ __device__ __forceinline__ double small_int_to_double(int x) {
 struct TileArgs {
   const uint4 *coef_image;  // replicated coefficient image (global)
   uint32_t coef_bytes;      // its size in bytes (multiple of 128)
-  int rep_shift;            // log2(R)
   TableGeom g;
   int size_x, size_y;
   const uint32_t *tiles;
@@ -137,7 +136,29 @@ struct Acc4 {
   double f, su, sv, st;
 };
 
-template <bool kJac, int kThreads>
+// index of the most significant set bit (x != 0): one FLO, no bit reversal
+__device__ __forceinline__ int top_bit(unsigned x) {
+  int r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+
+// DPOSE_TILE_CVT: how the walk turns a bit / row index into a double.
+//   0: 2^52 trick (one DADD on the FP64 pipe + register-pair set-up), 1: I2F.F64 (conversion pipe)
+#ifndef DPOSE_TILE_CVT
+#define DPOSE_TILE_CVT 1
+#endif
+__device__ __forceinline__ double index_to_double(int x) {
+#if DPOSE_TILE_CVT == 0
+  return small_int_to_double(x);
+#else
+  return (double)x;
+#endif
+}
+
+// kRepShift: log2 of the coefficient replicas; kSlots: row slots scanned per chunk (a chunk's rows start
+// at slot (y & 7) of its first tile row, so kSlots >= min(32, largest window height) + 7)
+template <bool kJac, int kThreads, int kRepShift, int kSlots>
 __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long s_bar;
@@ -174,13 +195,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     if (!ok) __trap();
   }
 
-  uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + tid;  // [row * kThreads]
-  const uint32_t my_coef = coef_u32 + ((uint32_t)lane & ((1u << a.rep_shift) - 1u)) * 16u;
-  const int patch_shift = a.rep_shift + 5;  // patch stride = 2 halves * R * 16 bytes
-  const uint32_t half_off = 16u << a.rep_shift;
+  uint32_t *s_slot = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + tid;  // [slot * kThreads]
+  constexpr uint32_t kPatchStride = 32u << kRepShift, kHalfOff = 16u << kRepShift;
   const int cols = a.g.cols;
+  // Kernel coordinates are carried as k' = k + 0.5 - 2 = k - 1.5: floor(k') = k_upper - 2 (k_upper = round(k),
+  // dpose_core.cpp:177), frac(k') = c_rel (:193), and the bounds test (:181-182) becomes
+  // 0 <= floor(k') <= dim - 4.  The patch of k_upper = (2, 2) therefore sits at the base address.
+  const uint32_t my_coef =
+      coef_u32 + ((uint32_t)lane & ((1u << kRepShift) - 1u)) * 16u + (uint32_t)(2 * cols + 2) * kPatchStride;
   const unsigned cols_m4 = (unsigned)(a.g.cols - 4), rows_m4 = (unsigned)(a.g.rows - 4);
-  const float hi_u = (float)a.g.cols - 1.0f, hi_v = (float)a.g.rows - 1.0f;  // k + 0.5 < dim - 1
+  const float hi_u = (float)a.g.cols - 3.0f, hi_v = (float)a.g.rows - 3.0f;  // 0 <= k' < dim - 3
+  const double cx15 = a.g.cx - 1.5, cy15 = a.g.cy - 1.5;
 
   for (size_t base = (size_t)blockIdx.x * kThreads; base < a.n; base += (size_t)gridDim.x * kThreads) {
     const size_t idx = base + tid;
@@ -191,25 +216,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     sincos(th, &s, &c);
     const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y);
     const int W = w.x1 - w.x0 + 1, H = w.y1 - w.y0 + 1;  // <= 0 when empty
-    double ku0 = 0.0, kv0 = 0.0;
+    double ku0, kv0;  // k' at the window origin
     {
       const double dx = (double)w.x0 - tx, dy = (double)w.y0 - ty;
-      ku0 = (a.g.cx + 0.5) + fma(c, dx, s * dy);  // k + 0.5 at the window origin
-      kv0 = (a.g.cy + 0.5) + fma(c, dy, -s * dx);
+      ku0 = cx15 + fma(c, dx, s * dy);
+      kv0 = cy15 + fma(c, dy, -s * dx);
     }
-    // conservative fp32 x-interval of the kernel rectangle per window row y (on k + 0.5):
-    //   2 <= ku0 + s y + c x < cols - 1   and   2 <= kv0 + c y - s x < rows - 1, each linear in y
-    float l1 = -1e30f, h1 = 1e30f, d1 = 0.f, l2 = -1e30f, h2 = 1e30f, d2 = 0.f;
+    // conservative fp32 x-interval of the kernel rectangle per window row y:
+    //   0 <= ku0 + s y + c x < cols - 3   and   0 <= kv0 + c y - s x < rows - 3, each linear in y.
+    // All values stay far below 2^22, which the integer extraction in phase 1 relies on.
+    float l1 = -1000.f, h1 = 1000.f, d1 = 0.f, l2 = -1000.f, h2 = 1000.f, d2 = 0.f;
     {
       const float cf = (float)c, sf = (float)s, ku0f = (float)ku0, kv0f = (float)kv0;
       if (fabsf(cf) > 0.02f) {
         const float inv = rcp_approx(cf);
-        const float t0 = (2.0f - ku0f) * inv, t1 = (hi_u - ku0f) * inv;
+        const float t0 = -ku0f * inv, t1 = (hi_u - ku0f) * inv;
         l1 = fminf(t0, t1) - 0.02f, h1 = fmaxf(t0, t1) + 0.02f, d1 = -sf * inv;
       }
       if (fabsf(sf) > 0.02f) {
         const float inv = rcp_approx(sf);
-        const float t0 = (kv0f - 2.0f) * inv, t1 = (kv0f - hi_v) * inv;
+        const float t0 = kv0f * inv, t1 = (kv0f - hi_v) * inv;
         l2 = fminf(t0, t1) - 0.02f, h2 = fmaxf(t0, t1) + 0.02f, d2 = cf * inv;
       }
     }
@@ -219,76 +245,94 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
       const int hc = min(32, H - rb), ys = w.y0 + rb;
       for (int cb = 0; cb < W; cb += 32) {
         const int wc = min(32, W - cb), xs = w.x0 + cb;
-        // ---- phase 1: row masks of this chunk --------------------------------------------------------------
-        unsigned rowmask = 0u;
+        const int off = ys & 7;  // chunk row i sits in row slot i + off of the chunk's tile rows
+        // ---- phase 1: row masks of this chunk; branch-free per slot, every slot is stored ---------------------
+        unsigned rowmask;
         {
           const unsigned sh = (unsigned)xs & 31u;
           const bool need_b = (int)sh + wc > 32;
-          const int tb0 = ys >> 3, tb_last = (ys + hc - 1) >> 3;
+          const int tb0 = ys >> 3, n_tb = ((ys + hc - 1) >> 3) - tb0;  // last tile row index, relative
           const uint32_t *tp = a.tiles + ((size_t)tb0 * a.ntx + (size_t)(xs >> 5)) * 8;
-          const float fcb = (float)cb, frb = (float)rb;
-          const float l1c = fmaf(frb, d1, l1) - fcb, h1c = fmaf(frb, d1, h1) - fcb;
-          const float l2c = fmaf(frb, d2, l2) - fcb, h2c = fmaf(frb, d2, h2) - fcb;
+          const size_t tstride = (size_t)a.ntx * 8;
+          const float fcb = (float)cb, fr0 = (float)(rb - off);
+          const float l1c = fmaf(fr0, d1, l1) - fcb, h1c = fmaf(fr0, d1, h1) - fcb;
+          const float l2c = fmaf(fr0, d2, l2) - fcb, h2c = fmaf(fr0, d2, h2) - fcb;
           const float wmax = (float)(wc - 1);
-          const int off = ys & 7;  // chunk row i sits at tile row (off + i) & 7 of tile row tb0 + ((off + i) >> 3)
+          unsigned sm_lo = 0u, sm_hi = 0u;  // non-empty slots
+          Tile8 A, B, An, Bn;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) A.w[r] = B.w[r] = An.w[r] = Bn.w[r] = 0u;
+          A = ldg_tile(tp);
+          if (need_b) B = ldg_tile(tp + 8);
 #pragma unroll
           for (int t = 0; t < 5; ++t) {
-            if (tb0 + t <= tb_last) {
-              const Tile8 A = ldg_tile(tp + (size_t)t * a.ntx * 8);
-              Tile8 B;
-#pragma unroll
-              for (int r = 0; r < 8; ++r) B.w[r] = 0u;
-              if (need_b) B = ldg_tile(tp + (size_t)t * a.ntx * 8 + 8);
+            if (t * 8 < kSlots) {
+              if ((t + 1) * 8 < kSlots && t + 1 <= n_tb) {  // prefetch the next tile row
+                An = ldg_tile(tp + (size_t)(t + 1) * tstride);
+                if (need_b) Bn = ldg_tile(tp + (size_t)(t + 1) * tstride + 8);
+              }
 #pragma unroll
               for (int r = 0; r < 8; ++r) {
-                const int i = t * 8 + r - off;
-                if ((unsigned)i < (unsigned)hc) {
-                  const float fi = (float)i;
-                  const float lo = fmaxf(fmaxf(fmaf(fi, d1, l1c), fmaf(fi, d2, l2c)), 0.0f);
-                  const float hi = fminf(fminf(fmaf(fi, d1, h1c), fmaf(fi, d2, h2c)), wmax);
+                const int j = t * 8 + r;
+                if (j < kSlots) {
+                  const float fj = (float)j;
+                  const float lo = fmaxf(fmaxf(fmaf(fj, d1, l1c), fmaf(fj, d2, l2c)), 0.0f);
+                  const float hi = fminf(fminf(fmaf(fj, d1, h1c), fmaf(fj, d2, h2c)), wmax);
                   // ceil / floor through the 1.5 * 2^23 trick: the integer lands in the low mantissa bits
-                  const int xlo = __float_as_int(__fadd_ru(fminf(lo, 40.0f), 12582912.0f)) - 0x4B400000;
-                  const int xhi = __float_as_int(__fadd_rd(fmaxf(hi, -1.0f), 12582912.0f)) - 0x4B400000;
+                  const int xlo = __float_as_int(__fadd_ru(lo, 12582912.0f)) - 0x4B400000;  // >= 0
+                  const int xhi = __float_as_int(__fadd_rd(hi, 12582912.0f)) - 0x4B400000;  // <= 31
                   unsigned m = __funnelshift_r(A.w[r], B.w[r], sh);
                   m &= shl_clamp(0xffffffffu, (unsigned)xlo) & shr_clamp(0xffffffffu, (unsigned)(31 - xhi));
-                  s_mask[i * kThreads] = m;
-                  if (m) rowmask |= 1u << i;
+                  s_slot[j * kThreads] = m;
+                  if (m) {
+                    if (j < 32)
+                      sm_lo |= 1u << (j & 31);
+                    else
+                      sm_hi |= 1u << (j & 31);
+                  }
                 }
               }
+              A = An;
+              B = Bn;
             }
           }
+          // slots [off, off + hc) are the chunk's rows; everything else (stale tiles, rows past the window) is dropped
+          rowmask = __funnelshift_r(sm_lo, sm_hi, (unsigned)off) & shr_clamp(0xffffffffu, (unsigned)(32 - hc));
         }
-        // ---- phase 2: walk the set bits ----------------------------------------------------------------------
+        // ---- phase 2: walk the set bits, highest row / highest bit first ---------------------------------------
+        const uint32_t *srow = s_slot + off * kThreads;
+        const double dcb = (double)cb, drb = (double)rb;
+        const double kuc = fma(c, dcb, fma(s, drb, ku0)), kvc = fma(c, drb, fma(-s, dcb, kv0));
         unsigned mask = 0u;
         int row = 0;
         while (true) {
           if (mask == 0u) {
             if (rowmask == 0u) break;
-            row = __ffs((int)rowmask) - 1;
-            rowmask &= rowmask - 1u;
-            mask = s_mask[row * kThreads];
+            row = top_bit(rowmask);
+            rowmask ^= 1u << row;
+            mask = srow[row * kThreads];
           }
-          const int b = __ffs((int)mask) - 1;
-          mask &= mask - 1u;
-          const double X = small_int_to_double(cb + b), Y = small_int_to_double(rb + row);
-          const double ku = fma(c, X, fma(s, Y, ku0));
-          const double kv = fma(c, Y, fma(-s, X, kv0));
+          const int b = top_bit(mask);
+          mask ^= 1u << b;
+          const double X = index_to_double(b), Y = index_to_double(row);
+          const double ku = fma(c, X, fma(s, Y, kuc));
+          const double kv = fma(c, Y, fma(-s, X, kvc));
           const double M = 6755399441055744.0;  // 1.5 * 2^52: adding it (rounding down) floors to an integer
           const double tu = __dadd_rd(ku, M), tv = __dadd_rd(kv, M);
-          const int ux = __double2loint(tu), uy = __double2loint(tv);
-          if ((unsigned)(ux - 2) <= cols_m4 && (unsigned)(uy - 2) <= rows_m4) {  // dpose_core.cpp:181-182
-            const double rx = ku - (tu - M), ry = kv - (tv - M);                 // c_rel in [0, 1)  (:193)
-            const uint32_t addr = my_coef + ((uint32_t)(uy * cols + ux) << patch_shift);
+          const int ux = __double2loint(tu), uy = __double2loint(tv);  // k_upper - 2
+          if ((unsigned)ux <= cols_m4 && (unsigned)uy <= rows_m4) {    // dpose_core.cpp:181-182
+            const double rx = ku - (tu - M), ry = kv - (tv - M);       // c_rel in [0, 1)  (:193)
+            const uint32_t addr = my_coef + (uint32_t)(uy * cols + ux) * kPatchStride;
             double a00, a10, a01, a11;
             asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a00), "=d"(a10) : "r"(addr));
-            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a01), "=d"(a11) : "r"(addr + half_off));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(a01), "=d"(a11) : "r"(addr), "n"(kHalfOff));
             const double fv = fma(a11, rx, a01);
             acc.f += fma(ry, fv, fma(a10, rx, a00));
             if (kJac) {
               const double fu = fma(a11, ry, a10);
               acc.su += fu;
               acc.sv += fv;
-              acc.st = fma(fu, kv, acc.st);  // Sum(fu*(kv+.5) - fv*(ku+.5)); center terms folded in below
+              acc.st = fma(fu, kv, acc.st);  // Sum(fu * kv' - fv * ku'); center terms folded in below
               acc.st = fma(-fv, ku, acc.st);
             }
           }
@@ -299,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     if (kJac) {
       jx = -c * acc.su + s * acc.sv;
       jy = -s * acc.su - c * acc.sv;
-      jt = acc.st - (a.g.cy + 0.5) * acc.su + (a.g.cx + 0.5) * acc.sv;
+      jt = acc.st - cy15 * acc.su + cx15 * acc.sv;
     }
     stg_result(a.out + 4 * idx, acc.f, jx, jy, jt);
   }
@@ -307,13 +351,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
 
 std::mutex g_tile_mu;  // guards the lazily built per-handle state below
 
-template <bool kJac, int kThreads>
-int launch_tile(const TileArgs &a, int grid, size_t smem_bytes, cudaStream_t stream) {
-  auto kern = k_cost_batch_tile<kJac, kThreads>;
+template <bool kJac, int kThreads, int kRepShift, int kSlots>
+int launch_tile4(const TileArgs &a, int grid, size_t smem_bytes, cudaStream_t stream) {
+  auto kern = k_cost_batch_tile<kJac, kThreads, kRepShift, kSlots>;
   DPOSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   kern<<<grid, kThreads, smem_bytes, stream>>>(a);
   DPOSE_LAUNCHED();
   return DPOSE_OK;
+}
+template <bool kJac, int kThreads, int kRepShift>
+int launch_tile3(const TileArgs &a, int slots, int grid, size_t smem_bytes, cudaStream_t stream) {
+  if (slots == 25) return launch_tile4<kJac, kThreads, kRepShift, 25>(a, grid, smem_bytes, stream);
+  if (slots == 33) return launch_tile4<kJac, kThreads, kRepShift, 33>(a, grid, smem_bytes, stream);
+  return launch_tile4<kJac, kThreads, kRepShift, 40>(a, grid, smem_bytes, stream);
+}
+template <bool kJac, int kThreads>
+int launch_tile2(const TileArgs &a, int rep_shift, int slots, int grid, size_t smem_bytes, cudaStream_t stream) {
+  if (rep_shift == 0) return launch_tile3<kJac, kThreads, 0>(a, slots, grid, smem_bytes, stream);
+  if (rep_shift == 2) return launch_tile3<kJac, kThreads, 2>(a, slots, grid, smem_bytes, stream);
+  return launch_tile3<kJac, kThreads, 3>(a, slots, grid, smem_bytes, stream);
+}
+template <bool kJac>
+int launch_tile1(const TileArgs &a, int threads, int rep_shift, int slots, int grid, size_t smem_bytes,
+                 cudaStream_t stream) {
+  if (threads == 512) return launch_tile2<kJac, 512>(a, rep_shift, slots, grid, smem_bytes, stream);
+  if (threads == 768) return launch_tile2<kJac, 768>(a, rep_shift, slots, grid, smem_bytes, stream);
+  return launch_tile2<kJac, 1024>(a, rep_shift, slots, grid, smem_bytes, stream);
+}
+
+int env_int(const char *name) {
+  const char *e = std::getenv(name);
+  return e ? std::atoi(e) : 0;
 }
 
 }  // namespace
@@ -338,25 +406,25 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pg->device);
 
-  static const int env_threads = []() {
-    const char *e = std::getenv("DPOSE_TILE_THREADS");
-    return e ? std::atoi(e) : 0;
-  }();
-  static const int env_rep = []() {
-    const char *e = std::getenv("DPOSE_TILE_REPLICAS");
-    return e ? std::atoi(e) : 0;
-  }();
-  int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 768;
+  // tuning overrides (A/B measurements): threads per CTA and coefficient replicas
+  static const int env_threads = env_int("DPOSE_TILE_THREADS"), env_rep = env_int("DPOSE_TILE_REPLICAS");
+  const int slots = pg->win_max <= 18 ? 25 : pg->win_max <= 26 ? 33 : 40;
   const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols;
-  const size_t mask_bytes = (size_t)32 * 4 * threads;
   const size_t budget = (size_t)smem_optin - 64;
-  if (table_bytes + mask_bytes > budget) {
-    threads = 512;
-    if (table_bytes + (size_t)32 * 4 * threads > budget) return DPOSE_OK;  // table too big for shared memory
+  // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts)
+  int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 768;
+  int rep_shift = env_rep == 1 ? 0 : env_rep == 4 ? 2 : env_rep == 8 ? 3 : 2;
+  auto fits = [&](int th, int rs) { return (table_bytes << rs) + (size_t)slots * 4 * th <= budget; };
+  while (!fits(threads, rep_shift)) {
+    if (rep_shift == 3)
+      rep_shift = 2;
+    else if (rep_shift == 2)
+      rep_shift = 0;
+    else if (threads > 512) {
+      threads -= 256;
+    } else
+      return DPOSE_OK;  // table too big for shared memory
   }
-  int rep_shift = 3;
-  if (env_rep == 1 || env_rep == 2 || env_rep == 4 || env_rep == 8) rep_shift = env_rep == 1 ? 0 : env_rep == 2 ? 1 : env_rep == 4 ? 2 : 3;
-  while (rep_shift > 0 && (table_bytes << rep_shift) + (size_t)32 * 4 * threads > budget) --rep_shift;
 
   dpose_pg *p = const_cast<dpose_pg *>(pg);
   dpose_map *m = const_cast<dpose_map *>(map);
@@ -364,7 +432,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
     std::lock_guard<std::mutex> lock(g_tile_mu);
     if (!p->d_coef_image || p->coef_image_shift != rep_shift) {
       if (p->d_coef_image) {
-        DPOSE_CUDA(cudaStreamSynchronize(stream));
+        DPOSE_CUDA(cudaDeviceSynchronize());
         DPOSE_CUDA(cudaFree(p->d_coef_image));
         p->d_coef_image = nullptr;
       }
@@ -389,7 +457,6 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   TileArgs a;
   a.coef_image = reinterpret_cast<const uint4 *>(p->d_coef_image);
   a.coef_bytes = (uint32_t)(table_bytes << rep_shift);
-  a.rep_shift = rep_shift;
   a.g = TableGeom{pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
   a.size_x = (int)map->size_x;
   a.size_y = (int)map->size_y;
@@ -398,17 +465,12 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.poses = d_poses;
   a.out = d_out;
   a.n = n;
-  const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)32 * 4 * threads;
+  const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)slots * 4 * threads;
   const size_t want = (n + threads - 1) / threads;
   const int grid = (int)std::min<size_t>(want, (size_t)sms);
   *handled = true;
-#define DPOSE_TILE_DISPATCH(T)                                                      \
-  return want_jacobian ? launch_tile<true, T>(a, grid, smem_bytes, stream)          \
-                       : launch_tile<false, T>(a, grid, smem_bytes, stream)
-  if (threads == 512) DPOSE_TILE_DISPATCH(512);
-  if (threads == 1024) DPOSE_TILE_DISPATCH(1024);
-  DPOSE_TILE_DISPATCH(768);
-#undef DPOSE_TILE_DISPATCH
+  return want_jacobian ? launch_tile1<true>(a, threads, rep_shift, slots, grid, smem_bytes, stream)
+                       : launch_tile1<false>(a, threads, rep_shift, slots, grid, smem_bytes, stream);
 }
 
 }  // namespace dpose
