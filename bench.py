@@ -298,11 +298,28 @@ def main():
         te = torch.tensor([dt], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_checksum_ok = bool(np.array_equal(np_out[:4096], d_out[:4096].cpu().numpy()))
+        # context for the e2e figure: what the box's PCIe link gives plain pinned copies of the same sizes
+        def _copy_gbs(dst, src, nbytes):
+            best = 0.0
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                dst.copy_(src, non_blocking=True)
+                b.record(stream)
+                torch.cuda.synchronize()
+                best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+            return best
+        h2d_gbs = _copy_gbs(d_poses, h_poses, n_poses * 24)
+        scratch = torch.empty_like(d_out)
+        d2h_gbs = _copy_gbs(h_out, scratch, n_poses * 32)
+        del scratch
         e2e = {"value": world * n_poses * e2e_steps / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(n_poses * 24), "d2h_bytes_per_step": int(n_poses * 32),
                "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
+               "pcie_h2d_gbs": h2d_gbs, "pcie_d2h_gbs": d2h_gbs,
+               "pcie_bound_ms_per_step": 1e3 * max(n_poses * 24 / (h2d_gbs * 1e9), n_poses * 32 / (d2h_gbs * 1e9)),
                "timing": "host wall clock around the synchronous C-ABI call (it drives its own streams), max over ranks"}
-        e2e_checksum_ok = bool(np.array_equal(np_out[:4096], d_out[:4096].cpu().numpy()))
     else:
         e2e_checksum_ok = None
 

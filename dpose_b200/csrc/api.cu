@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <thread>
 
@@ -42,6 +43,71 @@ static int check_device(int device) {
 }  // namespace dpose
 
 using namespace dpose;
+
+namespace {
+constexpr int kBuf = 3;
+constexpr size_t kChunkPoses = (size_t)1 << 19;
+
+struct BatchCtx {
+  std::mutex mu;
+  size_t cap = 0;  // poses per staging buffer
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t in_done[kBuf] = {}, k_done[kBuf] = {}, out_done[kBuf] = {};
+  double *d_p[kBuf] = {}, *d_o[kBuf] = {};
+
+  int init() {
+    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < kBuf; ++b) {
+      DPOSE_CUDA(cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming));
+      DPOSE_CUDA(cudaEventCreateWithFlags(&k_done[b], cudaEventDisableTiming));
+      DPOSE_CUDA(cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming));
+    }
+    return DPOSE_OK;
+  }
+  int reserve(size_t poses) {
+    if (poses <= cap) return DPOSE_OK;
+    for (int b = 0; b < kBuf; ++b) {
+      cudaFree(d_p[b]);
+      cudaFree(d_o[b]);
+      d_p[b] = d_o[b] = nullptr;
+    }
+    cap = 0;
+    for (int b = 0; b < kBuf; ++b) {
+      DPOSE_CUDA(cudaMalloc(&d_p[b], sizeof(double) * 3 * poses));
+      DPOSE_CUDA(cudaMalloc(&d_o[b], sizeof(double) * 4 * poses));
+    }
+    cap = poses;
+    return DPOSE_OK;
+  }
+  void release() {
+    for (int b = 0; b < kBuf; ++b) {
+      cudaFree(d_p[b]);
+      cudaFree(d_o[b]);
+      if (in_done[b]) cudaEventDestroy(in_done[b]);
+      if (k_done[b]) cudaEventDestroy(k_done[b]);
+      if (out_done[b]) cudaEventDestroy(out_done[b]);
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_k) cudaStreamDestroy(s_k);
+    if (s_out) cudaStreamDestroy(s_out);
+  }
+};
+
+std::mutex g_ctx_mu;  // guards creation of the per-handle context
+}  // namespace
+
+namespace dpose {
+void pg_release_batch_ctx(dpose_pg *pg) {
+  BatchCtx *ctx = static_cast<BatchCtx *>(pg->batch_ctx);
+  if (!ctx) return;
+  ctx->release();
+  delete ctx;
+  pg->batch_ctx = nullptr;
+}
+}  // namespace dpose
+
 
 extern "C" {
 
@@ -139,6 +205,7 @@ void dpose_pg_destroy(dpose_pg *pg) {
     cudaFree(pg->d_cost);
     cudaFree(pg->d_coef);
     cudaFree(pg->d_coef_image);
+    pg_release_batch_ctx(pg);
   }
   delete pg;
 }
@@ -383,7 +450,9 @@ int dpose_pg_get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, con
   return get_cost_batch_device(pg, map, d_poses, n, d_out, want_jacobian, (cudaStream_t)stream);
 }
 
-// host buffers: H2D / kernel / D2H chunks on three streams, double-buffered device staging
+// host buffers: H2D / kernel / D2H chunks on three streams, triple-buffered device staging.  The
+// streams, events and staging buffers live in the pose_gradient handle (created on first use, grown
+// on demand), so a call costs no cudaMalloc / cudaFree; concurrent calls on one handle serialise.
 int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n,
                             double *out, int want_jacobian) {
   if (!pg || !map || (n && (!poses || !out))) return fail(DPOSE_EINVAL, "NULL argument");
@@ -391,55 +460,50 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
   DPOSE_TRY(check_device(pg->device));
   DeviceGuard guard(pg->device);
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
-  constexpr int kBuf = 3;
-  const size_t chunk = std::min<size_t>(n, (size_t)1 << 19);
-  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-  cudaEvent_t in_done[kBuf] = {}, k_done[kBuf] = {}, out_done[kBuf] = {};
-  double *d_p[kBuf] = {}, *d_o[kBuf] = {};
-  auto body = [&]() -> int {
-    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-    DPOSE_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    for (int b = 0; b < kBuf; ++b) {
-      DPOSE_CUDA(cudaMalloc(&d_p[b], sizeof(double) * 3 * chunk));
-      DPOSE_CUDA(cudaMalloc(&d_o[b], sizeof(double) * 4 * chunk));
-      DPOSE_CUDA(cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming));
-      DPOSE_CUDA(cudaEventCreateWithFlags(&k_done[b], cudaEventDisableTiming));
-      DPOSE_CUDA(cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming));
+  BatchCtx *ctx;
+  {
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    dpose_pg *p = const_cast<dpose_pg *>(pg);
+    if (!p->batch_ctx) {
+      BatchCtx *fresh = new (std::nothrow) BatchCtx();
+      if (!fresh) return fail(DPOSE_ENOMEM, "out of host memory");
+      const int rc = fresh->init();
+      if (rc != DPOSE_OK) {
+        fresh->release();
+        delete fresh;
+        return rc;
+      }
+      p->batch_ctx = fresh;
     }
+    ctx = static_cast<BatchCtx *>(p->batch_ctx);
+  }
+  std::lock_guard<std::mutex> call_lock(ctx->mu);
+  const size_t chunk = std::min<size_t>(n, kChunkPoses);
+  DPOSE_TRY(ctx->reserve(chunk));
+  auto body = [&]() -> int {
     size_t it = 0;
     for (size_t off = 0; off < n; off += chunk, ++it) {
       const int b = (int)(it % kBuf);
       const size_t m = std::min(chunk, n - off);
       if (it >= kBuf) {  // buffer reuse: its previous D2H must be complete
-        DPOSE_CUDA(cudaStreamWaitEvent(s_in, out_done[b], 0));
+        DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->out_done[b], 0));
       }
-      DPOSE_CUDA(cudaMemcpyAsync(d_p[b], poses + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, s_in));
-      DPOSE_CUDA(cudaEventRecord(in_done[b], s_in));
-      DPOSE_CUDA(cudaStreamWaitEvent(s_k, in_done[b], 0));
-      DPOSE_TRY(get_cost_batch_device(pg, map, d_p[b], m, d_o[b], want_jacobian, s_k));
-      DPOSE_CUDA(cudaEventRecord(k_done[b], s_k));
-      DPOSE_CUDA(cudaStreamWaitEvent(s_out, k_done[b], 0));
-      DPOSE_CUDA(cudaMemcpyAsync(out + 4 * off, d_o[b], sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s_out));
-      DPOSE_CUDA(cudaEventRecord(out_done[b], s_out));
+      DPOSE_CUDA(cudaMemcpyAsync(ctx->d_p[b], poses + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, ctx->s_in));
+      DPOSE_CUDA(cudaEventRecord(ctx->in_done[b], ctx->s_in));
+      DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_done[b], 0));
+      DPOSE_TRY(get_cost_batch_device(pg, map, ctx->d_p[b], m, ctx->d_o[b], want_jacobian, ctx->s_k));
+      DPOSE_CUDA(cudaEventRecord(ctx->k_done[b], ctx->s_k));
+      DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->k_done[b], 0));
+      DPOSE_CUDA(cudaMemcpyAsync(out + 4 * off, ctx->d_o[b], sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, ctx->s_out));
+      DPOSE_CUDA(cudaEventRecord(ctx->out_done[b], ctx->s_out));
     }
-    DPOSE_CUDA(cudaStreamSynchronize(s_out));
-    DPOSE_CUDA(cudaStreamSynchronize(s_k));
-    DPOSE_CUDA(cudaStreamSynchronize(s_in));
+    DPOSE_CUDA(cudaStreamSynchronize(ctx->s_out));
+    DPOSE_CUDA(cudaStreamSynchronize(ctx->s_k));
+    DPOSE_CUDA(cudaStreamSynchronize(ctx->s_in));
     return DPOSE_OK;
   };
   const int rc = body();
   if (rc != DPOSE_OK) cudaDeviceSynchronize();
-  for (int b = 0; b < kBuf; ++b) {
-    cudaFree(d_p[b]);
-    cudaFree(d_o[b]);
-    if (in_done[b]) cudaEventDestroy(in_done[b]);
-    if (k_done[b]) cudaEventDestroy(k_done[b]);
-    if (out_done[b]) cudaEventDestroy(out_done[b]);
-  }
-  if (s_in) cudaStreamDestroy(s_in);
-  if (s_k) cudaStreamDestroy(s_k);
-  if (s_out) cudaStreamDestroy(s_out);
   return rc;
 }
 

@@ -89,6 +89,8 @@ struct dpose_pg {
   // built on first use: R = 1 << coef_image_shift replicas
   void *d_coef_image = nullptr;
   int coef_image_shift = -1;
+  // streams, events and staging buffers of the host-buffer batch entry point (api.cu), built on first use
+  void *batch_ctx = nullptr;
 };
 
 struct dpose_map {
@@ -121,6 +123,8 @@ struct dpose_cells {
 };
 
 namespace dpose {
+// api.cu
+void pg_release_batch_ctx(dpose_pg *pg);
 // precompute.cu
 int precompute_run(dpose_pg *pg, const int32_t *shifted_fp_xy, int n);
 // lethal.cu

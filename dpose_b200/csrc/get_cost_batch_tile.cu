@@ -363,6 +363,7 @@ template <bool kJac, int kThreads, int kRepShift>
 int launch_tile3(const TileArgs &a, int slots, int grid, size_t smem_bytes, cudaStream_t stream) {
   if (slots == 25) return launch_tile4<kJac, kThreads, kRepShift, 25>(a, grid, smem_bytes, stream);
   if (slots == 33) return launch_tile4<kJac, kThreads, kRepShift, 33>(a, grid, smem_bytes, stream);
+  if (slots == 36) return launch_tile4<kJac, kThreads, kRepShift, 36>(a, grid, smem_bytes, stream);
   return launch_tile4<kJac, kThreads, kRepShift, 40>(a, grid, smem_bytes, stream);
 }
 template <bool kJac, int kThreads>
@@ -408,7 +409,9 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
 
   // tuning overrides (A/B measurements): threads per CTA and coefficient replicas
   static const int env_threads = env_int("DPOSE_TILE_THREADS"), env_rep = env_int("DPOSE_TILE_REPLICAS");
-  const int slots = pg->win_max <= 18 ? 25 : pg->win_max <= 26 ? 33 : 40;
+  // row slots per chunk: rows of a chunk start at slot (y & 7) of its first tile row
+  const int need = std::min(32, pg->win_max) + 7;
+  const int slots = need <= 25 ? 25 : need <= 33 ? 33 : need <= 36 ? 36 : 40;
   const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols;
   const size_t budget = (size_t)smem_optin - 64;
   // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts)

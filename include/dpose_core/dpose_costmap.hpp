@@ -1,0 +1,144 @@
+// dpose_costmap.hpp — costmap-side helpers of dpose_core on top of the B200 C ABI.
+//
+// Mirrors upstream dpose_core/src/dpose_core/dpose_costmap.hpp:36-85 (make_footprint, raytrace,
+// interval, cell_rays, to_rays, lethal_cells_within) with the same names, argument meaning and
+// exceptions.  lethal_cells_within runs the stream-compaction kernel; raytrace / to_rays /
+// make_footprint are integer host arithmetic (a few dozen cells).
+//
+// NOT provided here: is_inside, bresenham::*, x_bresenham, check_footprint (upstream
+// dpose_costmap.hpp:87-196, dpose_costmap.cpp:186-582).  They validate a solved pose, are not on
+// the cost/Jacobian path and keep compiling from the upstream sources —
+// see INTEGRATION.md.
+#ifndef DPOSE_CORE__DPOSE_COSTMAP__HPP
+#define DPOSE_CORE__DPOSE_COSTMAP__HPP
+
+#include "dpose_core.hpp"
+
+#if DPOSE_HAVE_COSTMAP_2D
+#include <costmap_2d/layered_costmap.h>
+#endif
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <mutex>
+#include <unordered_map>
+
+namespace dpose_core {
+
+/// metric footprint -> cells, round(p / resolution) per coordinate, order kept, not closed
+/// (upstream dpose_costmap.cpp:40-55).  @throws std::runtime_error if the resolution is <= 0
+inline polygon
+make_footprint(const std::vector<geometry_msgs::Point>& _fp, double _resolution) {
+  if (!(_resolution > 0)) throw std::runtime_error("resolution must be positive");
+  std::vector<double> xy(2 * _fp.size());
+  for (size_t i = 0; i < _fp.size(); ++i) {
+    xy[2 * i] = _fp[i].x;
+    xy[2 * i + 1] = _fp[i].y;
+  }
+  polygon out(2, (int)_fp.size());
+  detail::check(dpose_make_footprint(xy.data(), (int)_fp.size(), _resolution, out.data()));
+  return out;
+}
+
+inline polygon
+make_footprint(costmap_2d::LayeredCostmap& _cm) {
+  return make_footprint(_cm.getFootprint(), _cm.getCostmap()->getResolution());
+}
+
+/// Bresenham ray from _begin to _end (exclusive), ROS raytraceLine compatible (upstream :57-104)
+inline cell_vector
+raytrace(const cell& _begin, const cell& _end) noexcept {
+  const int32_t b[2] = {_begin.x(), _begin.y()}, e[2] = {_end.x(), _end.y()};
+  const size_t n = (size_t)std::max(std::abs(e[0] - b[0]), std::abs(e[1] - b[1]));
+  cell_vector out(n);
+  size_t got = 0;
+  if (n) dpose_raytrace(b, e, reinterpret_cast<int32_t*>(out.data()), n, &got);
+  return out;
+}
+
+/// closed interval [min, max], grown with extend() (upstream dpose_costmap.hpp:57-70)
+template <typename _T>
+struct interval {
+  interval() : min{std::numeric_limits<_T>::max()}, max{std::numeric_limits<_T>::lowest()} {}
+
+  inline void
+  extend(const _T& _v) noexcept {
+    min = std::min(min, _v);
+    max = std::max(max, _v);
+  }
+
+  _T min, max;
+};
+
+using cell_interval = interval<size_t>;
+using cell_rays = std::unordered_map<int, cell_interval>;
+using cell_rectangle = rectangle<int>;
+
+/// per-row [min x, max x] of the ring's four edges (upstream dpose_costmap.cpp:106-115)
+inline cell_rays
+to_rays(const cell_rectangle& _rect) noexcept {
+  cell_rays rays;
+  for (int i = 0; i < 4; ++i) {
+    const cell_vector ray = raytrace(cell(_rect(0, i), _rect(1, i)), cell(_rect(0, i + 1), _rect(1, i + 1)));
+    for (const auto& c : ray) rays[c.y()].extend((size_t)c.x());
+  }
+  return rays;
+}
+
+/// lethal (== 254) cells inside _bounds, on a costmap that already lives on the device
+inline cell_vector
+lethal_cells_within(const device_costmap& _map, const cell_rectangle& _bounds) {
+  int32_t ring[10];
+  for (int i = 0; i < 5; ++i) {
+    ring[2 * i] = _bounds(0, i);
+    ring[2 * i + 1] = _bounds(1, i);
+  }
+  int32_t* xy = nullptr;
+  size_t n = 0;
+  detail::check(dpose_lethal_cells_within(_map.handle(), ring, &xy, &n));
+  cell_vector out(n);
+  if (n) std::memcpy(static_cast<void*>(out.data()), xy, sizeof(int32_t) * 2 * n);
+  dpose_free(xy);
+  return out;
+}
+
+/// upstream signature (dpose_costmap.hpp:84-85, dpose_costmap.cpp:117-184): takes the costmap's
+/// mutex (:138), uploads the bounding rows/columns of the clamped box and compacts on the GPU.
+/// Rows come back y ascending, x ascending (the reference's row order is unspecified).
+inline cell_vector
+lethal_cells_within(costmap_2d::Costmap2D& _map, const cell_rectangle& _bounds) {
+  const int sx = (int)_map.getSizeInCellsX(), sy = (int)_map.getSizeInCellsY();
+  if (sx == 0 || sy == 0) return {};  // :124-125
+  // clamp into the map (:121,:128-129), then move the ring into the frame of its bounding window
+  cell_rectangle ring = _bounds;
+  int x0 = sx - 1, y0 = sy - 1, x1 = 0, y1 = 0;
+  for (int i = 0; i < 5; ++i) {
+    ring(0, i) = std::min(std::max(ring(0, i), 0), sx - 1);
+    ring(1, i) = std::min(std::max(ring(1, i), 0), sy - 1);
+    x0 = std::min(x0, ring(0, i));
+    x1 = std::max(x1, ring(0, i));
+    y0 = std::min(y0, ring(1, i));
+    y1 = std::max(y1, ring(1, i));
+  }
+  for (int i = 0; i < 5; ++i) {
+    ring(0, i) -= x0;
+    ring(1, i) -= y0;
+  }
+  cell_vector out;
+  {
+    std::lock_guard<costmap_2d::Costmap2D::mutex_t> lock(*_map.getMutex());
+    const device_costmap window(_map.getCharMap() + _map.getIndex((unsigned)x0, (unsigned)y0), (uint32_t)(x1 - x0 + 1),
+                                (uint32_t)(y1 - y0 + 1), (size_t)sx);
+    out = lethal_cells_within(window, ring);
+  }
+  for (auto& c : out) {
+    c.x() += x0;
+    c.y() += y0;
+  }
+  return out;
+}
+
+}  // namespace dpose_core
+
+#endif  // DPOSE_CORE__DPOSE_COSTMAP__HPP
