@@ -2,7 +2,7 @@
  * dpose_oracle.c — CPU restatement of dpose_core's footprint-cost path (plain C11).
  *
  * TEST INFRASTRUCTURE ONLY (see dpose_oracle.h).  Parity pin: the image pipeline is
- * checked bit-for-bit against OpenCV (cv2 4.13.0, IPP off) by tests/test_oracle_cv2.py
+ * checked bit-for-bit against OpenCV (cv2 4.13.0, IPP off) by tests/test_oracle.py
  * and frozen in tests/golden/; get_cost is checked against the known-answer vectors of
  * SURVEY.md §8(c) and the reference's own Jacobian self-consistency test.
  *

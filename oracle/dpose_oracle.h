@@ -11,7 +11,7 @@
  * image (Eigen, OpenCV C++, costmap_2d, boost are absent), and the image arithmetic
  * lives in OpenCV (un-vendored; ROS noetic's libopencv-dev).  The restatement is
  * therefore pinned against the same OpenCV functions through the cv2 4.13.0 Python
- * wheel (oracle/py/cv_pipeline.py, tests/golden/make_golden.py) and against the
+ * wheel (oracle/cv_pipeline.py, tests/golden/make_golden.py) and against the
  * known-answer vectors of SURVEY.md §8(c).
  */
 #ifndef DPOSE_ORACLE_H
