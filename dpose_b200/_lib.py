@@ -36,6 +36,7 @@ SYMBOLS = {
     "dpose_map_destroy": (None, [_vp]),
     "dpose_raytrace": (_i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "dpose_lethal_cells_within": (_i, [_vp, _vp, _pp, C.POINTER(_sz)]),
+    "dpose_map_lethal_us": (_i, [_vp, C.POINTER(C.c_float)]),
     "dpose_lethal_cells_within_device": (_i, [_vp, _vp, _pp]),
     "dpose_cells_upload": (_i, [_vp, _sz, _i, _pp]),
     "dpose_cells_size": (_i, [_vp, C.POINTER(_sz)]),

@@ -93,6 +93,12 @@ class Costmap:
         w = np.ascontiguousarray(np.asarray(window, dtype=np.uint8))
         check(lib().dpose_map_update(self._h, w.ctypes.data, w.strides[0], int(x0), int(y0), w.shape[1], w.shape[0]))
 
+    def lethal_us(self):
+        """device time of the last lethal_cells_within on this map, microseconds"""
+        us = C.c_float(0)
+        check(lib().dpose_map_lethal_us(self._h, C.byref(us)))
+        return us.value
+
     def close(self):
         if self._h:
             lib().dpose_map_destroy(self._h)

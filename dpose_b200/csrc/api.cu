@@ -328,6 +328,7 @@ void dpose_map_destroy(dpose_map *map) {
   {
     DeviceGuard guard(map->device);
     map_release_cache(map);
+    map_release_lethal_ws(map);
     cudaFree(map->d_data);
     cudaFree(map->d_bits);
     cudaFree(map->d_tiles);
@@ -357,6 +358,12 @@ int dpose_lethal_cells_within_device(const dpose_map *map, const int32_t box[10]
     return rc;
   }
   *out = c;
+  return DPOSE_OK;
+}
+
+int dpose_map_lethal_us(const dpose_map *map, float *us) {
+  if (!map || !us) return fail(DPOSE_EINVAL, "NULL argument");
+  *us = lethal_last_kernel_us(map);
   return DPOSE_OK;
 }
 

@@ -114,6 +114,8 @@ struct dpose_map {
   uint32_t tiles_ntx = 0, tiles_nty = 0;
   bool tiles_dirty = true;
   cudaEvent_t tiles_ready = nullptr;
+  // scratch buffers, pinned staging and stream of lethal_cells_within (lethal.cu), built on first use
+  void *lethal_ws = nullptr;
 };
 
 struct dpose_cells {
@@ -129,6 +131,8 @@ void pg_release_batch_ctx(dpose_pg *pg);
 int precompute_run(dpose_pg *pg, const int32_t *shifted_fp_xy, int n);
 // lethal.cu
 int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, size_t *n);
+void map_release_lethal_ws(dpose_map *map);
+float lethal_last_kernel_us(const dpose_map *map);
 size_t host_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_xy, size_t cap);
 // get_cost.cu
 int get_cost_cells(const dpose_pg *pg, const double se2[3], const int2 *d_cells, size_t n,

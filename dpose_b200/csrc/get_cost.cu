@@ -159,7 +159,8 @@ struct CellScratch {
   size_t cap = 0;
   double *d_partials = nullptr;  // kMaxCellCtas * 4
   unsigned *d_ticket = nullptr;
-  double *d_out = nullptr;  // 4
+  double *h_out = nullptr;  // 4 doubles of pinned host memory the kernel writes its result into (UVA)
+  cudaStream_t stream = nullptr;  // private non-blocking stream: no implicit sync with the caller's streams
 };
 constexpr int kMaxCellCtas = 592;  // 4 per SM
 
@@ -173,7 +174,8 @@ static int ensure_scratch(CellScratch &sc, int device, size_t ncells) {
     DPOSE_CUDA(cudaMalloc(&sc.d_partials, sizeof(double) * 4 * kMaxCellCtas));
     DPOSE_CUDA(cudaMalloc(&sc.d_ticket, sizeof(unsigned)));
     DPOSE_CUDA(cudaMemset(sc.d_ticket, 0, sizeof(unsigned)));
-    DPOSE_CUDA(cudaMalloc(&sc.d_out, sizeof(double) * 4));
+    DPOSE_CUDA(cudaHostAlloc(&sc.h_out, sizeof(double) * 4, cudaHostAllocMapped));
+    DPOSE_CUDA(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
     sc.device = device;
   }
   if (ncells > sc.cap) {
@@ -197,21 +199,21 @@ static int cost_cells_impl(const dpose_pg *pg, const double se2[3], const int2 *
   std::lock_guard<std::mutex> lock(sc.mu);
   DPOSE_TRY(ensure_scratch(sc, pg->device, h_cells ? n : 0));
   if (h_cells && n) {
-    DPOSE_CUDA(cudaMemcpy(sc.d_cells, h_cells, sizeof(int2) * n, cudaMemcpyHostToDevice));
+    DPOSE_CUDA(cudaMemcpyAsync(sc.d_cells, h_cells, sizeof(int2) * n, cudaMemcpyHostToDevice, sc.stream));
     d_cells = sc.d_cells;
   }
   const TableGeom g = {pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
   int grid = (int)((n + 4 * kCellThreads - 1) / (4 * kCellThreads));
   grid = grid < 1 ? 1 : (grid > kMaxCellCtas ? kMaxCellCtas : grid);
   if (J)
-    k_cost_cells<true><<<grid, kCellThreads>>>(pg->d_coef, g, se2[0], se2[1], se2[2], d_cells, n,
-                                               sc.d_partials, sc.d_ticket, sc.d_out);
+    k_cost_cells<true><<<grid, kCellThreads, 0, sc.stream>>>(pg->d_coef, g, se2[0], se2[1], se2[2], d_cells, n,
+                                                             sc.d_partials, sc.d_ticket, sc.h_out);
   else
-    k_cost_cells<false><<<grid, kCellThreads>>>(pg->d_coef, g, se2[0], se2[1], se2[2], d_cells, n,
-                                                sc.d_partials, sc.d_ticket, sc.d_out);
+    k_cost_cells<false><<<grid, kCellThreads, 0, sc.stream>>>(pg->d_coef, g, se2[0], se2[1], se2[2], d_cells, n,
+                                                              sc.d_partials, sc.d_ticket, sc.h_out);
   DPOSE_LAUNCHED();
-  double h[4];
-  DPOSE_CUDA(cudaMemcpy(h, sc.d_out, sizeof(h), cudaMemcpyDeviceToHost));
+  DPOSE_CUDA(cudaStreamSynchronize(sc.stream));  // the result is already in pinned host memory
+  const double *h = sc.h_out;
   *cost = h[0];
   if (J) {
     J[0] = h[1];

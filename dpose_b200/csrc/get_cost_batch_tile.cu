@@ -259,17 +259,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const float l2c = fmaf(fr0, d2, l2) - fcb, h2c = fmaf(fr0, d2, h2) - fcb;
           const float wmax = (float)(wc - 1);
           unsigned sm_lo = 0u, sm_hi = 0u;  // non-empty slots
+          // with 1024 threads (64 registers) the next tile row is not prefetched: the extra warps hide the latency
+          constexpr bool kPrefetch = kThreads < 1024;
           Tile8 A, B, An, Bn;
 #pragma unroll
           for (int r = 0; r < 8; ++r) A.w[r] = B.w[r] = An.w[r] = Bn.w[r] = 0u;
-          A = ldg_tile(tp);
-          if (need_b) B = ldg_tile(tp + 8);
+          if (kPrefetch) {
+            A = ldg_tile(tp);
+            if (need_b) B = ldg_tile(tp + 8);
+          }
 #pragma unroll
           for (int t = 0; t < 5; ++t) {
             if (t * 8 < kSlots) {
-              if ((t + 1) * 8 < kSlots && t + 1 <= n_tb) {  // prefetch the next tile row
-                An = ldg_tile(tp + (size_t)(t + 1) * tstride);
-                if (need_b) Bn = ldg_tile(tp + (size_t)(t + 1) * tstride + 8);
+              if (kPrefetch) {
+                if ((t + 1) * 8 < kSlots && t + 1 <= n_tb) {  // prefetch the next tile row
+                  An = ldg_tile(tp + (size_t)(t + 1) * tstride);
+                  if (need_b) Bn = ldg_tile(tp + (size_t)(t + 1) * tstride + 8);
+                }
+              } else if (t <= n_tb) {
+                A = ldg_tile(tp + (size_t)t * tstride);
+                if (need_b) B = ldg_tile(tp + (size_t)t * tstride + 8);
               }
 #pragma unroll
               for (int r = 0; r < 8; ++r) {
@@ -292,8 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
                   }
                 }
               }
-              A = An;
-              B = Bn;
+              if (kPrefetch) {
+                A = An;
+                B = Bn;
+              }
             }
           }
           // slots [off, off + hc) are the chunk's rows; everything else (stale tiles, rows past the window) is dropped
@@ -415,7 +426,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols;
   const size_t budget = (size_t)smem_optin - 64;
   // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts)
-  int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 768;
+  int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 1024;
   int rep_shift = env_rep == 1 ? 0 : env_rep == 4 ? 2 : env_rep == 8 ? 3 : 2;
   auto fits = [&](int th, int rs) { return (table_bytes << rs) + (size_t)slots * 4 * th <= budget; };
   while (!fits(threads, rep_shift)) {

@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
+#include <mutex>
+#include <new>
 
 #include "common.cuh"
 
@@ -218,7 +220,96 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
   }
 }
 
+// Per-map workspace: scratch buffers, pinned staging and a private stream live in the map handle
+// (grow-only), so a call costs no cudaMalloc / cudaFree besides the stream-ordered allocation of its
+// result.  Calls on one map serialise on the workspace mutex (the reference holds the costmap mutex
+// for the whole extraction anyway, dpose_costmap.cpp:138).
+struct LethalWs {
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  RowSpan *d_spans = nullptr, *h_spans = nullptr;  // h_spans pinned
+  size_t rows_cap = 0;
+  unsigned *d_count = nullptr, *d_prefix = nullptr;
+  size_t tiles_cap = 0;
+  unsigned long long *d_chunk = nullptr;  // n_chunks + 1 (last = grand total)
+  size_t chunks_cap = 0;
+  unsigned long long *h_total = nullptr;  // pinned
+  float last_kernel_us = 0.f;
+
+  int init(int device) {
+    DPOSE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    DPOSE_CUDA(cudaEventCreate(&ev0));
+    DPOSE_CUDA(cudaEventCreate(&ev1));
+    DPOSE_CUDA(cudaHostAlloc(&h_total, sizeof(*h_total), cudaHostAllocDefault));
+    // keep freed result buffers in the device's default pool instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return DPOSE_OK;
+  }
+  int reserve(size_t rows, size_t tiles, size_t chunks) {
+    if (rows > rows_cap) {
+      cudaFree(d_spans);
+      cudaFreeHost(h_spans);
+      d_spans = h_spans = nullptr;
+      rows_cap = 0;
+      const size_t cap = rows + rows / 2 + 64;
+      DPOSE_CUDA(cudaMalloc(&d_spans, sizeof(RowSpan) * cap));
+      DPOSE_CUDA(cudaHostAlloc(&h_spans, sizeof(RowSpan) * cap, cudaHostAllocDefault));
+      rows_cap = cap;
+    }
+    if (tiles > tiles_cap) {
+      cudaFree(d_count);
+      cudaFree(d_prefix);
+      d_count = d_prefix = nullptr;
+      tiles_cap = 0;
+      const size_t cap = tiles + tiles / 2 + 1024;
+      DPOSE_CUDA(cudaMalloc(&d_count, sizeof(unsigned) * cap));
+      DPOSE_CUDA(cudaMalloc(&d_prefix, sizeof(unsigned) * cap));
+      tiles_cap = cap;
+    }
+    if (chunks + 1 > chunks_cap) {
+      cudaFree(d_chunk);
+      d_chunk = nullptr;
+      chunks_cap = 0;
+      const size_t cap = chunks + chunks / 2 + 16;
+      DPOSE_CUDA(cudaMalloc(&d_chunk, sizeof(unsigned long long) * cap));
+      chunks_cap = cap;
+    }
+    return DPOSE_OK;
+  }
+  void release() {
+    cudaFree(d_spans);
+    cudaFreeHost(h_spans);
+    cudaFree(d_count);
+    cudaFree(d_prefix);
+    cudaFree(d_chunk);
+    cudaFreeHost(h_total);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+std::mutex g_ws_mu;  // guards creation of the per-map workspace
+
 }  // namespace
+
+void map_release_lethal_ws(dpose_map *map) {
+  LethalWs *ws = static_cast<LethalWs *>(map->lethal_ws);
+  if (!ws) return;
+  ws->release();
+  delete ws;
+  map->lethal_ws = nullptr;
+}
+
+float lethal_last_kernel_us(const dpose_map *map) {
+  const LethalWs *ws = static_cast<const LethalWs *>(map->lethal_ws);
+  return ws ? ws->last_kernel_us : 0.f;
+}
 
 int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, size_t *n) {
   *d_cells = nullptr;
@@ -236,7 +327,30 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
     y_hi = std::max(y_hi, ring[2 * i + 1]);
   }
   const int nrows = y_hi - y_lo + 1;
-  std::vector<RowSpan> spans((size_t)nrows, RowSpan{INT_MAX, INT_MIN});
+
+  DeviceGuard guard(map->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", map->device);
+  LethalWs *ws;
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    dpose_map *m = const_cast<dpose_map *>(map);
+    if (!m->lethal_ws) {
+      LethalWs *fresh = new (std::nothrow) LethalWs();
+      if (!fresh) return fail(DPOSE_ENOMEM, "out of host memory");
+      const int rc = fresh->init(map->device);
+      if (rc != DPOSE_OK) {
+        fresh->release();
+        delete fresh;
+        return rc;
+      }
+      m->lethal_ws = fresh;
+    }
+    ws = static_cast<LethalWs *>(m->lethal_ws);
+  }
+  std::lock_guard<std::mutex> call_lock(ws->mu);
+  DPOSE_TRY(ws->reserve((size_t)nrows, 0, 0));
+  RowSpan *spans = ws->h_spans;
+  for (int r = 0; r < nrows; ++r) spans[r] = RowSpan{INT_MAX, INT_MIN};
   for (int e = 0; e < 4; ++e)  // to_rays (:106-115)
     trace_line(ring[2 * e], ring[2 * e + 1], ring[2 * e + 2], ring[2 * e + 3], [&](int x, int y) {
       RowSpan &s = spans[(size_t)(y - y_lo)];
@@ -244,15 +358,13 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       s.xmax = std::max(s.xmax, x);
     });
   int gx_min = INT_MAX, gx_max = INT_MIN;
-  for (const RowSpan &s : spans)
-    if (s.xmin <= s.xmax) {
-      gx_min = std::min(gx_min, s.xmin);
-      gx_max = std::max(gx_max, s.xmax);
+  for (int r = 0; r < nrows; ++r)
+    if (spans[r].xmin <= spans[r].xmax) {
+      gx_min = std::min(gx_min, spans[r].xmin);
+      gx_max = std::max(gx_max, spans[r].xmax);
     }
   if (gx_min > gx_max) return DPOSE_OK;  // degenerate ring (all four edges empty)
 
-  DeviceGuard guard(map->device);
-  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", map->device);
   LethalArgs a;
   a.map = map->d_data;
   a.pitch = map->pitch;
@@ -262,43 +374,39 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
   a.tiles_x = (gx_max - a.x_base) / kTileBytes + 1;
   a.n_tiles = (long long)nrows * a.tiles_x;
   const int n_chunks = (int)((a.n_tiles + kScanChunk - 1) / kScanChunk);
+  DPOSE_TRY(ws->reserve((size_t)nrows, (size_t)a.n_tiles, (size_t)n_chunks));
+  a.spans = ws->d_spans;
 
-  RowSpan *d_spans = nullptr;
-  unsigned *d_count = nullptr, *d_prefix = nullptr;
-  unsigned long long *d_chunk = nullptr;  // n_chunks + 1 (last = grand total)
+  cudaStream_t st = ws->stream;
   int2 *d_out = nullptr;
   auto body = [&]() -> int {
-    DPOSE_CUDA(cudaMalloc(&d_spans, sizeof(RowSpan) * nrows));
-    DPOSE_CUDA(cudaMalloc(&d_count, sizeof(unsigned) * a.n_tiles));
-    DPOSE_CUDA(cudaMalloc(&d_prefix, sizeof(unsigned) * a.n_tiles));
-    DPOSE_CUDA(cudaMalloc(&d_chunk, sizeof(unsigned long long) * (n_chunks + 1)));
-    DPOSE_CUDA(cudaMemcpy(d_spans, spans.data(), sizeof(RowSpan) * nrows, cudaMemcpyHostToDevice));
-    a.spans = d_spans;
+    DPOSE_CUDA(cudaMemcpyAsync(ws->d_spans, ws->h_spans, sizeof(RowSpan) * nrows, cudaMemcpyHostToDevice, st));
     const unsigned grid = (unsigned)((a.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta);
-    k_count<<<grid, kWarpsPerCta * 32>>>(a, d_count);
+    DPOSE_CUDA(cudaEventRecord(ws->ev0, st));
+    k_count<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_count);
     DPOSE_LAUNCHED();
-    k_scan_chunks<<<n_chunks, 512>>>(d_count, d_prefix, d_chunk, a.n_tiles);
+    k_scan_chunks<<<n_chunks, 512, 0, st>>>(ws->d_count, ws->d_prefix, ws->d_chunk, a.n_tiles);
     DPOSE_LAUNCHED();
-    k_scan_totals<<<1, 1024>>>(d_chunk, n_chunks, d_chunk + n_chunks);
+    k_scan_totals<<<1, 1024, 0, st>>>(ws->d_chunk, n_chunks, ws->d_chunk + n_chunks);
     DPOSE_LAUNCHED();
-    unsigned long long total = 0;
-    DPOSE_CUDA(cudaMemcpy(&total, d_chunk + n_chunks, sizeof(total), cudaMemcpyDeviceToHost));
+    DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_chunk + n_chunks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    DPOSE_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long total = *ws->h_total;
     if (total == 0) return DPOSE_OK;  // :157-158
-    DPOSE_CUDA(cudaMalloc(&d_out, sizeof(int2) * total));
-    k_write<<<grid, kWarpsPerCta * 32>>>(a, d_prefix, d_chunk, d_out);
+    DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * total, st));
+    k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_chunk, d_out);
     DPOSE_LAUNCHED();
-    DPOSE_CUDA(cudaDeviceSynchronize());
+    DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
+    DPOSE_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ws->last_kernel_us, ws->ev0, ws->ev1);  // ms, includes the host round trip for the total
+    ws->last_kernel_us *= 1000.f;
     *d_cells = d_out;
     *n = (size_t)total;
     d_out = nullptr;
     return DPOSE_OK;
   };
   const int rc = body();
-  cudaFree(d_spans);
-  cudaFree(d_count);
-  cudaFree(d_prefix);
-  cudaFree(d_chunk);
-  cudaFree(d_out);
+  if (d_out) cudaFree(d_out);
   return rc;
 }
 

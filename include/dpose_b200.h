@@ -109,6 +109,9 @@ int dpose_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_xy
  * library (dpose_free). */
 int dpose_lethal_cells_within(const dpose_map *map, const int32_t box[10], int32_t **cells_xy,
                               size_t *n);
+/* device time of the last dpose_lethal_cells_within* call on this map: both sweeps and the scans,
+ * including the host round trip that sizes the result; microseconds */
+int dpose_map_lethal_us(const dpose_map *map, float *us);
 /* same, result stays on the device */
 int dpose_lethal_cells_within_device(const dpose_map *map, const int32_t box[10],
                                      dpose_cells **out);

@@ -162,4 +162,11 @@ def lethal_cells_within(costmap, box):
 
 
 def max_threads():
-    return lib().oracle_max_threads()
+    """host threads the CPU baseline may use: the cores this process is allowed on.  Deliberately NOT
+    omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn
+    the all-cores baseline into a single-thread one (num_threads() in the C code overrides the env)."""
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)

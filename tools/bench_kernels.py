@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Side measurements of the non-headline kernels of the path (run under gpurun, one GPU):
+
+  precompute  : k_precompute device time per footprint vs the CPU pipelines (oracle C, cv2)
+  lethal      : lethal_cells_within on the full 10000x10000 map and on a typical search box
+  single      : BASELINE config 1 — one pose, explicit cell list (the reference's call shape)
+  loop4096    : BASELINE config 4 call pattern — 4096 poses per call, 20 calls
+
+Prints one JSON line per measurement; each is parity-checked against the oracle where cheap.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import fixtures as fx  # noqa: E402
+import dpose_b200 as dp  # noqa: E402
+from oracle import capi  # noqa: E402
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def best_of(fn, reps):
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def bench_precompute():
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        cv2.ipp.setUseIPP(False)
+        from oracle import cv_pipeline
+    except Exception:
+        cv2 = None
+    for name in ("rect_pad2", "star40_pad2", "ship_pad10", "arrow_pad3"):
+        fp, pad = fx.FOOTPRINTS[name]
+        dp.cost_data(fp, pad)  # warm-up (module load)
+        us = min(dp.cost_data(fp, pad).precompute_us() for _ in range(5))
+        wall = best_of(lambda: dp.cost_data(fp, pad), 5)
+        cd = dp.cost_data(fp, pad)
+        oc = capi.CostData(fp, pad)
+        exact = bool(np.array_equal(cd.get_data().view(np.uint32), oc.cost.view(np.uint32)) and
+                     np.array_equal(cd.stages()[0], oc.edt_sq))
+        cpu_oracle = best_of(lambda: capi.CostData(fp, pad), 5)
+        cpu_cv2 = best_of(lambda: cv_pipeline.cv_cost_data(fp, pad), 5) if cv2 is not None else None
+        emit(what="precompute", footprint=name, table=[cd.rows, cd.cols], gpu_kernel_us=us,
+             gpu_call_wall_us=wall * 1e6, cpu_oracle_us=cpu_oracle * 1e6,
+             cpu_cv2_us=None if cpu_cv2 is None else cpu_cv2 * 1e6, bit_exact_vs_oracle=exact)
+
+
+def bench_lethal():
+    import torch
+    side = 10000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4)
+    d_map = torch.where(torch.rand((side, side), generator=g, device="cuda") < 0.10,
+                        torch.tensor(254, dtype=torch.uint8, device="cuda"),
+                        torch.tensor(0, dtype=torch.uint8, device="cuda")).contiguous()
+    cm = dp.Costmap(device_ptr=d_map.data_ptr(), size_x=side, size_y=side, pitch=side)
+    for label, ring in (("full 10000x10000", fx.to_rectangle(side - 1, side - 1)),
+                        ("search box 101x101", fx.to_rectangle((4950, 4950), (5050, 5050))),
+                        ("rotated 2000x1200 box", fx.rotated_ring(fx.to_rectangle((-1000, -600), (1000, 600)),
+                                                                  (5000.0, 5000.0, 0.5)))):
+        cells = dp.lethal_cells_within(cm, ring, on_device=True)
+        n = len(cells)
+        del cells
+        torch.cuda.synchronize()
+
+        def run():
+            c = dp.lethal_cells_within(cm, ring, on_device=True)
+            del c
+        wall = best_of(run, 5)
+        dev_us = cm.lethal_us()
+        xs, ys = ring[:, 0], ring[:, 1]
+        box_bytes = int((xs.max() - xs.min() + 1) * (ys.max() - ys.min() + 1))
+        algo = 2 * box_bytes + 8 * n  # two sweeps over the box + the cells written
+        emit(what="lethal_cells_within", box=label, cells=n, call_wall_us=wall * 1e6, device_us=dev_us,
+             algorithmic_bytes=algo, achieved_gbs_device=algo / (dev_us * 1e-6) / 1e9,
+             achieved_gbs_whole_call=algo / wall / 1e9)
+    # parity on a host map small enough for the oracle
+    m = fx.bernoulli_map(2000, 2000, 0.10, 1)
+    ring = fx.rotated_ring(fx.to_rectangle((-300, -200), (300, 200)), (1000.0, 1000.0, 0.7))
+    ok = bool(np.array_equal(dp.lethal_cells_within(dp.Costmap(m), ring), capi.lethal_cells_within(m, ring)))
+    emit(what="lethal_cells_within", parity_vs_oracle_2000x2000=ok)
+
+
+def bench_single():
+    fp, pad = fx.FOOTPRINTS["rect_pad2"]
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+    oc = capi.CostData(fp, pad)
+    m = fx.bernoulli_map(200, 200, 0.10, 0)
+    cm = dp.Costmap(m)
+    pose = [100.0, 100.0, 0.3]
+    ring = fx.rotated_ring(pg.get_data().get_box(), pose)
+    cells = dp.lethal_cells_within(cm, ring)
+    dcells = dp.cell_vector_device.upload(cells)
+    c, J = pg.get_cost(pose, cells)
+    rc, rJ = oc.get_cost(pose, cells)
+    ok = bool(fx.tol_ok(c, rc) and fx.tol_ok(J, rJ).all())
+    reps = 2000
+    t_host = best_of(lambda: [pg.get_cost(pose, cells) for _ in range(reps)], 3) / reps
+    t_dev = best_of(lambda: [pg.get_cost(pose, dcells) for _ in range(reps)], 3) / reps
+    t_cpu = best_of(lambda: [oc.get_cost(pose, cells) for _ in range(reps)], 3) / reps
+    emit(what="single_pose_get_cost (BASELINE cfg1)", cells=int(len(cells)), gpu_call_us_host_cells=t_host * 1e6,
+         gpu_call_us_device_cells=t_dev * 1e6, cpu_oracle_call_us=t_cpu * 1e6, parity=ok,
+         note="one pose per call is launch-latency bound on a GPU; the batched entry point exists for this reason")
+    # the literal perf bench of the reference (dpose_core/perf/dpose_core.cpp:17-57)
+    fp, pad = fx.FOOTPRINTS["arrow_pad3"]
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+    oc = capi.CostData(fp, pad)
+    cells = np.array([[x, y] for x in range(10) for y in range(10)], np.int32)
+    t_host = best_of(lambda: [pg.get_cost([0, 0, 0], cells) for _ in range(reps)], 3) / reps
+    t_cpu = best_of(lambda: [oc.get_cost([0, 0, 0], cells) for _ in range(reps)], 3) / reps
+    emit(what="perf_dpose_core literal (arrow pad 3, 100 cells)", gpu_call_us=t_host * 1e6, cpu_oracle_call_us=t_cpu * 1e6)
+
+
+def bench_loop4096():
+    fp, pad = fx.FOOTPRINTS["rect_pad2"]
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+    m = fx.bernoulli_map(2000, 2000, 0.10, 1)
+    cm = dp.Costmap(m)
+    rng = np.random.default_rng(3)
+    r, a = rng.uniform(0, 20, 4096), rng.uniform(-np.pi, np.pi, 4096)
+    poses = np.stack([1000 + r * np.cos(a), 1000 + r * np.sin(a), rng.uniform(-1, 1, 4096)], axis=1)
+    out = np.empty((4096, 4))
+    pg.get_cost_batch(cm, poses, out=out)
+    t = best_of(lambda: [pg.get_cost_batch(cm, poses, out=out) for _ in range(20)], 5) / 20
+    oc = capi.CostData(fp, pad)
+    ref = oc.get_cost_batch(m, poses, nthreads=capi.max_threads())
+    t_cpu = best_of(lambda: oc.get_cost_batch(m, poses, nthreads=capi.max_threads()), 3)
+    emit(what="4096-pose call (BASELINE cfg4 call pattern, host buffers)", gpu_call_us=t * 1e6,
+         gpu_poses_per_s=4096 / t, cpu_oracle_call_us=t_cpu * 1e6, cpu_threads=capi.max_threads(),
+         parity=bool(fx.tol_ok(out, ref).all()))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["precompute", "lethal", "single", "loop4096"]
+    for w in which:
+        {"precompute": bench_precompute, "lethal": bench_lethal, "single": bench_single,
+         "loop4096": bench_loop4096}[w]()
