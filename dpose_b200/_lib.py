@@ -47,6 +47,12 @@ SYMBOLS = {
     "dpose_pg_get_cost_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
     "dpose_pg_get_cost_batch_device": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "dpose_pg_get_cost_batch_multi": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _i]),
+    "dpose_problem_create": (_i, [_vp, _vp, _pp]),
+    "dpose_problem_destroy": (None, [_vp]),
+    "dpose_problem_init": (_i, [_vp, _vp, _vp, _vp]),
+    "dpose_problem_info": (_i, [_vp, _vp, _vp]),
+    "dpose_problem_eval_batch": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "dpose_problem_eval_batch_device": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dpose_pg_window_bytes": (_i, [_vp, _vp, _vp, _sz, C.POINTER(_u64)]),
 }
 

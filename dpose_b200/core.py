@@ -293,3 +293,72 @@ def get_cost_batch_multi(pgs, maps, poses, jacobian=True, out=None):
     check(lib().dpose_pg_get_cost_batch_multi(pg_arr, map_arr, n, p.ctypes.data, p.shape[0], out.ctypes.data,
                                               int(bool(jacobian))))
     return out
+
+
+class problem:
+    """dpose_goal_tolerance::problem (dpose_goal_tolerance.hpp:115-200, dpose_goal_tolerance.cpp:90-292) with the
+    Ipopt TNLP evaluations batched over displacements.  Same member names and argument meaning; poses in cells."""
+
+    CONFIG_KEYS = ("lin_tolerance", "rot_tolerance", "weight_goal_lin", "weight_goal_rot", "weight_start_lin",
+                   "weight_start_rot")
+
+    def __init__(self, pg, costmap):
+        self._pg, self._map = pg, costmap  # keep the borrowed handles alive
+        self._h = C.c_void_p()
+        check(lib().dpose_problem_create(pg._data._h, costmap._h, C.byref(self._h)))
+
+    def init(self, start, goal, config=None, **kw):
+        """config: mapping with the DposeGoalToleranceConfig keys (cfg/DposeGoalTolerance.cfg:7-12, defaults 1);
+        lin_tolerance in cells"""
+        cfg = dict(config or {})
+        cfg.update(kw)
+        c = np.array([float(cfg.get(k, 1.0)) for k in self.CONFIG_KEYS], dtype=np.float64)
+        s = np.ascontiguousarray(np.asarray(start, np.float64).reshape(3))
+        g = np.ascontiguousarray(np.asarray(goal, np.float64).reshape(3))
+        check(lib().dpose_problem_init(self._h, s.ctypes.data, g.ctypes.data, c.ctypes.data))
+
+    def get_nlp_info(self):
+        """(n, m, nnz_jac_g) — :183-191"""
+        return 3, 2, 3
+
+    def get_bounds_info(self):
+        """x in [-1e6, 1e6]^3, g in [0, (lin_tol^2, rot_tol^2)] — :193-207"""
+        gu = np.zeros(2)
+        check(lib().dpose_problem_info(self._h, None, gu.ctypes.data))
+        return np.full(3, -1e6), np.full(3, 1e6), np.zeros(2), gu
+
+    @property
+    def search_box(self):
+        b = np.zeros(10, np.int32)
+        check(lib().dpose_problem_info(self._h, b.ctypes.data, None))
+        return b.reshape(5, 2)
+
+    def eval_batch(self, x, want=("f", "grad_f", "g", "jac_g")):
+        """n displacements -> dict of f (n), grad_f (n,3), g (n,2), jac_g (n,3)"""
+        x = np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1, 3))
+        n = x.shape[0]
+        shapes = {"f": (n,), "grad_f": (n, 3), "g": (n, 2), "jac_g": (n, 3)}
+        out = {k: np.empty(shapes[k]) for k in want}
+        ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+        check(lib().dpose_problem_eval_batch(self._h, x.ctypes.data, n, ptr("f"), ptr("grad_f"), ptr("g"), ptr("jac_g")))
+        return out
+
+    # the single-x TNLP callbacks, for callers that keep Ipopt's one-iterate-at-a-time shape
+    def eval_f(self, x):
+        return float(self.eval_batch([x], want=("f",))["f"][0])
+
+    def eval_grad_f(self, x):
+        return self.eval_batch([x], want=("grad_f",))["grad_f"][0]
+
+    def eval_g(self, x):
+        return self.eval_batch([x], want=("g",))["g"][0]
+
+    def eval_jac_g(self, x):
+        return self.eval_batch([x], want=("jac_g",))["jac_g"][0]
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().dpose_problem_destroy(self._h)
+        except Exception:
+            pass

@@ -488,6 +488,13 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
   const size_t chunk = std::min<size_t>(n, kChunkPoses);
   DPOSE_TRY(ctx->reserve(chunk));
   auto body = [&]() -> int {
+    if (n <= chunk) {  // one chunk: in-order on a single stream, no cross-stream events (latency path)
+      DPOSE_CUDA(cudaMemcpyAsync(ctx->d_p[0], poses, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->s_k));
+      DPOSE_TRY(get_cost_batch_device(pg, map, ctx->d_p[0], n, ctx->d_o[0], want_jacobian, ctx->s_k));
+      DPOSE_CUDA(cudaMemcpyAsync(out, ctx->d_o[0], sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, ctx->s_k));
+      DPOSE_CUDA(cudaStreamSynchronize(ctx->s_k));
+      return DPOSE_OK;
+    }
     size_t it = 0;
     for (size_t off = 0; off < n; off += chunk, ++it) {
       const int b = (int)(it % kBuf);

@@ -130,6 +130,7 @@ struct TileArgs {
   const double *poses;
   double *out;
   size_t n;
+  int out_aligned;  // out is 32-byte aligned: one 256-bit store per result
 };
 
 struct Acc4 {
@@ -356,7 +357,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
       jy = -s * acc.su - c * acc.sv;
       jt = acc.st - cy15 * acc.su + cx15 * acc.sv;
     }
-    stg_result(a.out + 4 * idx, acc.f, jx, jy, jt);
+    if (a.out_aligned) {
+      stg_result(a.out + 4 * idx, acc.f, jx, jy, jt);
+    } else {
+      double *o = a.out + 4 * idx;
+      o[0] = acc.f, o[1] = jx, o[2] = jy, o[3] = jt;
+    }
   }
 }
 
@@ -479,6 +485,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.poses = d_poses;
   a.out = d_out;
   a.n = n;
+  a.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 31u) == 0;
   const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)slots * 4 * threads;
   const size_t want = (n + threads - 1) / threads;
   const int grid = (int)std::min<size_t>(want, (size_t)sms);

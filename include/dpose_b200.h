@@ -36,6 +36,7 @@ extern "C" {
 typedef struct dpose_pg dpose_pg;       /* pose_gradient + its cost_data on one device */
 typedef struct dpose_map dpose_map;     /* device-resident costmap */
 typedef struct dpose_cells dpose_cells; /* device-resident cell_vector */
+typedef struct dpose_problem dpose_problem; /* dpose_goal_tolerance::problem, batched */
 
 const char *dpose_last_error(void);
 int dpose_device_count(int *n);
@@ -150,6 +151,36 @@ int dpose_pg_get_cost_batch_multi(dpose_pg *const *pgs, dpose_map *const *maps, 
  * clipped to the map.  Host arithmetic. */
 int dpose_pg_window_bytes(const dpose_pg *pg, const dpose_map *map, const double *poses,
                           size_t n, uint64_t *bytes);
+
+/* ---- dpose_goal_tolerance::problem, batched (the caller of the hot path) ---------------------
+ * The NLP the gpp plugin hands to Ipopt (dpose_goal_tolerance.cpp:90-292): displacement x of the goal,
+ *   f(x) = get_cost(goal + x, lethal cells inside the search box) + pose regularisers (:54-88, :96-110)
+ *   g(x) = (x^2 + y^2, theta^2) <= (lin_tol^2, rot_tol^2)                            (:196-207, :238-247)
+ * evaluated for n displacements per call (multi-start in lock-step) instead of one per callback. */
+typedef struct {
+  /* DposeGoalToleranceConfig (cfg/DposeGoalTolerance.cfg:7-12); lin_tolerance in CELLS
+   * (dpose_goal_tolerance.cpp:530-535 converts metres to cells before problem::init sees it) */
+  double lin_tolerance, rot_tolerance;
+  double weight_goal_lin, weight_goal_rot, weight_start_lin, weight_start_rot;
+} dpose_gt_config;
+
+/* problem::problem (:90-94).  pg and map are borrowed and must outlive the problem. */
+int dpose_problem_create(const dpose_pg *pg, const dpose_map *map, dpose_problem **out);
+void dpose_problem_destroy(dpose_problem *problem);
+/* problem::init(start, goal, config) (:112-181): search box, its lethal cells (kept on the device as a
+ * cropped costmap), regularisers.  Poses in cells / radians. */
+int dpose_problem_init(dpose_problem *problem, const double start[3], const double goal[3],
+                       const dpose_gt_config *cfg);
+/* the search box ring (:129-138) and get_bounds_info's constraint upper bounds (:203-206); either may be NULL */
+int dpose_problem_info(const dpose_problem *problem, int32_t search_box[10], double g_upper[2]);
+/* eval_f / eval_grad_f / eval_g / eval_jac_g (:215-281) for n displacements x (n x 3).
+ * f: n, grad_f: n x 3, g: n x 2, jac_g: n x 3 (the three structural non-zeros dg0/dx, dg0/dy, dg1/dtheta);
+ * any output may be NULL.  Host buffers. */
+int dpose_problem_eval_batch(dpose_problem *problem, const double *x, size_t n, double *f, double *grad_f,
+                             double *g, double *jac_g);
+/* device pointers, asynchronous on `stream`; d_work: 7 n doubles of scratch */
+int dpose_problem_eval_batch_device(const dpose_problem *problem, const double *d_x, size_t n, double *d_work,
+                                    double *d_f, double *d_grad_f, double *d_g, double *d_jac_g, void *stream);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,21 @@ class _CostData(C.Structure):
     ]
 
 
+class _GtConfig(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("lin_tolerance", "rot_tolerance", "weight_goal_lin", "weight_goal_rot",
+                                          "weight_start_lin", "weight_start_rot")]
+
+
+class _Reg(C.Structure):
+    _fields_ = [("goal", C.c_double * 3), ("norm", C.c_double * 3)]
+
+
+class _Problem(C.Structure):
+    _fields_ = [("pose", C.c_double * 3), ("lin_tol_sq", C.c_double), ("rot_tol_sq", C.c_double),
+                ("search_box", C.c_int32 * 10), ("n_regs", C.c_int), ("regs", _Reg * 2),
+                ("cells", C.POINTER(C.c_int32)), ("n_cells", C.c_size_t)]
+
+
 def build(force=False):
     src_newer = (not os.path.exists(_SO)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
@@ -55,6 +70,13 @@ def lib():
         L.oracle_get_cost_batch_truth.argtypes = [C.POINTER(_CostData), C.c_void_p, C.c_uint32, C.c_uint32,
                                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_normalize_angle.restype = C.c_double
+        L.oracle_normalize_angle.argtypes = [C.c_double]
+        L.oracle_problem_init.argtypes = [C.POINTER(_CostData), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                          C.c_void_p, C.POINTER(_GtConfig), C.POINTER(_Problem)]
+        L.oracle_problem_free.argtypes = [C.POINTER(_Problem)]
+        L.oracle_problem_eval_batch.argtypes = [C.POINTER(_CostData), C.POINTER(_Problem), C.c_void_p, C.c_size_t,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -170,3 +192,55 @@ def max_threads():
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
+
+
+def normalize_angle(a):
+    return lib().oracle_normalize_angle(float(a))
+
+
+class Problem:
+    """dpose_goal_tolerance::problem restated (dpose_goal_tolerance.cpp:90-292): init() + the TNLP evaluations."""
+
+    def __init__(self, cost_data, costmap):
+        self.cd = cost_data
+        self.map = np.ascontiguousarray(np.asarray(costmap, dtype=np.uint8))
+        self._p = _Problem()
+        self._live = False
+
+    def init(self, start, goal, **cfg):
+        if self._live:
+            lib().oracle_problem_free(C.byref(self._p))
+        c = _GtConfig(**{k: float(cfg.get(k, 1.0)) for k, _ in _GtConfig._fields_})
+        s = np.ascontiguousarray(np.asarray(start, np.float64).reshape(3))
+        g = np.ascontiguousarray(np.asarray(goal, np.float64).reshape(3))
+        lib().oracle_problem_init(C.byref(self.cd._cd), self.map.ctypes.data, self.map.shape[1], self.map.shape[0],
+                                  s.ctypes.data, g.ctypes.data, C.byref(c), C.byref(self._p))
+        self._live = True
+
+    @property
+    def search_box(self):
+        return np.array(self._p.search_box[:], np.int32).reshape(5, 2)
+
+    @property
+    def n_cells(self):
+        return int(self._p.n_cells)
+
+    @property
+    def bounds(self):
+        """get_bounds_info (:196-207): g upper bounds (lin_tol^2, rot_tol^2)"""
+        return self._p.lin_tol_sq, self._p.rot_tol_sq
+
+    def eval_batch(self, x, nthreads=1):
+        x = np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1, 3))
+        n = x.shape[0]
+        f, grad, g, jac = np.empty(n), np.empty((n, 3)), np.empty((n, 2)), np.empty((n, 3))
+        lib().oracle_problem_eval_batch(C.byref(self.cd._cd), C.byref(self._p), x.ctypes.data, n, f.ctypes.data,
+                                        grad.ctypes.data, g.ctypes.data, jac.ctypes.data, int(nthreads))
+        return f, grad, g, jac
+
+    def __del__(self):
+        try:
+            if self._live:
+                lib().oracle_problem_free(C.byref(self._p))
+        except Exception:
+            pass

@@ -660,3 +660,115 @@ void oracle_get_cost_batch_truth(const oracle_cost_data *cd, const uint8_t *map,
   }
   (void)nthreads;
 }
+
+
+/* ------------------------------------------------------------------------- */
+/* dpose_goal_tolerance::problem — dpose_goal_tolerance.cpp:54-292            */
+/* ------------------------------------------------------------------------- */
+#define ORACLE_PI 3.14159265358979323846 /* M_PI (not in strict C11) */
+double oracle_normalize_angle(double a) {
+  /* angles::normalize_angle (ROS `angles`, noetic): */
+  const double r = fmod(a + ORACLE_PI, 2.0 * ORACLE_PI);
+  return r <= 0.0 ? r + ORACLE_PI : r - ORACLE_PI;
+}
+
+static double shortest_angular_distance(double from, double to) { return oracle_normalize_angle(to - from); }
+
+/* pose_regularization::init (:62-74) */
+static void reg_init(oracle_reg *r, double w_lin_unscaled, double w_rot_unscaled, const double start[3],
+                     const double goal[3]) {
+  double w_lin = (start[0] - goal[0]) * (start[0] - goal[0]) + (start[1] - goal[1]) * (start[1] - goal[1]);
+  double w_rot = pow(shortest_angular_distance(start[2], goal[2]), 2);
+  w_lin = w_lin_unscaled / fmax(w_lin, 1e-3); /* :70-71 avoid division by zero */
+  w_rot = w_rot_unscaled / fmax(w_rot, 1e-3);
+  for (int i = 0; i < 3; ++i) r->goal[i] = goal[i];
+  r->norm[0] = w_lin, r->norm[1] = w_lin, r->norm[2] = w_rot;
+}
+
+/* pose_regularization::get_cost (:76-88): cost, and J = 2 * norm .* diff */
+static double reg_cost(const oracle_reg *r, const double pose[3], double J[3]) {
+  double diff[3] = {pose[0] - r->goal[0], pose[1] - r->goal[1], pose[2] - r->goal[2]};
+  diff[2] = oracle_normalize_angle(diff[2]);
+  double cost = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    J[i] = 2 * (r->norm[i] * diff[i]);
+    cost += r->norm[i] * (diff[i] * diff[i]);
+  }
+  return cost;
+}
+
+int oracle_problem_init(const oracle_cost_data *cd, const uint8_t *map, uint32_t size_x, uint32_t size_y,
+                        const double start[3], const double goal[3], const oracle_gt_config *cfg,
+                        oracle_problem *out) {
+  memset(out, 0, sizeof(*out));
+  for (int i = 0; i < 3; ++i) out->pose[i] = goal[i]; /* :114 */
+  out->lin_tol_sq = pow(cfg->lin_tolerance, 2);       /* :115-116 */
+  out->rot_tol_sq = pow(cfg->rot_tolerance, 2);
+  int max_coeff = 0; /* :122-123 */
+  for (int i = 0; i < 10; ++i) max_coeff = abs(cd->box[i]) > max_coeff ? abs(cd->box[i]) : max_coeff;
+  const double h = max_coeff + fabs(cfg->lin_tolerance); /* :126 */
+  const double bx[5] = {-h, h, h, -h, -h}, by[5] = {-h, -h, h, h, -h}; /* :129-133 */
+  for (int i = 0; i < 5; ++i) {                                        /* :134-138, Eigen round = std::round */
+    out->search_box[2 * i] = (int32_t)round(bx[i] + goal[0]);
+    out->search_box[2 * i + 1] = (int32_t)round(by[i] + goal[1]);
+  }
+  out->n_cells = oracle_lethal_cells_within(map, size_x, size_y, out->search_box, &out->cells); /* :141 */
+  out->n_regs = 0;
+  if (cfg->weight_goal_lin != 0 || cfg->weight_goal_rot != 0) { /* :145-150 */
+    const double s[3] = {goal[0] + cfg->lin_tolerance, goal[1] + 0, goal[2] + cfg->rot_tolerance};
+    reg_init(&out->regs[out->n_regs++], cfg->weight_goal_lin, cfg->weight_goal_rot, s, goal);
+  }
+  if (cfg->weight_start_lin != 0 || cfg->weight_start_rot != 0) { /* :152-180 */
+    double s[3] = {start[0], start[1], start[2]};
+    double diff[3] = {start[0] - goal[0], start[1] - goal[1], start[2] - goal[2]};
+    diff[2] = oracle_normalize_angle(diff[2]);
+    const double lin_norm = sqrt(diff[0] * diff[0] + diff[1] * diff[1]);
+    const double rot_norm = fabs(diff[2]);
+    if (lin_norm != 0 && lin_norm > cfg->lin_tolerance) /* :170-171 (theta corrected below) */
+      for (int i = 0; i < 3; ++i) s[i] = goal[i] + diff[i] * cfg->lin_tolerance / lin_norm;
+    if (rot_norm != 0 && rot_norm > cfg->rot_tolerance) /* :174-177 */
+      s[2] = goal[2] + diff[2] * cfg->rot_tolerance / rot_norm;
+    else
+      s[2] = start[2];
+    reg_init(&out->regs[out->n_regs++], cfg->weight_start_lin, cfg->weight_start_rot, goal, s); /* :179 */
+  }
+  return 0;
+}
+
+void oracle_problem_free(oracle_problem *p) {
+  free(p->cells);
+  p->cells = NULL;
+  p->n_cells = 0;
+}
+
+void oracle_problem_eval(const oracle_cost_data *cd, const oracle_problem *p, const double x[3], double *f,
+                         double grad_f[3], double g[2], double jac_g[3]) {
+  const double pose[3] = {x[0] + p->pose[0], x[1] + p->pose[1], x[2] + p->pose[2]}; /* :98-100 */
+  double J[3];
+  double cost = oracle_get_cost(cd, pose, p->cells, p->n_cells, J); /* :103 */
+  for (int r = 0; r < p->n_regs; ++r) {                             /* :106-109 */
+    double Jr[3];
+    cost += reg_cost(&p->regs[r], pose, Jr);
+    for (int i = 0; i < 3; ++i) J[i] += Jr[i];
+  }
+  if (f) *f = cost;
+  if (grad_f)
+    for (int i = 0; i < 3; ++i) grad_f[i] = J[i];
+  if (g) { /* :238-247 */
+    g[0] = x[0] * x[0] + x[1] * x[1];
+    g[1] = x[2] * x[2];
+  }
+  if (jac_g) /* :270-279 */
+    for (int i = 0; i < 3; ++i) jac_g[i] = x[i] * 2;
+}
+
+void oracle_problem_eval_batch(const oracle_cost_data *cd, const oracle_problem *p, const double *x, size_t n,
+                               double *f, double *grad_f, double *g, double *jac_g, int nthreads) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 1 ? nthreads : 1)
+#endif
+  for (long long i = 0; i < (long long)n; ++i)
+    oracle_problem_eval(cd, p, x + 3 * i, f ? f + i : NULL, grad_f ? grad_f + 3 * i : NULL, g ? g + 2 * i : NULL,
+                        jac_g ? jac_g + 3 * i : NULL);
+  (void)nthreads;
+}

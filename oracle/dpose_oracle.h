@@ -94,6 +94,46 @@ void oracle_get_cost_batch_truth(const oracle_cost_data *cd, const uint8_t *map,
                                  uint32_t size_x, uint32_t size_y, const double *poses,
                                  size_t n, double *out, int nthreads);
 
+/* ---- dpose_goal_tolerance::problem: the NLP the Ipopt loop evaluates ------------- */
+/* DposeGoalToleranceConfig (cfg/DposeGoalTolerance.cfg:7-12); lin_tolerance already in CELLS
+ * (dpose_goal_tolerance.cpp:530-535 converts it in the reconfigure callback). */
+typedef struct {
+  double lin_tolerance, rot_tolerance;
+  double weight_goal_lin, weight_goal_rot, weight_start_lin, weight_start_rot;
+} oracle_gt_config;
+
+/* pose_regularization after init() (dpose_goal_tolerance.cpp:54-74) */
+typedef struct {
+  double goal[3], norm[3];
+} oracle_reg;
+
+/* problem after init() (dpose_goal_tolerance.cpp:112-181) */
+typedef struct {
+  double pose[3];            /* pose_ = goal */
+  double lin_tol_sq, rot_tol_sq;
+  int32_t search_box[10];    /* :129-138 */
+  int n_regs;
+  oracle_reg regs[2];        /* :144-180: goal regulariser first, then start */
+  int32_t *cells;            /* lethal_cells_ (:141), malloc'ed */
+  size_t n_cells;
+} oracle_problem;
+
+/* angles::normalize_angle / shortest_angular_distance (ROS package `angles`, un-vendored; restated
+ * from its published header: fmod(angle + pi, 2 pi), result <= 0 ? + pi : - pi) */
+double oracle_normalize_angle(double a);
+
+int oracle_problem_init(const oracle_cost_data *cd, const uint8_t *map, uint32_t size_x, uint32_t size_y,
+                        const double start[3], const double goal[3], const oracle_gt_config *cfg,
+                        oracle_problem *out);
+void oracle_problem_free(oracle_problem *p);
+/* on_new_x + eval_f / eval_grad_f / eval_g / eval_jac_g (dpose_goal_tolerance.cpp:96-110, 215-281)
+ * for one displacement x; any output may be NULL. */
+void oracle_problem_eval(const oracle_cost_data *cd, const oracle_problem *p, const double x[3], double *f,
+                         double grad_f[3], double g[2], double jac_g[3]);
+/* the same for n displacements (OpenMP over x when nthreads > 1) */
+void oracle_problem_eval_batch(const oracle_cost_data *cd, const oracle_problem *p, const double *x, size_t n,
+                               double *f, double *grad_f, double *g, double *jac_g, int nthreads);
+
 /* number of OpenMP threads available (1 if built without OpenMP) */
 int oracle_max_threads(void);
 

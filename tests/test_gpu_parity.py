@@ -368,6 +368,14 @@ def test_batch_device_pointer_entry(dp):
                              stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(d_o.cpu().numpy(), ref)
+    # buffers that are only 8-byte aligned (the fast kernel stores 32-byte results when it can)
+    d_p2 = torch.empty(len(poses) * 3 + 1, dtype=torch.float64, device="cuda")
+    d_o2 = torch.empty(len(poses) * 4 + 1, dtype=torch.float64, device="cuda")
+    d_p2[1:] = d_p.reshape(-1)
+    pg.get_cost_batch_device(cm, d_p2.data_ptr() + 8, len(poses), d_o2.data_ptr() + 8,
+                             stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_o2[1:].reshape(-1, 4).cpu().numpy(), ref)
     # map built from a device buffer
     cm2 = dp.Costmap(device_ptr=torch.from_numpy(m).cuda().data_ptr(), size_x=512, size_y=512)
     assert np.array_equal(pg.get_cost_batch(cm2, poses), ref)

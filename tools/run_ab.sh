@@ -1,3 +1,3 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-cpu-baseline 2>/dev/null | cut -c1-900
-python tools/bench_kernels.py lethal single loop4096 2>&1 | tee gpurun_out/kernels_v8.jsonl
+python tools/bench_kernels.py cfg4 loop4096 2>&1 | tee gpurun_out/kernels_v9.jsonl
+python bench.py --no-cpu-baseline --no-e2e 2>/dev/null | cut -c1-200
