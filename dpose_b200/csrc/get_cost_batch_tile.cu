@@ -25,9 +25,12 @@
 //            with the row's x-interval of the rotated kernel rectangle (fp32, conservative by 0.02
 //            cell; linear in the row index, so 4 FMAs per row), park the row mask, note non-empty
 //            rows in a 32-bit row mask.
-//   phase 2  walk the set bits (find-first-set over row mask, then mask): k + 0.5 = k0 + x (c,-s) +
-//            y (s, c) in FP64; floor by adding 1.5 * 2^52 rounding down; exact bounds test
-//            (dpose_core.cpp:181-182); two LDS.128 for the patch; f, f_u, f_v by FMA; accumulate.
+//   phase 2  walk the set bits (find-leading-one over the row mask, then the mask): k' = k - 1.5 =
+//            k0 + x (c,-s) + y (s, c) in FP64; floor(k') by adding 1.5 * 2^52 rounding down selects the
+//            patch; two LDS.128 fetch its bilinear polynomial in absolute k' coordinates (so no per-cell
+//            fraction); f, f_u, f_v by FMA; accumulate.  There is no bounds test (dpose_core.cpp:181-182):
+//            patches outside the valid range are zero and the clip keeps every cell within one patch of
+//            it (CLIP INVARIANT in the kernel) — the loop body is branch-free, 41 instructions, 15 FP64.
 // Tensor cores are not used: there is no dense contraction on this path.
 //
 // Algorithmic bytes per pose: 24 (pose) + 32 (result) + |window| map bytes.
@@ -75,11 +78,34 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ 
 }
 
 // ---- replicated coefficient image -----------------------------------------------------------------------
-// image[((patch * 2 + half) * R + rep)] (16 bytes each) = half `half` of PatchCoef[patch]
-__global__ void k_replicate_coef(const uint4 *__restrict__ coef, uint4 *__restrict__ image, int n_halves, int rep_shift) {
-  const int total = n_halves << rep_shift;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
-    image[i] = __ldg(coef + (i >> rep_shift));
+// The kernel evaluates a patch in ABSOLUTE shifted kernel coordinates k' = k - 1.5 (no per-cell fraction):
+//   f(k') = b00 + b10 ku + b01 kv + b11 ku kv,   with  (U, V) = floor(k') = k_upper - 2  and
+//   b11 = a11, b10 = a10 - a11 V, b01 = a01 - a11 U, b00 = a00 - a10 U - a01 V + a11 U V
+// (the bilinear patch of dpose_core.cpp:189-198 expanded around the patch origin; |U|, |V| < 2^8 keeps
+// the cancellation error below 1e-13, eight orders under the parity tolerance).  Patches that fail the
+// reference's bounds test (:181-182) hold zeros and contribute exactly 0: the walk needs no bounds test
+// as long as every visited cell lands within one patch of the valid range — see the clip invariant
+// in the kernel.
+// image[((patch * 2 + half) * R + rep)] (16 bytes each), patch = k_upper.y * cols + k_upper.x
+__global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *__restrict__ image, int rows, int cols,
+                                   int rep_shift) {
+  const int n_patches = rows * cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_patches; i += gridDim.x * blockDim.x) {
+    const int uy = i / cols, ux = i - uy * cols;
+    double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);  // (b00, b10), (b01, b11)
+    if (ux >= 2 && uy >= 2 && ux <= cols - 2 && uy <= rows - 2) {
+      const PatchCoef a = coef[i];
+      const double U = (double)(ux - 2), V = (double)(uy - 2);
+      hi.y = a.a11;
+      lo.y = a.a10 - a.a11 * V;
+      hi.x = a.a01 - a.a11 * U;
+      lo.x = (a.a00 - a.a10 * U) - (a.a01 * V - (a.a11 * U) * V);
+    }
+    for (int r = 0; r < (1 << rep_shift); ++r) {
+      image[(((size_t)i * 2 + 0) << rep_shift) + r] = lo;
+      image[(((size_t)i * 2 + 1) << rep_shift) + r] = hi;
+    }
+  }
 }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -131,6 +157,7 @@ struct TileArgs {
   double *out;
   size_t n;
   int out_aligned;  // out is 32-byte aligned: one 256-bit store per result
+  float clip_thr;   // a strip of the kernel rectangle is clipped per row only if |cos| (|sin|) exceeds this
 };
 
 struct Acc4 {
@@ -204,7 +231,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   // 0 <= floor(k') <= dim - 4.  The patch of k_upper = (2, 2) therefore sits at the base address.
   const uint32_t my_coef =
       coef_u32 + ((uint32_t)lane & ((1u << kRepShift) - 1u)) * 16u + (uint32_t)(2 * cols + 2) * kPatchStride;
-  const unsigned cols_m4 = (unsigned)(a.g.cols - 4), rows_m4 = (unsigned)(a.g.rows - 4);
   const float hi_u = (float)a.g.cols - 3.0f, hi_v = (float)a.g.rows - 3.0f;  // 0 <= k' < dim - 3
   const double cx15 = a.g.cx - 1.5, cy15 = a.g.cy - 1.5;
 
@@ -226,15 +252,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     // conservative fp32 x-interval of the kernel rectangle per window row y:
     //   0 <= ku0 + s y + c x < cols - 3   and   0 <= kv0 + c y - s x < rows - 3, each linear in y.
     // All values stay far below 2^22, which the integer extraction in phase 1 relies on.
+    // CLIP INVARIANT (what lets phase 2 drop the bounds test): every cell that survives has k' within one
+    // patch of the valid range, so floor(k') is in [-1, dim - 3] and addresses a patch of the table (zeros
+    // outside the valid range).  A clipped strip overshoots by 0.02 |c| cell; a strip left unclipped because
+    // |c| <= clip_thr = 0.5 / win_max varies by at most |c| * window width <= 0.5 cell along a window row,
+    // and every window row crosses the valid rectangle (the window is its bounding box).
     float l1 = -1000.f, h1 = 1000.f, d1 = 0.f, l2 = -1000.f, h2 = 1000.f, d2 = 0.f;
     {
       const float cf = (float)c, sf = (float)s, ku0f = (float)ku0, kv0f = (float)kv0;
-      if (fabsf(cf) > 0.02f) {
+      if (fabsf(cf) > a.clip_thr) {
         const float inv = rcp_approx(cf);
         const float t0 = -ku0f * inv, t1 = (hi_u - ku0f) * inv;
         l1 = fminf(t0, t1) - 0.02f, h1 = fmaxf(t0, t1) + 0.02f, d1 = -sf * inv;
       }
-      if (fabsf(sf) > 0.02f) {
+      if (fabsf(sf) > a.clip_thr) {
         const float inv = rcp_approx(sf);
         const float t0 = kv0f * inv, t1 = (kv0f - hi_v) * inv;
         l2 = fminf(t0, t1) - 0.02f, h2 = fmaxf(t0, t1) + 0.02f, d2 = cf * inv;
@@ -330,23 +361,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const double ku = fma(c, X, fma(s, Y, kuc));
           const double kv = fma(c, Y, fma(-s, X, kvc));
           const double M = 6755399441055744.0;  // 1.5 * 2^52: adding it (rounding down) floors to an integer
-          const double tu = __dadd_rd(ku, M), tv = __dadd_rd(kv, M);
-          const int ux = __double2loint(tu), uy = __double2loint(tv);  // k_upper - 2
-          if ((unsigned)ux <= cols_m4 && (unsigned)uy <= rows_m4) {    // dpose_core.cpp:181-182
-            const double rx = ku - (tu - M), ry = kv - (tv - M);       // c_rel in [0, 1)  (:193)
-            const uint32_t addr = my_coef + (uint32_t)(uy * cols + ux) * kPatchStride;
-            double a00, a10, a01, a11;
-            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a00), "=d"(a10) : "r"(addr));
-            asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(a01), "=d"(a11) : "r"(addr), "n"(kHalfOff));
-            const double fv = fma(a11, rx, a01);
-            acc.f += fma(ry, fv, fma(a10, rx, a00));
-            if (kJac) {
-              const double fu = fma(a11, ry, a10);
-              acc.su += fu;
-              acc.sv += fv;
-              acc.st = fma(fu, kv, acc.st);  // Sum(fu * kv' - fv * ku'); center terms folded in below
-              acc.st = fma(-fv, ku, acc.st);
-            }
+          const int ux = __double2loint(__dadd_rd(ku, M)), uy = __double2loint(__dadd_rd(kv, M));  // k_upper - 2
+          // no bounds test (dpose_core.cpp:181-182): out-of-range patches are zero, see the clip invariant
+          const uint32_t addr = my_coef + (uint32_t)(uy * cols + ux) * kPatchStride;
+          double b00, b10, b01, b11;
+          asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
+          asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(b01), "=d"(b11) : "r"(addr), "n"(kHalfOff));
+          const double fv = fma(b11, ku, b01);  // df/dkv
+          acc.f += fma(kv, fv, fma(b10, ku, b00));
+          if (kJac) {
+            const double fu = fma(b11, kv, b10);  // df/dku
+            acc.su += fu;
+            acc.sv += fv;
+            acc.st = fma(fu, kv, acc.st);  // Sum(fu * kv' - fv * ku'); center terms folded in below
+            acc.st = fma(-fv, ku, acc.st);
           }
         }
       }
@@ -457,9 +485,8 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
         p->d_coef_image = nullptr;
       }
       DPOSE_CUDA(cudaMalloc(&p->d_coef_image, table_bytes << rep_shift));
-      const int n_halves = pg->rows * pg->cols * 2;
-      k_replicate_coef<<<64, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(pg->d_coef),
-                                               reinterpret_cast<uint4 *>(p->d_coef_image), n_halves, rep_shift);
+      k_build_coef_image<<<64, 256, 0, stream>>>(pg->d_coef, reinterpret_cast<double2 *>(p->d_coef_image), pg->rows,
+                                                 pg->cols, rep_shift);
       DPOSE_LAUNCHED();
       DPOSE_CUDA(cudaStreamSynchronize(stream));  // other streams may use the image right after
       p->coef_image_shift = rep_shift;
@@ -486,6 +513,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.out = d_out;
   a.n = n;
   a.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 31u) == 0;
+  a.clip_thr = 0.5f / (float)std::max(pg->win_max, 25);
   const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)slots * 4 * threads;
   const size_t want = (n + threads - 1) / threads;
   const int grid = (int)std::min<size_t>(want, (size_t)sms);
