@@ -336,6 +336,29 @@ def test_batch_border_and_degenerate_poses(dp):
         assert fx.tol_ok(r[0], c, rel=1e-12, abs_=1e-12) and np.all(fx.tol_ok(r[1:], J, rel=1e-10, abs_=1e-10))
 
 
+@pytest.mark.parametrize("name", ["rect_pad2", "star40_pad2", "triangle_pad5"])
+def test_batch_clip_invariant_on_a_fully_lethal_map(dp, name):
+    """The thread-per-pose kernel has no per-cell bounds test: cells outside the kernel must land on zero
+    patches.  Every window cell is lethal here and the angles sit on / next to the thresholds where a strip
+    of the kernel rectangle stops being clipped (|cos| or |sin| ~ 0.5 / window side) — any cell that
+    escaped the table would read garbage and show up against the list kernel (which does test bounds)."""
+    fp, pad = fx.FOOTPRINTS[name]
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+    side = 320
+    full = dp.Costmap(np.full((side, side), fx.LETHAL, np.uint8))
+    yy, xx = np.mgrid[0:side, 0:side]
+    allc = dp.cell_vector_device.upload(np.stack([xx.ravel(), yy.ravel()], 1).astype(np.int32))
+    rng = np.random.default_rng(12)
+    eps = [0.0, 1e-12, 1e-6, 1e-3, 0.005, 0.008, 0.0089, 0.009, 0.0178, 0.0179, 0.018, 0.0199, 0.02, 0.0201, 0.03, 0.05]
+    thetas = [k * math.pi / 2 + sgn * e for k in range(-2, 3) for e in eps for sgn in (-1, 1)]
+    poses = np.array([[rng.uniform(100, 220), rng.uniform(100, 220), th] for th in thetas] +
+                     [[rng.uniform(-10, 330), rng.uniform(-10, 330), rng.uniform(-4, 4)] for _ in range(200)])
+    out = pg.get_cost_batch(full, poses)
+    for p, o in zip(poses, out):
+        c, J = pg.get_cost(p, allc)
+        assert fx.tol_ok(o[0], c, rel=1e-11, abs_=1e-11) and np.all(fx.tol_ok(o[1:], J, rel=1e-9, abs_=1e-8)), p
+
+
 def test_batch_sees_map_updates(dp):
     """the batched kernel reads a derived bit plane: it must follow dpose_map_update and the volatile mode"""
     m = fx.bernoulli_map(300, 200, 0.10, 4)
