@@ -46,7 +46,7 @@ using namespace dpose;
 
 namespace {
 constexpr int kBuf = 3;
-constexpr size_t kChunkPoses = (size_t)1 << 19;
+constexpr size_t kChunkPoses = (size_t)1 << 17;  // 3 MB in / 4 MB out per chunk: short pipeline fill and drain
 
 struct BatchCtx {
   std::mutex mu;
@@ -205,6 +205,7 @@ void dpose_pg_destroy(dpose_pg *pg) {
     cudaFree(pg->d_cost);
     cudaFree(pg->d_coef);
     cudaFree(pg->d_coef_image);
+    cudaFree(pg->d_arena);
     pg_release_batch_ctx(pg);
   }
   delete pg;
@@ -224,6 +225,11 @@ int dpose_pg_table(const dpose_pg *pg, const float **cost, int *rows, int *cols,
 int dpose_pg_stages(const dpose_pg *pg, const int32_t **edt_sq, const uint8_t **outline,
                     const uint8_t **mask, const float **pre_blur) {
   if (!pg) return fail(DPOSE_EINVAL, "pg is NULL");
+  {
+    static std::mutex mu;  // the lazy download mutates the handle
+    std::lock_guard<std::mutex> lock(mu);
+    DPOSE_TRY(precompute_fetch_stages(const_cast<dpose_pg *>(pg)));
+  }
   if (edt_sq) *edt_sq = pg->h_edt_sq.data();
   if (outline) *outline = pg->h_outline.data();
   if (mask) *mask = pg->h_mask.data();
@@ -505,7 +511,8 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
       DPOSE_CUDA(cudaMemcpyAsync(ctx->d_p[b], poses + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, ctx->s_in));
       DPOSE_CUDA(cudaEventRecord(ctx->in_done[b], ctx->s_in));
       DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_done[b], 0));
-      DPOSE_TRY(get_cost_batch_device(pg, map, ctx->d_p[b], m, ctx->d_o[b], want_jacobian, ctx->s_k));
+      // volatile maps: the lethal plane is rebuilt for the first chunk only (once per call)
+      DPOSE_TRY(get_cost_batch_device(pg, map, ctx->d_p[b], m, ctx->d_o[b], want_jacobian, ctx->s_k, it > 0));
       DPOSE_CUDA(cudaEventRecord(ctx->k_done[b], ctx->s_k));
       DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->k_done[b], 0));
       DPOSE_CUDA(cudaMemcpyAsync(out + 4 * off, ctx->d_o[b], sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, ctx->s_out));

@@ -83,6 +83,9 @@ struct dpose_pg {
   std::vector<int32_t> h_edt_sq;
   std::vector<uint8_t> h_outline, h_mask;
   float precompute_us = 0.f;
+  // device arena of the precompute (footprint + intermediate images) and the offsets dpose_pg_stages reads
+  void *d_arena = nullptr;
+  size_t o_outline = 0, o_mask = 0, o_d2 = 0, o_pre = 0;
   // batched kernel geometry: side of the largest window (cells) any pose can touch
   int win_max = 0;
   // replicated, bank-interleaved copy of d_coef for the thread-per-pose kernel (get_cost_batch_tile.cu),
@@ -129,6 +132,7 @@ namespace dpose {
 void pg_release_batch_ctx(dpose_pg *pg);
 // precompute.cu
 int precompute_run(dpose_pg *pg, const int32_t *shifted_fp_xy, int n);
+int precompute_fetch_stages(dpose_pg *pg);
 // lethal.cu
 int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, size_t *n);
 void map_release_lethal_ws(dpose_map *map);
@@ -140,8 +144,11 @@ int get_cost_cells(const dpose_pg *pg, const double se2[3], const int2 *d_cells,
 int get_cost_cells_host(const dpose_pg *pg, const double se2[3], const int32_t *cells_xy, size_t n,
                         double *cost, double *J);
 uint64_t window_bytes_host(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n);
+// hold_planes: do not rebuild the lethal planes of a volatile map (the host-buffer entry point streams the
+// chunks of ONE call through this function and rebuilds for the first chunk only)
 int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses,
-                          size_t n, double *d_out, int want_jacobian, cudaStream_t stream);
+                          size_t n, double *d_out, int want_jacobian, cudaStream_t stream,
+                          bool hold_planes = false);
 void map_release_cache(dpose_map *map);
 // bitplane.cu: (re)build the lethal bit plane on `stream`
 int bitplane_build(const dpose_map *map, cudaStream_t stream);
@@ -149,7 +156,7 @@ int bitplane_build(const dpose_map *map, cudaStream_t stream);
 // when the table does not fit its shared-memory layout (the caller then uses the TMA / generic kernel)
 int tileplane_build(const dpose_map *map, cudaStream_t stream);
 int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
-                        double *d_out, int want_jacobian, cudaStream_t stream, bool *handled);
+                        double *d_out, int want_jacobian, cudaStream_t stream, bool hold_planes, bool *handled);
 // host window geometry shared by the kernel launch code and dpose_pg_window_bytes
 struct WindowRect {
   int x0, y0, x1, y1;  // inclusive cell range, already clipped; empty if x1 < x0

@@ -449,7 +449,7 @@ void map_release_cache(dpose_map *map) {
 }
 
 int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
-                          double *d_out, int want_jacobian, cudaStream_t stream) {
+                          double *d_out, int want_jacobian, cudaStream_t stream, bool hold_planes) {
   if (n == 0) return DPOSE_OK;
   if (pg->device != map->device) return fail(DPOSE_EINVAL, "pose_gradient and map live on different devices");
   DeviceGuard guard(pg->device);
@@ -466,7 +466,7 @@ int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double
   }();
   if (forced == 0 && map->size_x > 0 && map->size_y > 0) {
     bool handled = false;
-    DPOSE_TRY(get_cost_batch_tile(pg, map, d_poses, n, d_out, want_jacobian, stream, &handled));
+    DPOSE_TRY(get_cost_batch_tile(pg, map, d_poses, n, d_out, want_jacobian, stream, hold_planes, &handled));
     if (handled) return DPOSE_OK;
   }
 
@@ -534,7 +534,7 @@ int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double
     dpose_map *m = const_cast<dpose_map *>(map);
     std::lock_guard<std::mutex> lock(g_map_mu);
     if (!m->bits_ready) DPOSE_CUDA(cudaEventCreateWithFlags(&m->bits_ready, cudaEventDisableTiming));
-    if (m->bits_dirty || m->is_volatile) {
+    if (m->bits_dirty || (m->is_volatile && !hold_planes)) {
       DPOSE_TRY(bitplane_build(map, stream));
       DPOSE_CUDA(cudaEventRecord(m->bits_ready, stream));
       m->bits_dirty = false;

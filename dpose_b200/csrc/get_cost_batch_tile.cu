@@ -445,7 +445,7 @@ int tileplane_build(const dpose_map *map, cudaStream_t stream) {
 
 // Returns DPOSE_OK and sets *handled = false if this kernel cannot take the table (shared memory).
 int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n, double *d_out,
-                        int want_jacobian, cudaStream_t stream, bool *handled) {
+                        int want_jacobian, cudaStream_t stream, bool hold_planes, bool *handled) {
   *handled = false;
   if (!map->d_tiles || pg->rows < 4 || pg->cols < 4) return DPOSE_OK;
   int sms = 148, smem_optin = 0;
@@ -492,7 +492,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
       p->coef_image_shift = rep_shift;
     }
     if (!m->tiles_ready) DPOSE_CUDA(cudaEventCreateWithFlags(&m->tiles_ready, cudaEventDisableTiming));
-    if (m->tiles_dirty || m->is_volatile) {
+    if (m->tiles_dirty || (m->is_volatile && !hold_planes)) {
       DPOSE_TRY(tileplane_build(map, stream));
       DPOSE_CUDA(cudaEventRecord(m->tiles_ready, stream));
       m->tiles_dirty = false;

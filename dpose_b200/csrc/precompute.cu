@@ -252,76 +252,75 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
 
 }  // namespace
 
+// One device arena holds the footprint and every intermediate image; it stays with the handle so that
+// dpose_pg_stages can download the intermediates on demand (they are a debugging / parity aid, like the
+// /tmp/*.jpg dumps of the reference's assert-enabled build, dpose_core.cpp:76,85,135).
 int precompute_run(dpose_pg *pg, const int32_t *fp_xy, int n) {
   const int rows = pg->rows, cols = pg->cols;
   const size_t np = (size_t)rows * cols;
-  int2 *d_fp = nullptr;
-  uint8_t *d_outline = nullptr, *d_mask = nullptr;
-  int *d_g = nullptr, *d_d2 = nullptr;
-  float *d_pre = nullptr, *d_tmp = nullptr;
-  long long *d_scratch = nullptr;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t o_fp = 0, o_outline = o_fp + up(sizeof(int2) * n), o_mask = o_outline + up(np),
+               o_g = o_mask + up(np), o_d2 = o_g + up(sizeof(int) * np), o_pre = o_d2 + up(sizeof(int) * np),
+               o_tmp = o_pre + up(sizeof(float) * np), o_scratch = o_tmp + up(sizeof(float) * np),
+               total = o_scratch + up(sizeof(long long) * kWarps * 2 * (size_t)n);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  int rc = DPOSE_OK;
   auto body = [&]() -> int {
-    DPOSE_CUDA(cudaMalloc(&d_fp, sizeof(int2) * n));
-    DPOSE_CUDA(cudaMalloc(&d_outline, np));
-    DPOSE_CUDA(cudaMalloc(&d_mask, np));
-    DPOSE_CUDA(cudaMalloc(&d_g, sizeof(int) * np));
-    DPOSE_CUDA(cudaMalloc(&d_d2, sizeof(int) * np));
-    DPOSE_CUDA(cudaMalloc(&d_pre, sizeof(float) * np));
-    DPOSE_CUDA(cudaMalloc(&d_tmp, sizeof(float) * np));
-    DPOSE_CUDA(cudaMalloc(&d_scratch, sizeof(long long) * kWarps * 2 * (size_t)n));
+    DPOSE_CUDA(cudaMalloc(&pg->d_arena, total));
     DPOSE_CUDA(cudaMalloc(&pg->d_cost, sizeof(float) * np));
     DPOSE_CUDA(cudaMalloc(&pg->d_coef, sizeof(PatchCoef) * np));
-    DPOSE_CUDA(cudaMemcpy(d_fp, fp_xy, sizeof(int2) * n, cudaMemcpyHostToDevice));
+    unsigned char *base = static_cast<unsigned char *>(pg->d_arena);
+    DPOSE_CUDA(cudaMemcpy(base + o_fp, fp_xy, sizeof(int2) * n, cudaMemcpyHostToDevice));
     DPOSE_CUDA(cudaEventCreate(&e0));
     DPOSE_CUDA(cudaEventCreate(&e1));
     PrecomputeArgs a;
-    a.fp = d_fp;
+    a.fp = reinterpret_cast<const int2 *>(base + o_fp);
     a.n = n;
     a.rows = rows;
     a.cols = cols;
-    a.outline = d_outline;
-    a.mask = d_mask;
-    a.g = d_g;
-    a.d2 = d_d2;
-    a.pre = d_pre;
-    a.tmp = d_tmp;
+    a.outline = base + o_outline;
+    a.mask = base + o_mask;
+    a.g = reinterpret_cast<int *>(base + o_g);
+    a.d2 = reinterpret_cast<int *>(base + o_d2);
+    a.pre = reinterpret_cast<float *>(base + o_pre);
+    a.tmp = reinterpret_cast<float *>(base + o_tmp);
     a.cost = pg->d_cost;
     a.coef = pg->d_coef;
-    a.scratch = d_scratch;
+    a.scratch = reinterpret_cast<long long *>(base + o_scratch);
+    pg->o_outline = o_outline, pg->o_mask = o_mask, pg->o_d2 = o_d2, pg->o_pre = o_pre;
     DPOSE_CUDA(cudaEventRecord(e0));
     k_precompute<<<1, kThreads>>>(a);
     DPOSE_LAUNCHED();
     DPOSE_CUDA(cudaEventRecord(e1));
-    DPOSE_CUDA(cudaEventSynchronize(e1));
+    pg->h_cost.resize(np);
+    DPOSE_CUDA(cudaMemcpy(pg->h_cost.data(), pg->d_cost, sizeof(float) * np, cudaMemcpyDeviceToHost));
     float ms = 0.f;
     DPOSE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     pg->precompute_us = ms * 1000.f;
-    pg->h_cost.resize(np);
-    pg->h_pre_blur.resize(np);
-    pg->h_edt_sq.resize(np);
-    pg->h_outline.resize(np);
-    pg->h_mask.resize(np);
-    DPOSE_CUDA(cudaMemcpy(pg->h_cost.data(), pg->d_cost, sizeof(float) * np, cudaMemcpyDeviceToHost));
-    DPOSE_CUDA(cudaMemcpy(pg->h_pre_blur.data(), d_pre, sizeof(float) * np, cudaMemcpyDeviceToHost));
-    DPOSE_CUDA(cudaMemcpy(pg->h_edt_sq.data(), d_d2, sizeof(int) * np, cudaMemcpyDeviceToHost));
-    DPOSE_CUDA(cudaMemcpy(pg->h_outline.data(), d_outline, np, cudaMemcpyDeviceToHost));
-    DPOSE_CUDA(cudaMemcpy(pg->h_mask.data(), d_mask, np, cudaMemcpyDeviceToHost));
     return DPOSE_OK;
   };
-  rc = body();
-  cudaFree(d_fp);
-  cudaFree(d_outline);
-  cudaFree(d_mask);
-  cudaFree(d_g);
-  cudaFree(d_d2);
-  cudaFree(d_pre);
-  cudaFree(d_tmp);
-  cudaFree(d_scratch);
+  const int rc = body();
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   return rc;
+}
+
+// downloads the intermediate images on first request
+int precompute_fetch_stages(dpose_pg *pg) {
+  if (!pg->h_edt_sq.empty() || !pg->d_arena) return DPOSE_OK;
+  const size_t np = (size_t)pg->rows * pg->cols;
+  DeviceGuard guard(pg->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
+  const unsigned char *base = static_cast<const unsigned char *>(pg->d_arena);
+  pg->h_pre_blur.resize(np);
+  pg->h_outline.resize(np);
+  pg->h_mask.resize(np);
+  std::vector<int32_t> d2(np);
+  DPOSE_CUDA(cudaMemcpy(pg->h_pre_blur.data(), base + pg->o_pre, sizeof(float) * np, cudaMemcpyDeviceToHost));
+  DPOSE_CUDA(cudaMemcpy(d2.data(), base + pg->o_d2, sizeof(int) * np, cudaMemcpyDeviceToHost));
+  DPOSE_CUDA(cudaMemcpy(pg->h_outline.data(), base + pg->o_outline, np, cudaMemcpyDeviceToHost));
+  DPOSE_CUDA(cudaMemcpy(pg->h_mask.data(), base + pg->o_mask, np, cudaMemcpyDeviceToHost));
+  pg->h_edt_sq.swap(d2);  // last: h_edt_sq non-empty marks "fetched"
+  return DPOSE_OK;
 }
 
 }  // namespace dpose
