@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libdpose_b200.so")
-SOURCES = ["api.cu", "precompute.cu", "lethal.cu", "get_cost.cu", "get_cost_batch.cu", "get_cost_batch_tile.cu", "bitplane.cu", "problem.cu"]
+SOURCES = ["api.cu", "precompute.cu", "lethal.cu", "get_cost.cu", "get_cost_batch.cu", "get_cost_batch_tile.cu", "bitplane.cu", "problem.cu", "check_footprint.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cost_math.cuh"), os.path.join(HERE, "..", "include", "dpose_b200.h")]
 # problem.cu mirrors scalar host arithmetic of the reference (x*x + y*y, regulariser sums): no FMA contraction there,
 # so the constraint values are bit-identical to a plain x86-64 build of the reference

@@ -362,3 +362,30 @@ class problem:
                 lib().dpose_problem_destroy(self._h)
         except Exception:
             pass
+
+
+def check_footprint(costmap, footprint, cost=254):
+    """dpose_costmap.cpp:460-582: True iff the polygon (cells, closed or open) lies inside the map and covers no
+    cell equal to `cost`.  costmap: Costmap (or a uint8 array, uploaded on the fly)."""
+    own = None
+    if not isinstance(costmap, Costmap):
+        own = costmap = Costmap(costmap)
+    try:
+        fp = _i32(footprint).reshape(-1, 2)
+        ok = C.c_int(0)
+        check(lib().dpose_check_footprint(costmap._h, fp.ctypes.data, fp.shape[0], int(cost), C.byref(ok)))
+        return bool(ok.value)
+    finally:
+        if own is not None:
+            own.close()
+
+
+def check_footprint_batch(costmap, footprint, poses, cost=254):
+    """the plugin's validation step (dpose_goal_tolerance.cpp:386-399) for many candidate poses: footprint (cells,
+    robot frame) transformed by each pose, rounded, checked.  Returns a bool array."""
+    fp = _i32(footprint).reshape(-1, 2)
+    p = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 3))
+    ok = np.zeros(p.shape[0], np.uint8)
+    check(lib().dpose_check_footprint_batch(costmap._h, fp.ctypes.data, fp.shape[0], p.ctypes.data, p.shape[0],
+                                            int(cost), ok.ctypes.data))
+    return ok.astype(bool)

@@ -182,6 +182,20 @@ int dpose_problem_eval_batch(dpose_problem *problem, const double *x, size_t n, 
 int dpose_problem_eval_batch_device(const dpose_problem *problem, const double *d_x, size_t n, double *d_work,
                                     double *d_f, double *d_grad_f, double *d_g, double *d_jac_g, void *stream);
 
+/* ---- check_footprint (validation of solved poses) -----------------------------------------------
+ * replaces check_footprint(map, footprint, cost) (dpose_costmap.cpp:460-582, with is_inside :186-199 and the
+ * x_bresenham iterators :201-317): *ok = 1 iff every vertex is inside the map and no cell covered by the polygon
+ * (outline rays + scan-line interior) equals `cost`.  footprint_xy: n <= 64 vertices in cells, closed or open. */
+int dpose_check_footprint(const dpose_map *map, const int32_t *footprint_xy, int n, uint8_t cost, int *ok);
+/* the plugin's use (dpose_goal_tolerance.cpp:386-399) for n_poses candidates at once: the footprint is
+ * transformed by T(x, y) R(theta) and rounded to cells per pose, then checked.  ok: n_poses bytes (1 = free). */
+int dpose_check_footprint_batch(const dpose_map *map, const int32_t *footprint_xy, int n, const double *poses,
+                                size_t n_poses, uint8_t cost, uint8_t *ok);
+/* device pointers, asynchronous on `stream` */
+int dpose_check_footprint_batch_device(const dpose_map *map, const int32_t *footprint_xy, int n,
+                                       const double *d_poses, size_t n_poses, uint8_t cost, uint8_t *d_ok,
+                                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,10 +5,10 @@
 // exceptions.  lethal_cells_within runs the stream-compaction kernel; raytrace / to_rays /
 // make_footprint are integer host arithmetic (a few dozen cells).
 //
-// NOT provided here: is_inside, bresenham::*, x_bresenham, check_footprint (upstream
-// dpose_costmap.hpp:87-196, dpose_costmap.cpp:186-582).  They validate a solved pose, are not on
-// the cost/Jacobian path and keep compiling from the upstream sources —
-// see INTEGRATION.md.
+// is_inside, x_bresenham and check_footprint (upstream dpose_costmap.hpp:87-196, dpose_costmap.cpp:186-582)
+// validate a solved pose; check_footprint runs on the GPU (one thread per candidate pose, same scan-line
+// algorithm) with a batched overload for multi-start.  The four bresenham::* iterator classes are folded
+// into x_bresenham (same get_x / get_dx / advance_x behaviour).
 #ifndef DPOSE_CORE__DPOSE_COSTMAP__HPP
 #define DPOSE_CORE__DPOSE_COSTMAP__HPP
 
@@ -137,6 +137,114 @@ lethal_cells_within(costmap_2d::Costmap2D& _map, const cell_rectangle& _bounds) 
     c.y() += y0;
   }
   return out;
+}
+
+/// true if every vertex of _footprint lies inside _map (upstream dpose_costmap.cpp:186-199)
+inline bool
+is_inside(const costmap_2d::Costmap2D& _map, const polygon& _footprint) noexcept {
+  const int sx = (int)_map.getSizeInCellsX(), sy = (int)_map.getSizeInCellsY();
+  for (int c = 0; c < (int)_footprint.cols(); ++c)
+    if (_footprint(0, c) < 0 || _footprint(1, c) < 0 || _footprint(0, c) >= sx || _footprint(1, c) >= sy) return false;
+  return true;
+}
+
+/// x-value of a line per scan-line, starting at the end point with the lower y (upstream :201-317: the
+/// x_minor / x_major, ascending / descending Bresenham iterators behind one interface)
+struct x_bresenham {
+  x_bresenham(const cell& _c0, const cell& _c1) noexcept {
+    const int ddx = _c1.x() - _c0.x(), ddy = _c1.y() - _c0.y();
+    const int ax = std::abs(ddx), ay = std::abs(ddy);
+    x_sign = (ddx > 0) - (ddx < 0);
+    den = std::max(ax, ay);
+    add = std::min(ax, ay);
+    num = den / 2;
+    dx = static_cast<double>(ddx) / ddy;
+    const bool up = _c1.y() > _c0.y();
+    kind = ax > ay ? (up ? 2 : 3) : (up ? 0 : 1);
+    x_curr = up ? _c0.x() : _c1.x();
+  }
+
+  inline void
+  advance_x() noexcept {
+    switch (kind) {
+      case 0:  // x-minor, ascending (:226-237)
+        num += add;
+        if (num >= den) num -= den, x_curr += x_sign;
+        break;
+      case 1:  // x-minor, descending (:244-255)
+        num -= add;
+        if (num < 0) num += den, x_curr -= x_sign;
+        break;
+      case 2: {  // x-major, ascending (:264-279)
+        const int step = (den - num) / add;
+        num += step * add, x_curr += step * x_sign;
+        if (num < den) num += add, x_curr += x_sign;
+        num -= den;
+        break;
+      }
+      default: {  // x-major, descending (:286-301)
+        const int step = num / add;
+        num -= step * add, x_curr -= step * x_sign;
+        if (num >= 0) num -= add, x_curr -= x_sign;
+        num += den;
+        break;
+      }
+    }
+  }
+
+  inline const int&
+  get_x() const noexcept {
+    return x_curr;
+  }
+
+  inline const double&
+  get_dx() const noexcept {
+    return dx;
+  }
+
+private:
+  int x_curr, x_sign, den, add, num, kind;
+  double dx;
+};
+
+/// true iff _footprint lies inside the map and covers no cell equal to _cost, on a device-resident costmap
+inline bool
+check_footprint(const device_costmap& _map, const polygon& _footprint, uint8_t _cost) {
+  int ok = 0;
+  detail::check(dpose_check_footprint(_map.handle(), _footprint.data(), (int)_footprint.cols(), _cost, &ok));
+  return ok != 0;
+}
+
+/// upstream signature (dpose_costmap.hpp:194-196, dpose_costmap.cpp:460-582); uploads the bounding window of
+/// the footprint.  The caller is expected to hold the costmap's mutex, as with the reference.
+inline bool
+check_footprint(const costmap_2d::Costmap2D& _map, const polygon& _footprint, uint8_t _cost) {
+  if (!is_inside(_map, _footprint)) return false;
+  const int n = (int)_footprint.cols();
+  if (n == 0) return true;
+  int x0 = _footprint(0, 0), x1 = x0, y0 = _footprint(1, 0), y1 = y0;
+  for (int c = 1; c < n; ++c) {
+    x0 = std::min(x0, _footprint(0, c)), x1 = std::max(x1, _footprint(0, c));
+    y0 = std::min(y0, _footprint(1, c)), y1 = std::max(y1, _footprint(1, c));
+  }
+  polygon local = _footprint;
+  for (int c = 0; c < n; ++c) {
+    local(0, c) -= x0;
+    local(1, c) -= y0;
+  }
+  const device_costmap window(_map.getCharMap() + _map.getIndex((unsigned)x0, (unsigned)y0), (uint32_t)(x1 - x0 + 1),
+                              (uint32_t)(y1 - y0 + 1), (size_t)_map.getSizeInCellsX());
+  return check_footprint(window, local, _cost);
+}
+
+/// NEW: the plugin's validation step (dpose_goal_tolerance.cpp:386-399) for many candidate poses at once:
+/// _footprint (cells, robot frame) is transformed by every pose (x, y, theta), rounded and checked.
+inline std::vector<uint8_t>
+check_footprint(const device_costmap& _map, const polygon& _footprint, const double* _poses, size_t _n, uint8_t _cost) {
+  std::vector<uint8_t> ok(_n);
+  detail::check(dpose_check_footprint_batch(_map.handle(), _footprint.data(), (int)_footprint.cols(), _poses, _n, _cost,
+                                            ok.data()));
+  return ok;
 }
 
 }  // namespace dpose_core

@@ -22,6 +22,11 @@ class _CostData(C.Structure):
     ]
 
 
+class _XB(C.Structure):
+    _fields_ = [("x_curr", C.c_int), ("x_sign", C.c_int), ("den", C.c_int), ("add", C.c_int), ("num", C.c_int),
+                ("dx", C.c_double), ("kind", C.c_int)]
+
+
 class _GtConfig(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("lin_tolerance", "rot_tolerance", "weight_goal_lin", "weight_goal_rot",
                                           "weight_start_lin", "weight_start_rot")]
@@ -70,6 +75,12 @@ def lib():
         L.oracle_get_cost_batch_truth.argtypes = [C.POINTER(_CostData), C.c_void_p, C.c_uint32, C.c_uint32,
                                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_is_inside.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
+        L.oracle_xb_init.argtypes = [C.POINTER(_XB), C.c_void_p, C.c_void_p]
+        L.oracle_xb_advance.argtypes = [C.POINTER(_XB)]
+        L.oracle_check_footprint.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_uint8]
+        L.oracle_check_footprint_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p,
+                                                   C.c_size_t, C.c_uint8, C.c_void_p, C.c_int]
         L.oracle_normalize_angle.restype = C.c_double
         L.oracle_normalize_angle.argtypes = [C.c_double]
         L.oracle_problem_init.argtypes = [C.POINTER(_CostData), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
@@ -244,3 +255,42 @@ class Problem:
                 lib().oracle_problem_free(C.byref(self._p))
         except Exception:
             pass
+
+
+def is_inside(size_x, size_y, footprint):
+    fp = _i32(footprint).reshape(-1, 2)
+    return bool(lib().oracle_is_inside(int(size_x), int(size_y), fp.ctypes.data, fp.shape[0]))
+
+
+class XBresenham:
+    """x_bresenham (dpose_costmap.cpp:303-317)"""
+
+    def __init__(self, c0, c1):
+        self._b = _XB()
+        a, b = _i32(c0), _i32(c1)
+        lib().oracle_xb_init(C.byref(self._b), a.ctypes.data, b.ctypes.data)
+
+    def get_x(self):
+        return int(self._b.x_curr)
+
+    def get_dx(self):
+        return float(self._b.dx)
+
+    def advance_x(self):
+        lib().oracle_xb_advance(C.byref(self._b))
+
+
+def check_footprint(costmap, footprint, cost=254):
+    m = np.ascontiguousarray(np.asarray(costmap, dtype=np.uint8))
+    fp = _i32(footprint).reshape(-1, 2)
+    return bool(lib().oracle_check_footprint(m.ctypes.data, m.shape[1], m.shape[0], fp.ctypes.data, fp.shape[0], int(cost)))
+
+
+def check_footprint_batch(costmap, footprint, poses, cost=254, nthreads=1):
+    m = np.ascontiguousarray(np.asarray(costmap, dtype=np.uint8))
+    fp = _i32(footprint).reshape(-1, 2)
+    p = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 3))
+    ok = np.zeros(p.shape[0], np.uint8)
+    lib().oracle_check_footprint_batch(m.ctypes.data, m.shape[1], m.shape[0], fp.ctypes.data, fp.shape[0], p.ctypes.data,
+                                       p.shape[0], int(cost), ok.ctypes.data, int(nthreads))
+    return ok.astype(bool)

@@ -772,3 +772,243 @@ void oracle_problem_eval_batch(const oracle_cost_data *cd, const oracle_problem 
                         jac_g ? jac_g + 3 * i : NULL);
   (void)nthreads;
 }
+
+
+/* ------------------------------------------------------------------------- */
+/* check_footprint — dpose_costmap.cpp:186-582                                */
+/* ------------------------------------------------------------------------- */
+int oracle_is_inside(uint32_t size_x, uint32_t size_y, const int32_t *fp, int n) { /* :186-199 */
+  for (int i = 0; i < n; ++i)
+    if (fp[2 * i] < 0 || fp[2 * i + 1] < 0 || fp[2 * i] >= (int)size_x || fp[2 * i + 1] >= (int)size_y) return 0;
+  return 1;
+}
+
+/* base_iterator (:203-219) */
+static void xb_base(oracle_xb *b, const int32_t begin[2], const int32_t end[2]) {
+  const int ddx = end[0] - begin[0], ddy = end[1] - begin[1];
+  const int ax = abs(ddx), ay = abs(ddy);
+  b->x_sign = (ddx > 0) - (ddx < 0);
+  b->den = ax > ay ? ax : ay;
+  b->add = ax < ay ? ax : ay;
+  b->num = b->den / 2;
+  b->dx = (double)ddx / ddy;
+}
+
+void oracle_xb_init(oracle_xb *b, const int32_t c0[2], const int32_t c1[2]) { /* :303-317 */
+  const int ax = abs(c1[0] - c0[0]), ay = abs(c1[1] - c0[1]);
+  if (ax > ay) {
+    if (c1[1] > c0[1]) { /* x_major_ascending(c0, c1) :259-262 */
+      b->kind = 2;
+      xb_base(b, c0, c1);
+      b->x_curr = c0[0];
+    } else { /* x_major_descending(begin = c1, end = c0): base_iterator(end, begin) :281-284 */
+      b->kind = 3;
+      xb_base(b, c0, c1);
+      b->x_curr = c1[0];
+    }
+  } else {
+    if (c1[1] > c0[1]) { /* x_minor_ascending(c0, c1) :221-224 */
+      b->kind = 0;
+      xb_base(b, c0, c1);
+      b->x_curr = c0[0];
+    } else { /* x_minor_descending(begin = c1, end = c0): base_iterator(end, begin) :239-242 */
+      b->kind = 1;
+      xb_base(b, c0, c1);
+      b->x_curr = c1[0];
+    }
+  }
+}
+
+void oracle_xb_advance(oracle_xb *b) {
+  switch (b->kind) {
+    case 0: /* :226-237 */
+      b->num += b->add;
+      if (b->num >= b->den) {
+        b->num -= b->den;
+        b->x_curr += b->x_sign;
+      }
+      break;
+    case 1: /* :244-255 */
+      b->num -= b->add;
+      if (b->num < 0) {
+        b->num += b->den;
+        b->x_curr -= b->x_sign;
+      }
+      break;
+    case 2: { /* :264-279 */
+      const int diff = b->den - b->num, step = diff / b->add;
+      b->num += step * b->add;
+      b->x_curr += step * b->x_sign;
+      if (b->num < b->den) {
+        b->num += b->add;
+        b->x_curr += b->x_sign;
+      }
+      b->num -= b->den;
+      break;
+    }
+    default: { /* :286-301 */
+      const int step = b->num / b->add;
+      b->num -= step * b->add;
+      b->x_curr -= step * b->x_sign;
+      if (b->num >= 0) {
+        b->num -= b->add;
+        b->x_curr -= b->x_sign;
+      }
+      b->num += b->den;
+      break;
+    }
+  }
+}
+
+typedef struct {
+  oracle_xb xb;
+  int lower_y; /* line::lower.y (:320-325): y of the edge's FIRST vertex as given */
+  int active;
+} cf_line;
+
+static int ray_is_good(const uint8_t *map, uint32_t size_x, const int32_t a[2], const int32_t b[2], uint8_t cost) {
+  const int dx = abs(b[0] - a[0]), dy = abs(b[1] - a[1]);
+  const size_t cap = (size_t)(dx > dy ? dx : dy);
+  if (cap == 0) return 1;
+  int32_t *cells = (int32_t *)malloc(sizeof(int32_t) * 2 * cap);
+  const size_t k = oracle_raytrace(a, b, cells);
+  int good = 1;
+  for (size_t i = 0; i < k && good; ++i)
+    if (map[(size_t)cells[2 * i + 1] * size_x + cells[2 * i]] == cost) good = 0;
+  free(cells);
+  return good;
+}
+
+int oracle_check_footprint(const uint8_t *map, uint32_t size_x, uint32_t size_y, const int32_t *fp, int n,
+                           uint8_t cost) {
+  if (!oracle_is_inside(size_x, size_y, fp, n)) return 0; /* :464-465 */
+  if (n < 3) {                                            /* check_without_area :392-422 */
+    if (n == 0) return 1;
+    if (n == 1) return map[(size_t)fp[1] * size_x + fp[0]] != cost;
+    return ray_is_good(map, size_x, fp, fp + 2, cost);
+  }
+  /* check_outline :432-458 */
+  for (int i = 1; i < n; ++i)
+    if (!ray_is_good(map, size_x, fp + 2 * (i - 1), fp + 2 * i, cost)) return 0;
+  const int is_closed = fp[2 * (n - 1)] == fp[0] && fp[2 * (n - 1) + 1] == fp[1];
+  if (!is_closed && !ray_is_good(map, size_x, fp + 2 * (n - 1), fp, cost)) return 0;
+
+  /* edges, horizontal ones skipped (:487-496) */
+  cf_line *lines = (cf_line *)malloc(sizeof(cf_line) * (size_t)(n + 1));
+  int nl = 0;
+  for (int c = 1; c < n; ++c)
+    if (fp[2 * (c - 1) + 1] != fp[2 * c + 1]) {
+      oracle_xb_init(&lines[nl].xb, fp + 2 * (c - 1), fp + 2 * c);
+      lines[nl].lower_y = fp[2 * (c - 1) + 1];
+      lines[nl].active = 0;
+      ++nl;
+    }
+  if (!is_closed && fp[2 * (n - 1) + 1] != fp[1]) {
+    oracle_xb_init(&lines[nl].xb, fp + 2 * (n - 1), fp);
+    lines[nl].lower_y = fp[2 * (n - 1) + 1];
+    lines[nl].active = 0;
+    ++nl;
+  }
+  if (nl == 0) { /* degenerate: every edge horizontal; upstream would dereference lines.front() — treat as outline only */
+    free(lines);
+    return 1;
+  }
+  /* vertex_set (:503-510): multimap keyed by y, equal keys in insertion order */
+  int *vy = (int *)malloc(sizeof(int) * (size_t)nl), *vl = (int *)malloc(sizeof(int) * (size_t)nl),
+      *vr = (int *)malloc(sizeof(int) * (size_t)nl), *order = (int *)malloc(sizeof(int) * (size_t)nl);
+  int nv = 0;
+  for (int l = 0; l + 1 < nl; ++l) {
+    vy[nv] = lines[l + 1].lower_y;
+    vl[nv] = l;
+    vr[nv] = l + 1;
+    ++nv;
+  }
+  vy[nv] = lines[0].lower_y;
+  vl[nv] = nl - 1;
+  vr[nv] = 0;
+  ++nv;
+  for (int i = 0; i < nv; ++i) order[i] = i;
+  for (int i = 1; i < nv; ++i) { /* stable insertion sort by y */
+    const int o = order[i];
+    int j = i - 1;
+    while (j >= 0 && vy[order[j]] > vy[o]) {
+      order[j + 1] = order[j];
+      --j;
+    }
+    order[j + 1] = o;
+  }
+  int *active = (int *)malloc(sizeof(int) * (size_t)nl), na = 0;
+  int ymin = fp[1];
+  for (int i = 1; i < n; ++i) ymin = fp[2 * i + 1] < ymin ? fp[2 * i + 1] : ymin;
+  int yy = ymin - 1; /* :519 */
+  int result = 1;
+  for (int v = 0; v < nv && result;) {
+    for (; yy < vy[order[v]] && result; ++yy) { /* :549-556 */
+      /* check_line (:349-378): pairwise sweep between the active lines */
+      for (int a = 0; a + 1 < na && result; a += 2) {
+        const int lx = lines[active[a]].xb.x_curr + 1, rx = lines[active[a + 1]].xb.x_curr;
+        for (int x = lx; x < rx; ++x)
+          if (map[(size_t)yy * size_x + x] == cost) {
+            result = 0;
+            break;
+          }
+      }
+      for (int a = 0; a < na; ++a) oracle_xb_advance(&lines[active[a]].xb);
+    }
+    if (!result) break;
+    for (; v < nv && vy[order[v]] == yy; ++v) { /* :562-581 */
+      const int pair[2] = {vl[order[v]], vr[order[v]]};
+      for (int k = 0; k < 2; ++k) {
+        const int l = pair[k];
+        if (lines[l].active) {
+          int pos = 0;
+          while (pos < na && active[pos] != l) ++pos;
+          if (pos < na) { /* swap and pop */
+            active[pos] = active[na - 1];
+            --na;
+          }
+        } else {
+          lines[l].active = 1;
+          active[na++] = l;
+        }
+      }
+    }
+    /* std::sort(active, lines_compare) :583 — by x, then dx; insertion sort (stable) for determinism */
+    for (int i = 1; i < na; ++i) {
+      const int o = active[i];
+      int j = i - 1;
+      while (j >= 0 && (lines[active[j]].xb.x_curr > lines[o].xb.x_curr ||
+                        (lines[active[j]].xb.x_curr == lines[o].xb.x_curr && lines[active[j]].xb.dx > lines[o].xb.dx))) {
+        active[j + 1] = active[j];
+        --j;
+      }
+      active[j + 1] = o;
+    }
+  }
+  free(lines);
+  free(vy);
+  free(vl);
+  free(vr);
+  free(order);
+  free(active);
+  return result;
+}
+
+void oracle_check_footprint_batch(const uint8_t *map, uint32_t size_x, uint32_t size_y, const int32_t *fp, int n,
+                                  const double *poses, size_t n_poses, uint8_t cost, uint8_t *ok, int nthreads) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 1 ? nthreads : 1)
+#endif
+  for (long long i = 0; i < (long long)n_poses; ++i) {
+    int32_t *t = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(n > 0 ? n : 1));
+    const double c = cos(poses[3 * i + 2]), s = sin(poses[3 * i + 2]);
+    for (int k = 0; k < n; ++k) { /* dpose_goal_tolerance.cpp:388-392 */
+      const double x = fp[2 * k], y = fp[2 * k + 1];
+      t[2 * k] = (int32_t)round((c * x + -s * y) + poses[3 * i]);
+      t[2 * k + 1] = (int32_t)round((s * x + c * y) + poses[3 * i + 1]);
+    }
+    ok[i] = (uint8_t)oracle_check_footprint(map, size_x, size_y, t, n, cost);
+    free(t);
+  }
+  (void)nthreads;
+}

@@ -134,6 +134,28 @@ void oracle_problem_eval(const oracle_cost_data *cd, const oracle_problem *p, co
 void oracle_problem_eval_batch(const oracle_cost_data *cd, const oracle_problem *p, const double *x, size_t n,
                                double *f, double *grad_f, double *g, double *jac_g, int nthreads);
 
+/* ---- check_footprint: dpose_costmap.cpp:186-582 ------------------------------------ */
+/* is_inside (:186-199): 1 if every vertex lies inside the map */
+int oracle_is_inside(uint32_t size_x, uint32_t size_y, const int32_t *fp_xy, int n);
+
+/* x_bresenham (:201-317): x of a line per scan-line, starting at the vertex with the lower y */
+typedef struct {
+  int x_curr, x_sign, den, add, num;
+  double dx;
+  int kind; /* 0 x_minor_ascending, 1 x_minor_descending, 2 x_major_ascending, 3 x_major_descending */
+} oracle_xb;
+void oracle_xb_init(oracle_xb *b, const int32_t c0[2], const int32_t c1[2]);
+void oracle_xb_advance(oracle_xb *b);
+
+/* check_footprint (:460-582): 1 if no cell covered by the polygon (outline + scan-line interior) holds
+ * `cost`; 0 otherwise or if a vertex is outside the map.  fp_xy: vertices in cells (closed or open). */
+int oracle_check_footprint(const uint8_t *map, uint32_t size_x, uint32_t size_y, const int32_t *fp_xy, int n,
+                           uint8_t cost);
+/* the plugin's use (dpose_goal_tolerance.cpp:386-395): footprint transformed by T(x, y) R(theta), rounded
+ * (Eigen round = std::round), then check_footprint.  ok: n_poses bytes. */
+void oracle_check_footprint_batch(const uint8_t *map, uint32_t size_x, uint32_t size_y, const int32_t *fp_xy, int n,
+                                  const double *poses, size_t n_poses, uint8_t cost, uint8_t *ok, int nthreads);
+
 /* number of OpenMP threads available (1 if built without OpenMP) */
 int oracle_max_threads(void);
 

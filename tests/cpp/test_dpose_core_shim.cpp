@@ -99,6 +99,32 @@ test_host() {
   const cell_rays rays = to_rays(to_rectangle(6, 3));
   CHECK(rays.size() == 4);
   for (const auto& kv : rays) CHECK(kv.second.min == 0 && kv.second.max == 6);
+  // x_bresenham follows raytrace row by row (check_footprint.cpp:92-146) and starts at the lower end (:148-160)
+  for (int k = 1; k < 14; ++k) {
+    const double ang = 0.1 * k;
+    const cell zero(0, 0), end((int)(std::cos(ang) * 100), (int)(std::sin(ang) * 100));
+    x_bresenham br(zero, end);
+    int curr_y = -1;
+    for (const auto& pt : raytrace(zero, end))
+      if (pt.y() != curr_y) {
+        CHECK(pt.x() == br.get_x());
+        br.advance_x();
+        curr_y = pt.y();
+      }
+  }
+  CHECK(x_bresenham(cell(0, 0), cell(10, 12)).get_x() == x_bresenham(cell(10, 12), cell(0, 0)).get_x());
+  {  // is_inside (check_footprint.cpp:23-88)
+    costmap_2d::Costmap2D cm(30, 40, 0.1, 0, 0);
+    CHECK(is_inside(cm, polygon()));
+    polygon fit = make_polygon({{0, 0}, {29, 0}, {29, 39}, {0, 39}});
+    CHECK(is_inside(cm, fit));
+    const int pert[8][2] = {{0, -1}, {1, -1}, {2, 1}, {3, -1}, {4, 1}, {5, 1}, {6, -1}, {7, 1}};
+    for (const auto& pp : pert) {
+      polygon moved = fit;
+      moved(pp[0] % 2, pp[0] / 2) += pp[1];
+      CHECK(!is_inside(cm, moved));
+    }
+  }
   // default-constructed objects are inert
   pose_gradient empty;
   CHECK(throws_runtime_error([&] { cell_vector c; empty.get_cost({0, 0, 0}, c.cbegin(), c.cend(), nullptr); }, "not initialised"));
@@ -248,6 +274,35 @@ test_lethal() {
   }
 }
 
+// ---- check_footprint (check_footprint.cpp:162-212): regression against the ROS outline / convex fill ------------------
+static void
+test_check_footprint() {
+  const polygon square = make_polygon({{10, -10}, {10, 8}, {-12, 9}, {-5, -7}});  // :137-147
+  for (int k = 0; k < 63; k += 3) {
+    const double ang = 0.1 * k, c = std::cos(ang), s = std::sin(ang);
+    polygon fp(2, 4);
+    cell_rectangle ring;
+    for (int i = 0; i < 4; ++i) {
+      fp(0, i) = (int)std::round(50 + c * square(0, i) - s * square(1, i));
+      fp(1, i) = (int)std::round(50 + s * square(0, i) + c * square(1, i));
+      ring(0, i) = fp(0, i), ring(1, i) = fp(1, i);
+    }
+    ring(0, 4) = fp(0, 0), ring(1, 4) = fp(1, 0);
+    const auto area = convex_fill_cells_ros(ring);
+    costmap_2d::Costmap2D cm(100, 100, 0.1, 0, 0, costmap_2d::LETHAL_OBSTACLE);
+    for (const auto& xy : area) cm.setCost(xy.first, xy.second, costmap_2d::FREE_SPACE);
+    CHECK(check_footprint(cm, fp, costmap_2d::LETHAL_OBSTACLE));
+    int i = 0;
+    for (int e = 0; e < 4; ++e)
+      for (const auto& oc : raytrace(cell(ring(0, e), ring(1, e)), cell(ring(0, e + 1), ring(1, e + 1))))
+        if (i++ % 7 == 0) {
+          cm.setCost(oc.x(), oc.y(), costmap_2d::LETHAL_OBSTACLE);
+          CHECK(!check_footprint(cm, fp, costmap_2d::LETHAL_OBSTACLE));
+          cm.setCost(oc.x(), oc.y(), costmap_2d::FREE_SPACE);
+        }
+  }
+}
+
 // ---- batched get_cost == lethal_cells_within + get_cost per pose --------------------------------------------------------
 static void
 test_batch() {
@@ -297,6 +352,7 @@ main(int argc, char** argv) {
     test_cost_data();
     test_jacobian();
     test_lethal();
+    test_check_footprint();
     test_batch();
   } else {
     // without a device the constructors must fail loudly, not fall back to a CPU path

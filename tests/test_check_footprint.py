@@ -1,0 +1,174 @@
+"""check_footprint: the oracle restatement against the reference's own tests
+(dpose_core/test/check_footprint.cpp) and a brute-force even-odd/outline check; the batched GPU version against
+the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+import fixtures as fx
+from oracle import capi
+
+# test cpp:137-147 (Eigen comma init fills row-wise: first all x, then all y)
+SQUARE = np.array(list(zip([10, 10, -12, -5], [-10, 8, 9, -7])), dtype=np.int32)
+HAND = np.array(list(zip([20, 20, 10, 10, 30, 30, 11, 11, 32, 32, 11, 11, 31, 31, 5, 10, 9, -5, -6],
+                         [12, 11, 10, 8, 8, 6, 6, 3, 2, -1, -2, -4, -5, -7, -6, -10, -11, -6, 9])), dtype=np.int32)
+
+
+def transformed(fp, x, y, th):
+    c, s = math.cos(th), math.sin(th)
+    f = np.asarray(fp, np.float64)
+    return np.stack([fx.round_half_away((c * f[:, 0] + -s * f[:, 1]) + x), fx.round_half_away((s * f[:, 0] + c * f[:, 1]) + y)], 1)
+
+
+def ros_outline(poly):
+    """costmap_2d::Costmap2D::polygonOutlineCells restated: raytraceLine along every edge incl. the closing one"""
+    cells = []
+    n = len(poly)
+    for i in range(n):
+        a, b = poly[i], poly[(i + 1) % n]
+        cells += [tuple(c) for c in capi.raytrace(a, b).tolist()]
+        cells.append((int(b[0]), int(b[1])))  # ROS' raytraceLine marks the end cell too
+    return cells
+
+
+def ros_convex_fill(outline):
+    """convexFillCells restated: per x column, fill between the smallest and largest outline y"""
+    cols = {}
+    for x, y in outline:
+        lo, hi = cols.get(x, (y, y))
+        cols[x] = (min(lo, y), max(hi, y))
+    return {(x, y) for x, (lo, hi) in cols.items() for y in range(lo, hi + 1)}
+
+
+# ---- is_inside (test cpp:23-88) ---------------------------------------------------------------------------
+def test_is_inside():
+    assert capi.is_inside(30, 40, np.empty((0, 2), np.int32))
+    fit = np.array([[0, 0], [29, 0], [29, 39], [0, 39]], np.int32)
+    assert capi.is_inside(30, 40, fit)
+    # Eigen linear (column-major) index into the 2 x 4 matrix: index k -> vertex k // 2, coordinate k % 2
+    for idx, off in [(0, -1), (1, -1), (2, 1), (3, -1), (4, 1), (5, 1), (6, -1), (7, 1)]:
+        p = fit.copy()
+        p[idx // 2, idx % 2] += off
+        assert not capi.is_inside(30, 40, p)
+
+
+# ---- x_bresenham (test cpp:92-160) ----------------------------------------------------------------------------
+@pytest.mark.parametrize("angle", [round(0.1 * k, 1) for k in range(1, 14)])
+def test_x_bresenham_follows_raytrace(angle):
+    end = np.array([int(math.cos(angle) * 100), int(math.sin(angle) * 100)])  # Eigen << double -> int truncates
+    assert end[1] > 0
+    br = capi.XBresenham([0, 0], end)
+    curr_y = -1
+    for x, y in capi.raytrace([0, 0], end).tolist():
+        if y != curr_y:
+            assert x == br.get_x()
+            br.advance_x()
+            curr_y = y
+
+
+def test_x_bresenham_order_invariance():
+    assert capi.XBresenham([0, 0], [10, 12]).get_x() == capi.XBresenham([10, 12], [0, 0]).get_x()
+
+
+# ---- check_footprint (test cpp:162-212) --------------------------------------------------------------------------
+@pytest.mark.parametrize("yaw", [round(0.1 * k, 1) for k in range(0, 63)])
+def test_check_footprint_regression_vs_ros_fill(yaw):
+    fp = transformed(SQUARE, 50, 50, yaw)
+    outline = ros_outline(fp)
+    area = ros_convex_fill(outline)
+    assert area
+    m = np.full((100, 100), fx.LETHAL, np.uint8)
+    for x, y in area:
+        m[y, x] = 0
+    assert capi.check_footprint(m, fp)
+    for x, y in set(outline):
+        m[y, x] = fx.LETHAL
+        assert not capi.check_footprint(m, fp), (x, y)
+        m[y, x] = 0
+
+
+def test_check_footprint_small_and_outside():
+    m = np.zeros((20, 30), np.uint8)
+    m[5, 7] = fx.LETHAL
+    assert capi.check_footprint(m, np.empty((0, 2), np.int32))          # empty footprint (:402-404)
+    assert capi.check_footprint(m, [[3, 3]]) and not capi.check_footprint(m, [[7, 5]])  # point (:406-408)
+    assert not capi.check_footprint(m, [[5, 5], [10, 5]]) and capi.check_footprint(m, [[5, 6], [10, 6]])  # line
+    assert not capi.check_footprint(m, [[0, 0], [30, 0], [5, 5]])       # vertex outside the map (:464-465)
+    assert capi.check_footprint(m, [[0, 0], [6, 0], [6, 4], [0, 4]])    # clear rectangle
+    assert not capi.check_footprint(m, [[2, 2], [12, 2], [12, 9], [2, 9]])  # lethal cell strictly inside
+    assert not capi.check_footprint(m, [[2, 2], [12, 2], [12, 9], [2, 9], [2, 2]])  # same, closed
+
+
+@pytest.mark.parametrize("name", ["hand", "star40", "lshape"])
+def test_check_footprint_non_convex_interior(name):
+    """every cell strictly inside the polygon (even-odd, by exact point-in-polygon on cell centres) and off the
+    outline must be seen; cells far outside must not"""
+    fp = {"hand": HAND, "star40": fx.star40(), "lshape": fx.cells_m(fx.LSHAPE_M, 0.05)}[name]
+    rng = np.random.default_rng(2)
+    for th in rng.uniform(-math.pi, math.pi, 6):
+        poly = transformed(fp, 60, 60, th)
+        free = np.zeros((120, 120), np.uint8)
+        assert capi.check_footprint(free, poly)
+        outline = set(ros_outline(poly))
+        xs, ys = poly[:, 0].astype(float), poly[:, 1].astype(float)
+        n = len(poly)
+        for _ in range(60):
+            x, y = int(rng.integers(0, 120)), int(rng.integers(0, 120))
+            m = free.copy()
+            m[y, x] = fx.LETHAL
+            got = capi.check_footprint(m, poly)
+            if (x, y) in outline:
+                assert not got
+                continue
+            inside = False  # crossing number on the cell centre
+            for i in range(n):
+                j = (i + 1) % n
+                if (ys[i] > y) != (ys[j] > y) and x < (xs[j] - xs[i]) * (y - ys[i]) / (ys[j] - ys[i]) + xs[i]:
+                    inside = not inside
+            # cells within one cell of the outline are discretisation-dependent: only assert the clear cases
+            near = any(abs(x - ox) <= 1 and abs(y - oy) <= 1 for ox, oy in outline)
+            if not near:
+                assert got == (not inside), (x, y, inside)
+
+
+# ---- GPU ----------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def dp():
+    import dpose_b200 as dp
+    if dp.device_count() == 0:
+        pytest.skip("no CUDA device")
+    return dp
+
+
+@pytest.mark.gpu
+def test_gpu_check_footprint_reference_regression(dp):  # test cpp:162-212 on the GPU path
+    for yaw in [round(0.1 * k, 1) for k in range(0, 63, 4)]:
+        fp = transformed(SQUARE, 50, 50, yaw)
+        outline = ros_outline(fp)
+        m = np.full((100, 100), fx.LETHAL, np.uint8)
+        for x, y in ros_convex_fill(outline):
+            m[y, x] = 0
+        assert dp.check_footprint(m, fp)
+        for x, y in list(set(outline))[::5]:
+            m[y, x] = fx.LETHAL
+            assert not dp.check_footprint(m, fp), (x, y)
+            m[y, x] = 0
+    m = np.zeros((20, 30), np.uint8)
+    m[5, 7] = fx.LETHAL
+    for fp in ([], [[3, 3]], [[7, 5]], [[5, 5], [10, 5]], [[5, 6], [10, 6]], [[0, 0], [30, 0], [5, 5]],
+               [[0, 0], [6, 0], [6, 4], [0, 4]], [[2, 2], [12, 2], [12, 9], [2, 9]], [[2, 2], [12, 2], [12, 9], [2, 9], [2, 2]]):
+        fp = np.array(fp, np.int32).reshape(-1, 2)
+        assert dp.check_footprint(m, fp) == capi.check_footprint(m, fp), fp.tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,density", [("rect", 0.002), ("hand", 0.001), ("star40", 0.002), ("lshape", 0.004), ("square", 0.01)])
+def test_gpu_check_footprint_batch_vs_oracle(dp, name, density):
+    fp = {"rect": fx.RECT, "hand": HAND, "star40": fx.star40(), "lshape": fx.cells_m(fx.LSHAPE_M, 0.05), "square": SQUARE}[name]
+    m = fx.bernoulli_map(600, 500, density, 21)
+    poses = fx.random_poses(20000, 600, 500, 22, margin=-20.0)  # some candidates stick out of the map
+    got = dp.check_footprint_batch(dp.Costmap(m), fp, poses)
+    want = capi.check_footprint_batch(m, fp, poses, nthreads=capi.max_threads())
+    assert 0.02 < want.mean() < 0.98  # the case is not trivial either way
+    assert np.array_equal(got, want), int((got != want).sum())
