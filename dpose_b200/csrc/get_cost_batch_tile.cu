@@ -173,6 +173,12 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 
 // DPOSE_TILE_CVT: how the walk turns a bit / row index into a double.
 //   0: 2^52 trick (one DADD on the FP64 pipe + register-pair set-up), 1: I2F.F64 (conversion pipe)
+// DPOSE_TILE_COMPACT 1 stores only the rows that can belong to a chunk (less shared memory, room for 8
+// coefficient replicas at 1024 threads).  Measured on B200: the store predicates cost 7 %, the conflict-free
+// gathers win back 3 % -> off by default (profiles/r1_v13_ab.txt).
+#ifndef DPOSE_TILE_COMPACT
+#define DPOSE_TILE_COMPACT 0
+#endif
 #ifndef DPOSE_TILE_CVT
 #define DPOSE_TILE_CVT 1
 #endif
@@ -184,9 +190,10 @@ __device__ __forceinline__ double index_to_double(int x) {
 #endif
 }
 
-// kRepShift: log2 of the coefficient replicas; kSlots: row slots scanned per chunk (a chunk's rows start
-// at slot (y & 7) of its first tile row, so kSlots >= min(32, largest window height) + 7)
-template <bool kJac, int kThreads, int kRepShift, int kSlots>
+// kRepShift: log2 of the coefficient replicas; kRows: rows of a chunk (>= min(32, largest window height)).  A
+// chunk's rows start at slot (y & 7) of its first tile row, so kRows + 7 row slots are scanned; only the
+// kRows that can belong to the chunk are stored.
+template <bool kJac, int kThreads, int kRepShift, int kRows>
 __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long s_bar;
@@ -223,7 +230,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     if (!ok) __trap();
   }
 
-  uint32_t *s_slot = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + tid;  // [slot * kThreads]
+  constexpr int kSlots = kRows + 7;
+  // DPOSE_TILE_COMPACT 1: only the kRows rows that can belong to a chunk are stored (less shared memory, room
+  // for 8 coefficient replicas at 1024 threads); 0: every scanned slot is stored (no store predicates)
+  constexpr int kStored = DPOSE_TILE_COMPACT ? kRows : kSlots;
+  uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + tid;  // [row * kThreads], row < kStored
   constexpr uint32_t kPatchStride = 32u << kRepShift, kHalfOff = 16u << kRepShift;
   const int cols = a.g.cols;
   // Kernel coordinates are carried as k' = k + 0.5 - 2 = k - 1.5: floor(k') = k_upper - 2 (k_upper = round(k),
@@ -291,6 +302,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const float l2c = fmaf(fr0, d2, l2) - fcb, h2c = fmaf(fr0, d2, h2) - fcb;
           const float wmax = (float)(wc - 1);
           unsigned sm_lo = 0u, sm_hi = 0u;  // non-empty slots
+          // slot j holds chunk row j - off; rows outside [0, kRows) are not stored (slots 7 .. kRows - 1 always are)
+          uint32_t *s_slot = DPOSE_TILE_COMPACT ? s_mask - off * kThreads : s_mask;
           // with 1024 threads (64 registers) the next tile row is not prefetched: the extra warps hide the latency
           constexpr bool kPrefetch = kThreads < 1024;
           Tile8 A, B, An, Bn;
@@ -324,7 +337,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
                   const int xhi = __float_as_int(__fadd_rd(hi, 12582912.0f)) - 0x4B400000;  // <= 31
                   unsigned m = __funnelshift_r(A.w[r], B.w[r], sh);
                   m &= shl_clamp(0xffffffffu, (unsigned)xlo) & shr_clamp(0xffffffffu, (unsigned)(31 - xhi));
-                  s_slot[j * kThreads] = m;
+                  if (!DPOSE_TILE_COMPACT || (j >= 7 && j < kRows))
+                    s_slot[j * kThreads] = m;
+                  else if ((unsigned)(j - off) < (unsigned)kRows)
+                    s_slot[j * kThreads] = m;
                   if (m) {
                     if (j < 32)
                       sm_lo |= 1u << (j & 31);
@@ -343,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           rowmask = __funnelshift_r(sm_lo, sm_hi, (unsigned)off) & shr_clamp(0xffffffffu, (unsigned)(32 - hc));
         }
         // ---- phase 2: walk the set bits, highest row / highest bit first ---------------------------------------
-        const uint32_t *srow = s_slot + off * kThreads;
+        const uint32_t *srow = DPOSE_TILE_COMPACT ? s_mask : s_mask + off * kThreads;
         const double dcb = (double)cb, drb = (double)rb;
         const double kuc = fma(c, dcb, fma(s, drb, ku0)), kvc = fma(c, drb, fma(-s, dcb, kv0));
         unsigned mask = 0u;
@@ -396,33 +412,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
 
 std::mutex g_tile_mu;  // guards the lazily built per-handle state below
 
-template <bool kJac, int kThreads, int kRepShift, int kSlots>
+template <bool kJac, int kThreads, int kRepShift, int kRows>
 int launch_tile4(const TileArgs &a, int grid, size_t smem_bytes, cudaStream_t stream) {
-  auto kern = k_cost_batch_tile<kJac, kThreads, kRepShift, kSlots>;
+  auto kern = k_cost_batch_tile<kJac, kThreads, kRepShift, kRows>;
   DPOSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   kern<<<grid, kThreads, smem_bytes, stream>>>(a);
   DPOSE_LAUNCHED();
   return DPOSE_OK;
 }
 template <bool kJac, int kThreads, int kRepShift>
-int launch_tile3(const TileArgs &a, int slots, int grid, size_t smem_bytes, cudaStream_t stream) {
-  if (slots == 25) return launch_tile4<kJac, kThreads, kRepShift, 25>(a, grid, smem_bytes, stream);
-  if (slots == 33) return launch_tile4<kJac, kThreads, kRepShift, 33>(a, grid, smem_bytes, stream);
-  if (slots == 36) return launch_tile4<kJac, kThreads, kRepShift, 36>(a, grid, smem_bytes, stream);
-  return launch_tile4<kJac, kThreads, kRepShift, 40>(a, grid, smem_bytes, stream);
+int launch_tile3(const TileArgs &a, int rows, int grid, size_t smem_bytes, cudaStream_t stream) {
+  if (rows == 20) return launch_tile4<kJac, kThreads, kRepShift, 20>(a, grid, smem_bytes, stream);
+  if (rows == 28) return launch_tile4<kJac, kThreads, kRepShift, 28>(a, grid, smem_bytes, stream);
+  return launch_tile4<kJac, kThreads, kRepShift, 32>(a, grid, smem_bytes, stream);
 }
 template <bool kJac, int kThreads>
-int launch_tile2(const TileArgs &a, int rep_shift, int slots, int grid, size_t smem_bytes, cudaStream_t stream) {
-  if (rep_shift == 0) return launch_tile3<kJac, kThreads, 0>(a, slots, grid, smem_bytes, stream);
-  if (rep_shift == 2) return launch_tile3<kJac, kThreads, 2>(a, slots, grid, smem_bytes, stream);
-  return launch_tile3<kJac, kThreads, 3>(a, slots, grid, smem_bytes, stream);
+int launch_tile2(const TileArgs &a, int rep_shift, int rows, int grid, size_t smem_bytes, cudaStream_t stream) {
+  if (rep_shift == 0) return launch_tile3<kJac, kThreads, 0>(a, rows, grid, smem_bytes, stream);
+  if (rep_shift == 2) return launch_tile3<kJac, kThreads, 2>(a, rows, grid, smem_bytes, stream);
+  return launch_tile3<kJac, kThreads, 3>(a, rows, grid, smem_bytes, stream);
 }
 template <bool kJac>
-int launch_tile1(const TileArgs &a, int threads, int rep_shift, int slots, int grid, size_t smem_bytes,
+int launch_tile1(const TileArgs &a, int threads, int rep_shift, int rows, int grid, size_t smem_bytes,
                  cudaStream_t stream) {
-  if (threads == 512) return launch_tile2<kJac, 512>(a, rep_shift, slots, grid, smem_bytes, stream);
-  if (threads == 768) return launch_tile2<kJac, 768>(a, rep_shift, slots, grid, smem_bytes, stream);
-  return launch_tile2<kJac, 1024>(a, rep_shift, slots, grid, smem_bytes, stream);
+  if (threads == 512) return launch_tile2<kJac, 512>(a, rep_shift, rows, grid, smem_bytes, stream);
+  if (threads == 768) return launch_tile2<kJac, 768>(a, rep_shift, rows, grid, smem_bytes, stream);
+  return launch_tile2<kJac, 1024>(a, rep_shift, rows, grid, smem_bytes, stream);
 }
 
 int env_int(const char *name) {
@@ -454,15 +469,16 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
 
   // tuning overrides (A/B measurements): threads per CTA and coefficient replicas
   static const int env_threads = env_int("DPOSE_TILE_THREADS"), env_rep = env_int("DPOSE_TILE_REPLICAS");
-  // row slots per chunk: rows of a chunk start at slot (y & 7) of its first tile row
-  const int need = std::min(32, pg->win_max) + 7;
-  const int slots = need <= 25 ? 25 : need <= 33 ? 33 : need <= 36 ? 36 : 40;
+  // rows kept per chunk
+  const int need = std::min(32, pg->win_max);
+  const int rows = need <= 20 ? 20 : need <= 28 ? 28 : 32;
+  const int stored = DPOSE_TILE_COMPACT ? rows : rows + 7;
   const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols;
   const size_t budget = (size_t)smem_optin - 64;
   // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts)
   int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 1024;
-  int rep_shift = env_rep == 1 ? 0 : env_rep == 4 ? 2 : env_rep == 8 ? 3 : 2;
-  auto fits = [&](int th, int rs) { return (table_bytes << rs) + (size_t)slots * 4 * th <= budget; };
+  int rep_shift = env_rep == 1 ? 0 : env_rep == 4 ? 2 : 3;  // 8 replicas if they fit (conflict-free LDS.128 gathers)
+  auto fits = [&](int th, int rs) { return (table_bytes << rs) + (size_t)stored * 4 * th <= budget; };
   while (!fits(threads, rep_shift)) {
     if (rep_shift == 3)
       rep_shift = 2;
@@ -514,12 +530,12 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.n = n;
   a.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 31u) == 0;
   a.clip_thr = 0.5f / (float)std::max(pg->win_max, 25);
-  const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)slots * 4 * threads;
+  const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)stored * 4 * threads;
   const size_t want = (n + threads - 1) / threads;
   const int grid = (int)std::min<size_t>(want, (size_t)sms);
   *handled = true;
-  return want_jacobian ? launch_tile1<true>(a, threads, rep_shift, slots, grid, smem_bytes, stream)
-                       : launch_tile1<false>(a, threads, rep_shift, slots, grid, smem_bytes, stream);
+  return want_jacobian ? launch_tile1<true>(a, threads, rep_shift, rows, grid, smem_bytes, stream)
+                       : launch_tile1<false>(a, threads, rep_shift, rows, grid, smem_bytes, stream);
 }
 
 }  // namespace dpose

@@ -1,18 +1,8 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python - <<'PY'
-import sys, time, json
-sys.path.insert(0, "tests")
-import numpy as np, fixtures as fx
-import dpose_b200 as dp
-from oracle import capi
-m = fx.bernoulli_map(2000, 2000, 0.002, 1)
-cm = dp.Costmap(m)
-for name, fp in (("rect", fx.RECT), ("star40", fx.star40())):
-    for n in (4096, 1000000):
-        poses = fx.random_poses(n, 2000, 2000, 2)
-        dp.check_footprint_batch(cm, fp, poses)
-        t0 = time.perf_counter(); got = dp.check_footprint_batch(cm, fp, poses); tg = time.perf_counter() - t0
-        t0 = time.perf_counter(); want = capi.check_footprint_batch(m, fp, poses, nthreads=capi.max_threads()); tc = time.perf_counter() - t0
-        print(json.dumps({"what": "check_footprint_batch", "footprint": name, "poses": n, "gpu_call_us": tg * 1e6, "cpu_oracle_us": tc * 1e6,
-                          "cpu_threads": capi.max_threads(), "free_fraction": float(want.mean()), "identical": bool(np.array_equal(got, want))}))
-PY
+q() { python bench.py --workload ${2:-cfg5} --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1', d['value'], d['roofline']['frac'])"; }
+q "compact 1024,rep8"
+DPOSE_TILE_REPLICAS=4 q "compact 1024,rep4"
+DPOSE_TILE_THREADS=768 q "compact 768,rep8"
+DPOSE_NVCC_EXTRA=-DDPOSE_TILE_COMPACT=0 python -m dpose_b200.build --force >/dev/null 2>&1
+q "allslots 1024,(rep4)"
+DPOSE_TILE_THREADS=768 q "allslots 768,rep8"
+DPOSE_TILE_THREADS=768 DPOSE_TILE_REPLICAS=4 q "allslots 768,rep4"
