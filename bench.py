@@ -67,59 +67,87 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+def _nvml_handle(local_rank):
+    """NVML handle of the CUDA device `local_rank` (matched by UUID: CUDA_VISIBLE_DEVICES may renumber)"""
+    import pynvml
+    import torch
+    pynvml.nvmlInit()
+    try:
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        return pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+    except Exception:
+        return pynvml.nvmlDeviceGetHandleByIndex(local_rank)
 
-    def __init__(self, index):
-        self.index = index
+
+def bind_to_gpu_numa_node(local_rank):
+    """run this rank on the CPUs NVML reports as local to its GPU, so that pinned host buffers (first touch) land
+    on the GPU's NUMA node; returns the previous affinity (restored around the CPU baseline)."""
+    try:
+        import pynvml
+        h = _nvml_handle(local_rank)
+        prev = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1} & prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """samples SM clock, power and throttle reasons of one GPU through NVML every ~2 ms while the timed region
+    runs (the region lasts tens of milliseconds: nvidia-smi's 100 ms loop would miss it)"""
+
+    def __init__(self, local_rank):
+        self.local_rank = local_rank
         self.rows = []
-        self.proc = None
+        self.stop_flag = threading.Event()
         self.thread = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+            import pynvml
+            self.nv = pynvml
+            self.h = _nvml_handle(self.local_rank)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, pw, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                smax.append(float(f[1]))
-                power.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [self.err or "NVML unavailable"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in self.rows))
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax,
+                "power_w_max": max((r[1] for r in self.rows), default=None), "samples": len(sm), "reasons": reasons,
+                "source": "NVML, 2 ms period, timed region only"}
 
 
 def make_host_workload(side, n_poses, seed_map, seed_pose):
@@ -213,6 +241,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    # NUMA: keep this rank (and the pinned host buffers it first-touches) on the CPUs local to its GPU
+    prev_affinity = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -319,6 +349,7 @@ def main():
                "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
                "pcie_h2d_gbs": h2d_gbs, "pcie_d2h_gbs": d2h_gbs,
                "pcie_bound_ms_per_step": 1e3 * max(n_poses * 24 / (h2d_gbs * 1e9), n_poses * 32 / (d2h_gbs * 1e9)),
+               "host_threads_bound_to_gpu_numa_node": bool(prev_affinity),
                "timing": "host wall clock around the synchronous C-ABI call (it drives its own streams), max over ranks"}
     else:
         e2e_checksum_ok = None
@@ -348,6 +379,8 @@ def main():
                 "avg_launch_ms": avg_launch_s * 1e3}
 
     # ---- parity spot check + CPU baseline (rank 0, N == 1 only for the baseline) ---------------------------
+    if prev_affinity:  # the CPU baseline may use every core of the box again
+        os.sched_setaffinity(0, prev_affinity)
     from oracle import capi
     oc = capi.CostData(fp, pad)
     host_map = d_map.cpu().numpy()

@@ -53,6 +53,8 @@ SYMBOLS = {
     "dpose_problem_info": (_i, [_vp, _vp, _vp]),
     "dpose_problem_eval_batch": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "dpose_problem_eval_batch_device": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dpose_world_to_cell": (_i, [_vp, _sz, _d, _d, _d, _u32, _u32, _vp, _vp]),
+    "dpose_cell_to_world": (_i, [_vp, _sz, _d, _d, _d, _vp, _vp]),
     "dpose_check_footprint": (_i, [_vp, _vp, _i, C.c_uint8, C.POINTER(_i)]),
     "dpose_check_footprint_batch": (_i, [_vp, _vp, _i, _vp, _sz, C.c_uint8, _vp]),
     "dpose_check_footprint_batch_device": (_i, [_vp, _vp, _i, _vp, _sz, C.c_uint8, _vp, _vp]),

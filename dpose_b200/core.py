@@ -389,3 +389,23 @@ def check_footprint_batch(costmap, footprint, poses, cost=254):
     check(lib().dpose_check_footprint_batch(costmap._h, fp.ctypes.data, fp.shape[0], p.ctypes.data, p.shape[0],
                                             int(cost), ok.ctypes.data))
     return ok.astype(bool)
+
+
+def to_cell(world_poses, origin, resolution, size):
+    """to_cell (dpose_goal_tolerance.cpp:294-309) for n metric poses (x, y, yaw): Costmap2D::worldToMap + yaw.
+    Returns (cells (n, 3), ok (n,) bool); a False entry is the reference's "pose outside of the map"."""
+    w = np.ascontiguousarray(np.asarray(world_poses, np.float64).reshape(-1, 3))
+    out, ok = np.empty_like(w), np.zeros(w.shape[0], np.uint8)
+    check(lib().dpose_world_to_cell(w.ctypes.data, w.shape[0], float(origin[0]), float(origin[1]), float(resolution),
+                                    int(size[0]), int(size[1]), out.ctypes.data, ok.ctypes.data))
+    return out, ok.astype(bool)
+
+
+def to_msg(cell_poses, origin, resolution):
+    """to_msg (dpose_goal_tolerance.cpp:311-330) for n cell poses: round to a cell, Costmap2D::mapToWorld (cell
+    centre).  Returns (world (n, 3), ok (n,) bool); a False entry is the reference's "negative pose"."""
+    c = np.ascontiguousarray(np.asarray(cell_poses, np.float64).reshape(-1, 3))
+    out, ok = np.empty_like(c), np.zeros(c.shape[0], np.uint8)
+    check(lib().dpose_cell_to_world(c.ctypes.data, c.shape[0], float(origin[0]), float(origin[1]), float(resolution),
+                                    out.ctypes.data, ok.ctypes.data))
+    return out, ok.astype(bool)

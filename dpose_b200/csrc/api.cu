@@ -146,6 +146,43 @@ int dpose_make_footprint(const double *xy_m, int n, double resolution, int32_t *
   return DPOSE_OK;
 }
 
+// ---- world <-> cell poses (dpose_goal_tolerance.cpp:294-330) -----------------------------------------------
+int dpose_world_to_cell(const double *world, size_t n, double origin_x, double origin_y, double resolution,
+                        uint32_t size_x, uint32_t size_y, double *cells, uint8_t *ok) {
+  if (n && (!world || !cells)) return fail(DPOSE_EINVAL, "NULL argument");
+  if (!(resolution > 0)) return fail(DPOSE_EINVAL, "resolution must be positive");
+  for (size_t i = 0; i < n; ++i) {
+    const double wx = world[3 * i], wy = world[3 * i + 1];
+    bool good = !(wx < origin_x || wy < origin_y) && std::isfinite(wx) && std::isfinite(wy);  // Costmap2D::worldToMap
+    double mx = 0, my = 0;
+    if (good) {
+      mx = std::floor((wx - origin_x) / resolution);  // (int) cast of a non-negative value
+      my = std::floor((wy - origin_y) / resolution);
+      good = mx < (double)size_x && my < (double)size_y;
+    }
+    cells[3 * i] = good ? mx : 0.0;
+    cells[3 * i + 1] = good ? my : 0.0;
+    cells[3 * i + 2] = world[3 * i + 2];
+    if (ok) ok[i] = good ? 1 : 0;
+  }
+  return DPOSE_OK;
+}
+
+int dpose_cell_to_world(const double *cells, size_t n, double origin_x, double origin_y, double resolution,
+                        double *world, uint8_t *ok) {
+  if (n && (!cells || !world)) return fail(DPOSE_EINVAL, "NULL argument");
+  for (size_t i = 0; i < n; ++i) {
+    const double cx = cells[3 * i], cy = cells[3 * i + 1];
+    const bool good = !(cx < 0 || cy < 0) && std::isfinite(cx) && std::isfinite(cy);  // :314-315 "negative pose"
+    const double mx = good ? std::round(cx) : 0.0, my = good ? std::round(cy) : 0.0;   // :318-319
+    world[3 * i] = origin_x + (mx + 0.5) * resolution;  // Costmap2D::mapToWorld
+    world[3 * i + 1] = origin_y + (my + 0.5) * resolution;
+    world[3 * i + 2] = cells[3 * i + 2];
+    if (ok) ok[i] = good ? 1 : 0;
+  }
+  return DPOSE_OK;
+}
+
 // ---- pose_gradient / cost_data ----------------------------------------------------------------
 int dpose_pg_create(const int32_t *fp, int n, uint32_t padding, int device, dpose_pg **out) {
   if (!out) return fail(DPOSE_EINVAL, "out is NULL");
@@ -302,16 +339,28 @@ int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", map->device);
   DPOSE_CUDA(cudaMemcpy2D(map->d_data + (size_t)y0 * map->pitch + x0, map->pitch, data, pitch, w, h,
                           cudaMemcpyHostToDevice));
-  map->bits_dirty = true;
-  map->tiles_dirty = true;
+  // narrow the lazy plane rebuilds to the rows of this window (union with what is already pending)
+  auto widen = [&](bool &dirty, uint32_t &lo, uint32_t &hi) {
+    if (!dirty) {
+      lo = y0;
+      hi = y0 + h;
+    } else {
+      lo = std::min(lo, y0);
+      hi = std::max(hi, y0 + h);
+    }
+    dirty = true;
+  };
+  widen(map->bits_dirty, map->bits_dirty_lo, map->bits_dirty_hi);
+  widen(map->tiles_dirty, map->tiles_dirty_lo, map->tiles_dirty_hi);
   return DPOSE_OK;
 }
 
 int dpose_map_set_volatile(dpose_map *map, int is_volatile) {
   if (!map) return fail(DPOSE_EINVAL, "map is NULL");
   map->is_volatile = is_volatile != 0;
-  map->bits_dirty = true;
-  map->tiles_dirty = true;
+  map->bits_dirty = map->tiles_dirty = true;
+  map->bits_dirty_lo = map->tiles_dirty_lo = 0;
+  map->bits_dirty_hi = map->tiles_dirty_hi = 0xffffffffu;
   return DPOSE_OK;
 }
 

@@ -22,10 +22,10 @@ __device__ __forceinline__ unsigned lethal_bits16(const uint4 v) {
   return n0 | (n1 << 4) | (n2 << 8) | (n3 << 12);
 }
 
-__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t *__restrict__ map, size_t pitch, uint32_t size_y,
-                                                   uint32_t *__restrict__ bits, uint32_t words_per_row) {
-  const size_t total = (size_t)size_y * words_per_row;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t *__restrict__ map, size_t pitch, uint32_t y_lo,
+                                                   uint32_t y_hi, uint32_t *__restrict__ bits, uint32_t words_per_row) {
+  const size_t first = (size_t)y_lo * words_per_row, total = (size_t)y_hi * words_per_row;
+  for (size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t y = (uint32_t)(i / words_per_row), w = (uint32_t)(i - (size_t)y * words_per_row);
     const size_t x = (size_t)w * 32;
     unsigned out = 0u;
@@ -41,10 +41,17 @@ __global__ void __launch_bounds__(256) k_pack_bits(const uint8_t *__restrict__ m
 
 int bitplane_build(const dpose_map *map, cudaStream_t stream) {
   if (!map->d_bits || map->size_x == 0 || map->size_y == 0) return DPOSE_OK;
+  // only the dirty rows (all of them after create / in volatile mode)
+  dpose_map *m = const_cast<dpose_map *>(map);
+  const uint32_t lo = map->is_volatile ? 0u : std::min(map->bits_dirty_lo, map->size_y);
+  const uint32_t hi = map->is_volatile ? map->size_y : std::min(map->bits_dirty_hi, map->size_y);
+  m->bits_dirty_lo = 0xffffffffu;
+  m->bits_dirty_hi = 0;
+  if (hi <= lo) return DPOSE_OK;
   const uint32_t words_per_row = (uint32_t)(map->bits_pitch / 4);
-  const size_t total = (size_t)map->size_y * words_per_row;
+  const size_t total = (size_t)(hi - lo) * words_per_row;
   const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
-  k_pack_bits<<<grid, 256, 0, stream>>>(map->d_data, map->pitch, map->size_y, map->d_bits, words_per_row);
+  k_pack_bits<<<grid, 256, 0, stream>>>(map->d_data, map->pitch, lo, hi, map->d_bits, words_per_row);
   DPOSE_LAUNCHED();
   return DPOSE_OK;
 }

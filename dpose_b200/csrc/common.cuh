@@ -107,6 +107,10 @@ struct dpose_map {
   uint32_t *d_bits = nullptr;
   size_t bits_pitch = 0;  // bytes per bit-plane row, multiple of 16
   bool bits_dirty = true;
+  // rows [lo, hi) whose uint8 bytes changed since each plane was last built (dpose_map_update narrows the
+  // rebuild to them; create / volatile mean all rows)
+  uint32_t bits_dirty_lo = 0, bits_dirty_hi = 0xffffffffu;
+  uint32_t tiles_dirty_lo = 0, tiles_dirty_hi = 0xffffffffu;
   bool is_volatile = false;
   cudaEvent_t bits_ready = nullptr;  // recorded after a rebuild; other streams wait on it
   // TMA descriptor cache (get_cost_batch.cu), keyed by box dims

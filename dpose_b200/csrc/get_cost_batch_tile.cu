@@ -56,14 +56,16 @@ __device__ __forceinline__ unsigned lethal_bits16(const uint4 v) {
 // One thread per plane word.  Lane l of a warp handles row (l >> 2) of tile column 4 * warp + (l & 3):
 // the warp reads 8 map rows x 128 contiguous bytes and writes 4 tiles = 128 contiguous bytes.
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ map, size_t pitch, uint32_t size_y,
-                                                    uint32_t *__restrict__ tiles, uint32_t ntx, uint32_t nty) {
+                                                    uint32_t *__restrict__ tiles, uint32_t ntx, uint32_t ty0,
+                                                    uint32_t ty1) {
   const uint32_t quads = (ntx + 3) / 4;  // groups of 4 tile columns
-  const size_t n_warps = (size_t)quads * nty;
+  const size_t n_warps = (size_t)quads * (ty1 - ty0);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t r = lane >> 2, j = lane & 3;
   for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps;
        w += ((size_t)gridDim.x * blockDim.x) >> 5) {
-    const uint32_t by = (uint32_t)(w / quads), bx = (uint32_t)(w - (size_t)by * quads) * 4 + j;
+    const uint32_t byr = (uint32_t)(w / quads), bx = (uint32_t)(w - (size_t)byr * quads) * 4 + j;
+    const uint32_t by = ty0 + byr;
     if (bx >= ntx) continue;
     const uint32_t y = by * 8 + r;
     const size_t x = (size_t)bx * 32;
@@ -449,11 +451,18 @@ int env_int(const char *name) {
 
 int tileplane_build(const dpose_map *map, cudaStream_t stream) {
   if (!map->d_tiles || map->size_x == 0 || map->size_y == 0) return DPOSE_OK;
+  // only the tile rows that cover the dirty map rows (all of them after create / in volatile mode)
+  dpose_map *m = const_cast<dpose_map *>(map);
+  const uint32_t lo = map->is_volatile ? 0u : std::min(map->tiles_dirty_lo, map->size_y);
+  const uint32_t hi = map->is_volatile ? map->size_y : std::min(map->tiles_dirty_hi, map->size_y);
+  m->tiles_dirty_lo = 0xffffffffu;
+  m->tiles_dirty_hi = 0;
+  if (hi <= lo) return DPOSE_OK;
+  const uint32_t ty0 = lo / 8, ty1 = (hi + 7) / 8;
   const uint32_t quads = (map->tiles_ntx + 3) / 4;
-  const size_t n_warps = (size_t)quads * map->tiles_nty;
+  const size_t n_warps = (size_t)quads * (ty1 - ty0);
   const unsigned grid = (unsigned)std::min<size_t>((n_warps + 7) / 8, (size_t)148 * 32);
-  k_pack_tiles<<<grid, 256, 0, stream>>>(map->d_data, map->pitch, map->size_y, map->d_tiles, map->tiles_ntx,
-                                         map->tiles_nty);
+  k_pack_tiles<<<grid, 256, 0, stream>>>(map->d_data, map->pitch, map->size_y, map->d_tiles, map->tiles_ntx, ty0, ty1);
   DPOSE_LAUNCHED();
   return DPOSE_OK;
 }

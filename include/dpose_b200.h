@@ -182,6 +182,20 @@ int dpose_problem_eval_batch(dpose_problem *problem, const double *x, size_t n, 
 int dpose_problem_eval_batch_device(const dpose_problem *problem, const double *d_x, size_t n, double *d_work,
                                     double *d_f, double *d_grad_f, double *d_g, double *d_jac_g, void *stream);
 
+/* ---- world <-> cell poses ------------------------------------------------------------------------
+ * replaces to_cell / to_msg (dpose_goal_tolerance.cpp:294-330) for n poses; host arithmetic.  The costmap
+ * geometry is costmap_2d::Costmap2D's (getOriginX/Y, getResolution, getSizeInCellsX/Y); yaw <-> quaternion
+ * stays with the caller (tf2).
+ * to_cell: Costmap2D::worldToMap — cell = (int)((w - origin) / resolution), valid iff w >= origin and
+ * cell < size; out pose = (cell x, cell y, yaw).  ok[i] = 0 marks "pose outside of the map" (:303-304). */
+int dpose_world_to_cell(const double *world /* n x (x, y, yaw) */, size_t n, double origin_x, double origin_y,
+                        double resolution, uint32_t size_x, uint32_t size_y, double *cells /* n x 3 */,
+                        uint8_t *ok /* n, may be NULL */);
+/* to_msg: cell = round(pose) (std::round), Costmap2D::mapToWorld — w = origin + (cell + 0.5) * resolution.
+ * ok[i] = 0 marks "negative pose" (:314-315). */
+int dpose_cell_to_world(const double *cells /* n x (x, y, theta) */, size_t n, double origin_x, double origin_y,
+                        double resolution, double *world /* n x 3 */, uint8_t *ok /* n, may be NULL */);
+
 /* ---- check_footprint (validation of solved poses) -----------------------------------------------
  * replaces check_footprint(map, footprint, cost) (dpose_costmap.cpp:460-582, with is_inside :186-199 and the
  * x_bresenham iterators :201-317): *ok = 1 iff every vertex is inside the map and no cell covered by the polygon

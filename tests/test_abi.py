@@ -44,6 +44,24 @@ def test_host_side_functions_match_oracle(built):
     assert np.array_equal(dp.to_rectangle((1, 2), (3, 4)), fx.to_rectangle((1, 2), (3, 4)))
 
 
+def test_world_cell_conversions(built):  # dpose_goal_tolerance.cpp:294-330 (Costmap2D::worldToMap / mapToWorld)
+    import dpose_b200 as dp
+    origin, res, size = (-10.0, 5.0), 0.05, (400, 300)
+    world = np.array([[-10.0, 5.0, 0.1], [-9.951, 5.149, -3.0], [9.99, 19.99, 1.0], [10.0, 6.0, 0.0], [-10.01, 6.0, 0.0],
+                      [0.0, 20.0, 0.0]])
+    cells, ok = dp.to_cell(world, origin, res, size)
+    assert ok.tolist() == [True, True, True, False, False, False]
+    assert cells[:3].tolist() == [[0.0, 0.0, 0.1], [0.0, 2.0, -3.0], [399.0, 299.0, 1.0]]
+    back, ok2 = dp.to_msg(np.array([[0.0, 0.0, 0.1], [12.4, 7.5, 2.0], [-0.1, 3.0, 0.0]]), origin, res)
+    assert ok2.tolist() == [True, True, False]
+    assert np.allclose(back[0], [-10.0 + 0.025, 5.0 + 0.025, 0.1]) and np.allclose(back[1], [-10.0 + 12.5 * res, 5.0 + 8.5 * res, 2.0])
+    # a pose converted to its cell and back lands on that cell's centre
+    w = np.array([[3.333, 12.777, 0.5]])
+    c, _ = dp.to_cell(w, origin, res, size)
+    b, _ = dp.to_msg(c, origin, res)
+    assert np.all(np.abs(b[0, :2] - w[0, :2]) <= res / 2 + 1e-12)
+
+
 def test_error_contract(built):
     import dpose_b200 as dp
     with pytest.raises(RuntimeError, match="resolution must be positive"):  # dpose_costmap.cpp:44-45

@@ -373,6 +373,13 @@ def test_batch_sees_map_updates(dp):
     after = pg.get_cost_batch(cm, poses)
     fresh = pg.get_cost_batch(dp.Costmap(m2), poses)
     assert np.array_equal(after, fresh) and not np.array_equal(after, before)
+    # several dirty windows before one batch call: the lazy plane rebuild covers the union of their rows
+    for (x0, y0, w, h, seed) in [(3, 1, 40, 7, 7), (250, 190, 50, 10, 8), (0, 96, 300, 1, 9)]:
+        patch = fx.bernoulli_map(w, h, 0.5, seed)
+        m2[y0:y0 + h, x0:x0 + w] = patch
+        cm.update(patch, x0, y0)
+    assert np.array_equal(pg.get_cost_batch(cm, poses), pg.get_cost_batch(dp.Costmap(m2), poses))
+    fresh = pg.get_cost_batch(dp.Costmap(m2), poses)
     cm.set_volatile(True)
     assert np.array_equal(pg.get_cost_batch(cm, poses), fresh)
     assert np.array_equal(pg.get_cost_batch(cm, poses), fresh)
