@@ -4,12 +4,14 @@
 // raytraceLine-compatible) into per-row [xmin, xmax] intervals (to_rays, :106-115).
 // Device: stream compaction over the uint8 grid, two sweeps like the reference
 // (:143-155 count, :167-179 write) with an exclusive scan between them:
-//   k_count : one warp per 512-byte row tile, one aligned 16-byte load per lane, byte
-//             compare against 254 -> 16-bit lane mask -> popc -> per-tile count
+//   k_count : one warp per 2 KB row tile, four aligned 16-byte loads per lane (all in flight before the
+//             first use), byte compare against 254 -> 16-bit lane masks -> popc -> per-tile count
 //   k_scan  : two-level exclusive scan of the tile counts
-//   k_write : same tiling; warp prefix over the lane counts, each lane emits its (x, y)
+//   k_write : same tiling; one warp prefix per 512-byte piece, each lane emits its (x, y)
 // Output order is row-major (y ascending, x ascending) and deterministic.
 // HBM traffic: 2 x box bytes read + 8 B per lethal cell written.
+// Boxes up to 4 M cells (the plugin's search box is ~1e4) size the result by the box and run both sweeps back
+// to back with one synchronisation; larger boxes read the total back before allocating.
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -61,7 +63,8 @@ size_t host_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_
 
 namespace {
 
-constexpr int kTileBytes = 512;  // one warp x 16 B
+constexpr int kSub = 4;                  // 512-byte pieces per warp tile: 4 independent 16-byte loads per lane in flight
+constexpr int kTileBytes = 512 * kSub;   // one warp x 4 x 16 B
 constexpr int kWarpsPerCta = 8;
 constexpr int kScanChunk = 2048;  // tiles per scan CTA (512 threads x 4)
 
@@ -91,23 +94,33 @@ __device__ __forceinline__ unsigned lethal_mask16(const uint4 v, int x_first, in
   }
   // clip to the row interval
   const int lo = xmin - x_first, hi = xmax - x_first;  // valid bit range [lo, hi]
-  if (hi < 0 || lo > 15) return 0u;
   const unsigned lo_mask = lo <= 0 ? 0xFFFFu : (0xFFFFu << lo) & 0xFFFFu;
   const unsigned hi_mask = hi >= 15 ? 0xFFFFu : (0xFFFFu >> (15 - hi));
   return m & lo_mask & hi_mask;
 }
 
-__device__ __forceinline__ unsigned tile_lane_mask(const LethalArgs &a, long long tile, int lane,
-                                                   int *x_first, int *y) {
+// the lane's kSub 16-byte pieces of a tile: piece c covers x = x_first + 512 c ... + 15 of row y; all loads are
+// issued before the first use
+__device__ __forceinline__ void tile_lane_masks(const LethalArgs &a, long long tile, int lane, unsigned m[kSub],
+                                                int *x_first, int *y) {
   const int r = (int)(tile / a.tiles_x), j = (int)(tile - (long long)r * a.tiles_x);
   const RowSpan s = a.spans[r];
   const int x0 = a.x_base + j * kTileBytes + lane * 16;
   *x_first = x0;
   *y = a.y_lo + r;
-  if (s.xmin > s.xmax || x0 > s.xmax || x0 + 15 < s.xmin) return 0u;
-  // x0 is 16-byte aligned and < size_x <= pitch, pitch % 16 == 0: the load stays in the row
-  const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.map + (size_t)(a.y_lo + r) * a.pitch + x0));
-  return lethal_mask16(v, x0, s.xmin, s.xmax);
+  const uint8_t *row = a.map + (size_t)(a.y_lo + r) * a.pitch;
+  uint4 v[kSub];
+  bool live[kSub];
+#pragma unroll
+  for (int c = 0; c < kSub; ++c) {
+    const int xc = x0 + 512 * c;
+    // xc is 16-byte aligned; a piece that overlaps the span starts below size_x <= pitch (pitch % 16 == 0)
+    live[c] = s.xmin <= s.xmax && xc <= s.xmax && xc + 15 >= s.xmin;
+    v[c] = make_uint4(0u, 0u, 0u, 0u);
+    if (live[c]) v[c] = __ldg(reinterpret_cast<const uint4 *>(row + xc));
+  }
+#pragma unroll
+  for (int c = 0; c < kSub; ++c) m[c] = live[c] ? lethal_mask16(v[c], x0 + 512 * c, s.xmin, s.xmax) : 0u;
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_count(LethalArgs a, unsigned *tile_count) {
@@ -115,7 +128,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_count(LethalArgs a, unsig
   const long long tile = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (tile >= a.n_tiles) return;
   int xf, y;
-  unsigned c = __popc(tile_lane_mask(a, tile, lane, &xf, &y));
+  unsigned m[kSub];
+  tile_lane_masks(a, tile, lane, m, &xf, &y);
+  unsigned c = 0;
+#pragma unroll
+  for (int k = 0; k < kSub; ++k) c += __popc(m[k]);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
   if (lane == 0) tile_count[tile] = c;
@@ -204,19 +221,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
   const long long tile = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (tile >= a.n_tiles) return;
   int xf, y;
-  unsigned m = tile_lane_mask(a, tile, lane, &xf, &y);
-  const unsigned c = __popc(m);
-  unsigned inc = c;
+  unsigned m[kSub];
+  tile_lane_masks(a, tile, lane, m, &xf, &y);
+  // x ascending inside the tile = piece-major, then lane, then bit: one warp prefix per piece
+  unsigned long long base = chunk_offset[tile / kScanChunk] + tile_prefix[tile];
 #pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
-    if (lane >= off) inc += t;
-  }
-  unsigned long long dst = chunk_offset[tile / kScanChunk] + tile_prefix[tile] + (inc - c);
-  while (m) {
-    const int b = __ffs(m) - 1;
-    m &= m - 1;
-    out[dst++] = make_int2(xf + b, y);
+  for (int k = 0; k < kSub; ++k) {
+    const unsigned c = __popc(m[k]);
+    unsigned inc = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += t;
+    }
+    unsigned long long dst = base + (inc - c);
+    unsigned mk = m[k];
+    while (mk) {
+      const int b = __ffs(mk) - 1;
+      mk &= mk - 1;
+      out[dst++] = make_int2(xf + 512 * k + b, y);
+    }
+    base += __shfl_sync(0xffffffffu, inc, 31);
   }
 }
 
@@ -295,6 +320,7 @@ struct LethalWs {
 };
 
 std::mutex g_ws_mu;  // guards creation of the per-map workspace
+constexpr unsigned long long kSingleSyncCells = 1ull << 22;  // boxes up to 4 M cells: result sized by the box (32 MB)
 
 }  // namespace
 
@@ -358,10 +384,12 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       s.xmax = std::max(s.xmax, x);
     });
   int gx_min = INT_MAX, gx_max = INT_MIN;
+  unsigned long long box_cells = 0;  // cells inside the row intervals: an upper bound of the result size
   for (int r = 0; r < nrows; ++r)
     if (spans[r].xmin <= spans[r].xmax) {
       gx_min = std::min(gx_min, spans[r].xmin);
       gx_max = std::max(gx_max, spans[r].xmax);
+      box_cells += (unsigned long long)(spans[r].xmax - spans[r].xmin + 1);
     }
   if (gx_min > gx_max) return DPOSE_OK;  // degenerate ring (all four edges empty)
 
@@ -390,14 +418,31 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
     k_scan_totals<<<1, 1024, 0, st>>>(ws->d_chunk, n_chunks, ws->d_chunk + n_chunks);
     DPOSE_LAUNCHED();
     DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_chunk + n_chunks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    DPOSE_CUDA(cudaStreamSynchronize(st));
-    const unsigned long long total = *ws->h_total;
-    if (total == 0) return DPOSE_OK;  // :157-158
-    DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * total, st));
-    k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_chunk, d_out);
-    DPOSE_LAUNCHED();
-    DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
-    DPOSE_CUDA(cudaStreamSynchronize(st));
+    unsigned long long total;
+    if (box_cells <= kSingleSyncCells) {
+      // small boxes (the plugin's search box): size the result by the box and run both sweeps back to back —
+      // one synchronisation per call instead of a host round trip between the sweeps
+      DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * box_cells, st));
+      k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_chunk, d_out);
+      DPOSE_LAUNCHED();
+      DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
+      DPOSE_CUDA(cudaStreamSynchronize(st));
+      total = *ws->h_total;
+      if (total == 0) {  // :157-158
+        cudaFreeAsync(d_out, st);
+        d_out = nullptr;
+        return DPOSE_OK;
+      }
+    } else {
+      DPOSE_CUDA(cudaStreamSynchronize(st));
+      total = *ws->h_total;
+      if (total == 0) return DPOSE_OK;  // :157-158
+      DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * total, st));
+      k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_chunk, d_out);
+      DPOSE_LAUNCHED();
+      DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
+      DPOSE_CUDA(cudaStreamSynchronize(st));
+    }
     cudaEventElapsedTime(&ws->last_kernel_us, ws->ev0, ws->ev1);  // ms, includes the host round trip for the total
     ws->last_kernel_us *= 1000.f;
     *d_cells = d_out;

@@ -1,8 +1,2 @@
-q() { python bench.py --workload ${2:-cfg5} --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1', d['value'], d['roofline']['frac'])"; }
-q "compact 1024,rep8"
-DPOSE_TILE_REPLICAS=4 q "compact 1024,rep4"
-DPOSE_TILE_THREADS=768 q "compact 768,rep8"
-DPOSE_NVCC_EXTRA=-DDPOSE_TILE_COMPACT=0 python -m dpose_b200.build --force >/dev/null 2>&1
-q "allslots 1024,(rep4)"
-DPOSE_TILE_THREADS=768 q "allslots 768,rep8"
-DPOSE_TILE_THREADS=768 DPOSE_TILE_REPLICAS=4 q "allslots 768,rep4"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/bench_kernels.py lethal 2>&1 | tee gpurun_out/kernels_v15.jsonl | cut -c1-420
