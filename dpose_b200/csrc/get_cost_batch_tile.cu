@@ -437,6 +437,8 @@ int launch_tile2(const TileArgs &a, int rep_shift, int rows, int grid, size_t sm
 template <bool kJac>
 int launch_tile1(const TileArgs &a, int threads, int rep_shift, int rows, int grid, size_t smem_bytes,
                  cudaStream_t stream) {
+  if (threads == 128) return launch_tile2<kJac, 128>(a, rep_shift, rows, grid, smem_bytes, stream);
+  if (threads == 256) return launch_tile2<kJac, 256>(a, rep_shift, rows, grid, smem_bytes, stream);
   if (threads == 512) return launch_tile2<kJac, 512>(a, rep_shift, rows, grid, smem_bytes, stream);
   if (threads == 768) return launch_tile2<kJac, 768>(a, rep_shift, rows, grid, smem_bytes, stream);
   return launch_tile2<kJac, 1024>(a, rep_shift, rows, grid, smem_bytes, stream);
@@ -497,6 +499,17 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
       threads -= 256;
     } else
       return DPOSE_OK;  // table too big for shared memory
+  }
+  // small batches are latency bound: spread them over all SMs with smaller CTAs (the replica count, and with it
+  // the cached coefficient image, stays the one chosen for the largest CTA)
+  if (env_threads == 0) {
+    const size_t per_sm = (n + (size_t)sms - 1) / (size_t)sms;
+    const int choices[5] = {128, 256, 512, 768, 1024};
+    for (int c : choices)
+      if ((size_t)c >= per_sm || c >= threads) {
+        threads = std::min(threads, c);
+        break;
+      }
   }
 
   dpose_pg *p = const_cast<dpose_pg *>(pg);
