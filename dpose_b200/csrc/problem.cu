@@ -111,16 +111,19 @@ struct dpose_problem {
   cudaStream_t stream = nullptr;
   size_t cap = 0;
   double *d_x = nullptr, *d_work = nullptr, *d_res = nullptr;  // 3n, 7n, 9n
+  double *h_stage = nullptr;  // pinned, 12n: x in, then [f | grad | g | jac] out — one copy each way
 };
 
 static int problem_reserve(dpose_problem *p, size_t n) {
   if (!p->stream) DPOSE_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   if (n <= p->cap) return DPOSE_OK;
   cudaFree(p->d_x);
-  p->d_x = nullptr;
+  cudaFreeHost(p->h_stage);
+  p->d_x = p->h_stage = nullptr;
   p->cap = 0;
   const size_t cap = n + n / 2 + 256;
   DPOSE_CUDA(cudaMalloc(&p->d_x, sizeof(double) * 19 * cap));
+  DPOSE_CUDA(cudaHostAlloc(&p->h_stage, sizeof(double) * 12 * cap, cudaHostAllocDefault));
   p->d_work = p->d_x + 3 * cap;  // 7 n: cost4 | poses
   p->d_res = p->d_work + 7 * cap;
   p->cap = cap;
@@ -147,6 +150,7 @@ void dpose_problem_destroy(dpose_problem *p) {
   {
     DeviceGuard guard(p->pg->device);
     cudaFree(p->d_x);
+    cudaFreeHost(p->h_stage);
     if (p->stream) cudaStreamDestroy(p->stream);
   }
   dpose_map_destroy(p->crop);
@@ -256,14 +260,18 @@ int dpose_problem_eval_batch(dpose_problem *p, const double *x, size_t n, double
   cudaStream_t st = p->stream;
   double *d_f = p->d_res, *d_grad = d_f + n, *d_g = d_grad + 3 * n, *d_jac = d_g + 2 * n;
   auto body = [&]() -> int {
-    DPOSE_CUDA(cudaMemcpyAsync(p->d_x, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+    // pinned staging: one H2D of x, one D2H of [f | grad | g | jac]
+    double *h_x = p->h_stage, *h_res = p->h_stage + 3 * n;
+    std::memcpy(h_x, x, sizeof(double) * 3 * n);
+    DPOSE_CUDA(cudaMemcpyAsync(p->d_x, h_x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
     DPOSE_TRY(problem_eval_device(p, p->d_x, n, p->d_work, f ? d_f : nullptr, grad_f ? d_grad : nullptr,
                                   g ? d_g : nullptr, jac_g ? d_jac : nullptr, st));
-    if (f) DPOSE_CUDA(cudaMemcpyAsync(f, d_f, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    if (grad_f) DPOSE_CUDA(cudaMemcpyAsync(grad_f, d_grad, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
-    if (g) DPOSE_CUDA(cudaMemcpyAsync(g, d_g, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, st));
-    if (jac_g) DPOSE_CUDA(cudaMemcpyAsync(jac_g, d_jac, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    DPOSE_CUDA(cudaMemcpyAsync(h_res, p->d_res, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
     DPOSE_CUDA(cudaStreamSynchronize(st));
+    if (f) std::memcpy(f, h_res, sizeof(double) * n);
+    if (grad_f) std::memcpy(grad_f, h_res + n, sizeof(double) * 3 * n);
+    if (g) std::memcpy(g, h_res + 4 * n, sizeof(double) * 2 * n);
+    if (jac_g) std::memcpy(jac_g, h_res + 6 * n, sizeof(double) * 3 * n);
     return DPOSE_OK;
   };
   const int rc = body();

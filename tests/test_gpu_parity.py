@@ -423,3 +423,49 @@ def test_batch_multi_gpu_shards(dp):
     maps = [dp.Costmap(m, device=d) for d in range(n)]
     ref = pgs[0].get_cost_batch(maps[0], poses)
     assert np.array_equal(get_cost_batch_multi(pgs, maps, poses), ref)
+
+
+def test_full_size_properties_cfg5(dp):
+    """BASELINE config 5 at full size (10000 x 10000 map, 1e7 poses), checked through size-independent
+    properties of the path rather than against the (too slow) CPU oracle:
+      * batch-position independence: a permuted batch gives bit-identical per-pose results
+      * additivity over the obstacle set: cost / J over the map = over its even-x cells + over its odd-x cells
+      * angle periodicity: theta and theta + 2 pi agree
+      * a random sample agrees with the oracle (shifted-input protocol)"""
+    from oracle import capi
+    side, n = 10000, 10_000_000
+    rng = np.random.default_rng(4)
+    m = np.zeros((side, side), np.uint8)
+    for r0 in range(0, side, 1000):  # in slabs: keeps the float64 scratch at 80 MB
+        m[r0:r0 + 1000] = np.where(rng.random((1000, side)) < 0.10, fx.LETHAL, 0)
+    poses = np.empty((n, 3))
+    poses[:, 0] = rng.uniform(32, side - 32, n)
+    poses[:, 1] = rng.uniform(32, side - 32, n)
+    poses[:, 2] = rng.uniform(-math.pi, math.pi, n)
+    pg = dp.pose_gradient(fx.RECT)
+    cm = dp.Costmap(m)
+    out = pg.get_cost_batch(cm, poses)
+    assert np.isfinite(out).all() and (out[:, 0] >= 0).all() and (out[:, 0] > 0).mean() > 0.99
+    # batch-position independence (bit-exact)
+    perm = rng.permutation(n)
+    out_p = pg.get_cost_batch(cm, poses[perm])
+    assert np.array_equal(out_p, out[perm])
+    del out_p
+    # additivity over a partition of the obstacle set
+    even = m.copy()
+    even[:, 1::2] = 0
+    odd = m.copy()
+    odd[:, 0::2] = 0
+    parts = pg.get_cost_batch(dp.Costmap(even), poses) + pg.get_cost_batch(dp.Costmap(odd), poses)
+    del even, odd
+    assert np.all(np.abs(parts - out) <= 1e-9 + 1e-11 * np.abs(out))
+    del parts
+    # periodicity in theta (sin / cos of theta + 2 pi differ in the last bits only)
+    sub = slice(0, 1_000_000)
+    turned = poses[sub].copy()
+    turned[:, 2] += 2.0 * math.pi
+    assert np.all(fx.tol_ok(pg.get_cost_batch(cm, turned), out[sub], rel=1e-9, abs_=1e-8))
+    # a sample against the oracle
+    idx = rng.choice(n, 3000, replace=False)
+    ref = capi.CostData(fx.RECT, 2).get_cost_batch(m, poses[idx], shift=True, nthreads=capi.max_threads())
+    assert fx.tol_ok(out[idx], ref).all()
