@@ -1,2 +1,6 @@
-python -m pytest tests -m gpu -x -q --durations=5 2>&1 | tail -12
-python tools/bench_kernels.py cfg4 2>&1 | cut -c1-400
+q() { python bench.py --workload ${2:-cfg5} --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1', d['value'], d['roofline']['frac'], d['parity']['pass_rate_vs_shifted_reference'])"; }
+q "walk0"
+DPOSE_NVCC_EXTRA=-DDPOSE_TILE_WALK=1 python -m dpose_b200.build --force >/dev/null 2>&1
+q "walk1"
+q "walk1 cfg3" cfg3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
