@@ -242,6 +242,8 @@ void dpose_pg_destroy(dpose_pg *pg) {
     cudaFree(pg->d_cost);
     cudaFree(pg->d_coef);
     cudaFree(pg->d_coef_image);
+    if (pg->tex_hi) cudaDestroyTextureObject((cudaTextureObject_t)pg->tex_hi);
+    cudaFree(pg->d_coef_hi);
     cudaFree(pg->d_arena);
     pg_release_batch_ctx(pg);
   }

@@ -92,6 +92,9 @@ struct dpose_pg {
   // built on first use: R = 1 << coef_image_shift replicas
   void *d_coef_image = nullptr;
   int coef_image_shift = -1;
+  // DPOSE_TILE_TEX builds: second halves of the patch polynomials, read through a texture object
+  void *d_coef_hi = nullptr;
+  unsigned long long tex_hi = 0;
   // streams, events and staging buffers of the host-buffer batch entry point (api.cu), built on first use
   void *batch_ctx = nullptr;
 };

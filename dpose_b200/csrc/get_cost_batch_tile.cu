@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ 
 // as long as every visited cell lands within one patch of the valid range — see the clip invariant
 // in the kernel.
 // image[((patch * 2 + half) * R + rep)] (16 bytes each), patch = k_upper.y * cols + k_upper.x
-__global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *__restrict__ image, int rows, int cols,
-                                   int rep_shift) {
+__global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *__restrict__ image,
+                                   double2 *__restrict__ hi_only, int rows, int cols, int rep_shift) {
   const int n_patches = rows * cols;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_patches; i += gridDim.x * blockDim.x) {
     const int uy = i / cols, ux = i - uy * cols;
@@ -103,9 +103,14 @@ __global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *
       hi.x = a.a01 - a.a11 * U;
       lo.x = (a.a00 - a.a10 * U) - (a.a01 * V - (a.a11 * U) * V);
     }
-    for (int r = 0; r < (1 << rep_shift); ++r) {
-      image[(((size_t)i * 2 + 0) << rep_shift) + r] = lo;
-      image[(((size_t)i * 2 + 1) << rep_shift) + r] = hi;
+    if (hi_only) {  // DPOSE_TILE_TEX layout: shared image = first halves only, second halves in their own array
+      hi_only[i] = hi;
+      for (int r = 0; r < (1 << rep_shift); ++r) image[((size_t)i << rep_shift) + r] = lo;
+    } else {
+      for (int r = 0; r < (1 << rep_shift); ++r) {
+        image[(((size_t)i * 2 + 0) << rep_shift) + r] = lo;
+        image[(((size_t)i * 2 + 1) << rep_shift) + r] = hi;
+      }
     }
   }
 }
@@ -158,6 +163,7 @@ struct TileArgs {
   const double *poses;
   double *out;
   size_t n;
+  cudaTextureObject_t tex_hi;  // DPOSE_TILE_TEX: second halves of the patch polynomials (int4 texels)
   int out_aligned;  // out is 32-byte aligned: one 256-bit store per result
   float clip_thr;   // a strip of the kernel rectangle is clipped per row only if |cos| (|sin|) exceeds this
 };
@@ -183,6 +189,12 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 #endif
 // DPOSE_TILE_WALK 1: branch-free row advance in the cell walk (37-instruction loop body, +0.7 % on B200);
 // 0: nested branch (41 instructions)
+// DPOSE_TILE_TEX 1: the (b01, b11) half of every patch polynomial is fetched through the texture unit from a
+// plain global array, only the (b00, b10) halves stay in shared memory (8 replicas fit): an experiment to take
+// gather wavefronts off the LSU data pipe, which ncu shows as the busiest unit (85 %).
+#ifndef DPOSE_TILE_TEX
+#define DPOSE_TILE_TEX 0
+#endif
 #ifndef DPOSE_TILE_WALK
 #define DPOSE_TILE_WALK 1
 #endif
@@ -243,7 +255,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   constexpr int kStored = DPOSE_TILE_COMPACT ? kRows : kSlots;
   (void)kStored;
   uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + tid;  // [row * kThreads], row < kStored
-  constexpr uint32_t kPatchStride = 32u << kRepShift, kHalfOff = 16u << kRepShift;
+  constexpr uint32_t kPatchStride = (DPOSE_TILE_TEX ? 16u : 32u) << kRepShift, kHalfOff = 16u << kRepShift;
+  (void)kHalfOff;
   const int cols = a.g.cols;
   // Kernel coordinates are carried as k' = k + 0.5 - 2 = k - 1.5: floor(k') = k_upper - 2 (k_upper = round(k),
   // dpose_core.cpp:177), frac(k') = c_rel (:193), and the bounds test (:181-182) becomes
@@ -397,10 +410,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const double M = 6755399441055744.0;  // 1.5 * 2^52: adding it (rounding down) floors to an integer
           const int ux = __double2loint(__dadd_rd(ku, M)), uy = __double2loint(__dadd_rd(kv, M));  // k_upper - 2
           // no bounds test (dpose_core.cpp:181-182): out-of-range patches are zero, see the clip invariant
-          const uint32_t addr = my_coef + (uint32_t)(uy * cols + ux) * kPatchStride;
+          const int pidx = uy * cols + ux;
+          const uint32_t addr = my_coef + (uint32_t)pidx * kPatchStride;
           double b00, b10, b01, b11;
           asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
+#if DPOSE_TILE_TEX
+          {
+            const int4 t = tex1Dfetch<int4>(a.tex_hi, pidx + 2 * cols + 2);
+            b01 = __hiloint2double(t.y, t.x);
+            b11 = __hiloint2double(t.w, t.z);
+          }
+#else
           asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(b01), "=d"(b11) : "r"(addr), "n"(kHalfOff));
+#endif
           const double fv = fma(b11, ku, b01);  // df/dkv
           acc.f += fma(kv, fv, fma(b10, ku, b00));
           if (kJac) {
@@ -500,7 +522,8 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   const int need = std::min(32, pg->win_max);
   const int rows = need <= 20 ? 20 : need <= 28 ? 28 : 32;
   const int stored = DPOSE_TILE_COMPACT ? rows : rows + 7;
-  const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols;
+  // bytes of one replica of the shared-memory image
+  const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols / (DPOSE_TILE_TEX ? 2 : 1);
   const size_t budget = (size_t)smem_optin - 64;
   // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts)
   int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 1024;
@@ -539,8 +562,24 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
         p->d_coef_image = nullptr;
       }
       DPOSE_CUDA(cudaMalloc(&p->d_coef_image, table_bytes << rep_shift));
-      k_build_coef_image<<<64, 256, 0, stream>>>(pg->d_coef, reinterpret_cast<double2 *>(p->d_coef_image), pg->rows,
-                                                 pg->cols, rep_shift);
+#if DPOSE_TILE_TEX
+      if (!p->d_coef_hi) {
+        const size_t hi_bytes = sizeof(double2) * (size_t)pg->rows * pg->cols;
+        DPOSE_CUDA(cudaMalloc(&p->d_coef_hi, hi_bytes));
+        cudaResourceDesc res = {};
+        res.resType = cudaResourceTypeLinear;
+        res.res.linear.devPtr = p->d_coef_hi;
+        res.res.linear.desc = cudaCreateChannelDesc<int4>();
+        res.res.linear.sizeInBytes = hi_bytes;
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t tex = 0;
+        DPOSE_CUDA(cudaCreateTextureObject(&tex, &res, &td, nullptr));
+        p->tex_hi = (unsigned long long)tex;
+      }
+#endif
+      k_build_coef_image<<<64, 256, 0, stream>>>(pg->d_coef, reinterpret_cast<double2 *>(p->d_coef_image),
+                                                 reinterpret_cast<double2 *>(p->d_coef_hi), pg->rows, pg->cols, rep_shift);
       DPOSE_LAUNCHED();
       DPOSE_CUDA(cudaStreamSynchronize(stream));  // other streams may use the image right after
       p->coef_image_shift = rep_shift;
@@ -566,6 +605,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.poses = d_poses;
   a.out = d_out;
   a.n = n;
+  a.tex_hi = (cudaTextureObject_t)p->tex_hi;
   a.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 31u) == 0;
   a.clip_thr = 0.5f / (float)std::max(pg->win_max, 25);
   const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)stored * 4 * threads;
