@@ -118,6 +118,12 @@ __global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ unsigned lds_u32(uint32_t addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 struct Tile8 {
   unsigned w[8];
 };
@@ -181,11 +187,12 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 
 // DPOSE_TILE_CVT: how the walk turns a bit / row index into a double.
 //   0: 2^52 trick (one DADD on the FP64 pipe + register-pair set-up), 1: I2F.F64 (conversion pipe)
-// DPOSE_TILE_COMPACT 1 stores only the rows that can belong to a chunk (less shared memory, room for 8
-// coefficient replicas at 1024 threads).  Measured on B200: the store predicates cost 7 %, the conflict-free
-// gathers win back 3 % -> off by default (profiles/r1_v13_ab.txt).
+// DPOSE_TILE_COMPACT 1 stores only the rows that can belong to a chunk: less shared memory, so that 8
+// coefficient replicas (conflict-free LDS.128 gathers) fit next to 1024 threads' row masks.  Measured on B200
+// (cfg5): 9.26e9 poses/s against 8.89e9 for "every slot stored, 4 replicas"; the L1/shared data pipe drops from
+// 85 % to ~60 % busy.  0 keeps every scanned slot (no store predicates).
 #ifndef DPOSE_TILE_COMPACT
-#define DPOSE_TILE_COMPACT 0
+#define DPOSE_TILE_COMPACT 1
 #endif
 // DPOSE_TILE_WALK 1: branch-free row advance in the cell walk (37-instruction loop body, +0.7 % on B200);
 // 0: nested branch (41 instructions)
@@ -380,7 +387,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           rowmask = __funnelshift_r(sm_lo, sm_hi, (unsigned)off) & shr_clamp(0xffffffffu, (unsigned)(32 - hc));
         }
         // ---- phase 2: walk the set bits, highest row / highest bit first ---------------------------------------
-        const uint32_t *srow = DPOSE_TILE_COMPACT ? s_mask : s_mask + off * kThreads;
+        // 32-bit shared address of chunk row 0, pinned in a register: without the opaque asm the compiler
+        // re-derives it from threadIdx and the kernel arguments inside the walk (measured: +20 % instructions)
+        uint32_t srow = smem_u32(DPOSE_TILE_COMPACT ? s_mask : s_mask + off * kThreads);
+        asm volatile("" : "+r"(srow));
         const double dcb = (double)cb, drb = (double)rb;
         const double kuc = fma(c, dcb, fma(s, drb, ku0)), kvc = fma(c, drb, fma(-s, dcb, kv0));
         unsigned mask = 0u;
@@ -393,13 +403,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const int r2 = top_bit(rowmask);  // -1 when no row is left; then adv is false and nothing below uses it
           row = adv ? r2 : row;
           rowmask = adv ? rowmask ^ shl_clamp(1u, (unsigned)r2) : rowmask;
-          if (adv) mask = srow[row * kThreads];
+          if (adv) mask = lds_u32(srow + (uint32_t)row * (uint32_t)(kThreads * 4));
 #else
           if (mask == 0u) {
             if (rowmask == 0u) break;
             row = top_bit(rowmask);
             rowmask ^= 1u << row;
-            mask = srow[row * kThreads];
+            mask = lds_u32(srow + (uint32_t)row * (uint32_t)(kThreads * 4));
           }
 #endif
           const int b = top_bit(mask);
