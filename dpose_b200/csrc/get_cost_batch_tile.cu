@@ -103,7 +103,7 @@ __global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *
       hi.x = a.a01 - a.a11 * U;
       lo.x = (a.a00 - a.a10 * U) - (a.a01 * V - (a.a11 * U) * V);
     }
-    if (hi_only) {  // DPOSE_TILE_TEX layout: shared image = first halves only, second halves in their own array
+    if (hi_only) {  // texture-mode layout: shared image = first halves only, second halves in their own array
       hi_only[i] = hi;
       for (int r = 0; r < (1 << rep_shift); ++r) image[((size_t)i << rep_shift) + r] = lo;
     } else {
@@ -169,7 +169,7 @@ struct TileArgs {
   const double *poses;
   double *out;
   size_t n;
-  cudaTextureObject_t tex_hi;  // DPOSE_TILE_TEX: second halves of the patch polynomials (int4 texels)
+  cudaTextureObject_t tex_hi;  // texture mode: second halves of the patch polynomials (int4 texels)
   int out_aligned;  // out is 32-byte aligned: one 256-bit store per result
   float clip_thr;   // a strip of the kernel rectangle is clipped per row only if |cos| (|sin|) exceeds this
 };
@@ -196,12 +196,11 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 #endif
 // DPOSE_TILE_WALK 1: branch-free row advance in the cell walk (37-instruction loop body, +0.7 % on B200);
 // 0: nested branch (41 instructions)
-// DPOSE_TILE_TEX 1: the (b01, b11) half of every patch polynomial is fetched through the texture unit from a
-// plain global array, only the (b00, b10) halves stay in shared memory (8 replicas fit): an experiment to take
-// gather wavefronts off the LSU data pipe, which ncu shows as the busiest unit (85 %).
-#ifndef DPOSE_TILE_TEX
-#define DPOSE_TILE_TEX 0
-#endif
+// Big tables (the coefficient image fits shared memory only once: kRepShift == 0) run in "texture mode": shared
+// memory holds the (b00, b10) halves twice (same bytes as one full copy, half the bank conflicts) and the
+// (b01, b11) halves are fetched through the texture unit from a plain global array, which takes those gathers
+// off the LSU data pipe.  Measured on B200, 35 x 55 table (cfg3): +7 %; on the small rect table, where 8 full
+// replicas fit, it is 5 % SLOWER than shared memory only — hence tied to the single-replica case.
 #ifndef DPOSE_TILE_WALK
 #define DPOSE_TILE_WALK 1
 #endif
@@ -262,14 +261,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   constexpr int kStored = DPOSE_TILE_COMPACT ? kRows : kSlots;
   (void)kStored;
   uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + tid;  // [row * kThreads], row < kStored
-  constexpr uint32_t kPatchStride = (DPOSE_TILE_TEX ? 16u : 32u) << kRepShift, kHalfOff = 16u << kRepShift;
+  constexpr bool kTex = kRepShift == 0;             // texture mode, see above
+  constexpr int kLoShift = kTex ? 1 : kRepShift;    // log2 replicas of what lives in shared memory
+  constexpr uint32_t kPatchStride = (kTex ? 16u : 32u) << kLoShift, kHalfOff = 16u << kLoShift;
   (void)kHalfOff;
   const int cols = a.g.cols;
   // Kernel coordinates are carried as k' = k + 0.5 - 2 = k - 1.5: floor(k') = k_upper - 2 (k_upper = round(k),
   // dpose_core.cpp:177), frac(k') = c_rel (:193), and the bounds test (:181-182) becomes
   // 0 <= floor(k') <= dim - 4.  The patch of k_upper = (2, 2) therefore sits at the base address.
   const uint32_t my_coef =
-      coef_u32 + ((uint32_t)lane & ((1u << kRepShift) - 1u)) * 16u + (uint32_t)(2 * cols + 2) * kPatchStride;
+      coef_u32 + ((uint32_t)lane & ((1u << kLoShift) - 1u)) * 16u + (uint32_t)(2 * cols + 2) * kPatchStride;
   const float hi_u = (float)a.g.cols - 3.0f, hi_v = (float)a.g.rows - 3.0f;  // 0 <= k' < dim - 3
   const double cx15 = a.g.cx - 1.5, cy15 = a.g.cy - 1.5;
 
@@ -424,15 +425,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const uint32_t addr = my_coef + (uint32_t)pidx * kPatchStride;
           double b00, b10, b01, b11;
           asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
-#if DPOSE_TILE_TEX
-          {
+          if (kTex) {
             const int4 t = tex1Dfetch<int4>(a.tex_hi, pidx + 2 * cols + 2);
             b01 = __hiloint2double(t.y, t.x);
             b11 = __hiloint2double(t.w, t.z);
+          } else {
+            asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(b01), "=d"(b11) : "r"(addr), "n"(kHalfOff));
           }
-#else
-          asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(b01), "=d"(b11) : "r"(addr), "n"(kHalfOff));
-#endif
           const double fv = fma(b11, ku, b01);  // df/dkv
           acc.f += fma(kv, fv, fma(b10, ku, b00));
           if (kJac) {
@@ -533,7 +532,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   const int rows = need <= 20 ? 20 : need <= 28 ? 28 : 32;
   const int stored = DPOSE_TILE_COMPACT ? rows : rows + 7;
   // bytes of one replica of the shared-memory image
-  const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols / (DPOSE_TILE_TEX ? 2 : 1);
+  const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols;
   const size_t budget = (size_t)smem_optin - 64;
   // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts)
   int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 1024;
@@ -572,8 +571,8 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
         p->d_coef_image = nullptr;
       }
       DPOSE_CUDA(cudaMalloc(&p->d_coef_image, table_bytes << rep_shift));
-#if DPOSE_TILE_TEX
-      if (!p->d_coef_hi) {
+      const bool tex_mode = rep_shift == 0;  // first halves twice in the image, second halves behind a texture
+      if (tex_mode && !p->d_coef_hi) {
         const size_t hi_bytes = sizeof(double2) * (size_t)pg->rows * pg->cols;
         DPOSE_CUDA(cudaMalloc(&p->d_coef_hi, hi_bytes));
         cudaResourceDesc res = {};
@@ -587,9 +586,9 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
         DPOSE_CUDA(cudaCreateTextureObject(&tex, &res, &td, nullptr));
         p->tex_hi = (unsigned long long)tex;
       }
-#endif
       k_build_coef_image<<<64, 256, 0, stream>>>(pg->d_coef, reinterpret_cast<double2 *>(p->d_coef_image),
-                                                 reinterpret_cast<double2 *>(p->d_coef_hi), pg->rows, pg->cols, rep_shift);
+                                                 tex_mode ? reinterpret_cast<double2 *>(p->d_coef_hi) : nullptr, pg->rows,
+                                                 pg->cols, tex_mode ? 1 : rep_shift);
       DPOSE_LAUNCHED();
       DPOSE_CUDA(cudaStreamSynchronize(stream));  // other streams may use the image right after
       p->coef_image_shift = rep_shift;
