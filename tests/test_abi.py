@@ -95,3 +95,34 @@ def test_product_does_not_reference_oracle():
                     if re.search(r"(from|import)\s+oracle|oracle/|dpose_oracle", txt):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_argument_validation_without_a_device(built):
+    """NULL / out-of-range arguments are rejected with DPOSE_EINVAL before any CUDA call, on any box"""
+    from dpose_b200 import _lib
+    L = _lib.lib()
+    assert L.dpose_pg_create(None, 4, 2, 0, ctypes.byref(ctypes.c_void_p())) == _lib.EINVAL
+    fp = fx.RECT.copy()
+    assert L.dpose_pg_create(fp.ctypes.data, 4, 2, 0, None) == _lib.EINVAL
+    assert L.dpose_pg_create(fp.ctypes.data, 5000, 2, 0, ctypes.byref(ctypes.c_void_p())) == _lib.EINVAL  # vertex cap
+    assert L.dpose_pg_create(fp.ctypes.data, 4, 100000, 0, ctypes.byref(ctypes.c_void_p())) == _lib.EINVAL  # padding cap
+    assert b"footprint" in L.dpose_last_error() or b"padding" in L.dpose_last_error()
+    assert L.dpose_map_create(None, 8, 8, 8, 0, ctypes.byref(ctypes.c_void_p())) == _lib.EINVAL
+    m = np.zeros((8, 8), np.uint8)
+    assert L.dpose_map_create(m.ctypes.data, 8, 8, 4, 0, ctypes.byref(ctypes.c_void_p())) == _lib.EINVAL  # pitch < size_x
+    assert L.dpose_pg_get_cost_batch(None, None, None, 0, None, 1) == _lib.EINVAL
+    assert L.dpose_problem_create(None, None, ctypes.byref(ctypes.c_void_p())) == _lib.EINVAL
+    ok = ctypes.c_int(0)
+    assert L.dpose_check_footprint(None, fp.ctypes.data, 4, 254, ctypes.byref(ok)) == _lib.EINVAL
+    assert L.dpose_world_to_cell(None, 3, 0.0, 0.0, 0.05, 10, 10, None, None) == _lib.EINVAL
+    w = np.zeros((1, 3))
+    assert L.dpose_world_to_cell(w.ctypes.data, 1, 0.0, 0.0, 0.0, 10, 10, w.ctypes.data, None) == _lib.EINVAL  # res <= 0
+    n = ctypes.c_size_t(0)
+    assert L.dpose_raytrace(None, None, None, 0, ctypes.byref(n)) == _lib.EINVAL
+    # destroying NULL handles is a no-op
+    L.dpose_pg_destroy(None)
+    L.dpose_map_destroy(None)
+    L.dpose_cells_destroy(None)
+    L.dpose_problem_destroy(None)
+    L.dpose_free(None)
+    L.dpose_host_free(None)
