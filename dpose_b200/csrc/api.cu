@@ -409,6 +409,7 @@ int dpose_lethal_cells_within_device(const dpose_map *map, const int32_t box[10]
   dpose_cells *c = new (std::nothrow) dpose_cells();
   if (!c) return fail(DPOSE_ENOMEM, "out of host memory");
   c->device = map->device;
+  c->pooled = true;
   const int rc = lethal_extract(map, box, &c->d_xy, &c->n);
   if (rc != DPOSE_OK) {
     delete c;
@@ -489,7 +490,10 @@ void dpose_cells_destroy(dpose_cells *cells) {
   if (!cells) return;
   {
     DeviceGuard guard(cells->device);
-    cudaFree(cells->d_xy);
+    if (cells->pooled && cells->d_xy)
+      cudaFreeAsync(cells->d_xy, nullptr);  // back to the pool without a device-wide synchronisation
+    else
+      cudaFree(cells->d_xy);
   }
   delete cells;
 }

@@ -132,6 +132,7 @@ struct dpose_cells {
   int device = 0;
   size_t n = 0;
   int2 *d_xy = nullptr;
+  bool pooled = false;  // d_xy comes from the stream-ordered allocator (lethal extraction): freed with cudaFreeAsync
 };
 
 namespace dpose {

@@ -90,6 +90,18 @@ def bench_lethal():
         emit(what="lethal_cells_within", box=label, cells=n, call_wall_us=wall * 1e6, device_us=dev_us,
              algorithmic_bytes=algo, achieved_gbs_device=algo / (dev_us * 1e-6) / 1e9,
              achieved_gbs_whole_call=algo / wall / 1e9)
+    # the reference's own perf workload (dpose_core/perf/dpose_core.cpp:73-90): 200 x 200, every 2nd cell lethal
+    m = np.zeros((200, 200), np.uint8)
+    m.reshape(-1)[::2] = fx.LETHAL
+    cm2 = dp.Costmap(m)
+    ring = fx.to_rectangle(198, 198)
+    ok = bool(np.array_equal(dp.lethal_cells_within(cm2, ring), capi.lethal_cells_within(m, ring)))
+    t_gpu = best_of(lambda: dp.lethal_cells_within(cm2, ring, on_device=True), 20)
+    t_gpu_host = best_of(lambda: dp.lethal_cells_within(cm2, ring), 20)
+    t_cpu = best_of(lambda: capi.lethal_cells_within(m, ring), 20)
+    emit(what="perf_dpose_costmap literal (200x200, every 2nd cell lethal, box 198x198)", cells=int((m == fx.LETHAL).sum()),
+         gpu_call_us_result_on_device=t_gpu * 1e6, gpu_call_us_result_on_host=t_gpu_host * 1e6, cpu_oracle_call_us=t_cpu * 1e6,
+         parity=ok)
     # parity on a host map small enough for the oracle
     m = fx.bernoulli_map(2000, 2000, 0.10, 1)
     ring = fx.rotated_ring(fx.to_rectangle((-300, -200), (300, 200)), (1000.0, 1000.0, 0.7))
