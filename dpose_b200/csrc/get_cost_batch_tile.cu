@@ -165,7 +165,7 @@ struct TileArgs {
   TableGeom g;
   int size_x, size_y;
   const uint32_t *tiles;
-  uint32_t ntx;
+  uint32_t ntx, nty;
   const double *poses;
   double *out;
   size_t n;
@@ -201,6 +201,12 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 // (b01, b11) halves are fetched through the texture unit from a plain global array, which takes those gathers
 // off the LSU data pipe.  Measured on B200, 35 x 55 table (cfg3): +7 %; on the small rect table, where 8 full
 // replicas fit, it is 5 % SLOWER than shared memory only — hence tied to the single-replica case.
+// DPOSE_TILE_CHECK 1: debug build that traps on any access outside the coefficient image, the tile plane or the
+// row-mask block (compute-sanitizer is not available on the GPU pool): run the GPU tests and the bench with it
+// after touching the clip logic.
+#ifndef DPOSE_TILE_CHECK
+#define DPOSE_TILE_CHECK 0
+#endif
 #ifndef DPOSE_TILE_WALK
 #define DPOSE_TILE_WALK 1
 #endif
@@ -324,6 +330,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const unsigned sh = (unsigned)xs & 31u;
           const bool need_b = (int)sh + wc > 32;
           const int tb0 = ys >> 3, n_tb = ((ys + hc - 1) >> 3) - tb0;  // last tile row index, relative
+#if DPOSE_TILE_CHECK
+          if (tb0 < 0 || tb0 + n_tb >= (int)a.nty || (xs >> 5) < 0 || (xs >> 5) + (need_b ? 1 : 0) >= (int)a.ntx || hc > kRows ||
+              wc > 32 || n_tb > 4)
+            __trap();
+#endif
           const uint32_t *tp = a.tiles + ((size_t)tb0 * a.ntx + (size_t)(xs >> 5)) * 8;
           const size_t tstride = (size_t)a.ntx * 8;
           const float fcb = (float)cb, fr0 = (float)(rb - off);
@@ -422,6 +433,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const int ux = __double2loint(__dadd_rd(ku, M)), uy = __double2loint(__dadd_rd(kv, M));  // k_upper - 2
           // no bounds test (dpose_core.cpp:181-182): out-of-range patches are zero, see the clip invariant
           const int pidx = uy * cols + ux;
+#if DPOSE_TILE_CHECK
+          if (pidx + 2 * cols + 2 < 0 || pidx + 2 * cols + 2 >= a.g.rows * cols || row < 0 || row >= kRows || ux < -2 ||
+              ux > cols - 3 || uy < -2 || uy > a.g.rows - 3)
+            __trap();
+#endif
           const uint32_t addr = my_coef + (uint32_t)pidx * kPatchStride;
           double b00, b10, b01, b11;
           asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
@@ -611,6 +627,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.size_y = (int)map->size_y;
   a.tiles = map->d_tiles;
   a.ntx = map->tiles_ntx;
+  a.nty = map->tiles_nty;
   a.poses = d_poses;
   a.out = d_out;
   a.n = n;
