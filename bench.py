@@ -30,6 +30,11 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: NCCL prints its version banner to stdout when NCCL_DEBUG is VERSION or
+# WARN (and logs there for INFO / TRACE); this bench uses NCCL only for the timing barrier / max-reduction, so
+# its logging is switched off.  Must happen before torch / NCCL are loaded.
+if os.environ.get("NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "NONE"
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -248,9 +253,6 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION / INFO) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     side, n_poses, fp_name, desc = WORKLOADS[args.workload]
