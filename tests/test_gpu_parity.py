@@ -465,7 +465,23 @@ def test_full_size_properties_cfg5(dp):
     turned = poses[sub].copy()
     turned[:, 2] += 2.0 * math.pi
     assert np.all(fx.tol_ok(pg.get_cost_batch(cm, turned), out[sub], rel=1e-9, abs_=1e-8))
-    # a sample against the oracle
-    idx = rng.choice(n, 3000, replace=False)
-    ref = capi.CostData(fx.RECT, 2).get_cost_batch(m, poses[idx], shift=True, nthreads=capi.max_threads())
-    assert fx.tol_ok(out[idx], ref).all()
+    # EVERY pose against the oracle (translated-equivalent inputs): the CPU port does ~5e6 poses/s
+    # on the GPU box's cores, so the full batch takes a few seconds
+    oc = capi.CostData(fx.RECT, 2)
+    nt = capi.max_threads()
+    worst = 0.0
+    for lo in range(0, n, 2_000_000):
+        ref = oc.get_cost_batch(m, poses[lo:lo + 2_000_000], shift=True, nthreads=nt)
+        got = out[lo:lo + 2_000_000]
+        assert fx.tol_ok(got, ref).all(), lo
+        worst = max(worst, float(np.max(np.abs(got - ref) / (1e-6 + 1e-5 * np.abs(ref)))))
+    assert worst < 0.2  # the largest deviation uses under a fifth of the tolerance
+    # literal reference (no shift) on a slice: at coordinates ~1e4 its own FD round-off reaches the tolerance on
+    # ~1 % of the poses; each of those must be the reference's deviation from the long-double truth
+    sl = slice(0, 200_000)
+    lit = oc.get_cost_batch(m, poses[sl], nthreads=nt)
+    truth = oc.get_cost_batch_truth(m, poses[sl], nthreads=nt)
+    bad = ~fx.tol_ok(out[sl], lit)
+    assert bad.any(axis=1).mean() < 0.05
+    assert np.all(np.abs(out[sl][bad] - truth[bad]) <= 0.01 * np.abs(lit[bad] - truth[bad]) + 1e-12)
+    assert fx.tol_ok(out[sl][:, 0], lit[:, 0]).all()  # the cost itself never needs the protocol
