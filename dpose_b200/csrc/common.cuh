@@ -89,10 +89,12 @@ struct dpose_pg {
   // batched kernel geometry: side of the largest window (cells) any pose can touch
   int win_max = 0;
   // replicated, bank-interleaved copy of d_coef for the thread-per-pose kernel (get_cost_batch_tile.cu),
-  // built on first use: R = 1 << coef_image_shift replicas
+  // built on first use: R = 1 << coef_image_shift replicas (0: first halves twice, -1: nothing in shared memory;
+  // kNoCoefImage: not built yet)
   void *d_coef_image = nullptr;
-  int coef_image_shift = -1;
-  // DPOSE_TILE_TEX builds: second halves of the patch polynomials, read through a texture object
+  static constexpr int kNoCoefImage = -100;
+  int coef_image_shift = kNoCoefImage;
+  // texture modes (coef_image_shift <= 0): the patch polynomials as a plain global array behind a texture object
   void *d_coef_hi = nullptr;
   unsigned long long tex_hi = 0;
   // streams, events and staging buffers of the host-buffer batch entry point (api.cu), built on first use

@@ -103,9 +103,11 @@ __global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *
       hi.x = a.a01 - a.a11 * U;
       lo.x = (a.a00 - a.a10 * U) - (a.a01 * V - (a.a11 * U) * V);
     }
-    if (hi_only) {  // texture-mode layout: shared image = first halves only, second halves in their own array
-      hi_only[i] = hi;
-      for (int r = 0; r < (1 << rep_shift); ++r) image[((size_t)i << rep_shift) + r] = lo;
+    if (hi_only) {  // texture modes: shared image = first halves only (if any), both halves in a plain global array
+      hi_only[2 * (size_t)i] = lo;
+      hi_only[2 * (size_t)i + 1] = hi;
+      if (image)
+        for (int r = 0; r < (1 << rep_shift); ++r) image[((size_t)i << rep_shift) + r] = lo;
     } else {
       for (int r = 0; r < (1 << rep_shift); ++r) {
         image[(((size_t)i * 2 + 0) << rep_shift) + r] = lo;
@@ -201,6 +203,8 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 // (b01, b11) halves are fetched through the texture unit from a plain global array, which takes those gathers
 // off the LSU data pipe.  Measured on B200, 35 x 55 table (cfg3): +7 %; on the small rect table, where 8 full
 // replicas fit, it is 5 % SLOWER than shared memory only — hence tied to the single-replica case.
+// Tables that do not fit shared memory at all (kRepShift == -1) fetch both halves through the texture unit: the
+// kernel then has no table-size limit (L1 / L2 serve the gathers).
 // DPOSE_TILE_CHECK 1: debug build that traps on any access outside the coefficient image, the tile plane or the
 // row-mask block (compute-sanitizer is not available on the GPU pool): run the GPU tests and the bench with it
 // after touching the clip logic.
@@ -267,7 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   constexpr int kStored = DPOSE_TILE_COMPACT ? kRows : kSlots;
   (void)kStored;
   uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + tid;  // [row * kThreads], row < kStored
-  constexpr bool kTex = kRepShift == 0;             // texture mode, see above
+  constexpr bool kTex = kRepShift <= 0;             // texture mode, see above
+  constexpr bool kGlobal = kRepShift < 0;           // nothing of the table in shared memory
   constexpr int kLoShift = kTex ? 1 : kRepShift;    // log2 replicas of what lives in shared memory
   constexpr uint32_t kPatchStride = (kTex ? 16u : 32u) << kLoShift, kHalfOff = 16u << kLoShift;
   (void)kHalfOff;
@@ -440,9 +445,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
 #endif
           const uint32_t addr = my_coef + (uint32_t)pidx * kPatchStride;
           double b00, b10, b01, b11;
-          asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
+          if (kGlobal) {
+            const int4 t = tex1Dfetch<int4>(a.tex_hi, 2 * (pidx + 2 * cols + 2));
+            b00 = __hiloint2double(t.y, t.x);
+            b10 = __hiloint2double(t.w, t.z);
+          } else {
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
+          }
           if (kTex) {
-            const int4 t = tex1Dfetch<int4>(a.tex_hi, pidx + 2 * cols + 2);
+            const int4 t = tex1Dfetch<int4>(a.tex_hi, 2 * (pidx + 2 * cols + 2) + 1);
             b01 = __hiloint2double(t.y, t.x);
             b11 = __hiloint2double(t.w, t.z);
           } else {
@@ -493,6 +504,7 @@ int launch_tile3(const TileArgs &a, int rows, int grid, size_t smem_bytes, cudaS
 }
 template <bool kJac, int kThreads>
 int launch_tile2(const TileArgs &a, int rep_shift, int rows, int grid, size_t smem_bytes, cudaStream_t stream) {
+  if (rep_shift < 0) return launch_tile3<kJac, kThreads, -1>(a, rows, grid, smem_bytes, stream);
   if (rep_shift == 0) return launch_tile3<kJac, kThreads, 0>(a, rows, grid, smem_bytes, stream);
   if (rep_shift == 2) return launch_tile3<kJac, kThreads, 2>(a, rows, grid, smem_bytes, stream);
   return launch_tile3<kJac, kThreads, 3>(a, rows, grid, smem_bytes, stream);
@@ -553,7 +565,8 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts)
   int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 1024;
   int rep_shift = env_rep == 1 ? 0 : env_rep == 4 ? 2 : 3;  // 8 replicas if they fit (conflict-free LDS.128 gathers)
-  auto fits = [&](int th, int rs) { return (table_bytes << rs) + (size_t)stored * 4 * th <= budget; };
+  auto fits = [&](int th, int rs) { return (rs < 0 ? 0 : table_bytes << rs) + (size_t)stored * 4 * th <= budget; };
+  const int threads_wanted = threads;
   while (!fits(threads, rep_shift)) {
     if (rep_shift == 3)
       rep_shift = 2;
@@ -561,8 +574,10 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
       rep_shift = 0;
     else if (threads > 512) {
       threads -= 256;
-    } else
-      return DPOSE_OK;  // table too big for shared memory
+    } else {  // the table does not fit shared memory even once: both halves through the texture unit
+      rep_shift = -1;
+      threads = threads_wanted;
+    }
   }
   // small batches are latency bound: spread them over all SMs with smaller CTAs (the replica count, and with it
   // the cached coefficient image, stays the one chosen for the largest CTA)
@@ -580,16 +595,16 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   dpose_map *m = const_cast<dpose_map *>(map);
   {
     std::lock_guard<std::mutex> lock(g_tile_mu);
-    if (!p->d_coef_image || p->coef_image_shift != rep_shift) {
+    if (p->coef_image_shift != rep_shift || (rep_shift >= 0 && !p->d_coef_image)) {
       if (p->d_coef_image) {
         DPOSE_CUDA(cudaDeviceSynchronize());
         DPOSE_CUDA(cudaFree(p->d_coef_image));
         p->d_coef_image = nullptr;
       }
-      DPOSE_CUDA(cudaMalloc(&p->d_coef_image, table_bytes << rep_shift));
-      const bool tex_mode = rep_shift == 0;  // first halves twice in the image, second halves behind a texture
+      if (rep_shift >= 0) DPOSE_CUDA(cudaMalloc(&p->d_coef_image, table_bytes << rep_shift));
+      const bool tex_mode = rep_shift <= 0;  // first halves twice in the image (or nowhere), both halves behind a texture
       if (tex_mode && !p->d_coef_hi) {
-        const size_t hi_bytes = sizeof(double2) * (size_t)pg->rows * pg->cols;
+        const size_t hi_bytes = 2 * sizeof(double2) * (size_t)pg->rows * pg->cols;
         DPOSE_CUDA(cudaMalloc(&p->d_coef_hi, hi_bytes));
         cudaResourceDesc res = {};
         res.resType = cudaResourceTypeLinear;
@@ -621,7 +636,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
 
   TileArgs a;
   a.coef_image = reinterpret_cast<const uint4 *>(p->d_coef_image);
-  a.coef_bytes = (uint32_t)(table_bytes << rep_shift);
+  a.coef_bytes = rep_shift < 0 ? 0u : (uint32_t)(table_bytes << rep_shift);
   a.g = TableGeom{pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
   a.size_x = (int)map->size_x;
   a.size_y = (int)map->size_y;
