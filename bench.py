@@ -16,9 +16,12 @@ e2e    : same metric through the public host-buffer call (dpose_pg_get_cost_batc
          pinned host poses -> H2D -> kernel -> D2H results, all inside the timed region.
 roofline: algorithmic bytes (24 B pose + 32 B result + |window| map bytes, summed exactly on the
          host) / average kernel launch time, against the measured HBM copy peak.
-cpu_baseline / --impl reference: the CPU restatement of dpose_core's own path (oracle/, "port":
-         the reference needs Eigen/OpenCV/costmap_2d and cannot be compiled here), OpenMP over
-         poses on all host cores, on a bounded sample of the same workload.
+cpu_baseline / --impl reference: the reference's own dpose_core sources as compiled into oracle/_ref
+         (kind "reference"; oracle/refshim/README.md says how), driven per pose as BASELINE defines the
+         batch (rotated box -> lethal_cells_within -> get_cost), OpenMP over poses on all host cores, on a
+         bounded sample of the same workload.  `port_value` beside it is the oracle's C restatement
+         (bit-identical results, leaner data structures, hence faster) on the same sample; when
+         oracle/_ref is absent the port is timed instead and kind says "port".
 """
 import argparse
 import json
@@ -162,59 +165,86 @@ def make_host_workload(side, n_poses, seed_map, seed_pose):
     return m, poses
 
 
-def cpu_reference_rate(oc, host_map, poses, budget_s=12.0):
-    """times the oracle (CPU restatement of dpose_core's path) with all host threads on a bounded
-    sample; returns (poses/s, n_sample, threads, seconds)"""
-    from oracle import capi
+def cpu_impls(fp, pad):
+    """[(kind, batch_fn)] of the CPU implementations of the path, the one the baseline is quoted on first:
+    the reference's own sources compiled into oracle/_ref when that library is here, then the oracle port"""
+    from oracle import capi, refapi
     threads = capi.max_threads()
+    oc = capi.CostData(fp, pad)
+    impls = [("port", lambda m, p: oc.get_cost_batch(m, p, nthreads=threads))]
+    if os.environ.get("DPOSE_CPU_BASELINE", "") != "port" and refapi.available():
+        rc = refapi.PoseGradient(fp, pad)
+        impls.insert(0, ("reference", lambda m, p: rc.get_cost_batch(m, p, nthreads=threads)))
+    return impls, threads
+
+
+def cpu_reference_rate(fp, pad, host_map, poses, budget_s=12.0):
+    """times the CPU implementation(s) of the path with all host threads on a bounded sample;
+    returns the cpu_baseline object"""
+    impls, threads = cpu_impls(fp, pad)
+    kind, fn = impls[0]
     probe = min(len(poses), 20000)
     t0 = time.perf_counter()
-    oc.get_cost_batch(host_map, poses[:probe], nthreads=threads)
-    dt = time.perf_counter() - t0
-    rate = probe / max(dt, 1e-9)
+    fn(host_map, poses[:probe])
+    rate = probe / max(time.perf_counter() - t0, 1e-9)
     n = int(min(len(poses), max(probe, rate * budget_s)))
     t0 = time.perf_counter()
-    oc.get_cost_batch(host_map, poses[:n], nthreads=threads)
+    fn(host_map, poses[:n])
     dt = time.perf_counter() - t0
-    return n / dt, n, threads, dt
+    what = ("reference's dpose_core.cpp/dpose_costmap.cpp compiled into oracle/_ref" if kind == "reference"
+            else "oracle port")
+    out = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": kind,
+           "sample": f"first {n} poses of the same workload in {dt:.1f} s "
+                     f"({what}: lethal_cells_within(rotated box)+get_cost per pose, OpenMP)"}
+    if len(impls) > 1:
+        t0 = time.perf_counter()
+        impls[1][1](host_map, poses[:n])
+        out["port_value"] = n / (time.perf_counter() - t0)
+    return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU path (oracle port), all host threads, rank 0 only"""
+    """--impl reference: the reference's own CPU path (oracle/_ref, else the oracle port), all host threads,
+    rank 0 only"""
     if rank != 0:
         return 0
     import fixtures as fx
-    from oracle import capi
     side, n_per_gpu, fp_name, desc = WORKLOADS[args.workload]
     fp, pad = fx.FOOTPRINTS[fp_name]
-    oc = capi.CostData(fp, pad)
-    threads = capi.max_threads()
+    impls, threads = cpu_impls(fp, pad)
+    kind, fn = impls[0]
     host_map = fx.bernoulli_map(side, side, 0.10, 4)
     # bounded sample per step: sized from a probe so the whole run stays within a few minutes
     probe_poses = fx.random_poses(20000, side, side, 5)
     t0 = time.perf_counter()
-    oc.get_cost_batch(host_map, probe_poses, nthreads=threads)
+    fn(host_map, probe_poses)
     rate = len(probe_poses) / (time.perf_counter() - t0)
     total_steps = args.steps + args.warmup
     per_step = int(max(20000, min(n_per_gpu, rate * 60.0 / max(total_steps, 1))))
     poses = fx.random_poses(per_step, side, side, 5)
     for _ in range(args.warmup):
-        oc.get_cost_batch(host_map, poses, nthreads=threads)
+        fn(host_map, poses)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oc.get_cost_batch(host_map, poses, nthreads=threads)
+        fn(host_map, poses)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     sample = f"{per_step} poses/step of the same workload (bounded sample), {args.steps} steps"
+    cpu_baseline = {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+    if len(impls) > 1:
+        t0 = time.perf_counter()
+        impls[1][1](host_map, poses)
+        cpu_baseline["port_value"] = per_step / (time.perf_counter() - t0)
+    note = ("the reference's own dpose_core.cpp + dpose_costmap.cpp, compiled from /root/reference against the "
+            "stand-in headers of oracle/refshim into oracle/_ref" if kind == "reference" else
+            "CPU restatement of dpose_core (oracle port; oracle/_ref is not present on this box)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "poses_per_step": per_step,
-                   "note": "CPU restatement of dpose_core (oracle port; reference not compilable here: "
-                           "needs Eigen/OpenCV/costmap_2d), per pose lethal_cells_within(rotated box)+get_cost, "
-                           "OpenMP over poses"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                   "note": note + "; per pose lethal_cells_within(rotated box)+get_cost, OpenMP over poses"},
+        "cpu_baseline": cpu_baseline,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -397,10 +427,7 @@ def main():
               "tolerance": "1e-6 + 1e-5*|ref|", "e2e_equals_device_path": e2e_checksum_ok}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        v, n_s, threads, secs = cpu_reference_rate(oc, host_map, host_poses)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"first {n_s} poses of the same workload in {secs:.1f} s "
-                                  f"(oracle: lethal_cells_within(rotated box)+get_cost per pose, OpenMP)"}
+        cpu_baseline = cpu_reference_rate(fp, pad, host_map, host_poses)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

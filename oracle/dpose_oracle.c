@@ -206,6 +206,16 @@ static void exact_edt_sq(const uint8_t *img, int cols, int rows, int32_t *d2) {
   free(g);
 }
 
+/* The three OpenCV image primitives above, exported for oracle/refshim/opencv2 (the stand-in
+ * cv:: layer the reference's own dpose_core.cpp is compiled against in oracle/_ref). */
+void oracle_cv_polylines_closed(uint8_t *img, int cols, int rows, const int32_t *xy, int n, uint8_t color) {
+  cv_polylines_closed(img, cols, rows, xy, n, color);
+}
+void oracle_cv_fillpoly(uint8_t *img, int cols, int rows, const int32_t *xy, int n, uint8_t color) {
+  cv_fillpoly(img, cols, rows, xy, n, color);
+}
+void oracle_cv_edt_sq(const uint8_t *img, int cols, int rows, int32_t *d2) { exact_edt_sq(img, cols, rows, d2); }
+
 /* ------------------------------------------------------------------------- */
 /* _get_cost + cost_data::cost_data — dpose_core.cpp:55-139                    */
 /* ------------------------------------------------------------------------- */

@@ -7,12 +7,15 @@
  * and there only as the checker / the timed CPU baseline.
  *
  * Every function cites the reference file:line it restates (paths relative to the
- * upstream dorezyuk/dpose tree).  The reference itself cannot be compiled in this
- * image (Eigen, OpenCV C++, costmap_2d, boost are absent), and the image arithmetic
- * lives in OpenCV (un-vendored; ROS noetic's libopencv-dev).  The restatement is
- * therefore pinned against the same OpenCV functions through the cv2 4.13.0 Python
- * wheel (oracle/cv_pipeline.py, tests/golden/make_golden.py) and against the
- * known-answer vectors of SURVEY.md §8(c).
+ * upstream dorezyuk/dpose tree).  Pins, strongest first:
+ *   1. oracle/_ref — the reference's own dpose_core.cpp / dpose_costmap.cpp compiled from
+ *      /root/reference against the stand-in headers of oracle/refshim (the real Eigen,
+ *      OpenCV, costmap_2d and boost are absent from this image); every function below is
+ *      bit-identical to it (tests/test_reference_build.py);
+ *   2. the image arithmetic lives in OpenCV (un-vendored; ROS noetic's libopencv-dev) and is
+ *      pinned against the same OpenCV functions through the cv2 4.13.0 Python wheel
+ *      (oracle/cv_pipeline.py, tests/golden/make_golden.py);
+ *   3. the known-answer vectors of SURVEY.md §8(c) and the reference's own unit tests restated.
  */
 #ifndef DPOSE_ORACLE_H
 #define DPOSE_ORACLE_H
@@ -50,6 +53,12 @@ int oracle_make_footprint(const double *xy_m, int n, double res, int32_t *xy_cel
 int oracle_cost_data_create(const int32_t *fp_xy, int n, unsigned padding,
                             oracle_cost_data *out);
 void oracle_cost_data_free(oracle_cost_data *cd);
+
+/* OpenCV primitives behind _get_cost, one by one (cv::polylines closed / cv::fillPoly single contour /
+ * cv::distanceTransform DIST_L2 PRECISE as squared integers); used by oracle/refshim/opencv2. */
+void oracle_cv_polylines_closed(uint8_t *img, int cols, int rows, const int32_t *xy, int n, uint8_t color);
+void oracle_cv_fillpoly(uint8_t *img, int cols, int rows, const int32_t *xy, int n, uint8_t color);
+void oracle_cv_edt_sq(const uint8_t *img, int cols, int rows, int32_t *d2);
 
 /* pose_gradient::get_cost (dpose_core.cpp:200-260) incl. interpolator
  * (dpose_core.cpp:158-198): finite-difference Jacobian exactly as the reference.
