@@ -1,10 +1,9 @@
-// costmap_2d/layered_costmap.h — stand-in (TEST INFRASTRUCTURE ONLY, see oracle/refshim/README.md) for the
-// members of costmap_2d::Costmap2D / LayeredCostmap that dpose_costmap.cpp calls (ROS noetic signatures:
-// unsigned sizes, row-major unsigned char grid, index = my * size_x + mx, recursive mutex).
-#ifndef DPOSE_REFSHIM_COSTMAP_2D
-#define DPOSE_REFSHIM_COSTMAP_2D
+// costmap_2d/layered_costmap.h — stand-in (TEST INFRASTRUCTURE ONLY, see oracle/refshim/README.md): the two
+// LayeredCostmap accessors that make_footprint uses (dpose_costmap.cpp:40-55).
+#ifndef DPOSE_REFSHIM_LAYERED_COSTMAP
+#define DPOSE_REFSHIM_LAYERED_COSTMAP
 
-#include <boost/thread/lock_types.hpp>
+#include <costmap_2d/costmap_2d.h>
 
 #include <utility>
 #include <vector>
@@ -16,34 +15,6 @@ struct Point {
 }  // namespace geometry_msgs
 
 namespace costmap_2d {
-
-static const unsigned char NO_INFORMATION = 255;
-static const unsigned char LETHAL_OBSTACLE = 254;
-static const unsigned char INSCRIBED_INFLATED_OBSTACLE = 253;
-static const unsigned char FREE_SPACE = 0;
-
-class Costmap2D {
-public:
-  typedef boost::recursive_mutex mutex_t;
-
-  /// views a caller-owned grid (the bridge keeps it alive); nothing is copied
-  Costmap2D(unsigned char* grid, unsigned int size_x, unsigned int size_y, double resolution = 1.0) :
-      grid_(grid), size_x_(size_x), size_y_(size_y), resolution_(resolution) {}
-
-  unsigned int getSizeInCellsX() const { return size_x_; }
-  unsigned int getSizeInCellsY() const { return size_y_; }
-  double getResolution() const { return resolution_; }
-  unsigned char* getCharMap() const { return grid_; }
-  unsigned int getIndex(unsigned int mx, unsigned int my) const { return my * size_x_ + mx; }
-  unsigned char getCost(unsigned int mx, unsigned int my) const { return grid_[getIndex(mx, my)]; }
-  mutex_t* getMutex() { return &mutex_; }
-
-private:
-  unsigned char* grid_;
-  unsigned int size_x_, size_y_;
-  double resolution_;
-  mutex_t mutex_;
-};
 
 class LayeredCostmap {
 public:
@@ -58,4 +29,4 @@ private:
 
 }  // namespace costmap_2d
 
-#endif  // DPOSE_REFSHIM_COSTMAP_2D
+#endif  // DPOSE_REFSHIM_LAYERED_COSTMAP

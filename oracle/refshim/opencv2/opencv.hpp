@@ -20,6 +20,10 @@
 namespace cv {
 
 enum { CV_8U_ = 0, CV_32F_ = 5 };
+#ifndef CV_8U
+#define CV_8U 0
+#define CV_32F 5
+#endif
 enum { DIST_L2 = 2, DIST_MASK_PRECISE = 0 };
 
 template <typename T>
@@ -43,6 +47,16 @@ struct Size {
   Size() = default;
   Size(int w, int h) : width(w), height(h) {}
   int width = 0, height = 0;
+  Size operator+(const Size& o) const { return Size(width + o.width, height + o.height); }
+  bool operator==(const Size& o) const { return width == o.width && height == o.height; }
+  bool operator!=(const Size& o) const { return !(*this == o); }
+};
+
+/// cv::Mat::size: the dimensions, comparable
+struct MatSize {
+  int rows = 0, cols = 0;
+  bool operator==(const MatSize& o) const { return rows == o.rows && cols == o.cols; }
+  bool operator!=(const MatSize& o) const { return !(*this == o); }
 };
 
 struct Rect {
@@ -60,12 +74,15 @@ struct Scalar {
 class Mat {
 public:
   Mat() = default;
-  Mat(Size s, int type) : rows(s.height), cols(s.width), type_(type) {
+  Mat(Size s, int type) : Mat(s.height, s.width, type) {}
+  Mat(int r, int c, int type) : rows(r), cols(c), type_(type) {
+    size.rows = r, size.cols = c;
     buf_ = std::make_shared<std::vector<uint8_t>>((size_t)rows * cols * elem());
   }
   Mat(Size s, int type, const Scalar& v) : Mat(s, type) { setTo(v); }
 
   int rows = 0, cols = 0;
+  MatSize size;
   int type() const { return type_; }
   size_t elem() const { return type_ == CV_32F_ ? sizeof(float) : 1; }
   size_t total() const { return (size_t)rows * cols; }
@@ -78,6 +95,14 @@ public:
   template <typename T>
   const T* ptr() const {
     return reinterpret_cast<const T*>(buf_->data());
+  }
+  template <typename T>
+  T* ptr(int r) {
+    return ptr<T>() + (size_t)r * cols;
+  }
+  template <typename T>
+  const T* ptr(int r) const {
+    return ptr<T>() + (size_t)r * cols;
   }
   template <typename T>
   const T& at(int r, int c) const {

@@ -1,0 +1,95 @@
+"""Builds the REFERENCE'S OWN unit tests (dpose_core/test/*.cpp, compiled unmodified from /root/reference) twice:
+
+  on_reference : against the reference's own dpose_core sources (oracle/_ref objects)  -> oracle/_ref/tests/ref_<name>
+  on_b200      : against THIS repository's drop-in headers (include/dpose_core/*.hpp) and libdpose_b200.so
+                                                                                   -> tests/cpp/_build/b200_ref_<name>
+
+Both use the stand-in Eigen / OpenCV / costmap_2d / GoogleTest headers of oracle/refshim (none of those libraries is
+installed in this image; oracle/refshim/README.md).  The first build shows that the stand-ins carry the reference's
+tests on the reference's code; the second is the drop-in proof: the same test sources, not a restatement, pass on the
+CUDA implementation.  Binaries are git-ignored and travel prebuilt to the GPU box, where /root/reference is absent.
+TEST INFRASTRUCTURE ONLY."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REFERENCE_ROOT = os.environ.get("DPOSE_REFERENCE_ROOT", "/root/reference")
+TEST_DIR = os.path.join(REFERENCE_ROOT, "dpose_core", "test")
+SHIM = os.path.join(ROOT, "oracle", "refshim")
+# name -> number of test cases GoogleTest would run (TEST/TEST_F count + TEST_P count x parameters)
+SUITES = {"cost_data": 50, "jacobian_data": 28, "lethal_cells_within": 22, "pose_gradient": 2, "check_footprint": 87}
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def reference_present():
+    return all(os.path.exists(os.path.join(TEST_DIR, n + ".cpp")) for n in SUITES)
+
+
+def binary(kind, name):
+    if kind == "on_reference":
+        return os.path.join(ROOT, "oracle", "_ref", "tests", "ref_" + name)
+    return os.path.join(ROOT, "tests", "cpp", "_build", "b200_ref_" + name)
+
+
+def _stale(out, deps):
+    return not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps if os.path.exists(d))
+
+
+def _shim_headers():
+    return [os.path.join(dp, f) for dp, _, fs in os.walk(SHIM) for f in fs]
+
+
+def build_on_reference():
+    """the reference's tests on the reference's sources; returns {name: path} (empty without /root/reference)"""
+    if not reference_present():
+        return {n: binary("on_reference", n) for n in SUITES if os.path.exists(binary("on_reference", n))}
+    from oracle import refapi
+    refapi.build()
+    objs = [os.path.join(ROOT, "oracle", "_ref", o) for o in ("dpose_core.o", "dpose_costmap.o", "dpose_oracle.o")]
+    out = {}
+    for name in SUITES:
+        src, exe = os.path.join(TEST_DIR, name + ".cpp"), binary("on_reference", name)
+        if _stale(exe, [src] + objs + _shim_headers()):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            subprocess.run([CXX, "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-I", SHIM,
+                            "-I", os.path.join(REFERENCE_ROOT, "dpose_core", "src"), src,
+                            os.path.join(SHIM, "gtest", "gtest_main.cpp")] + objs + ["-fopenmp", "-lm", "-o", exe], check=True)
+        out[name] = exe
+    return out
+
+
+def build_on_b200():
+    """the reference's tests on include/dpose_core + libdpose_b200.so; returns {name: path}"""
+    if not reference_present():
+        return {n: binary("on_b200", n) for n in SUITES if os.path.exists(binary("on_b200", n))}
+    from dpose_b200 import build
+    lib = build.build()
+    include = os.path.join(ROOT, "include")
+    headers = [os.path.join(dp, f) for dp, _, fs in os.walk(include) for f in fs] + _shim_headers()
+    out = {}
+    for name in SUITES:
+        src, exe = os.path.join(TEST_DIR, name + ".cpp"), binary("on_b200", name)
+        if _stale(exe, [src] + headers):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            # include/ first: <dpose_core/*.hpp> must resolve to the drop-in headers, everything else to the stand-ins
+            subprocess.run([CXX, "-std=c++17", "-O2", "-w", "-I", include, "-I", SHIM, src,
+                            os.path.join(SHIM, "gtest", "gtest_main.cpp"), "-L", os.path.dirname(lib), "-ldpose_b200",
+                            "-Wl,-rpath,$ORIGIN/../../../dpose_b200/lib", "-o", exe], check=True)
+        out[name] = exe
+    return out
+
+
+def run(exe, timeout=600):
+    """-> (returncode, tests ran, tests failed, output)"""
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
+    ran = failed = -1
+    for line in r.stdout.splitlines():
+        if line.startswith("[==========]"):
+            parts = line.replace(".", " ").split()
+            ran, failed = int(parts[1]), int(parts[-1])
+    return r.returncode, ran, failed, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+if __name__ == "__main__":
+    print(build_on_reference())
+    print(build_on_b200())
