@@ -199,7 +199,8 @@ int dpose_cell_to_world(const double *cells /* n x (x, y, theta) */, size_t n, d
 /* ---- check_footprint (validation of solved poses) -----------------------------------------------
  * replaces check_footprint(map, footprint, cost) (dpose_costmap.cpp:460-582, with is_inside :186-199 and the
  * x_bresenham iterators :201-317): *ok = 1 iff every vertex is inside the map and no cell covered by the polygon
- * (outline rays + scan-line interior) equals `cost`.  footprint_xy: n <= 64 vertices in cells, closed or open. */
+ * (outline rays + scan-line interior) equals `cost`.  footprint_xy: n vertices in cells, closed or open; any n (up to 64
+ * vertices the per-pose state stays in registers / local memory, beyond that it lives in a device workspace). */
 int dpose_check_footprint(const dpose_map *map, const int32_t *footprint_xy, int n, uint8_t cost, int *ok);
 /* the plugin's use (dpose_goal_tolerance.cpp:386-399) for n_poses candidates at once: the footprint is
  * transformed by T(x, y) R(theta) and rounded to cells per pose, then checked.  ok: n_poses bytes (1 = free). */

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 
@@ -103,6 +104,42 @@ lethal_cells_within(const device_costmap& _map, const cell_rectangle& _bounds) {
   return out;
 }
 
+namespace detail {
+
+/// Device mirror of the host costmap this thread used last.  The upstream signatures take a host Costmap2D whose
+/// bytes may have changed since the previous call, so nothing cached is ever trusted: every call re-uploads exactly
+/// the window it is about to read (dpose_map_update) into the mirror and then runs on the device.  What the mirror
+/// saves is the allocation, stream and event set-up of a device costmap per call.  One mirror per thread; a costmap
+/// with another buffer or size replaces it.
+inline device_costmap&
+mirror_of(const costmap_2d::Costmap2D& _map) {
+  struct slot_t {
+    const unsigned char* data = nullptr;
+    unsigned int sx = 0, sy = 0;
+    std::unique_ptr<device_costmap> dev;
+  };
+  thread_local slot_t slot;
+  const unsigned int sx = _map.getSizeInCellsX(), sy = _map.getSizeInCellsY();
+  if (!slot.dev || slot.data != _map.getCharMap() || slot.sx != sx || slot.sy != sy) {
+    slot.dev.reset(new device_costmap(_map.getCharMap(), sx, sy, (size_t)sx));
+    slot.data = _map.getCharMap();
+    slot.sx = sx;
+    slot.sy = sy;
+  }
+  return *slot.dev;
+}
+
+/// uploads the cells [x0, x1] x [y0, y1] of _map into its mirror and returns the mirror
+inline device_costmap&
+mirror_window(const costmap_2d::Costmap2D& _map, int x0, int y0, int x1, int y1) {
+  device_costmap& dev = mirror_of(_map);
+  dev.update(_map.getCharMap() + _map.getIndex((unsigned)x0, (unsigned)y0), (size_t)_map.getSizeInCellsX(), (uint32_t)x0,
+             (uint32_t)y0, (uint32_t)(x1 - x0 + 1), (uint32_t)(y1 - y0 + 1));
+  return dev;
+}
+
+}  // namespace detail
+
 /// upstream signature (dpose_costmap.hpp:84-85, dpose_costmap.cpp:117-184): takes the costmap's
 /// mutex (:138), uploads the bounding rows/columns of the clamped box and compacts on the GPU.
 /// Rows come back y ascending, x ascending (the reference's row order is unspecified).
@@ -110,7 +147,7 @@ inline cell_vector
 lethal_cells_within(costmap_2d::Costmap2D& _map, const cell_rectangle& _bounds) {
   const int sx = (int)_map.getSizeInCellsX(), sy = (int)_map.getSizeInCellsY();
   if (sx == 0 || sy == 0) return {};  // :124-125
-  // clamp into the map (:121,:128-129), then move the ring into the frame of its bounding window
+  // clamp into the map (:121,:128-129); the bounding window of the clamped ring is what gets uploaded
   cell_rectangle ring = _bounds;
   int x0 = sx - 1, y0 = sy - 1, x1 = 0, y1 = 0;
   for (int i = 0; i < 5; ++i) {
@@ -121,22 +158,8 @@ lethal_cells_within(costmap_2d::Costmap2D& _map, const cell_rectangle& _bounds) 
     y0 = std::min(y0, ring(1, i));
     y1 = std::max(y1, ring(1, i));
   }
-  for (int i = 0; i < 5; ++i) {
-    ring(0, i) -= x0;
-    ring(1, i) -= y0;
-  }
-  cell_vector out;
-  {
-    std::lock_guard<costmap_2d::Costmap2D::mutex_t> lock(*_map.getMutex());
-    const device_costmap window(_map.getCharMap() + _map.getIndex((unsigned)x0, (unsigned)y0), (uint32_t)(x1 - x0 + 1),
-                                (uint32_t)(y1 - y0 + 1), (size_t)sx);
-    out = lethal_cells_within(window, ring);
-  }
-  for (auto& c : out) {
-    c.x() += x0;
-    c.y() += y0;
-  }
-  return out;
+  std::lock_guard<costmap_2d::Costmap2D::mutex_t> lock(*_map.getMutex());
+  return lethal_cells_within(detail::mirror_window(_map, x0, y0, x1, y1), ring);
 }
 
 /// true if every vertex of _footprint lies inside _map (upstream dpose_costmap.cpp:186-199)
@@ -216,7 +239,8 @@ check_footprint(const device_costmap& _map, const polygon& _footprint, uint8_t _
 }
 
 /// upstream signature (dpose_costmap.hpp:194-196, dpose_costmap.cpp:460-582); uploads the bounding window of
-/// the footprint.  The caller is expected to hold the costmap's mutex, as with the reference.
+/// the footprint into this thread's device mirror of the costmap.  The caller is expected to hold the costmap's
+/// mutex, as with the reference.
 inline bool
 check_footprint(const costmap_2d::Costmap2D& _map, const polygon& _footprint, uint8_t _cost) {
   if (!is_inside(_map, _footprint)) return false;
@@ -227,14 +251,7 @@ check_footprint(const costmap_2d::Costmap2D& _map, const polygon& _footprint, ui
     x0 = std::min(x0, _footprint(0, c)), x1 = std::max(x1, _footprint(0, c));
     y0 = std::min(y0, _footprint(1, c)), y1 = std::max(y1, _footprint(1, c));
   }
-  polygon local = _footprint;
-  for (int c = 0; c < n; ++c) {
-    local(0, c) -= x0;
-    local(1, c) -= y0;
-  }
-  const device_costmap window(_map.getCharMap() + _map.getIndex((unsigned)x0, (unsigned)y0), (uint32_t)(x1 - x0 + 1),
-                              (uint32_t)(y1 - y0 + 1), (size_t)_map.getSizeInCellsX());
-  return check_footprint(window, local, _cost);
+  return check_footprint(detail::mirror_window(_map, x0, y0, x1, y1), _footprint, _cost);
 }
 
 /// NEW: the plugin's validation step (dpose_goal_tolerance.cpp:386-399) for many candidate poses at once:

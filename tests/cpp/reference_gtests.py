@@ -11,6 +11,7 @@ CUDA implementation.  Binaries are git-ignored and travel prebuilt to the GPU bo
 TEST INFRASTRUCTURE ONLY."""
 import os
 import subprocess
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REFERENCE_ROOT = os.environ.get("DPOSE_REFERENCE_ROOT", "/root/reference")
@@ -19,6 +20,8 @@ SHIM = os.path.join(ROOT, "oracle", "refshim")
 # name -> number of test cases GoogleTest would run (TEST/TEST_F count + TEST_P count x parameters)
 SUITES = {"cost_data": 50, "jacobian_data": 28, "lethal_cells_within": 22, "pose_gradient": 2, "check_footprint": 87}
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def reference_present():
@@ -79,6 +82,43 @@ def build_on_b200():
     return out
 
 
+PERF_SOURCES = ("dpose_core.cpp", "dpose_costmap.cpp")  # dpose_core/perf/, one executable (dpose_core/CMakeLists.txt:76-79)
+
+
+def perf_binary(kind):
+    if kind == "on_reference":
+        return os.path.join(ROOT, "oracle", "_ref", "perf", "ref_dpose_core_perf")
+    return os.path.join(ROOT, "tests", "cpp", "_build", "b200_dpose_core_perf")
+
+
+def build_perf(kind):
+    """the reference's own Google-Benchmark file pair (perf/dpose_core.cpp + perf/dpose_costmap.cpp), unmodified, on the
+    reference's sources or on the drop-in; returns the path or None"""
+    exe = perf_binary(kind)
+    srcs = [os.path.join(REFERENCE_ROOT, "dpose_core", "perf", f) for f in PERF_SOURCES]
+    if not all(os.path.exists(f) for f in srcs):
+        return exe if os.path.exists(exe) else None
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    if kind == "on_reference":
+        from oracle import refapi
+        refapi.build()
+        objs = [os.path.join(ROOT, "oracle", "_ref", o) for o in ("dpose_core.o", "dpose_costmap.o", "dpose_oracle.o")]
+        if _stale(exe, srcs + objs + _shim_headers()):
+            subprocess.run([CXX, "-std=c++17", "-O3", "-DNDEBUG", "-ffp-contract=off", "-w", "-I", SHIM,
+                            "-I", os.path.join(REFERENCE_ROOT, "dpose_core", "src")] + srcs + objs +
+                           ["-fopenmp", "-lm", "-o", exe], check=True)
+    else:
+        from dpose_b200 import build
+        lib = build.build()
+        include = os.path.join(ROOT, "include")
+        headers = [os.path.join(dp, f) for dp, _, fs in os.walk(include) for f in fs] + _shim_headers()
+        if _stale(exe, srcs + headers):
+            subprocess.run([CXX, "-std=c++17", "-O3", "-DNDEBUG", "-w", "-I", include, "-I", SHIM] + srcs +
+                           ["-L", os.path.dirname(lib), "-ldpose_b200", "-Wl,-rpath,$ORIGIN/../../../dpose_b200/lib",
+                            "-o", exe], check=True)
+    return exe
+
+
 def run(exe, timeout=600):
     """-> (returncode, tests ran, tests failed, output)"""
     r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
@@ -93,3 +133,4 @@ def run(exe, timeout=600):
 if __name__ == "__main__":
     print(build_on_reference())
     print(build_on_b200())
+    print(build_perf("on_reference"), build_perf("on_b200"))

@@ -172,3 +172,45 @@ def test_gpu_check_footprint_batch_vs_oracle(dp, name, density):
     want = capi.check_footprint_batch(m, fp, poses, nthreads=capi.max_threads())
     assert 0.02 < want.mean() < 0.98  # the case is not trivial either way
     assert np.array_equal(got, want), int((got != want).sum())
+
+
+def circle(steps, radius, cx=0, cy=0):
+    """the reference's dense benchmark footprint (perf/dpose_costmap.cpp:103-113): rounded points of a circle, with
+    duplicate vertices and zero-length edges once steps exceeds the number of outline cells"""
+    ang = (math.pi * 2 * np.arange(steps)) / steps
+    return np.stack([fx.round_half_away(np.cos(ang) * radius) + cx, fx.round_half_away(np.sin(ang) * radius) + cy], 1).astype(np.int32)
+
+
+@pytest.mark.parametrize("steps", [65, 100, 1000])
+def test_check_footprint_many_vertices_oracle(steps):
+    """footprints beyond 64 vertices, as in the reference's benchmark: free disc, then one lethal cell inside / on the
+    outline / outside"""
+    fp = circle(steps, 50, 100, 100)
+    m = np.zeros((200, 200), np.uint8)
+    assert capi.check_footprint(m, fp)
+    for (x, y), want in (((100, 100), False), ((130, 120), False), ((150, 100), False), ((100, 50), False),
+                         ((160, 160), True), ((151, 100), True)):
+        m[y, x] = fx.LETHAL
+        assert capi.check_footprint(m, fp) == want, (x, y)
+        m[y, x] = 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("steps", [64, 65, 100, 1000])
+def test_gpu_check_footprint_many_vertices(dp, steps):
+    fp = circle(steps, 50, 100, 100)
+    m = np.zeros((200, 200), np.uint8)
+    assert dp.check_footprint(m, fp)
+    rng = np.random.default_rng(steps)
+    for x, y in [(100, 100), (150, 100), (151, 100), (100, 50), (160, 160)] + rng.integers(40, 160, size=(25, 2)).tolist():
+        m[y, x] = fx.LETHAL
+        assert dp.check_footprint(m, fp) == capi.check_footprint(m, fp), (x, y)
+        m[y, x] = 0
+    # batched, in the robot frame: the workspace path processes poses in chunks
+    fp0 = circle(steps, 20)
+    big = fx.bernoulli_map(400, 300, 0.0006, 5)
+    poses = fx.random_poses(3000, 400, 300, 6, margin=-10.0)
+    got = dp.check_footprint_batch(dp.Costmap(big), fp0, poses)
+    want = capi.check_footprint_batch(big, fp0, poses, nthreads=capi.max_threads())
+    assert 0.05 < want.mean() < 0.95
+    assert np.array_equal(got, want), int((got != want).sum())

@@ -204,3 +204,17 @@ def test_check_footprint_reference_shapes_and_degenerates():
     for cost in (0, 253, 254, 255):
         fp = np.array([[2, 2], [12, 3], [10, 12], [3, 9]], np.int32)
         assert capi.check_footprint(m2, fp, cost) == refapi.check_footprint(m2, fp, cost)
+
+
+@pytest.mark.parametrize("steps", [10, 100, 1000])
+def test_check_footprint_dense_circles(steps):
+    """the reference's dense benchmark footprints (perf/dpose_costmap.cpp:103-150): duplicate vertices, zero-length edges"""
+    ang = (math.pi * 2 * np.arange(steps)) / steps
+    fp = np.stack([fx.round_half_away(np.cos(ang) * 50) + 100, fx.round_half_away(np.sin(ang) * 50) + 100], 1).astype(np.int32)
+    m = np.zeros((200, 200), np.uint8)
+    assert refapi.check_footprint(m, fp) and capi.check_footprint(m, fp)
+    rng = rng_of("dense", steps)
+    for x, y in [(100, 100), (150, 100), (151, 100), (100, 50), (50, 100)] + rng.integers(40, 160, size=(200, 2)).tolist():
+        m[y, x] = 254
+        assert capi.check_footprint(m, fp) == refapi.check_footprint(m, fp), (x, y)
+        m[y, x] = 0
