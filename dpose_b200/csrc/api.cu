@@ -339,8 +339,25 @@ int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t
   if (w == 0 || h == 0) return DPOSE_OK;
   DeviceGuard guard(map->device);
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", map->device);
-  DPOSE_CUDA(cudaMemcpy2D(map->d_data + (size_t)y0 * map->pitch + x0, map->pitch, data, pitch, w, h,
-                          cudaMemcpyHostToDevice));
+  constexpr size_t kStageMax = (size_t)1 << 20;
+  const size_t bytes = (size_t)w * h;
+  if (bytes <= kStageMax && h > 1) {
+    if (map->update_stage_cap < bytes) {
+      if (map->h_update_stage) cudaFreeHost(map->h_update_stage);
+      map->h_update_stage = nullptr;
+      map->update_stage_cap = 0;
+      const size_t cap = std::max<size_t>(bytes * 2, (size_t)64 << 10);
+      DPOSE_CUDA(cudaHostAlloc(&map->h_update_stage, std::min(cap, kStageMax), cudaHostAllocDefault));
+      map->update_stage_cap = std::min(cap, kStageMax);
+    }
+    for (uint32_t r = 0; r < h; ++r) std::memcpy(map->h_update_stage + (size_t)r * w, data + (size_t)r * pitch, w);
+    DPOSE_CUDA(cudaMemcpy2DAsync(map->d_data + (size_t)y0 * map->pitch + x0, map->pitch, map->h_update_stage, w, w, h,
+                                 cudaMemcpyHostToDevice, nullptr));
+    DPOSE_CUDA(cudaStreamSynchronize(nullptr));  // the staging buffer is reused by the next call
+  } else {
+    DPOSE_CUDA(cudaMemcpy2D(map->d_data + (size_t)y0 * map->pitch + x0, map->pitch, data, pitch, w, h,
+                            cudaMemcpyHostToDevice));
+  }
   // narrow the lazy plane rebuilds to the rows of this window (union with what is already pending)
   auto widen = [&](bool &dirty, uint32_t &lo, uint32_t &hi) {
     if (!dirty) {
@@ -387,6 +404,7 @@ void dpose_map_destroy(dpose_map *map) {
     map_release_cache(map);
     map_release_lethal_ws(map);
     cudaFree(map->d_data);
+    if (map->h_update_stage) cudaFreeHost(map->h_update_stage);
     cudaFree(map->d_bits);
     cudaFree(map->d_tiles);
     if (map->bits_ready) cudaEventDestroy(map->bits_ready);

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -328,7 +329,10 @@ __global__ void __launch_bounds__(kCoopThreads) k_check_footprint_coop(const Che
   constexpr int kOutlineFirst = kCoopThreads > 32 ? 32 : 1;
   const int n = a.n, cap = n + 1;
   unsigned char *base = ws + i * coop_bytes(cap, span_cap);
-  const Scratch sc = scratch_at(base, cap);
+  // the sweep's state is read and written a few times per scan line by one thread: up to kMaxVertices vertices it
+  // sits in shared memory (latency), beyond that in this pose's slice of the workspace
+  __shared__ __align__(8) unsigned char s_state[((kMaxVertices + 1) * (sizeof(XB) + sizeof(int2) + 5 * sizeof(int) + 1) + 7) & ~7];
+  const Scratch sc = scratch_at(n <= kMaxVertices ? s_state : base, cap);
   int *prefix = reinterpret_cast<int *>(base + scratch_bytes(cap));
   Span *spans = reinterpret_cast<Span *>(base + scratch_bytes(cap) + ((((size_t)cap + 1) * sizeof(int) + 7) & ~(size_t)7));
   const int *fp = d_fp ? d_fp : a.fp;
@@ -449,6 +453,20 @@ static int coop_max_poses() {
   return v;
 }
 
+// per host thread: a page of mapped pinned memory the kernels of a small host-buffer call write their flags into
+constexpr size_t kPinnedOk = 4096;
+static uint8_t *pinned_ok() {
+  thread_local uint8_t *p = [] {
+    void *q = nullptr;
+    if (cudaHostAlloc(&q, kPinnedOk, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+      cudaGetLastError();
+      q = nullptr;
+    }
+    return static_cast<uint8_t *>(q);
+  }();
+  return p;
+}
+
 static int coop_threads(size_t n_poses) {
   static const int forced = [] {
     const char *e = getenv("DPOSE_CHECK_COOP_THREADS");
@@ -485,9 +503,11 @@ static int check_impl(const dpose_map *map, const int32_t *fp, int n, const doub
       DPOSE_CUDA(cudaMallocAsync(&d_poses, sizeof(double) * 3 * n_poses, stream));
       DPOSE_CUDA(cudaMemcpyAsync(d_poses, poses, sizeof(double) * 3 * n_poses, cudaMemcpyHostToDevice, stream));
     }
-    if (!dev_ok) DPOSE_CUDA(cudaMallocAsync(&d_ok, n_poses, stream));
+    // results of a small host-buffer call go straight into mapped pinned memory (no device buffer, no copy back)
+    uint8_t *h_ok = !dev_ok && n_poses <= kPinnedOk ? pinned_ok() : nullptr;
+    if (!dev_ok && !h_ok) DPOSE_CUDA(cudaMallocAsync(&d_ok, n_poses, stream));
     a.poses = poses ? (dev_poses ? poses : d_poses) : nullptr;
-    a.ok = dev_ok ? ok : d_ok;
+    a.ok = dev_ok ? ok : (h_ok ? h_ok : d_ok);
     // spans one pose can produce: at most one per pair of edges on every scan line of its bounding box
     long long height = 0;
     if (poses) {
@@ -533,7 +553,10 @@ static int check_impl(const dpose_map *map, const int32_t *fp, int n, const doub
         DPOSE_LAUNCHED();
       }
     }
-    if (!dev_ok) {
+    if (h_ok) {
+      DPOSE_CUDA(cudaStreamSynchronize(stream));
+      std::memcpy(ok, h_ok, n_poses);
+    } else if (!dev_ok) {
       DPOSE_CUDA(cudaMemcpyAsync(ok, d_ok, n_poses, cudaMemcpyDeviceToHost, stream));
       DPOSE_CUDA(cudaStreamSynchronize(stream));
     }

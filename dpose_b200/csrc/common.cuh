@@ -128,6 +128,10 @@ struct dpose_map {
   cudaEvent_t tiles_ready = nullptr;
   // scratch buffers, pinned staging and stream of lethal_cells_within (lethal.cu), built on first use
   void *lethal_ws = nullptr;
+  // pinned staging of dpose_map_update for small dirty windows (a 2-D copy out of pageable memory is staged row
+  // by row by the driver: 40 us for 92 x 92 cells; packed into pinned memory first it is one DMA), built on first use
+  uint8_t *h_update_stage = nullptr;
+  size_t update_stage_cap = 0;
 };
 
 struct dpose_cells {
