@@ -18,7 +18,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libdpose_ref.so")
 REFERENCE_ROOT = os.environ.get("DPOSE_REFERENCE_ROOT", "/root/reference")
 _SOURCES = ("dpose_core/src/dpose_core.cpp", "dpose_core/src/dpose_costmap.cpp",
-            "dpose_core/src/dpose_core/dpose_core.hpp", "dpose_core/src/dpose_core/dpose_costmap.hpp")
+            "dpose_core/src/dpose_core/dpose_core.hpp", "dpose_core/src/dpose_core/dpose_costmap.hpp",
+            "dpose_goal_tolerance/src/dpose_goal_tolerance.cpp",
+            "dpose_goal_tolerance/src/dpose_goal_tolerance/dpose_goal_tolerance.hpp")
 
 
 def reference_present():
@@ -72,6 +74,17 @@ def lib():
         L.ref_check_footprint.argtypes = [vp, u32, u32, vp, i32, C.c_uint8]
         L.ref_xb_trace.argtypes = [vp, vp, i32, vp, vp]
         L.ref_get_cost_batch.argtypes = [vp, vp, u32, u32, vp, sz, vp, i32, i32]
+        L.ref_problem_create.restype = vp
+        L.ref_problem_create.argtypes = [vp, u32, u32, vp, i32, C.c_uint]
+        L.ref_problem_free.argtypes = [vp]
+        L.ref_problem_init.restype = i32
+        L.ref_problem_init.argtypes = [vp, vp, vp, vp]
+        L.ref_problem_eval_batch.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+        L.ref_problem_info.argtypes = [vp] * 8
+        L.ref_to_cell.restype = i32
+        L.ref_to_cell.argtypes = [u32, u32, dbl, dbl, dbl, vp, vp]
+        L.ref_to_msg.restype = i32
+        L.ref_to_msg.argtypes = [u32, u32, dbl, dbl, dbl, vp, vp]
         _lib = L
     return _lib
 
@@ -173,3 +186,67 @@ def xb_trace(c0, c1, steps):
     dx = C.c_double()
     lib().ref_xb_trace(a.ctypes.data, b.ctypes.data, int(steps), xs.ctypes.data, C.byref(dx))
     return xs[:int(steps)].copy(), dx.value
+
+
+CONFIG_KEYS = ("lin_tolerance", "rot_tolerance", "weight_goal_lin", "weight_goal_rot", "weight_start_lin", "weight_start_rot")
+
+
+class Problem:
+    """dpose_goal_tolerance::problem (dpose_goal_tolerance.cpp:90-292) of the compiled reference: the NLP the plugin
+    hands to Ipopt.  footprint in cells (the bridge feeds make_footprint a resolution of 1)."""
+
+    def __init__(self, footprint, padding, costmap):
+        self.map = np.ascontiguousarray(np.asarray(costmap, dtype=np.uint8))  # viewed, not copied: keep it alive
+        fp = _i32(footprint).reshape(-1, 2)
+        self._h = lib().ref_problem_create(self.map.ctypes.data, self.map.shape[1], self.map.shape[0], fp.ctypes.data,
+                                           fp.shape[0], int(padding))
+        if not self._h:
+            raise RuntimeError("footprint must contain at least three points")
+
+    def init(self, start, goal, **cfg):
+        c = np.array([float(cfg.get(k, 1.0)) for k in CONFIG_KEYS])
+        s = np.ascontiguousarray(np.asarray(start, np.float64).reshape(3))
+        g = np.ascontiguousarray(np.asarray(goal, np.float64).reshape(3))
+        if lib().ref_problem_init(self._h, s.ctypes.data, g.ctypes.data, c.ctypes.data) != 0:
+            raise ValueError("both weights cannot be zero")
+
+    def eval_batch(self, x):
+        x = np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1, 3))
+        n = x.shape[0]
+        f, grad, g, jac = np.empty(n), np.empty((n, 3)), np.empty((n, 2)), np.empty((n, 3))
+        lib().ref_problem_eval_batch(self._h, x.ctypes.data, n, f.ctypes.data, grad.ctypes.data, g.ctypes.data, jac.ctypes.data)
+        return f, grad, g, jac
+
+    def info(self):
+        """(n, m, nnz_jac_g, index_style), x bounds, g bounds, Jacobian pattern (rows, cols)"""
+        dims = np.zeros(4, np.int32)
+        xl, xu, gl, gu = np.zeros(3), np.zeros(3), np.zeros(2), np.zeros(2)
+        rows, cols = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        lib().ref_problem_info(self._h, dims.ctypes.data, xl.ctypes.data, xu.ctypes.data, gl.ctypes.data, gu.ctypes.data,
+                               rows.ctypes.data, cols.ctypes.data)
+        return dims, (xl, xu), (gl, gu), (rows, cols)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().ref_problem_free(self._h)
+        except Exception:
+            pass
+
+
+def to_cell(world, origin, resolution, size):
+    """the plugin's to_cell (dpose_goal_tolerance.cpp:293-309): (x, y, theta) metres -> cells, None if it throws"""
+    w = np.ascontiguousarray(np.asarray(world, np.float64).reshape(3))
+    out = np.zeros(3)
+    rc = lib().ref_to_cell(int(size[0]), int(size[1]), float(resolution), float(origin[0]), float(origin[1]), w.ctypes.data,
+                           out.ctypes.data)
+    return out if rc == 0 else None
+
+
+def to_msg(cell, origin, resolution, size):
+    """the plugin's to_msg (dpose_goal_tolerance.cpp:311-330): cell pose -> (x, y, yaw) metres, None if it throws"""
+    c = np.ascontiguousarray(np.asarray(cell, np.float64).reshape(3))
+    out = np.zeros(3)
+    rc = lib().ref_to_msg(int(size[0]), int(size[1]), float(resolution), float(origin[0]), float(origin[1]), c.ctypes.data,
+                          out.ctypes.data)
+    return out if rc == 0 else None

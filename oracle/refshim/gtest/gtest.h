@@ -181,6 +181,14 @@ DPOSE_GTEST_CMP_(cmp_gt, >)
 DPOSE_GTEST_CMP_(cmp_ge, >=)
 #undef DPOSE_GTEST_CMP_
 
+template <typename A, typename B, typename T>
+Result near(const char* ea, const char* eb, const char* et, const A& a, const B& b, const T& tol) {
+  const double diff = a > b ? (double)(a - b) : (double)(b - a);
+  if (diff <= (double)tol) return {true, ""};
+  return {false, std::string("The difference between ") + ea + " and " + eb + " is " + show(diff) + ", which exceeds " + et +
+                     " (" + show(a) + " vs " + show(b) + ")"};
+}
+
 inline Result truth(const char* e, bool v, bool want) {
   if (v == want) return {true, ""};
   return {false, std::string("Value of: ") + e + "\n  Actual: " + (v ? "true" : "false") + "\nExpected: " + (want ? "true" : "false")};
@@ -317,6 +325,8 @@ inline int RunAllTests() {
 #define EXPECT_LE(a, b) DPOSE_GTEST_CHECK_(::testing::internal::cmp_le(#a, #b, a, b), DPOSE_GTEST_NONFATAL_)
 #define EXPECT_GT(a, b) DPOSE_GTEST_CHECK_(::testing::internal::cmp_gt(#a, #b, a, b), DPOSE_GTEST_NONFATAL_)
 #define EXPECT_GE(a, b) DPOSE_GTEST_CHECK_(::testing::internal::cmp_ge(#a, #b, a, b), DPOSE_GTEST_NONFATAL_)
+#define EXPECT_NEAR(a, b, tol) DPOSE_GTEST_CHECK_(::testing::internal::near(#a, #b, #tol, a, b, tol), DPOSE_GTEST_NONFATAL_)
+#define ASSERT_NEAR(a, b, tol) DPOSE_GTEST_CHECK_(::testing::internal::near(#a, #b, #tol, a, b, tol), DPOSE_GTEST_FATAL_)
 #define EXPECT_TRUE(c) DPOSE_GTEST_CHECK_(::testing::internal::truth(#c, static_cast<bool>(c), true), DPOSE_GTEST_NONFATAL_)
 #define EXPECT_FALSE(c) DPOSE_GTEST_CHECK_(::testing::internal::truth(#c, static_cast<bool>(c), false), DPOSE_GTEST_NONFATAL_)
 #define ASSERT_EQ(a, b) DPOSE_GTEST_CHECK_(::testing::internal::cmp_eq(#a, #b, a, b), DPOSE_GTEST_FATAL_)

@@ -1,4 +1,5 @@
-"""Builds the REFERENCE'S OWN unit tests (dpose_core/test/*.cpp, compiled unmodified from /root/reference) twice:
+"""Builds the REFERENCE'S OWN unit tests (dpose_core/test/*.cpp and the plugin's dpose_goal_tolerance/test/*.cpp together with
+the plugin's unmodified source, all compiled from /root/reference) twice:
 
   on_reference : against the reference's own dpose_core sources (oracle/_ref objects)  -> oracle/_ref/tests/ref_<name>
   on_b200      : against THIS repository's drop-in headers (include/dpose_core/*.hpp) and libdpose_b200.so
@@ -18,14 +19,24 @@ REFERENCE_ROOT = os.environ.get("DPOSE_REFERENCE_ROOT", "/root/reference")
 TEST_DIR = os.path.join(REFERENCE_ROOT, "dpose_core", "test")
 SHIM = os.path.join(ROOT, "oracle", "refshim")
 # name -> number of test cases GoogleTest would run (TEST/TEST_F count + TEST_P count x parameters)
-SUITES = {"cost_data": 50, "jacobian_data": 28, "lethal_cells_within": 22, "pose_gradient": 2, "check_footprint": 87}
+SUITES = {"cost_data": 50, "jacobian_data": 28, "lethal_cells_within": 22, "pose_gradient": 2, "check_footprint": 87,
+          # the plugin's own test (dpose_goal_tolerance/test/dpose_goal_tolerance.cpp, has its own main): built together with
+          # the UNMODIFIED plugin source dpose_goal_tolerance/src/dpose_goal_tolerance.cpp
+          "goal_tolerance": 21}
+PLUGIN_SRC = os.path.join(REFERENCE_ROOT, "dpose_goal_tolerance", "src")
+
+
+def _source(name):
+    if name == "goal_tolerance":
+        return os.path.join(REFERENCE_ROOT, "dpose_goal_tolerance", "test", "dpose_goal_tolerance.cpp")
+    return os.path.join(TEST_DIR, name + ".cpp")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
 def reference_present():
-    return all(os.path.exists(os.path.join(TEST_DIR, n + ".cpp")) for n in SUITES)
+    return all(os.path.exists(_source(n)) for n in SUITES)
 
 
 def binary(kind, name):
@@ -51,12 +62,15 @@ def build_on_reference():
     objs = [os.path.join(ROOT, "oracle", "_ref", o) for o in ("dpose_core.o", "dpose_costmap.o", "dpose_oracle.o")]
     out = {}
     for name in SUITES:
-        src, exe = os.path.join(TEST_DIR, name + ".cpp"), binary("on_reference", name)
-        if _stale(exe, [src] + objs + _shim_headers()):
+        src, exe = _source(name), binary("on_reference", name)
+        plugin = name == "goal_tolerance"
+        extra = ([os.path.join(ROOT, "oracle", "_ref", "dpose_goal_tolerance.o")] if plugin
+                 else [os.path.join(SHIM, "gtest", "gtest_main.cpp")])
+        if _stale(exe, [src] + objs + extra + _shim_headers()):
             os.makedirs(os.path.dirname(exe), exist_ok=True)
             subprocess.run([CXX, "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-I", SHIM,
-                            "-I", os.path.join(REFERENCE_ROOT, "dpose_core", "src"), src,
-                            os.path.join(SHIM, "gtest", "gtest_main.cpp")] + objs + ["-fopenmp", "-lm", "-o", exe], check=True)
+                            "-I", os.path.join(REFERENCE_ROOT, "dpose_core", "src"), "-I", PLUGIN_SRC, src] + extra + objs +
+                           ["-fopenmp", "-lm", "-o", exe], check=True)
         out[name] = exe
     return out
 
@@ -71,13 +85,16 @@ def build_on_b200():
     headers = [os.path.join(dp, f) for dp, _, fs in os.walk(include) for f in fs] + _shim_headers()
     out = {}
     for name in SUITES:
-        src, exe = os.path.join(TEST_DIR, name + ".cpp"), binary("on_b200", name)
-        if _stale(exe, [src] + headers):
+        src, exe = _source(name), binary("on_b200", name)
+        # the plugin's test links the plugin's own, unmodified translation unit — compiled here against the drop-in
+        extra = ([os.path.join(PLUGIN_SRC, "dpose_goal_tolerance.cpp")] if name == "goal_tolerance"
+                 else [os.path.join(SHIM, "gtest", "gtest_main.cpp")])
+        if _stale(exe, [src] + extra + headers):
             os.makedirs(os.path.dirname(exe), exist_ok=True)
             # include/ first: <dpose_core/*.hpp> must resolve to the drop-in headers, everything else to the stand-ins
-            subprocess.run([CXX, "-std=c++17", "-O2", "-w", "-I", include, "-I", SHIM, src,
-                            os.path.join(SHIM, "gtest", "gtest_main.cpp"), "-L", os.path.dirname(lib), "-ldpose_b200",
-                            "-Wl,-rpath,$ORIGIN/../../../dpose_b200/lib", "-o", exe], check=True)
+            subprocess.run([CXX, "-std=c++17", "-O2", "-w", "-I", include, "-I", SHIM, "-I", PLUGIN_SRC, src] + extra +
+                           ["-L", os.path.dirname(lib), "-ldpose_b200", "-Wl,-rpath,$ORIGIN/../../../dpose_b200/lib", "-o", exe],
+                           check=True)
         out[name] = exe
     return out
 

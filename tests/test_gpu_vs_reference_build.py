@@ -106,3 +106,35 @@ def test_check_footprint_batch(dp):
             assert bool(got[i]) == want, (poses[i], moved.tolist())
             seen.add(want)
         assert seen == {True, False}
+
+
+@pytest.mark.parametrize("name,cfg_over,goal", [
+    ("rect_pad2", {}, [300.25, 200.5, 0.3]),
+    ("star40_pad2", dict(lin_tolerance=10, weight_start_lin=0, weight_start_rot=0), [250.5, 250.5, 1.0]),
+    ("lshape_pad2", dict(lin_tolerance=5, weight_goal_lin=0, weight_goal_rot=0), [10.0, 12.0, 3.0]),  # box clamped at the border
+])
+def test_problem_eval_batch_vs_reference_plugin(dp, name, cfg_over, goal):
+    """dpose_problem_eval_batch against the NLP callbacks of the compiled, unmodified plugin source
+    (dpose_goal_tolerance.cpp:90-292): what Ipopt would be handed, for 2048 displacements at once"""
+    cfg = dict(lin_tolerance=1, rot_tolerance=1, weight_goal_lin=1, weight_goal_rot=1, weight_start_lin=1, weight_start_rot=1)
+    cfg.update(cfg_over)
+    fp, pad = fx.FOOTPRINTS[name]
+    m = fx.bernoulli_map(500, 500, 0.10, 1)
+    start = [goal[0] - 40.0, goal[1] + 25.0, goal[2] + 2.5]
+    pr = dp.problem(dp.pose_gradient(fp, dp.pose_gradient.parameter(pad)), dp.Costmap(m))
+    pr.init(start, goal, cfg)
+    ref = refapi.Problem(fp, pad, m)
+    ref.init(start, goal, **cfg)
+    rng = rng_of("problem", name)
+    n = 2048
+    r, a = rng.uniform(0, cfg["lin_tolerance"], n), rng.uniform(-np.pi, np.pi, n)  # the plugin's polar sampler (:333-357)
+    xs = np.stack([np.cos(a) * r, np.sin(a) * r, rng.uniform(0, cfg["rot_tolerance"], n)], axis=1)
+    xs[0] = 0.0
+    got = pr.eval_batch(xs)
+    f, grad, g, jac = ref.eval_batch(xs)
+    assert fx.tol_ok(got["f"], f).all()
+    assert fx.tol_ok(got["grad_f"], grad).all()
+    assert np.array_equal(got["g"], g) and np.array_equal(got["jac_g"], jac)
+    dims, _, (gl, gu), _ = ref.info()
+    assert pr.get_nlp_info() == tuple(dims[:3].tolist())
+    assert np.array_equal(pr.get_bounds_info()[3], gu)

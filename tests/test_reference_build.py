@@ -218,3 +218,86 @@ def test_check_footprint_dense_circles(steps):
         m[y, x] = 254
         assert capi.check_footprint(m, fp) == refapi.check_footprint(m, fp), (x, y)
         m[y, x] = 0
+
+
+# ---- dpose_goal_tolerance::problem (dpose_goal_tolerance.cpp:54-292), the NLP of the unchanged plugin -------------------
+PROBLEM_CASES = [
+    ("rect_pad2", {}, [150.3, 120.9, 2.9], [200.25, 150.5, -2.8]),
+    ("rect_pad2", dict(weight_goal_lin=0, weight_goal_rot=0), [10.0, 12.0, 0.1], [14.0, 9.0, 0.3]),
+    ("rect_pad2", dict(weight_start_lin=0, weight_start_rot=0), [380.0, 280.0, -3.0], [395.5, 296.5, 3.1]),
+    ("diamond_pad5", dict(lin_tolerance=20, rot_tolerance=0.5, weight_goal_lin=3, weight_start_rot=0.2), [99, 99, 0], [100, 100, 1.3]),
+    ("star40_pad2", dict(lin_tolerance=0.0, rot_tolerance=0.0), [200, 150, 0.5], [200, 150, 0.5]),
+    ("lshape_pad2", dict(lin_tolerance=5, weight_start_lin=0.0, weight_start_rot=2.0), [3.2, 4.1, 1.0], [2.0, 2.0, -1.0]),
+]
+
+
+@pytest.mark.parametrize("name,cfg_over,start,goal", PROBLEM_CASES)
+def test_problem_matches_reference_plugin(name, cfg_over, start, goal):
+    """oracle_problem_* against the compiled reference `problem`: f, grad f, g and the Jacobian of g for random
+    displacements.  The obstacle term sums the same cells in another order (unordered_map rows), everything else is
+    the same arithmetic: f and grad f agree to rounding, g and its Jacobian bit for bit."""
+    cfg = dict(lin_tolerance=1, rot_tolerance=1, weight_goal_lin=1, weight_goal_rot=1, weight_start_lin=1, weight_start_rot=1)
+    cfg.update(cfg_over)
+    fp, pad = fx.FOOTPRINTS[name]
+    m = fx.bernoulli_map(400, 300, 0.10, 11)
+    o = capi.Problem(capi.CostData(fp, pad), m)
+    r = refapi.Problem(fp, pad, m)
+    o.init(start, goal, **cfg)
+    r.init(start, goal, **cfg)
+    dims, (xl, xu), (gl, gu), (rows, cols) = r.info()
+    assert dims.tolist() == [3, 2, 3, 0]
+    assert (gl.tolist(), gu.tolist()) == ([0, 0], list(o.bounds))
+    assert (rows.tolist(), cols.tolist()) == ([0, 0, 1], [0, 1, 2])
+    assert np.all(xl == -1e6) and np.all(xu == 1e6)
+    rng = rng_of("problem", name)
+    xs = rng.uniform(-1, 1, (80, 3)) * np.array([max(cfg["lin_tolerance"], 1.0), max(cfg["lin_tolerance"], 1.0), 3.0])
+    xs[0] = 0
+    fo, grado, go, jaco = o.eval_batch(xs)
+    fr, gradr, gr, jacr = r.eval_batch(xs)
+    assert np.all(np.abs(fo - fr) <= 1e-12 * (1 + np.abs(fr)))
+    assert np.all(np.abs(grado - gradr) <= 1e-10 * (1 + np.abs(gradr)))
+    assert np.array_equal(go, gr) and np.array_equal(jaco, jacr)
+    assert np.abs(fr).max() > 0
+
+
+def test_problem_rejects_two_zero_weights_like_the_reference():
+    """pose_regularization throws if both of its weights are zero (:57-59) — reached with exactly one weight pair
+    of a regulariser zeroed is impossible (the pair is skipped), so the reference never throws from init; pinned"""
+    fp, pad = fx.FOOTPRINTS["rect_pad2"]
+    r = refapi.Problem(fp, pad, fx.bernoulli_map(100, 100, 0.1, 1))
+    r.init([10, 10, 0], [20, 20, 0], weight_goal_lin=0, weight_goal_rot=0, weight_start_lin=0, weight_start_rot=0)
+    f, grad, g, jac = r.eval_batch([[0.5, -0.25, 0.1]])
+    o = capi.Problem(capi.CostData(fp, pad), fx.bernoulli_map(100, 100, 0.1, 1))
+    o.init([10, 10, 0], [20, 20, 0], weight_goal_lin=0, weight_goal_rot=0, weight_start_lin=0, weight_start_rot=0)
+    fo, grado, go, jaco = o.eval_batch([[0.5, -0.25, 0.1]])
+    assert abs(fo[0] - f[0]) <= 1e-12 * (1 + abs(f[0])) and np.array_equal(go, g) and np.array_equal(jaco, jac)
+
+
+def test_pose_conversions_match_reference_plugin():
+    """the plugin's to_cell / to_msg (:293-330) against the vectorised C ABI versions (host arithmetic, no GPU).  The
+    reference reads the yaw out of a quaternion message (always in (-pi, pi]); the C ABI is handed the yaw itself and
+    passes it through, so angles are compared modulo 2 pi."""
+    import dpose_b200 as dp
+
+    def same_angle(a, b):
+        return abs(math.remainder(a - b, 2 * math.pi)) <= 1e-12
+    rng = rng_of("conv")
+    for origin, res, size in (((0.0, 0.0), 0.05, (200, 200)), ((-12.5, 3.25), 0.1, (300, 120)), ((5.0, -5.0), 0.025, (64, 64))):
+        span = np.array([size[0] * res, size[1] * res])
+        world = np.concatenate([rng.uniform(-0.2, 1.2, (300, 2)) * span + np.array(origin), rng.uniform(-4, 4, (300, 1))], 1)
+        world[:4, :2] = [origin, np.array(origin) + span, np.array(origin) + span - 1e-9, np.array(origin) - 1e-12]
+        cells, ok = dp.to_cell(world, origin, res, size)
+        for w, c, good in zip(world, cells, ok):
+            want = refapi.to_cell(w, origin, res, size)
+            assert (want is not None) == bool(good), w
+            if good:
+                assert np.array_equal(c[:2], want[:2]) and same_angle(c[2], want[2])
+        cell_poses = np.concatenate([rng.uniform(-2, size[0] + 2, (300, 1)), rng.uniform(-2, size[1] + 2, (300, 1)),
+                                     rng.uniform(-3.1, 3.1, (300, 1))], 1)
+        cell_poses[:3] = [[0.49, 0.5, 0.1], [-0.0, 3.5, -1.0], [-1e-9, 2.0, 2.0]]
+        msgs, ok = dp.to_msg(cell_poses, origin, res)
+        for c, w, good in zip(cell_poses, msgs, ok):
+            want = refapi.to_msg(c, origin, res, size)
+            assert (want is not None) == bool(good), c
+            if good:
+                assert np.array_equal(w[:2], want[:2]) and same_angle(w[2], want[2])
