@@ -467,6 +467,16 @@ static uint8_t *pinned_ok() {
   return p;
 }
 
+// device memory the per-pose working state of one call may take (DPOSE_CHECK_WS_MB overrides; tests use it to force
+// the chunked path)
+static size_t workspace_budget() {
+  static const size_t v = [] {
+    const char *e = getenv("DPOSE_CHECK_WS_MB");
+    return (size_t)(e ? std::max(1, atoi(e)) : 256) << 20;
+  }();
+  return v;
+}
+
 static int coop_threads(size_t n_poses) {
   static const int forced = [] {
     const char *e = getenv("DPOSE_CHECK_COOP_THREADS");
@@ -521,7 +531,7 @@ static int check_impl(const dpose_map *map, const int32_t *fp, int n, const doub
     }
     const int span_cap = (int)std::min<long long>(1 << 16, std::max<long long>(1, height * ((n + 1) / 2 + 1)));
     const size_t coop_per_pose = coop_bytes(n + 1, span_cap);
-    constexpr size_t kWorkspaceBudget = (size_t)256 << 20;  // bytes of per-pose state alive at once
+    const size_t kWorkspaceBudget = workspace_budget();  // bytes of per-pose state alive at once
     if (n_poses <= (size_t)coop_max_poses() && n_poses * coop_per_pose <= kWorkspaceBudget) {
       if (large) {
         DPOSE_CUDA(cudaMallocAsync(&d_fp, sizeof(int) * 2 * (size_t)n, stream));

@@ -214,3 +214,28 @@ def test_gpu_check_footprint_many_vertices(dp, steps):
     want = capi.check_footprint_batch(big, fp0, poses, nthreads=capi.max_threads())
     assert 0.05 < want.mean() < 0.95
     assert np.array_equal(got, want), int((got != want).sum())
+
+
+@pytest.mark.gpu
+def test_gpu_check_footprint_chunked_workspace(dp):
+    """a 1 MB workspace budget forces the >64-vertex thread-per-pose kernel to process its 700 poses in 9 chunks
+    (fresh process: the budget is read once per process)"""
+    import os
+    import subprocess
+    import sys
+    tests_dir = os.path.dirname(os.path.abspath(__file__))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "import numpy as np, fixtures as fx, dpose_b200 as dp\n"
+        "from oracle import capi\n"
+        "from test_check_footprint import circle\n"
+        "fp = circle(200, 20)\n"
+        "m = fx.bernoulli_map(400, 300, 0.0006, 5)\n"
+        "poses = fx.random_poses(700, 400, 300, 6, margin=-10.0)\n"
+        "got = dp.check_footprint_batch(dp.Costmap(m), fp, poses)\n"
+        "want = capi.check_footprint_batch(m, fp, poses, nthreads=2)\n"
+        "assert 0.05 < want.mean() < 0.95 and np.array_equal(got, want), int((got != want).sum())\n"
+        "print('chunked ok')\n" % (os.path.dirname(tests_dir), tests_dir))
+    env = dict(os.environ, DPOSE_CHECK_WS_MB="1", DPOSE_CHECK_COOP_MAX="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "chunked ok" in r.stdout, r.stdout + r.stderr
