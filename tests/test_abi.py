@@ -92,9 +92,20 @@ def test_product_does_not_reference_oracle():
             for f in files:
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                     txt = open(os.path.join(dirpath, f), errors="replace").read()
-                    if re.search(r"(from|import)\s+oracle|oracle/|dpose_oracle", txt):
+                    if re.search(r"(from|import)\s+oracle|oracle/|dpose_oracle|refshim|libdpose_ref|refapi", txt):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_product_library_does_not_link_the_checkers(built):
+    """libdpose_b200.so depends on neither the oracle nor the compiled reference (ldd), and exports none of their symbols"""
+    import subprocess
+    from dpose_b200 import build
+    so = build.build()
+    deps = subprocess.run(["ldd", so], capture_output=True, text=True, check=True).stdout
+    assert "dpose_oracle" not in deps and "dpose_ref" not in deps, deps
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    assert not re.search(r"\b(oracle_|ref_)\w+", syms)
 
 
 def test_argument_validation_without_a_device(built):
