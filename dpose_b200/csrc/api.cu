@@ -46,7 +46,16 @@ using namespace dpose;
 
 namespace {
 constexpr int kBuf = 3;
-constexpr size_t kChunkPoses = (size_t)1 << 17;  // 3 MB in / 4 MB out per chunk: short pipeline fill and drain
+constexpr size_t kChunkPosesDefault = (size_t)1 << 17;  // 3 MB in / 4 MB out per chunk: short pipeline fill and drain
+// DPOSE_BATCH_CHUNK_LOG2 overrides (A/B measurements)
+size_t chunk_poses() {
+  static const size_t v = [] {
+    const char *e = getenv("DPOSE_BATCH_CHUNK_LOG2");
+    const int l = e ? atoi(e) : 0;
+    return l >= 10 && l <= 24 ? (size_t)1 << l : kChunkPosesDefault;
+  }();
+  return v;
+}
 
 struct BatchCtx {
   std::mutex mu;
@@ -564,7 +573,7 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
     ctx = static_cast<BatchCtx *>(p->batch_ctx);
   }
   std::lock_guard<std::mutex> call_lock(ctx->mu);
-  const size_t chunk = std::min<size_t>(n, kChunkPoses);
+  const size_t chunk = std::min<size_t>(n, chunk_poses());
   DPOSE_TRY(ctx->reserve(chunk));
   auto body = [&]() -> int {
     if (n <= chunk) {  // one chunk: in-order on a single stream, no cross-stream events (latency path)
