@@ -104,8 +104,10 @@ __global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *
       lo.x = (a.a00 - a.a10 * U) - (a.a01 * V - (a.a11 * U) * V);
     }
     if (hi_only) {  // texture modes: shared image = first halves only (if any), both halves in a plain global array
-      hi_only[2 * (size_t)i] = lo;
-      hi_only[2 * (size_t)i + 1] = hi;
+      // two planes, second halves first: the single-replica mode fetches only those, and packed 16 bytes apart they
+      // take half the texture-cache footprint of an interleaved layout (cfg3: 1.24e9 against 1.16e9 poses/s)
+      hi_only[(size_t)i] = hi;
+      hi_only[(size_t)n_patches + i] = lo;
       if (image)
         for (int r = 0; r < (1 << rep_shift); ++r) image[((size_t)i << rep_shift) + r] = lo;
     } else {
@@ -173,6 +175,8 @@ struct TileArgs {
   size_t n;
   cudaTextureObject_t tex_hi;  // texture mode: second halves of the patch polynomials (int4 texels)
   int out_aligned;  // out is 32-byte aligned: one 256-bit store per result
+  uint32_t stride;  // poses a CTA takes per sweep (<= its thread count; a multiple of 32): batches that do not fill
+                    // grid x threads whole sweeps are spread evenly over the CTAs instead of leaving some idle
   float clip_thr;   // a strip of the kernel rectangle is clipped per row only if |cos| (|sin|) exceeds this
 };
 
@@ -285,9 +289,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   const float hi_u = (float)a.g.cols - 3.0f, hi_v = (float)a.g.rows - 3.0f;  // 0 <= k' < dim - 3
   const double cx15 = a.g.cx - 1.5, cy15 = a.g.cy - 1.5;
 
-  for (size_t base = (size_t)blockIdx.x * kThreads; base < a.n; base += (size_t)gridDim.x * kThreads) {
+  if ((uint32_t)tid >= a.stride) return;  // no barrier below: threads without poses just leave
+  for (size_t base = (size_t)blockIdx.x * a.stride; base < a.n; base += (size_t)gridDim.x * a.stride) {
     const size_t idx = base + tid;
-    if (idx >= a.n) break;  // no barrier below: threads past the end just leave
+    if (idx >= a.n) break;
     const double *pp = a.poses + 3 * idx;
     const double tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
     double s, c;
@@ -446,14 +451,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const uint32_t addr = my_coef + (uint32_t)pidx * kPatchStride;
           double b00, b10, b01, b11;
           if (kGlobal) {
-            const int4 t = tex1Dfetch<int4>(a.tex_hi, 2 * (pidx + 2 * cols + 2));
+            const int4 t = tex1Dfetch<int4>(a.tex_hi, a.g.rows * cols + pidx + 2 * cols + 2);
             b00 = __hiloint2double(t.y, t.x);
             b10 = __hiloint2double(t.w, t.z);
           } else {
             asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
           }
           if (kTex) {
-            const int4 t = tex1Dfetch<int4>(a.tex_hi, 2 * (pidx + 2 * cols + 2) + 1);
+            const int4 t = tex1Dfetch<int4>(a.tex_hi, pidx + 2 * cols + 2);
             b01 = __hiloint2double(t.y, t.x);
             b11 = __hiloint2double(t.w, t.z);
           } else {
@@ -651,7 +656,15 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.clip_thr = 0.5f / (float)std::max(pg->win_max, 25);
   const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)stored * 4 * threads;
   const size_t want = (n + threads - 1) / threads;
-  const int grid = (int)std::min<size_t>(want, (size_t)sms);
+  int grid = (int)std::min<size_t>(want, (size_t)sms);
+  a.stride = (uint32_t)threads;
+  static const int env_balance = env_int("DPOSE_TILE_BALANCE");  // 0 (unset): default, 1: off, 2: on (A/B)
+  if (env_balance != 1 && n >= (size_t)sms * 32) {  // every SM gets a CTA, every CTA the same share of every sweep
+    grid = sms;
+    const size_t sweeps = (n + (size_t)grid * threads - 1) / ((size_t)grid * threads);
+    const size_t share = (n + (size_t)grid * sweeps - 1) / ((size_t)grid * sweeps);
+    a.stride = (uint32_t)std::min<size_t>((size_t)threads, (share + 31) / 32 * 32);
+  }
   *handled = true;
   return want_jacobian ? launch_tile1<true>(a, threads, rep_shift, rows, grid, smem_bytes, stream)
                        : launch_tile1<false>(a, threads, rep_shift, rows, grid, smem_bytes, stream);
