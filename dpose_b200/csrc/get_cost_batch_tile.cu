@@ -174,6 +174,7 @@ struct TileArgs {
   double *out;
   size_t n;
   cudaTextureObject_t tex_hi;  // texture mode: second halves of the patch polynomials (int4 texels)
+  const int4 *planes;          // the same buffer as a plain pointer (DPOSE_TILE_LDG experiment)
   int out_aligned;  // out is 32-byte aligned: one 256-bit store per result
   uint32_t stride;  // poses a CTA takes per sweep (<= its thread count; a multiple of 32): batches that do not fill
                     // grid x threads whole sweeps are spread evenly over the CTAs instead of leaving some idle
@@ -212,6 +213,9 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 // DPOSE_TILE_CHECK 1: debug build that traps on any access outside the coefficient image, the tile plane or the
 // row-mask block (compute-sanitizer is not available on the GPU pool): run the GPU tests and the bench with it
 // after touching the clip logic.
+#ifndef DPOSE_TILE_LDG
+#define DPOSE_TILE_LDG 0  // 1: fetch the texture-mode planes with LDG.128.CONSTANT instead of TEX (A/B experiment)
+#endif
 #ifndef DPOSE_TILE_CHECK
 #define DPOSE_TILE_CHECK 0
 #endif
@@ -451,14 +455,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           const uint32_t addr = my_coef + (uint32_t)pidx * kPatchStride;
           double b00, b10, b01, b11;
           if (kGlobal) {
-            const int4 t = tex1Dfetch<int4>(a.tex_hi, a.g.rows * cols + pidx + 2 * cols + 2);
+            const int4 t = DPOSE_TILE_LDG ? __ldg(a.planes + (a.g.rows * cols + pidx + 2 * cols + 2))
+                                          : tex1Dfetch<int4>(a.tex_hi, a.g.rows * cols + pidx + 2 * cols + 2);
             b00 = __hiloint2double(t.y, t.x);
             b10 = __hiloint2double(t.w, t.z);
           } else {
             asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
           }
           if (kTex) {
-            const int4 t = tex1Dfetch<int4>(a.tex_hi, pidx + 2 * cols + 2);
+            const int4 t = DPOSE_TILE_LDG ? __ldg(a.planes + (pidx + 2 * cols + 2)) : tex1Dfetch<int4>(a.tex_hi, pidx + 2 * cols + 2);
             b01 = __hiloint2double(t.y, t.x);
             b11 = __hiloint2double(t.w, t.z);
           } else {
@@ -652,6 +657,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.out = d_out;
   a.n = n;
   a.tex_hi = (cudaTextureObject_t)p->tex_hi;
+  a.planes = reinterpret_cast<const int4 *>(p->d_coef_hi);
   a.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 31u) == 0;
   a.clip_thr = 0.5f / (float)std::max(pg->win_max, 25);
   const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)stored * 4 * threads;
