@@ -1,6 +1,7 @@
 // api.cu — the extern "C" surface of libdpose_b200.so (include/dpose_b200.h): argument
 // validation, handle lifetime, host<->device staging and the multi-GPU shard driver.
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -57,9 +58,22 @@ size_t chunk_poses() {
   return v;
 }
 
+// Calls of up to this many poses (the multi-start pattern: a few thousand candidates per solver iteration) skip the
+// device staging altogether: poses and results live in mapped pinned memory the kernel reads and writes over PCIe
+// (no staged copies of pageable buffers on either side).  4096 poses: 51 -> 42 us per call.
+constexpr size_t kZeroCopyPoses = 8192;
+
 struct BatchCtx {
   std::mutex mu;
   size_t cap = 0;  // poses per staging buffer
+  double *h_zc = nullptr;  // mapped pinned: kZeroCopyPoses x 3 poses | kZeroCopyPoses x 4 results
+  double *zc_in() const { return h_zc; }
+  double *zc_out() const { return h_zc + 3 * kZeroCopyPoses; }
+  int ensure_zc() {
+    if (h_zc) return DPOSE_OK;
+    DPOSE_CUDA(cudaHostAlloc(&h_zc, sizeof(double) * 7 * kZeroCopyPoses, cudaHostAllocMapped));
+    return DPOSE_OK;
+  }
   cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
   cudaEvent_t in_done[kBuf] = {}, k_done[kBuf] = {}, out_done[kBuf] = {};
   double *d_p[kBuf] = {}, *d_o[kBuf] = {};
@@ -101,6 +115,7 @@ struct BatchCtx {
     if (s_in) cudaStreamDestroy(s_in);
     if (s_k) cudaStreamDestroy(s_k);
     if (s_out) cudaStreamDestroy(s_out);
+    if (h_zc) cudaFreeHost(h_zc);
   }
 };
 
@@ -312,6 +327,10 @@ static int map_create_impl(const uint8_t *data, uint32_t size_x, uint32_t size_y
     DPOSE_CUDA(cudaMalloc(&m->d_data, m->pitch * size_y));
     if (m->pitch != size_x) DPOSE_CUDA(cudaMemset(m->d_data, 0, m->pitch * size_y));
     DPOSE_CUDA(cudaMemcpy2D(m->d_data, m->pitch, data, pitch, size_x, size_y, kind));
+    // A "synchronous" copy out of pageable host memory returns once the bytes are STAGED; the DMA may still be in
+    // flight, and only work on the legacy stream is ordered behind it.  The kernels that read this map run on
+    // non-blocking streams, so wait for the copy (and the memset) to land.
+    DPOSE_CUDA(cudaStreamSynchronize(nullptr));
     m->bits_pitch = (((size_t)size_x + 127) / 128) * 16;
     DPOSE_CUDA(cudaMalloc(&m->d_bits, m->bits_pitch * size_y));
     m->bits_dirty = true;
@@ -366,6 +385,7 @@ int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t
   } else {
     DPOSE_CUDA(cudaMemcpy2D(map->d_data + (size_t)y0 * map->pitch + x0, map->pitch, data, pitch, w, h,
                             cudaMemcpyHostToDevice));
+    DPOSE_CUDA(cudaStreamSynchronize(nullptr));  // staged copy: see dpose_map_create
   }
   // narrow the lazy plane rebuilds to the rows of this window (union with what is already pending)
   auto widen = [&](bool &dirty, uint32_t &lo, uint32_t &hi) {
@@ -487,6 +507,7 @@ int dpose_cells_upload(const int32_t *cells_xy, size_t n, int device, dpose_cell
     if (!n) return DPOSE_OK;
     DPOSE_CUDA(cudaMalloc(&c->d_xy, sizeof(int2) * n));
     DPOSE_CUDA(cudaMemcpy(c->d_xy, cells_xy, sizeof(int2) * n, cudaMemcpyHostToDevice));
+    DPOSE_CUDA(cudaStreamSynchronize(nullptr));  // staged copy: see dpose_map_create
     return DPOSE_OK;
   };
   const int rc = body();
@@ -573,6 +594,24 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
     ctx = static_cast<BatchCtx *>(p->batch_ctx);
   }
   std::lock_guard<std::mutex> call_lock(ctx->mu);
+  static const bool zero_copy_on = [] {
+    const char *e = getenv("DPOSE_BATCH_ZEROCOPY");  // "0" switches the latency path off (A/B, debugging)
+    return !(e && e[0] == '0');
+  }();
+  if (zero_copy_on && n <= kZeroCopyPoses) {  // latency path, see kZeroCopyPoses
+    DPOSE_TRY(ctx->ensure_zc());
+    std::memcpy(ctx->zc_in(), poses, sizeof(double) * 3 * n);
+    int rc = get_cost_batch_device(pg, map, ctx->zc_in(), n, ctx->zc_out(), want_jacobian, ctx->s_k);
+    if (rc == DPOSE_OK) {
+      // A stream synchronisation, not a flag polled in the result page: the results are written by every thread of
+      // the kernel, and only a synchronisation point guarantees that all of them have reached host memory.
+      const cudaError_t e = cudaStreamSynchronize(ctx->s_k);
+      if (e != cudaSuccess) rc = fail(DPOSE_ECUDA, "batched get_cost failed: %s", cudaGetErrorString(e));
+      if (rc == DPOSE_OK) std::memcpy(out, ctx->zc_out(), sizeof(double) * 4 * n);
+    }
+    if (rc != DPOSE_OK) cudaDeviceSynchronize();
+    return rc;
+  }
   const size_t chunk = std::min<size_t>(n, chunk_poses());
   DPOSE_TRY(ctx->reserve(chunk));
   auto body = [&]() -> int {

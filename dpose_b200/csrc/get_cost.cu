@@ -200,6 +200,7 @@ static int ensure_scratch(CellScratch &sc, int device, size_t ncells) {
     DPOSE_CUDA(cudaMalloc(&sc.d_partials, sizeof(double) * 4 * kMaxCellCtas));
     DPOSE_CUDA(cudaMalloc(&sc.d_ticket, sizeof(unsigned)));
     DPOSE_CUDA(cudaMemset(sc.d_ticket, 0, sizeof(unsigned)));
+    DPOSE_CUDA(cudaStreamSynchronize(nullptr));  // the memset is asynchronous; its users run on a non-blocking stream
     DPOSE_CUDA(cudaHostAlloc(&sc.h_out, sizeof(double) * 8, cudaHostAllocMapped));
     std::memset(sc.h_out, 0, sizeof(double) * 8);
     DPOSE_CUDA(cudaHostAlloc(&sc.h_cells, sizeof(int2) * kZeroCopyCells, cudaHostAllocMapped));
