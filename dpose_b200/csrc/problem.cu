@@ -123,7 +123,7 @@ static int problem_reserve(dpose_problem *p, size_t n) {
   p->cap = 0;
   const size_t cap = n + n / 2 + 256;
   DPOSE_CUDA(cudaMalloc(&p->d_x, sizeof(double) * 19 * cap));
-  DPOSE_CUDA(cudaHostAlloc(&p->h_stage, sizeof(double) * 12 * cap, cudaHostAllocDefault));
+  DPOSE_CUDA(cudaHostAlloc(&p->h_stage, sizeof(double) * 12 * cap, cudaHostAllocMapped));
   p->d_work = p->d_x + 3 * cap;  // 7 n: cost4 | poses
   p->d_res = p->d_work + 7 * cap;
   p->cap = cap;
@@ -248,6 +248,8 @@ static int problem_eval_device(const dpose_problem *p, const double *d_x, size_t
   return DPOSE_OK;
 }
 
+constexpr size_t kZeroCopyDisplacements = 8192;
+
 int dpose_problem_eval_batch(dpose_problem *p, const double *x, size_t n, double *f, double *grad_f, double *g,
                              double *jac_g) {
   if (!p || (n && !x)) return fail(DPOSE_EINVAL, "NULL argument");
@@ -263,10 +265,17 @@ int dpose_problem_eval_batch(dpose_problem *p, const double *x, size_t n, double
     // pinned staging: one H2D of x, one D2H of [f | grad | g | jac]
     double *h_x = p->h_stage, *h_res = p->h_stage + 3 * n;
     std::memcpy(h_x, x, sizeof(double) * 3 * n);
-    DPOSE_CUDA(cudaMemcpyAsync(p->d_x, h_x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
-    DPOSE_TRY(problem_eval_device(p, p->d_x, n, p->d_work, f ? d_f : nullptr, grad_f ? d_grad : nullptr,
-                                  g ? d_g : nullptr, jac_g ? d_jac : nullptr, st));
-    DPOSE_CUDA(cudaMemcpyAsync(h_res, p->d_res, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
+    if (n <= kZeroCopyDisplacements) {
+      // a solver iteration's worth of displacements: the kernels read x and write [f | grad | g | jac] in the mapped
+      // pinned staging itself, no copies in either direction (the writes overlap the evaluation)
+      DPOSE_TRY(problem_eval_device(p, h_x, n, p->d_work, f ? h_res : nullptr, grad_f ? h_res + n : nullptr,
+                                    g ? h_res + 4 * n : nullptr, jac_g ? h_res + 6 * n : nullptr, st));
+    } else {
+      DPOSE_CUDA(cudaMemcpyAsync(p->d_x, h_x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+      DPOSE_TRY(problem_eval_device(p, p->d_x, n, p->d_work, f ? d_f : nullptr, grad_f ? d_grad : nullptr,
+                                    g ? d_g : nullptr, jac_g ? d_jac : nullptr, st));
+      DPOSE_CUDA(cudaMemcpyAsync(h_res, p->d_res, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
+    }
     DPOSE_CUDA(cudaStreamSynchronize(st));
     if (f) std::memcpy(f, h_res, sizeof(double) * n);
     if (grad_f) std::memcpy(grad_f, h_res + n, sizeof(double) * 3 * n);
