@@ -133,11 +133,12 @@ struct Scratch {
   XB *xb;
   int2 *pt;
   int *lower_y, *vy, *vl, *vr, *active;
+  int *xk;  // x of every line on the current event's scan line (parallel form only; may be null otherwise)
   uint8_t *was_active;
 };
 
 __host__ __device__ inline size_t scratch_bytes(int cap) {  // one pose, 8-byte aligned
-  const size_t raw = (size_t)cap * (sizeof(XB) + sizeof(int2) + 5 * sizeof(int) + 1);
+  const size_t raw = (size_t)cap * (sizeof(XB) + sizeof(int2) + 6 * sizeof(int) + 1);
   return (raw + 7) & ~(size_t)7;
 }
 
@@ -150,87 +151,198 @@ __device__ inline Scratch scratch_at(unsigned char *base, int cap) {
   s.vl = s.vy + cap;
   s.vr = s.vl + cap;
   s.active = s.vr + cap;
-  s.was_active = reinterpret_cast<uint8_t *>(s.active + cap);
+  s.xk = s.active + cap;
+  s.was_active = reinterpret_cast<uint8_t *>(s.xk + cap);
   return s;
 }
 
-// The scan-line sweep of upstream check_footprint (:487-583) for a ring of n >= 3 vertices: calls
-// span(yy, lx, rx) for every pair of active edges on every scan line with lx < rx (the cells lx .. rx - 1 of row yy
-// are the interior to search) and stops with false as soon as span() returns false.
-template <typename SpanFn>
-__device__ bool sweep_spans(const int n, const Scratch sc, SpanFn span) {
+// ---- the scan-line sweep of upstream check_footprint (:487-583), in pieces shared by the serial and the parallel form
+struct SweepSetup {
+  int nl, nv, ymin;
+};
+
+// edges (horizontal ones skipped, :487-496) and the vertex set (:503-510): (y, left line, right line), ordered by y,
+// equal keys in insertion order.  An open footprint gets its first vertex appended, which turns upstream's special
+// cases for the closing edge (:450-456 outline, :495-496 scan-line edges) into the last iteration of the same loops.
+__device__ inline SweepSetup sweep_setup(const int n, const Scratch sc) {
   const int2 *pt = sc.pt;
   XB *xb = sc.xb;
-  int *lower_y = sc.lower_y, *vy = sc.vy, *vl = sc.vl, *vr = sc.vr, *active = sc.active;
-  uint8_t *was_active = sc.was_active;
-  // An open footprint gets its first vertex appended, which turns upstream's special cases for the closing
-  // edge (:450-456 outline, :495-496 scan-line edges) into the last iteration of the same loops.
+  int *lower_y = sc.lower_y, *vy = sc.vy, *vl = sc.vl, *vr = sc.vr;
   const bool is_closed = pt[n - 1].x == pt[0].x && pt[n - 1].y == pt[0].y;
   const int m = is_closed ? n : n + 1;  // vertices of the closed ring
   auto vx = [&](int i) { return pt[i == n ? 0 : i].x; };
   auto vyy = [&](int i) { return pt[i == n ? 0 : i].y; };
-  // edges, horizontal ones skipped (:487-496)
   int nl = 0;
   for (int c = 1; c < m; ++c)
     if (vyy(c - 1) != vyy(c)) {
       xb_init(xb[nl], vx(c - 1), vyy(c - 1), vx(c), vyy(c));
       lower_y[nl] = vyy(c - 1);
-      was_active[nl] = 0;
+      sc.was_active[nl] = 0;
       ++nl;
     }
-  if (nl == 0) return true;
-  // vertex_set (:503-510): (y, left line, right line), ordered by y, equal keys in insertion order
   int nv = 0;
-  auto insert_vertex = [&](int y, int l, int r) {  // stable insertion
-    int j = nv - 1;
-    while (j >= 0 && vy[j] > y) {
-      vy[j + 1] = vy[j], vl[j + 1] = vl[j], vr[j + 1] = vr[j];
-      --j;
-    }
-    vy[j + 1] = y, vl[j + 1] = l, vr[j + 1] = r;
-    ++nv;
-  };
-  for (int l = 0; l + 1 < nl; ++l) insert_vertex(lower_y[l + 1], l, l + 1);
-  insert_vertex(lower_y[0], nl - 1, 0);
-
-  int na = 0;
+  if (nl) {
+    auto insert_vertex = [&](int y, int l, int r) {  // stable insertion
+      int j = nv - 1;
+      while (j >= 0 && vy[j] > y) {
+        vy[j + 1] = vy[j], vl[j + 1] = vl[j], vr[j + 1] = vr[j];
+        --j;
+      }
+      vy[j + 1] = y, vl[j + 1] = l, vr[j + 1] = r;
+      ++nv;
+    };
+    for (int l = 0; l + 1 < nl; ++l) insert_vertex(lower_y[l + 1], l, l + 1);
+    insert_vertex(lower_y[0], nl - 1, 0);
+  }
   int ymin = pt[0].y;
   for (int i = 1; i < n; ++i) ymin = min(ymin, pt[i].y);
-  int yy = ymin - 1;  // :519
-  for (int v = 0; v < nv;) {
-    for (; yy < vy[v]; ++yy) {  // :549-556
+  return SweepSetup{nl, nv, ymin};
+}
+
+// vertex event v (:562-581): each of its two lines is taken out (swap with the last, pop) if it was in, else appended
+__device__ inline void sweep_toggle(const Scratch sc, int v, int &na) {
+  const int pair[2] = {sc.vl[v], sc.vr[v]};
+  for (int k = 0; k < 2; ++k) {
+    const int l = pair[k];
+    if (sc.was_active[l]) {
+      int pos = 0;
+      while (pos < na && sc.active[pos] != l) ++pos;
+      if (pos < na) sc.active[pos] = sc.active[--na];
+    } else {
+      sc.was_active[l] = 1;
+      sc.active[na++] = l;
+    }
+  }
+}
+
+// the active lines by (x on the current scan line, dx) (:583), stable insertion sort
+template <typename KeyFn>
+__device__ inline void sweep_sort(const Scratch sc, int na, KeyFn xkey) {
+  int *active = sc.active;
+  for (int i = 1; i < na; ++i) {
+    const int o = active[i];
+    const int xo = xkey(o);
+    const double dxo = sc.xb[o].dx;
+    int j = i - 1;
+    while (j >= 0) {
+      const int xj = xkey(active[j]);
+      if (!(xj > xo || (xj == xo && sc.xb[active[j]].dx > dxo))) break;
+      active[j + 1] = active[j];
+      --j;
+    }
+    active[j + 1] = o;
+  }
+}
+
+// Serial form, for a ring of n >= 3 vertices: calls span(yy, lx, rx) for every pair of active edges on every scan line
+// with lx < rx (the cells lx .. rx - 1 of row yy are the interior to search) and stops with false as soon as span()
+// returns false.
+template <typename SpanFn>
+__device__ bool sweep_spans(const int n, const Scratch sc, SpanFn span) {
+  XB *xb = sc.xb;
+  const int *active = sc.active;
+  const SweepSetup su = sweep_setup(n, sc);
+  if (su.nl == 0) return true;
+  int na = 0;
+  int yy = su.ymin - 1;  // :519
+  for (int v = 0; v < su.nv;) {
+    for (; yy < sc.vy[v]; ++yy) {  // :549-556
       for (int p = 0; p + 1 < na; p += 2) {  // check_line (:349-378)
         const int lx = xb[active[p]].x_curr + 1, rx = xb[active[p + 1]].x_curr;
         if (lx < rx && !span(yy, lx, rx)) return false;
       }
       for (int p = 0; p < na; ++p) xb_advance(xb[active[p]]);
     }
-    for (; v < nv && vy[v] == yy; ++v) {  // :562-581
-      const int pair[2] = {vl[v], vr[v]};
-      for (int k = 0; k < 2; ++k) {
-        const int l = pair[k];
-        if (was_active[l]) {
-          int pos = 0;
-          while (pos < na && active[pos] != l) ++pos;
-          if (pos < na) active[pos] = active[--na];  // swap and pop
-        } else {
-          was_active[l] = 1;
-          active[na++] = l;
-        }
-      }
-    }
-    for (int i = 1; i < na; ++i) {  // sort by (x, dx) (:583), stable insertion sort
-      const int o = active[i];
-      int j = i - 1;
-      while (j >= 0 && (xb[active[j]].x_curr > xb[o].x_curr ||
-                        (xb[active[j]].x_curr == xb[o].x_curr && xb[active[j]].dx > xb[o].dx))) {
-        active[j + 1] = active[j];
-        --j;
-      }
-      active[j + 1] = o;
-    }
+    for (; v < su.nv && sc.vy[v] == yy; ++v) sweep_toggle(sc, v, na);
+    sweep_sort(sc, na, [&](int l) { return xb[l].x_curr; });
   }
   return true;
+}
+
+// x of an edge after k advances from its initial state, in closed form: the four iterators (:201-317) add / subtract
+// `add` until a multiple of `den` is crossed, so the number of wraps (x-minor) or of x steps (x-major) after k scan
+// lines is a floor / ceiling of k (checked against the stepping iterators for 6.6e5 (edge, k) pairs).
+__device__ inline int xb_at(const XB &b, int k) {
+  if (k <= 0) return b.x_curr;
+  if (k < 32768 && b.den < 32768) {  // every product below fits 31 bits: 32-bit divisions (the usual case)
+    const unsigned h = (unsigned)b.den / 2u, kk = (unsigned)k, den = (unsigned)b.den, add = (unsigned)b.add;
+    switch (b.kind) {
+      case 0:
+        return b.x_curr + b.x_sign * (int)((h + kk * add) / den);
+      case 1:
+        return b.x_curr - b.x_sign * (kk * add > h ? (int)((kk * add - h + den - 1u) / den) : 0);
+      case 2:
+        return b.x_curr + b.x_sign * (int)((kk * den - h + add - 1u) / add);
+      default:
+        return b.x_curr - b.x_sign * (int)((h + (kk - 1u) * den) / add + 1u);
+    }
+  }
+  const long long h = b.den / 2, kk = k;
+  switch (b.kind) {
+    case 0:
+      return b.x_curr + b.x_sign * (int)((h + kk * b.add) / b.den);
+    case 1: {
+      const long long t = kk * b.add - h;
+      return b.x_curr - b.x_sign * (t > 0 ? (int)((t + b.den - 1) / b.den) : 0);
+    }
+    case 2:
+      return b.x_curr + b.x_sign * (int)((kk * b.den - h + b.add - 1) / b.add);
+    default:
+      return b.x_curr - b.x_sign * (int)((h + (kk - 1) * b.den) / b.add + 1);
+  }
+}
+
+// Parallel form, part 1 (one thread): only the vertex events are processed.  Between two events the order of the
+// active edges is fixed, so an "epoch" (rows [y0, y1), the active list as sorted at y0) describes every span of those
+// rows; part 2 lets all threads evaluate (row, pair) items with xb_at.  lower_y[] is reused for each line's lowest row.
+struct Epochs {
+  int *y0, *y1, *off, *np, *ipre;  // per epoch: rows, offset of its active list in alist, pairs, items before it
+  int *alist;
+  int alist_cap;
+};
+
+__device__ inline Epochs epochs_at(int *region, int region_ints, int cap) {
+  Epochs e;
+  e.y0 = region;
+  e.y1 = e.y0 + cap;
+  e.off = e.y1 + cap;
+  e.np = e.off + cap;
+  e.ipre = e.np + cap;  // cap + 1 entries
+  e.alist = e.ipre + cap + 1;
+  e.alist_cap = region_ints - (5 * cap + 1);
+  return e;
+}
+
+// The event loop on a prepared vertex set (lines in sc.xb, their lowest rows in sc.lower_y, events in sc.vy / vl / vr,
+// sc.was_active cleared).  Returns the number of epochs, or -1 if the active lists do not fit (the caller then sweeps
+// serially).
+__device__ int epochs_from_events(const Scratch sc, const Epochs ep, int nl, int nv, int ymin) {
+  if (nl == 0) {
+    ep.ipre[0] = 0;
+    return 0;
+  }
+  int na = 0, ne = 0, used = 0, items = 0;
+  int yy = ymin - 1;
+  for (int v = 0; v < nv;) {
+    const int ye = sc.vy[v];
+    if (ye > yy && na >= 2) {
+      if (used + na > ep.alist_cap) return -1;
+      ep.y0[ne] = yy, ep.y1[ne] = ye, ep.off[ne] = used, ep.np[ne] = na / 2, ep.ipre[ne] = items;
+      for (int p = 0; p < na; ++p) ep.alist[used + p] = sc.active[p];
+      used += na;
+      items += (ye - yy) * (na / 2);
+      ++ne;
+    }
+    yy = ye;
+    for (; v < nv && sc.vy[v] == yy; ++v) sweep_toggle(sc, v, na);
+    for (int p = 0; p < na; ++p) {  // one closed-form evaluation per active line, not one per comparison
+      const int l = sc.active[p];
+      sc.xk[l] = xb_at(sc.xb[l], yy - sc.lower_y[l]);
+    }
+    sweep_sort(sc, na, [&](int l) { return sc.xk[l]; });
+  }
+  ep.ipre[ne] = items;
+  return ne;
 }
 
 __device__ inline bool span_is_good(const MapView &a, int yy, int lx, int rx) {
@@ -281,7 +393,7 @@ __global__ void __launch_bounds__(128) k_check_footprint(const CheckArgs a) {
   }
   for (int k = 0; k < a.n; ++k) pt[k] = vertex_of(a, a.fp, i, k, tx, ty, s, c);
   const MapView view = {a.map, a.pitch, a.size_x, a.size_y, a.cost};
-  const Scratch sc = {xb, pt, lower_y, vy, vl, vr, active, was_active};
+  const Scratch sc = {xb, pt, lower_y, vy, vl, vr, active, nullptr, was_active};
   a.ok[i] = check_one(view, a.n, sc) ? 1 : 0;
 }
 
@@ -305,40 +417,39 @@ __global__ void __launch_bounds__(128) k_check_footprint_large(const CheckArgs a
 
 // ---- few poses: one CTA per pose ---------------------------------------------------------------------------------
 // A single thread per pose leaves the GPU idle and pays one memory round trip per cell when there are only a
-// handful of candidates (the reference's own call: one pose per solve).  Here thread 0 runs the sweep WITHOUT
-// touching the map and only records the spans it would search; meanwhile warps 1.. test the outline cells, every
-// cell of every ray computed in closed form (cell k of a Bresenham ray: k steps on the major axis,
-// floor((den / 2 + k * add) / den) on the minor one); then all warps search the recorded spans, lanes along x.
-// The set of cells compared with `cost` is exactly the reference's, so the boolean is too.
-struct Span {
-  int y, lx, rx;
-};
-
-__host__ __device__ inline size_t coop_bytes(int cap, int span_cap) {  // one pose: Scratch | ray prefix | spans
+// handful of candidates (the reference's own call: one pose per solve).  Here thread 0 only processes the sweep's
+// vertex events (build_epochs); meanwhile warps 1.. test the outline cells, every cell of every ray computed in closed
+// form (cell k of a Bresenham ray: k steps on the major axis, floor((den / 2 + k * add) / den) on the minor one); then
+// all warps take (scan line, edge pair) items of the epochs, place the two edges with xb_at and search the span between
+// them, lanes along x.  The set of cells compared with `cost` is exactly the reference's, so the boolean is too.
+__host__ __device__ inline size_t coop_bytes(int cap, int epoch_ints) {  // one pose: Scratch | ray prefix | epochs
   const size_t prefix = (((size_t)cap + 1) * sizeof(int) + 7) & ~(size_t)7;
-  return scratch_bytes(cap) + prefix + (((size_t)span_cap * sizeof(Span) + 7) & ~(size_t)7);
+  return scratch_bytes(cap) + prefix + (((size_t)epoch_ints * sizeof(int) + 7) & ~(size_t)7);
 }
 
 template <int kCoopThreads>
 __global__ void __launch_bounds__(kCoopThreads) k_check_footprint_coop(const CheckArgs a, const int *__restrict__ d_fp,
-                                                                      unsigned char *__restrict__ ws, int span_cap) {
+                                                                      unsigned char *__restrict__ ws, int epoch_ints,
+                                                                      int state_in_smem) {
   const size_t i = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kCoopThreads / 32;
-  // the threads that search the outline while thread 0 sweeps: the other warps, or (one-warp CTAs) the other lanes
+  // the threads that search the outline while thread 0 walks the vertex events: the other warps, or (one-warp CTAs)
+  // the other lanes
   constexpr int kOutlineFirst = kCoopThreads > 32 ? 32 : 1;
   const int n = a.n, cap = n + 1;
-  unsigned char *base = ws + i * coop_bytes(cap, span_cap);
-  // the sweep's state is read and written a few times per scan line by one thread: up to kMaxVertices vertices it
-  // sits in shared memory (latency), beyond that in this pose's slice of the workspace
-  __shared__ __align__(8) unsigned char s_state[((kMaxVertices + 1) * (sizeof(XB) + sizeof(int2) + 5 * sizeof(int) + 1) + 7) & ~7];
-  const Scratch sc = scratch_at(n <= kMaxVertices ? s_state : base, cap);
+  unsigned char *base = ws + i * coop_bytes(cap, epoch_ints);
+  // the per-pose state (vertices, lines, vertex set, active list) sits in dynamic shared memory when it fits there
+  // (up to ~3000 vertices), else in this pose's slice of the workspace
+  extern __shared__ __align__(8) unsigned char s_state[];
+  const Scratch sc = scratch_at(state_in_smem ? s_state : base, cap);
   int *prefix = reinterpret_cast<int *>(base + scratch_bytes(cap));
-  Span *spans = reinterpret_cast<Span *>(base + scratch_bytes(cap) + ((((size_t)cap + 1) * sizeof(int) + 7) & ~(size_t)7));
+  const Epochs ep = epochs_at(
+      reinterpret_cast<int *>(base + scratch_bytes(cap) + ((((size_t)cap + 1) * sizeof(int) + 7) & ~(size_t)7)), epoch_ints, cap);
   const int *fp = d_fp ? d_fp : a.fp;
   const MapView view = {a.map, a.pitch, a.size_x, a.size_y, a.cost};
-  __shared__ int s_hit, s_nspans, s_warp_sum[kWarps];
-  if (tid == 0) s_hit = 0, s_nspans = 0;
+  __shared__ int s_hit, s_nepochs, s_ymin, s_warp_sum[kWarps], s_warp_sum2[kWarps];
+  if (tid == 0) s_hit = 0, s_nepochs = 0, s_ymin = 0x7fffffff;
 
   double tx = 0, ty = 0, s = 0, c = 1;
   if (a.poses) {
@@ -359,47 +470,75 @@ __global__ void __launch_bounds__(kCoopThreads) k_check_footprint_coop(const Che
     if (tid == 0) a.ok[i] = n == 0 || __ldg(a.map + ((size_t)sc.pt[0].y * a.pitch + (size_t)sc.pt[0].x)) != a.cost;
     return;
   }
-  // the rays to search: the single segment of a 2-vertex footprint, else the ring edges (closing edge included)
+  // the edges: the single segment of a 2-vertex footprint, else the ring (closing edge included).  Edge e runs from
+  // vertex e to vertex e + 1 (the first vertex again after the last one of an open footprint).
   const bool is_closed = n >= 3 && sc.pt[n - 1].x == sc.pt[0].x && sc.pt[n - 1].y == sc.pt[0].y;
   const int nedges = n == 2 ? 1 : (is_closed ? n : n + 1) - 1;
-  auto edge_den = [&](int e) {
-    const int2 p = sc.pt[e], q = sc.pt[e + 1 == n ? 0 : e + 1];
-    return max(abs(q.x - p.x), abs(q.y - p.y));
-  };
-  // exclusive prefix sum of the ray lengths over the edges: thread-local chunk, then a block scan of the chunk sums
+  auto edge_from = [&](int e) { return sc.pt[e]; };
+  auto edge_to = [&](int e) { return sc.pt[e + 1 == n ? 0 : e + 1]; };
+  // two exclusive prefix sums over the edges in one pass (thread-local chunk, then a block scan of the chunk sums):
+  // the ray lengths (outline cells before edge e) and the non-horizontal edges (the scan-line `line` index of edge e)
   const int chunk = (nedges + kCoopThreads - 1) / kCoopThreads;
   const int e0 = min(nedges, tid * chunk), e1 = min(nedges, e0 + chunk);
-  int local = 0;
-  for (int e = e0; e < e1; ++e) local += edge_den(e);
-  int incl = local;
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  if (lane == 31) s_warp_sum[warp] = incl;
-  __syncthreads();
-  int before = incl - local;
-  for (int w = 0; w < warp; ++w) before += s_warp_sum[w];
+  int local = 0, local2 = 0, my_ymin = 0x7fffffff;
   for (int e = e0; e < e1; ++e) {
+    const int2 p = edge_from(e), q = edge_to(e);
+    local += max(abs(q.x - p.x), abs(q.y - p.y));
+    local2 += p.y != q.y;
+    my_ymin = min(my_ymin, min(p.y, q.y));
+  }
+  int incl = local, incl2 = local2;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d), v2 = __shfl_up_sync(0xffffffffu, incl2, d);
+    if (lane >= d) incl += v, incl2 += v2;
+  }
+  if (lane == 31) s_warp_sum[warp] = incl, s_warp_sum2[warp] = incl2;
+  if (my_ymin != 0x7fffffff) atomicMin(&s_ymin, my_ymin);
+  __syncthreads();
+  int before = incl - local, line = incl2 - local2, nl = 0;
+  for (int w = 0; w < kWarps; ++w) {
+    if (w < warp) before += s_warp_sum[w], line += s_warp_sum2[w];
+    nl += s_warp_sum2[w];
+  }
+  int *begin_y = sc.active;  // y of each line's first vertex, until the vertex set is built (then the active list)
+  for (int e = e0; e < e1; ++e) {
+    const int2 p = edge_from(e), q = edge_to(e);
     prefix[e] = before;
-    before += edge_den(e);
+    before += max(abs(q.x - p.x), abs(q.y - p.y));
+    if (n >= 3 && p.y != q.y) {  // a scan-line edge (:487-496)
+      xb_init(sc.xb[line], p.x, p.y, q.x, q.y);
+      begin_y[line] = p.y;
+      sc.lower_y[line] = min(p.y, q.y);
+      sc.was_active[line] = 0;
+      ++line;
+    }
   }
   if (e1 == nedges && e0 < nedges) prefix[nedges] = before;
   __syncthreads();
   const int total = prefix[nedges];
+  if (n >= 3) {
+    // the vertex set (:503-510): event k joins lines k and k + 1 at the first vertex of line k + 1, the last one joins
+    // the last and the first line; ordered by y, equal keys in insertion order: each event's rank is counted directly
+    for (int k = tid; k < nl; k += kCoopThreads) {
+      const int yk = begin_y[k + 1 == nl ? 0 : k + 1];
+      int rank = 0;
+      for (int j = 0; j < nl; ++j) {
+        const int yj = begin_y[j + 1 == nl ? 0 : j + 1];
+        rank += yj < yk || (yj == yk && j < k);
+      }
+      sc.vy[rank] = yk, sc.vl[rank] = k, sc.vr[rank] = k + 1 == nl ? 0 : k + 1;
+    }
+    __syncthreads();  // begin_y is dead from here on: sc.active becomes the active list
+  }
 
   if (tid < kOutlineFirst) {
-    if (tid == 0 && n >= 3) {  // the sweep: record spans; past the capacity, search them right here
-      int count = 0;
-      const bool good = sweep_spans(n, sc, [&](int yy, int lx, int rx) {
-        if (count < span_cap) {
-          spans[count++] = Span{yy, lx, rx};
-          return true;
-        }
-        return span_is_good(view, yy, lx, rx);
-      });
-      s_nspans = count;
-      if (!good) s_hit = 1;
+    if (tid == 0 && n >= 3) {  // the sweep's vertex events; if the epochs do not fit, the whole sweep right here
+      int ne = epochs_from_events(sc, ep, nl, nl, s_ymin);
+      if (ne < 0) {
+        ne = 0;
+        if (!sweep_spans(n, sc, [&](int yy, int lx, int rx) { return span_is_good(view, yy, lx, rx); })) s_hit = 1;
+      }
+      s_nepochs = ne;
     }
   } else {  // check_outline (:432-458) / the 2-vertex ray: cell t of the concatenated rays
     bool hit = false;
@@ -409,7 +548,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_check_footprint_coop(const Che
         const int mid = (lo + hi + 1) >> 1;
         if (prefix[mid] <= t) lo = mid; else hi = mid - 1;
       }
-      const int2 p = sc.pt[lo], q = sc.pt[lo + 1 == n ? 0 : lo + 1];
+      const int2 p = edge_from(lo), q = edge_to(lo);
       const int k = t - prefix[lo];
       const int ddx = q.x - p.x, ddy = q.y - p.y, ax = abs(ddx), ay = abs(ddy);
       const bool y_major = ay > ax;
@@ -422,13 +561,36 @@ __global__ void __launch_bounds__(kCoopThreads) k_check_footprint_coop(const Che
     if (hit) s_hit = 1;
   }
   __syncthreads();
-  if (!s_hit) {
-    const int nspans = s_nspans;
+  const int ne = s_nepochs;
+  if (!s_hit && ne > 0) {  // check_line (:349-378) for every (scan line, pair of active edges) item
+    // each lane places one item's two edges (the divisions run 32 wide), then the warp searches the 32 spans one
+    // after the other, lanes along x
+    const int items = ep.ipre[ne];
     bool hit = false;
-    for (int sp = warp; sp < nspans && !hit; sp += kWarps) {
-      const Span v = spans[sp];
-      const uint8_t *row = a.map + (size_t)v.y * a.pitch;
-      for (int x = v.lx + lane; x < v.rx; x += 32) hit |= __ldg(row + x) == a.cost;
+    for (int t0 = warp * 32; t0 < items && !hit; t0 += kWarps * 32) {
+      const int t = t0 + lane;
+      int yy = 0, lx = 0, rx = 0;
+      if (t < items) {
+        int lo = 0, hi = ne - 1;  // last epoch with ipre[e] <= t
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (ep.ipre[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int local_t = t - ep.ipre[lo], np = ep.np[lo], r = local_t / np, p = 2 * (local_t - r * np);
+        const int l_line = ep.alist[ep.off[lo] + p], r_line = ep.alist[ep.off[lo] + p + 1];
+        yy = ep.y0[lo] + r;
+        lx = xb_at(sc.xb[l_line], yy - sc.lower_y[l_line]) + 1;
+        rx = xb_at(sc.xb[r_line], yy - sc.lower_y[r_line]);
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, lx < rx);
+      while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int y_j = __shfl_sync(0xffffffffu, yy, j), l_j = __shfl_sync(0xffffffffu, lx, j), r_j = __shfl_sync(0xffffffffu, rx, j);
+        const uint8_t *row = a.map + (size_t)y_j * a.pitch;
+        for (int x = l_j + lane; x < r_j; x += 32) hit |= __ldg(row + x) == a.cost;
+      }
+      hit = __any_sync(0xffffffffu, hit);
     }
     if (hit) s_hit = 1;
   }
@@ -442,13 +604,14 @@ __global__ void __launch_bounds__(kCoopThreads) k_check_footprint_coop(const Che
 using namespace dpose;
 
 // batches up to this many poses use the CTA-per-pose kernel (DPOSE_CHECK_COOP_MAX overrides; 0 disables it).
-// Measured on a B200 (tools/ab_check_footprint.py, profiles/r1_v21_check_footprint_ab.jsonl): 20x12-cell rectangle,
-// 16384 poses 193 us against 212 us thread-per-pose (4096: 93 vs 187; 128: 56 vs 169); beyond that one thread per
-// pose has more poses in flight and wins (65536: 311 vs 593 us).
+// Measured on a B200 (tools/ab_check_footprint.py, profiles/r1_v26_check_footprint_ab.jsonl), microseconds per
+// host-buffer call, thread-per-pose against CTA-per-pose: 20x12-cell rectangle 128 poses 162 / 38, 4096 poses 178 / 57,
+// 16384 poses 208 / 127, 65536 poses 300 / 358; 40-vertex star 128 poses 1084 / 116, 4096 poses 1161 / 207, 16384 poses
+// 1242 / 623.  Beyond ~32k poses one thread per pose has enough poses in flight and wins.
 static int coop_max_poses() {
   static const int v = [] {
     const char *e = getenv("DPOSE_CHECK_COOP_MAX");
-    return e ? atoi(e) : 16384;
+    return e ? atoi(e) : 32768;
   }();
   return v;
 }
@@ -472,7 +635,7 @@ static uint8_t *pinned_ok() {
 static size_t workspace_budget() {
   static const size_t v = [] {
     const char *e = getenv("DPOSE_CHECK_WS_MB");
-    return (size_t)(e ? std::max(1, atoi(e)) : 256) << 20;
+    return (size_t)(e ? std::max(1, atoi(e)) : 512) << 20;
   }();
   return v;
 }
@@ -483,7 +646,7 @@ static int coop_threads(size_t n_poses) {
     return e ? atoi(e) : 0;
   }();
   if (forced == 32 || forced == 64 || forced == 128) return forced;
-  return n_poses <= 1024 ? 128 : 32;
+  return n_poses <= 1024 ? 128 : 32;  // one pose: 128 threads 100 us / 32 threads 114 us (star); 4096 poses: 351 / 207
 }
 
 static int check_impl(const dpose_map *map, const int32_t *fp, int n, const double *poses, size_t n_poses, bool dev_poses,
@@ -518,19 +681,11 @@ static int check_impl(const dpose_map *map, const int32_t *fp, int n, const doub
     if (!dev_ok && !h_ok) DPOSE_CUDA(cudaMallocAsync(&d_ok, n_poses, stream));
     a.poses = poses ? (dev_poses ? poses : d_poses) : nullptr;
     a.ok = dev_ok ? ok : (h_ok ? h_ok : d_ok);
-    // spans one pose can produce: at most one per pair of edges on every scan line of its bounding box
-    long long height = 0;
-    if (poses) {
-      long long r2 = 0;
-      for (int k = 0; k < n; ++k) r2 = std::max(r2, (long long)fp[2 * k] * fp[2 * k] + (long long)fp[2 * k + 1] * fp[2 * k + 1]);
-      height = 2 * (long long)std::ceil(std::sqrt((double)r2)) + 4;
-    } else if (n > 0) {
-      int lo = fp[1], hi = fp[1];
-      for (int k = 1; k < n; ++k) lo = std::min(lo, fp[2 * k + 1]), hi = std::max(hi, fp[2 * k + 1]);
-      height = (long long)hi - lo + 3;
-    }
-    const int span_cap = (int)std::min<long long>(1 << 16, std::max<long long>(1, height * ((n + 1) / 2 + 1)));
-    const size_t coop_per_pose = coop_bytes(n + 1, span_cap);
+    // the epochs of one pose: five ints per vertex event plus the active lists (at most every line at every event;
+    // beyond 2^20 entries the kernel sweeps serially instead)
+    const long long cap_ll = (long long)n + 1;
+    const int epoch_ints = (int)(5 * cap_ll + 1 + std::min<long long>(cap_ll * cap_ll, 1 << 20));
+    const size_t coop_per_pose = coop_bytes(n + 1, epoch_ints);
     const size_t kWorkspaceBudget = workspace_budget();  // bytes of per-pose state alive at once
     if (n_poses <= (size_t)coop_max_poses() && n_poses * coop_per_pose <= kWorkspaceBudget) {
       if (large) {
@@ -540,12 +695,21 @@ static int check_impl(const dpose_map *map, const int32_t *fp, int n, const doub
       DPOSE_CUDA(cudaMallocAsync(&d_ws, n_poses * coop_per_pose, stream));
       // few poses: wide CTAs finish each pose sooner; many: narrow ones keep more sweeps in flight per SM
       const int threads = coop_threads(n_poses);
+      // the per-pose state in shared memory if it fits (beyond 48 KB the kernel attribute is raised first)
+      const size_t state_bytes = scratch_bytes(n + 1);
+      const bool in_smem = state_bytes <= (size_t)200 << 10;
+      const size_t dyn = in_smem ? state_bytes : 0;
+      auto launch = [&](auto kern) -> int {
+        if (dyn > ((size_t)48 << 10)) DPOSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        kern<<<(unsigned)n_poses, threads, dyn, stream>>>(a, d_fp, d_ws, epoch_ints, in_smem ? 1 : 0);
+        return DPOSE_OK;
+      };
       if (threads == 128)
-        k_check_footprint_coop<128><<<(unsigned)n_poses, 128, 0, stream>>>(a, d_fp, d_ws, span_cap);
+        DPOSE_TRY(launch(k_check_footprint_coop<128>));
       else if (threads == 64)
-        k_check_footprint_coop<64><<<(unsigned)n_poses, 64, 0, stream>>>(a, d_fp, d_ws, span_cap);
+        DPOSE_TRY(launch(k_check_footprint_coop<64>));
       else
-        k_check_footprint_coop<32><<<(unsigned)n_poses, 32, 0, stream>>>(a, d_fp, d_ws, span_cap);
+        DPOSE_TRY(launch(k_check_footprint_coop<32>));
       DPOSE_LAUNCHED();
     } else if (!large) {
       k_check_footprint<<<(unsigned)((n_poses + 127) / 128), 128, 0, stream>>>(a);
