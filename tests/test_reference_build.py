@@ -301,3 +301,27 @@ def test_pose_conversions_match_reference_plugin():
             assert (want is not None) == bool(good), c
             if good:
                 assert np.array_equal(w[:2], want[:2]) and same_angle(w[2], want[2])
+
+
+def test_cost_data_random_polygons_match_reference_flow():
+    """random simple and self-intersecting polygons, collinear runs and repeated vertices included: table, centre and
+    box of the oracle equal the reference's cost_data flow bit for bit"""
+    rng = rng_of("polys")
+    for k in range(120):
+        n = int(rng.integers(3, 12))
+        if k % 3 == 0:  # angularly sorted: simple
+            ang = np.sort(rng.uniform(0, 2 * math.pi, n))
+            rad = rng.uniform(3, 30, n)
+            pts = np.stack([np.round(rad * np.cos(ang)), np.round(rad * np.sin(ang))], 1)
+        else:  # arbitrary order: self-intersecting, sometimes degenerate
+            pts = rng.integers(-25, 26, size=(n, 2)).astype(np.float64)
+        if k % 7 == 0:
+            pts[1] = pts[0]  # repeated vertex
+        pts = pts.astype(np.int32)
+        if len(np.unique(pts[:, 0])) < 2 or len(np.unique(pts[:, 1])) < 2:
+            continue  # the reference asserts a non-empty bounding box with an outline that is not the whole image
+        pad = int(rng.integers(0, 6))
+        o, r = capi.CostData(pts, pad), refapi.PoseGradient(pts, pad)
+        assert (o.rows, o.cols) == (r.rows, r.cols)
+        assert np.array_equal(o.center, r.center) and np.array_equal(o.box, r.box)
+        assert np.array_equal(o.cost, r.cost), pts.tolist()
