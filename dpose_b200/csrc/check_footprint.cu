@@ -4,14 +4,16 @@
 // (dpose_goal_tolerance.cpp:386-399): the footprint is transformed by the pose, rounded to cells, and the
 // outline (Bresenham rays) plus the scan-line interior between pairs of active edges (custom x-major /
 // x-minor Bresenham iterators, :201-317) is searched for a cell equal to `cost`.  With multi-start in
-// lock-step there are thousands of candidates per iteration, so the check runs here with one thread per
-// candidate pose.  Each thread executes the reference's algorithm step for step (same iterators, same
-// half-open vertex rule, same pairwise sweep l_x + 1 .. r_x - 1), so the boolean is identical by
-// construction; the work per pose is a few hundred byte reads, all L2 hits on the map.
-//
-// Footprints of up to kMaxVertices (64) vertices keep the per-pose state in thread-local arrays.  Larger ones (the
-// reference's own benchmark checks 100- and 1000-vertex circles, perf/dpose_costmap.cpp:103-150) run the same code
-// with the state in a global workspace, one slice per pose, poses processed in chunks that bound that workspace.
+// lock-step there are thousands of candidates per iteration.  Two kernels, chosen by the batch size:
+//   * k_check_footprint / k_check_footprint_large — one thread per pose, the reference's algorithm step for step
+//     (same iterators, same half-open vertex rule, same pairwise sweep l_x + 1 .. r_x - 1): large batches.
+//     Up to kMaxVertices (64) vertices the per-pose state is thread-local; larger footprints (the reference's own
+//     benchmark checks 100- and 1000-vertex circles, perf/dpose_costmap.cpp:103-150) keep it in a global workspace,
+//     one slice per pose, poses processed in chunks that bound that workspace.
+//   * k_check_footprint_coop — one CTA per pose, for up to 32768 poses: only the sweep's vertex events are serial,
+//     the outline cells and the (scan line, edge pair) spans are evaluated by all threads with closed forms of the
+//     Bresenham iterators (see the section further down).
+// Either way the set of map cells compared with `cost` is exactly the reference's, so the boolean is identical.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
