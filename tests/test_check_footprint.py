@@ -239,3 +239,40 @@ def test_gpu_check_footprint_chunked_workspace(dp):
     env = dict(os.environ, DPOSE_CHECK_WS_MB="1", DPOSE_CHECK_COOP_MAX="0")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "chunked ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_gpu_check_footprint_random_polygon_soak(dp):
+    """random footprints (convex-ish, self-intersecting, closed, with repeated vertices and horizontal runs), each
+    checked at a few hundred random poses through the CTA-per-pose kernel and, in a second batch large enough, the
+    thread-per-pose kernel: both must reproduce the oracle exactly"""
+    rng = np.random.default_rng(2026)
+    m = fx.bernoulli_map(500, 400, 0.0015, 77)
+    cm = dp.Costmap(m)
+    mismatches = 0
+    seen = set()
+    for k in range(160):
+        n = int(rng.integers(3, 24))
+        if k % 2 == 0:
+            ang = np.sort(rng.uniform(0, 2 * math.pi, n))
+            rad = rng.uniform(2, 40, n)
+            fp = np.stack([np.round(rad * np.cos(ang)), np.round(rad * np.sin(ang))], 1)
+        else:
+            fp = rng.integers(-30, 31, size=(n, 2)).astype(np.float64)
+        if k % 5 == 0:
+            fp[n // 2] = fp[n // 2 - 1]  # repeated vertex
+        if k % 7 == 0:
+            fp[-1, 1] = fp[0, 1]  # horizontal closing edge
+        if k % 11 == 0:
+            fp = np.vstack([fp, fp[:1]])  # closed ring
+        fp = fp.astype(np.int32)
+        if len(np.unique(fp[:, 1])) < 2:
+            continue  # every edge horizontal: undefined upstream (see tests/test_reference_build.py)
+        n_poses = 300 if k % 4 else 40000  # 40000 > 32768: thread-per-pose kernel
+        poses = np.stack([rng.uniform(-10, 510, n_poses), rng.uniform(-10, 410, n_poses), rng.uniform(-4, 4, n_poses)], 1)
+        got = dp.check_footprint_batch(cm, fp, poses)
+        want = capi.check_footprint_batch(m, fp, poses, nthreads=capi.max_threads())
+        mismatches += int((got != want).sum())
+        seen.update(np.unique(want).tolist())
+        assert mismatches == 0, (k, fp.tolist(), poses[np.argwhere(got != want).ravel()[:3]].tolist())
+    assert seen == {0, 1}
