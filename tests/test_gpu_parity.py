@@ -485,3 +485,31 @@ def test_full_size_properties_cfg5(dp):
     assert bad.any(axis=1).mean() < 0.05
     assert np.all(np.abs(out[sl][bad] - truth[bad]) <= 0.01 * np.abs(lit[bad] - truth[bad]) + 1e-12)
     assert fx.tol_ok(out[sl][:, 0], lit[:, 0]).all()  # the cost itself never needs the protocol
+
+
+def test_batch_random_footprints_all_table_modes(dp, capi):
+    """random footprints from a few cells to 150 cells across: the tile kernel's 8-replica, 4-replica, single-replica
+    (texture) and no-shared-memory (both halves through the texture unit) modes, multi-chunk windows included, against
+    the oracle on translated-equivalent inputs"""
+    rng = np.random.default_rng(99)
+    m = fx.bernoulli_map(900, 800, 0.05, 13)
+    cm = dp.Costmap(m)
+    sizes = []
+    for k, radius in enumerate([3, 6, 10, 16, 24, 35, 50, 75]):
+        n = int(rng.integers(3, 10))
+        ang = np.sort(rng.uniform(0, 2 * math.pi, n))
+        rad = rng.uniform(0.5, 1.0, n) * radius
+        fp = np.stack([np.round(rad * np.cos(ang)), np.round(rad * np.sin(ang))], 1).astype(np.int32)
+        if len(np.unique(fp[:, 0])) < 2 or len(np.unique(fp[:, 1])) < 2:
+            continue
+        pad = int(rng.integers(1, 5))
+        pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+        oc = capi.CostData(fp, pad)
+        sizes.append((oc.rows, oc.cols))
+        poses = fx.random_poses(1200 if radius < 40 else 300, 900, 800, 100 + k, margin=float(2 * radius + 10))
+        out = pg.get_cost_batch(cm, poses)
+        want = oc.get_cost_batch(m, poses, shift=True, nthreads=capi.max_threads())
+        ok = fx.tol_ok(out, want)
+        assert ok.all(), (fp.tolist(), pad, np.argwhere(~ok)[:4], out[~ok.all(1)][:2], want[~ok.all(1)][:2])
+        assert (want[:, 0] > 0).mean() > 0.5
+    assert min(r * c for r, c in sizes) < 400 and max(r * c for r, c in sizes) > 8000  # from 8 replicas to no shared-memory copy at all
