@@ -166,7 +166,11 @@ int dpose_problem_init(dpose_problem *p, const double start[3], const double goa
   p->rot_tol_sq = std::pow(cfg->rot_tolerance, 2);
   int max_coeff = 0;  // :122-123
   for (int i = 0; i < 10; ++i) max_coeff = std::max(max_coeff, std::abs(p->pg->box[i]));
-  const double h = max_coeff + std::abs(cfg->lin_tolerance);  // :126
+  // :126-133: h is a double, but the ring it is written into is a rectangle<int>: Eigen's comma initialiser converts
+  // every coefficient to int (truncation toward zero) BEFORE the goal is added and the sum rounded (:134-138)
+  const double h_real = max_coeff + std::abs(cfg->lin_tolerance);
+  if (!(h_real < 1e9)) return fail(DPOSE_EINVAL, "lin_tolerance %g out of range", cfg->lin_tolerance);
+  const double h = (double)(int)h_real;
   const double bx[5] = {-h, h, h, -h, -h}, by[5] = {-h, -h, h, h, -h};
   for (int i = 0; i < 5; ++i) {  // :129-138 (Eigen round = std::round)
     p->search_box[2 * i] = (int32_t)std::round(bx[i] + goal[0]);

@@ -716,7 +716,9 @@ int oracle_problem_init(const oracle_cost_data *cd, const uint8_t *map, uint32_t
   out->rot_tol_sq = pow(cfg->rot_tolerance, 2);
   int max_coeff = 0; /* :122-123 */
   for (int i = 0; i < 10; ++i) max_coeff = abs(cd->box[i]) > max_coeff ? abs(cd->box[i]) : max_coeff;
-  const double h = max_coeff + fabs(cfg->lin_tolerance); /* :126 */
+  /* :126-133: h is a double, the ring is a rectangle<int>: Eigen's comma initialiser truncates each coefficient
+   * toward zero before the goal is added and the sum rounded (:134-138) */
+  const double h = (double)(int)(max_coeff + fabs(cfg->lin_tolerance));
   const double bx[5] = {-h, h, h, -h, -h}, by[5] = {-h, -h, h, h, -h}; /* :129-133 */
   for (int i = 0; i < 5; ++i) {                                        /* :134-138, Eigen round = std::round */
     out->search_box[2 * i] = (int32_t)round(bx[i] + goal[0]);

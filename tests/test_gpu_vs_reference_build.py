@@ -112,6 +112,7 @@ def test_check_footprint_batch(dp):
     ("rect_pad2", {}, [300.25, 200.5, 0.3]),
     ("star40_pad2", dict(lin_tolerance=10, weight_start_lin=0, weight_start_rot=0), [250.5, 250.5, 1.0]),
     ("lshape_pad2", dict(lin_tolerance=5, weight_goal_lin=0, weight_goal_rot=0), [10.0, 12.0, 3.0]),  # box clamped at the border
+    ("rect_pad2", dict(lin_tolerance=16.67, rot_tolerance=0.7), [300.0, 200.0, 0.4]),  # fractional tolerance: truncated half size
 ])
 def test_problem_eval_batch_vs_reference_plugin(dp, name, cfg_over, goal):
     """dpose_problem_eval_batch against the NLP callbacks of the compiled, unmodified plugin source
@@ -130,6 +131,8 @@ def test_problem_eval_batch_vs_reference_plugin(dp, name, cfg_over, goal):
     r, a = rng.uniform(0, cfg["lin_tolerance"], n), rng.uniform(-np.pi, np.pi, n)  # the plugin's polar sampler (:333-357)
     xs = np.stack([np.cos(a) * r, np.sin(a) * r, rng.uniform(0, cfg["rot_tolerance"], n)], axis=1)
     xs[0] = 0.0
+    xs[1:600, :2] *= (1.2 * cfg["lin_tolerance"] / np.maximum(np.hypot(xs[1:600, 0], xs[1:600, 1]), 1e-9))[:, None]  # rim of the box
+    xs[1:600, 2] = rng.uniform(-np.pi, np.pi, 599)
     got = pr.eval_batch(xs)
     f, grad, g, jac = ref.eval_batch(xs)
     assert fx.tol_ok(got["f"], f).all()

@@ -87,7 +87,8 @@ def test_oracle_problem_passes_the_reference_rostest(yaw):  # test cpp:67-112
 
 
 @pytest.mark.parametrize("cfg_over", [{}, dict(weight_goal_lin=0, weight_goal_rot=0), dict(weight_start_lin=0, weight_start_rot=0),
-                                      dict(lin_tolerance=20, rot_tolerance=0.5, weight_goal_lin=3, weight_start_rot=0.2)])
+                                      dict(lin_tolerance=20, rot_tolerance=0.5, weight_goal_lin=3, weight_start_rot=0.2),
+                                      dict(lin_tolerance=16.67)])
 def test_oracle_problem_matches_independent_restatement(cfg_over):
     cfg = dict(CFG_ALL)
     cfg.update(cfg_over)
@@ -98,7 +99,7 @@ def test_oracle_problem_matches_independent_restatement(cfg_over):
     pr = capi.Problem(cd, m)
     pr.init(start, goal, **cfg)
     # search box (:119-138): axis-aligned square +-(max|box| + |lin_tol|) around the goal, rounded
-    h = float(np.abs(cd.box).max()) + abs(cfg["lin_tolerance"])
+    h = float(int(float(np.abs(cd.box).max()) + abs(cfg["lin_tolerance"])))  # rectangle<int> << double: truncated
     want_box = fx.round_half_away(np.array([[-h, -h], [h, -h], [h, h], [-h, h], [-h, -h]]) + np.array(goal[:2]))
     assert np.array_equal(pr.search_box, want_box)
     cells = capi.lethal_cells_within(m, pr.search_box)
@@ -130,6 +131,7 @@ def dp():
     ("rect_pad2", dict(lin_tolerance=20, rot_tolerance=1.0), [700.0, 1300.0, -2.0]),
     ("star40_pad2", dict(lin_tolerance=10, weight_start_lin=0, weight_start_rot=0), [500.5, 500.5, 1.0]),
     ("lshape_pad2", dict(lin_tolerance=5, weight_goal_lin=0, weight_goal_rot=0), [10.0, 12.0, 3.0]),  # box clamped at the border
+    ("rect_pad2", dict(lin_tolerance=16.67, rot_tolerance=0.7), [700.0, 1300.0, 0.4]),  # fractional tolerance: truncated half size
 ])
 def test_problem_eval_batch_vs_oracle(dp, name, cfg_over, goal):
     cfg = dict(CFG_ALL)

@@ -228,6 +228,10 @@ PROBLEM_CASES = [
     ("diamond_pad5", dict(lin_tolerance=20, rot_tolerance=0.5, weight_goal_lin=3, weight_start_rot=0.2), [99, 99, 0], [100, 100, 1.3]),
     ("star40_pad2", dict(lin_tolerance=0.0, rot_tolerance=0.0), [200, 150, 0.5], [200, 150, 0.5]),
     ("lshape_pad2", dict(lin_tolerance=5, weight_start_lin=0.0, weight_start_rot=2.0), [3.2, 4.1, 1.0], [2.0, 2.0, -1.0]),
+    # fractional tolerances (the plugin divides metres by the resolution, :530-535): the half size of the search box is
+    # truncated by Eigen's comma initialiser before the goal is added (:126-138) — 16.67 gives 29, not round(29.67)
+    ("rect_pad2", dict(lin_tolerance=16.67, rot_tolerance=0.7), [150.0, 120.0, 0.0], [200.0, 150.0, 0.4]),
+    ("rect_pad2", dict(lin_tolerance=7.5), [150.0, 120.0, 0.0], [200.5, 150.5, -0.4]),
 ]
 
 
@@ -252,6 +256,9 @@ def test_problem_matches_reference_plugin(name, cfg_over, start, goal):
     rng = rng_of("problem", name)
     xs = rng.uniform(-1, 1, (80, 3)) * np.array([max(cfg["lin_tolerance"], 1.0), max(cfg["lin_tolerance"], 1.0), 3.0])
     xs[0] = 0
+    ang = rng.uniform(-np.pi, np.pi, 600)  # on the tolerance circle and beyond: kernel corners sweep the rim of the search box
+    rim = np.stack([np.cos(ang), np.sin(ang)], 1) * cfg["lin_tolerance"] * rng.uniform(1.0, 1.2, (600, 1))
+    xs = np.concatenate([xs, np.concatenate([rim, rng.uniform(-np.pi, np.pi, (600, 1))], 1)])
     fo, grado, go, jaco = o.eval_batch(xs)
     fr, gradr, gr, jacr = r.eval_batch(xs)
     assert np.all(np.abs(fo - fr) <= 1e-12 * (1 + np.abs(fr)))
