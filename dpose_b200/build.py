@@ -13,11 +13,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libdpose_b200.so")
-SOURCES = ["api.cu", "precompute.cu", "lethal.cu", "get_cost.cu", "get_cost_batch.cu", "get_cost_batch_tile.cu", "bitplane.cu", "problem.cu", "check_footprint.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cost_math.cuh"), os.path.join(HERE, "..", "include", "dpose_b200.h")]
+SOURCES = ["api.cu", "precompute.cu", "lethal.cu", "get_cost.cu", "get_cost_batch_tile.cu", "get_cost_batch_coop.cu", "problem.cu", "solve.cu",
+           "check_footprint.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cost_math.cuh"), os.path.join(CSRC, "coop_eval.cuh"), os.path.join(HERE, "..", "include", "dpose_b200.h")]
 # problem.cu mirrors scalar host arithmetic of the reference (x*x + y*y, regulariser sums): no FMA contraction there,
 # so the constraint values are bit-identical to a plain x86-64 build of the reference
-PER_FILE_FLAGS = {"problem.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"problem.cu": ["-fmad=false"], "solve.cu": ["-fmad=false"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--cudart", "static",

@@ -295,6 +295,36 @@ def get_cost_batch_multi(pgs, maps, poses, jacobian=True, out=None):
     return out
 
 
+SOLVE_STATUS_MASK, SOLVE_FOOTPRINT_FREE, SOLVE_ACCEPTED = 0x3, 0x4, 0x8
+SOLVE_CONVERGED, SOLVE_MAXITER, SOLVE_STALLED = 1, 2, 3
+
+
+class _SolverOptions(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("tol", C.c_double), ("dual_inf_tol", C.c_double), ("armijo_c1", C.c_double),
+                ("lethal", C.c_uint8)]
+
+
+class _SolveSummary(C.Structure):
+    _fields_ = [("first", C.c_longlong), ("best", C.c_longlong), ("n_converged", C.c_ulonglong),
+                ("n_accepted", C.c_ulonglong), ("best_f", C.c_double), ("best_pose", C.c_double * 3),
+                ("first_pose", C.c_double * 3)]
+
+
+def solver_options():
+    """dpose_solver_options with the plugin's defaults (max_iter 20, tol 5: dpose_goal_tolerance.cpp:504-507)"""
+    o = _SolverOptions()
+    lib().dpose_solver_default_options(C.byref(o))
+    return o
+
+
+def sample_offsets(seed, lin_tolerance, rot_tolerance, n, first_zero=True):
+    """uniform_pose_generator (dpose_goal_tolerance.cpp:333-373) seeded with `seed`: (n, 3) starting offsets"""
+    out = np.zeros((int(n), 3))
+    check(lib().dpose_sample_offsets(int(seed), float(lin_tolerance), float(rot_tolerance), int(n),
+                                     int(bool(first_zero)), out.ctypes.data))
+    return out
+
+
 class problem:
     """dpose_goal_tolerance::problem (dpose_goal_tolerance.hpp:115-200, dpose_goal_tolerance.cpp:90-292) with the
     Ipopt TNLP evaluations batched over displacements.  Same member names and argument meaning; poses in cells."""
@@ -341,6 +371,31 @@ class problem:
         out = {k: np.empty(shapes[k]) for k in want}
         ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
         check(lib().dpose_problem_eval_batch(self._h, x.ctypes.data, n, ptr("f"), ptr("grad_f"), ptr("g"), ptr("jac_g")))
+        return out
+
+    def solve_batch(self, x0, options=None, trace=False, **kw):
+        """the attempt loop of DposeGoalTolerance::preProcess (dpose_goal_tolerance.cpp:376-459) for all starting
+        offsets x0 (n, 3) at once, device resident: projected BFGS descent on f, check_footprint of every final pose,
+        ranking.  options / kw: solver_options fields (max_iter, tol, dual_inf_tol, armijo_c1, lethal).
+        Returns a dict: x (n, 3), f (n), status (n, uint8 flags SOLVE_*), evals (n), summary (dict)[, trace]."""
+        x0 = np.ascontiguousarray(np.asarray(x0, np.float64).reshape(-1, 3))
+        n = x0.shape[0]
+        opt = solver_options()
+        for k, v in dict(options or {}, **kw).items():
+            setattr(opt, k, v)
+        x, f = np.empty((n, 3)), np.empty(n)
+        status, evals = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        summ = _SolveSummary()
+        tr = np.zeros((n, opt.max_iter + 1, 12)) if trace else None
+        check(lib().dpose_problem_solve_batch(self._h, x0.ctypes.data, n, C.byref(opt), x.ctypes.data, f.ctypes.data,
+                                              status.ctypes.data, evals.ctypes.data, C.byref(summ),
+                                              tr.ctypes.data if trace else None))
+        out = {"x": x, "f": f, "status": status, "evals": evals,
+               "summary": {"first": int(summ.first), "best": int(summ.best), "n_converged": int(summ.n_converged),
+                           "n_accepted": int(summ.n_accepted), "best_f": float(summ.best_f),
+                           "best_pose": np.array(summ.best_pose[:]), "first_pose": np.array(summ.first_pose[:])}}
+        if trace:
+            out["trace"] = tr
         return out
 
     # the single-x TNLP callbacks, for callers that keep Ipopt's one-iterate-at-a-time shape

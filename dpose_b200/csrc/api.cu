@@ -47,16 +47,13 @@ using namespace dpose;
 
 namespace {
 constexpr int kBuf = 3;
-constexpr size_t kChunkPosesDefault = (size_t)1 << 17;  // 3 MB in / 4 MB out per chunk: short pipeline fill and drain
-// DPOSE_BATCH_CHUNK_LOG2 overrides (A/B measurements)
-size_t chunk_poses() {
-  static const size_t v = [] {
-    const char *e = getenv("DPOSE_BATCH_CHUNK_LOG2");
-    const int l = e ? atoi(e) : 0;
-    return l >= 10 && l <= 24 ? (size_t)1 << l : kChunkPosesDefault;
-  }();
-  return v;
-}
+constexpr int kMaxTableSide = 512;
+// poses per staging chunk of the host-buffer call: 3 MB in / 4 MB out, short pipeline fill and drain.  Measured on
+// B200 (cfg5, 1e7 poses): 2^16 .. 2^21 poses give 7.50 / 6.68 / 6.54 / 6.58 / 6.79 / 7.27 ms per call.
+#ifndef DPOSE_BATCH_CHUNK_LOG2
+#define DPOSE_BATCH_CHUNK_LOG2 17
+#endif
+constexpr size_t kChunkPoses = (size_t)1 << DPOSE_BATCH_CHUNK_LOG2;
 
 // Calls of up to this many poses (the multi-start pattern: a few thousand candidates per solver iteration) skip the
 // device staging altogether: poses and results live in mapped pinned memory the kernel reads and writes over PCIe
@@ -223,12 +220,16 @@ int dpose_pg_create(const int32_t *fp, int n, uint32_t padding, int device, dpos
     maxy = std::max<long long>(maxy, fp[2 * i + 1]);
   }
   const long long cols = maxx - minx + 1 + 2ll * padding, rows = maxy - miny + 1 + 2ll * padding;
-  if (cols > 16384 || rows > 16384 || cols * rows > (1ll << 26))
-    return fail(DPOSE_EINVAL, "cost table %lld x %lld too large", rows, cols);
+  // 512 x 512 cells is a 25 m footprint at 0.05 m: beyond that neither the single-CTA precompute (< 10 ms up to here)
+  // nor the fp32 window clip of the batched kernel (get_cost_batch_tile.cu, clip_margin_for) is specified
+  if (cols > kMaxTableSide || rows > kMaxTableSide)
+    return fail(DPOSE_EINVAL, "cost table %lld x %lld too large (at most %d x %d cells)", rows, cols, kMaxTableSide,
+                kMaxTableSide);
   dpose_pg *pg = new (std::nothrow) dpose_pg();
   if (!pg) return fail(DPOSE_ENOMEM, "out of host memory");
   pg->device = device;
   pg->padding = padding;
+  pg->footprint.assign(fp, fp + 2 * (size_t)n);
   pg->rows = (int)rows;
   pg->cols = (int)cols;
   // dpose_core.cpp:124-125 center = padding - rowwise min; :138 box = ring(cols, rows) - center
@@ -268,6 +269,7 @@ void dpose_pg_destroy(dpose_pg *pg) {
     cudaFree(pg->d_coef_image);
     if (pg->tex_hi) cudaDestroyTextureObject((cudaTextureObject_t)pg->tex_hi);
     cudaFree(pg->d_coef_hi);
+    cudaFree(pg->d_coef_abs);
     cudaFree(pg->d_arena);
     pg_release_batch_ctx(pg);
   }
@@ -331,9 +333,6 @@ static int map_create_impl(const uint8_t *data, uint32_t size_x, uint32_t size_y
     // flight, and only work on the legacy stream is ordered behind it.  The kernels that read this map run on
     // non-blocking streams, so wait for the copy (and the memset) to land.
     DPOSE_CUDA(cudaStreamSynchronize(nullptr));
-    m->bits_pitch = (((size_t)size_x + 127) / 128) * 16;
-    DPOSE_CUDA(cudaMalloc(&m->d_bits, m->bits_pitch * size_y));
-    m->bits_dirty = true;
     m->tiles_ntx = (size_x + 31) / 32 + 1;
     m->tiles_nty = (size_y + 7) / 8;
     DPOSE_CUDA(cudaMalloc(&m->d_tiles, (size_t)m->tiles_ntx * m->tiles_nty * 32));
@@ -387,28 +386,26 @@ int dpose_map_update(dpose_map *map, const uint8_t *data, size_t pitch, uint32_t
                             cudaMemcpyHostToDevice));
     DPOSE_CUDA(cudaStreamSynchronize(nullptr));  // staged copy: see dpose_map_create
   }
-  // narrow the lazy plane rebuilds to the rows of this window (union with what is already pending)
-  auto widen = [&](bool &dirty, uint32_t &lo, uint32_t &hi) {
-    if (!dirty) {
-      lo = y0;
-      hi = y0 + h;
-    } else {
-      lo = std::min(lo, y0);
-      hi = std::max(hi, y0 + h);
-    }
-    dirty = true;
-  };
-  widen(map->bits_dirty, map->bits_dirty_lo, map->bits_dirty_hi);
-  widen(map->tiles_dirty, map->tiles_dirty_lo, map->tiles_dirty_hi);
+  // narrow the lazy plane rebuild to the rows of this window (union with what is already pending)
+  std::lock_guard<std::mutex> lock(map_state_mutex());
+  if (!map->tiles_dirty) {
+    map->tiles_dirty_lo = y0;
+    map->tiles_dirty_hi = y0 + h;
+  } else {
+    map->tiles_dirty_lo = std::min(map->tiles_dirty_lo, y0);
+    map->tiles_dirty_hi = std::max(map->tiles_dirty_hi, y0 + h);
+  }
+  map->tiles_dirty = true;
   return DPOSE_OK;
 }
 
 int dpose_map_set_volatile(dpose_map *map, int is_volatile) {
   if (!map) return fail(DPOSE_EINVAL, "map is NULL");
+  std::lock_guard<std::mutex> lock(map_state_mutex());
   map->is_volatile = is_volatile != 0;
-  map->bits_dirty = map->tiles_dirty = true;
-  map->bits_dirty_lo = map->tiles_dirty_lo = 0;
-  map->bits_dirty_hi = map->tiles_dirty_hi = 0xffffffffu;
+  map->tiles_dirty = true;
+  map->tiles_dirty_lo = 0;
+  map->tiles_dirty_hi = 0xffffffffu;
   return DPOSE_OK;
 }
 
@@ -430,13 +427,10 @@ void dpose_map_destroy(dpose_map *map) {
   if (!map) return;
   {
     DeviceGuard guard(map->device);
-    map_release_cache(map);
     map_release_lethal_ws(map);
     cudaFree(map->d_data);
     if (map->h_update_stage) cudaFreeHost(map->h_update_stage);
-    cudaFree(map->d_bits);
     cudaFree(map->d_tiles);
-    if (map->bits_ready) cudaEventDestroy(map->bits_ready);
     if (map->tiles_ready) cudaEventDestroy(map->tiles_ready);
   }
   delete map;
@@ -594,11 +588,7 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
     ctx = static_cast<BatchCtx *>(p->batch_ctx);
   }
   std::lock_guard<std::mutex> call_lock(ctx->mu);
-  static const bool zero_copy_on = [] {
-    const char *e = getenv("DPOSE_BATCH_ZEROCOPY");  // "0" switches the latency path off (A/B, debugging)
-    return !(e && e[0] == '0');
-  }();
-  if (zero_copy_on && n <= kZeroCopyPoses) {  // latency path, see kZeroCopyPoses
+  if (n <= kZeroCopyPoses) {  // latency path, see kZeroCopyPoses
     DPOSE_TRY(ctx->ensure_zc());
     std::memcpy(ctx->zc_in(), poses, sizeof(double) * 3 * n);
     int rc = get_cost_batch_device(pg, map, ctx->zc_in(), n, ctx->zc_out(), want_jacobian, ctx->s_k);
@@ -612,7 +602,7 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
     if (rc != DPOSE_OK) cudaDeviceSynchronize();
     return rc;
   }
-  const size_t chunk = std::min<size_t>(n, chunk_poses());
+  const size_t chunk = std::min<size_t>(n, kChunkPoses);
   DPOSE_TRY(ctx->reserve(chunk));
   auto body = [&]() -> int {
     if (n <= chunk) {  // one chunk: in-order on a single stream, no cross-stream events (latency path)

@@ -605,7 +605,8 @@ __global__ void __launch_bounds__(kCoopThreads) k_check_footprint_coop(const Che
 
 using namespace dpose;
 
-// batches up to this many poses use the CTA-per-pose kernel (DPOSE_CHECK_COOP_MAX overrides; 0 disables it).
+// batches up to this many poses use the CTA-per-pose kernel (test hook: the environment variable DPOSE_CHECK_COOP_MAX
+// overrides, 0 disables it, so that tests can reach the thread-per-pose kernel with small batches).
 // Measured on a B200 (tools/ab_check_footprint.py, profiles/r1_v26_check_footprint_ab.jsonl), microseconds per
 // host-buffer call, thread-per-pose against CTA-per-pose: 20x12-cell rectangle 128 poses 162 / 38, 4096 poses 178 / 57,
 // 16384 poses 208 / 127, 65536 poses 300 / 358; 40-vertex star 128 poses 1084 / 116, 4096 poses 1161 / 207, 16384 poses
@@ -643,11 +644,6 @@ static size_t workspace_budget() {
 }
 
 static int coop_threads(size_t n_poses) {
-  static const int forced = [] {
-    const char *e = getenv("DPOSE_CHECK_COOP_THREADS");
-    return e ? atoi(e) : 0;
-  }();
-  if (forced == 32 || forced == 64 || forced == 128) return forced;
   return n_poses <= 1024 ? 128 : 32;  // one pose: 128 threads 100 us / 32 threads 114 us (star); 4096 poses: 351 / 207
 }
 

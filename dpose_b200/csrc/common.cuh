@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -97,6 +98,11 @@ struct dpose_pg {
   // texture modes (coef_image_shift <= 0): the patch polynomials as a plain global array behind a texture object
   void *d_coef_hi = nullptr;
   unsigned long long tex_hi = 0;
+  // one 32-byte record (b00, b10, b01, b11) per patch, absolute k' coordinates, zeros outside the valid range: what the
+  // cooperative kernels gather from global memory (coef_abs_ensure, built on first use)
+  double *d_coef_abs = nullptr;
+  // the footprint as handed to dpose_pg_create (cells, robot frame): check_footprint of solved poses (solve.cu)
+  std::vector<int32_t> footprint;
   // streams, events and staging buffers of the host-buffer batch entry point (api.cu), built on first use
   void *batch_ctx = nullptr;
 };
@@ -106,26 +112,17 @@ struct dpose_map {
   uint32_t size_x = 0, size_y = 0;
   size_t pitch = 0;  // bytes, multiple of 16
   uint8_t *d_data = nullptr;
-  // lethal bit plane (bitplane.cu): bit x of row y = (cell == 254); rows padded to 16 bytes.
-  // Rebuilt from d_data when `bits_dirty` (after create / update) or on every batch call when the
-  // map is marked volatile (its bytes may change behind the library's back).
-  uint32_t *d_bits = nullptr;
-  size_t bits_pitch = 0;  // bytes per bit-plane row, multiple of 16
-  bool bits_dirty = true;
-  // rows [lo, hi) whose uint8 bytes changed since each plane was last built (dpose_map_update narrows the
-  // rebuild to them; create / volatile mean all rows)
-  uint32_t bits_dirty_lo = 0, bits_dirty_hi = 0xffffffffu;
-  uint32_t tiles_dirty_lo = 0, tiles_dirty_hi = 0xffffffffu;
-  bool is_volatile = false;
-  cudaEvent_t bits_ready = nullptr;  // recorded after a rebuild; other streams wait on it
-  // TMA descriptor cache (get_cost_batch.cu), keyed by box dims
-  void *tma_cache = nullptr;
-  // the same lethal bits in 32 x 8 cell tiles of 32 bytes (get_cost_batch_tile.cu): word
-  // ((ty * tiles_ntx + tx) * 8 + (y & 7)), bit x & 31; tiles_ntx includes one zero pad tile per tile row
+  // lethal tile plane (get_cost_batch_tile.cu): bit = (cell == 254), in 32 x 8 cell tiles of 32 bytes: word
+  // ((ty * tiles_ntx + tx) * 8 + (y & 7)), bit x & 31; tiles_ntx includes one zero pad tile per tile row.
+  // Rebuilt from d_data when `tiles_dirty` (after create / update; only the rows [lo, hi) that changed) or inside
+  // every batched call when the map is marked volatile (its bytes may change behind the library's back).
+  // tiles_dirty / the dirty rows / is_volatile are guarded by map_state_mutex() (get_cost_batch_tile.cu).
   uint32_t *d_tiles = nullptr;
   uint32_t tiles_ntx = 0, tiles_nty = 0;
   bool tiles_dirty = true;
-  cudaEvent_t tiles_ready = nullptr;
+  uint32_t tiles_dirty_lo = 0, tiles_dirty_hi = 0xffffffffu;
+  bool is_volatile = false;
+  cudaEvent_t tiles_ready = nullptr;  // recorded after a rebuild; readers on other streams wait on it
   // scratch buffers, pinned staging and stream of lethal_cells_within (lethal.cu), built on first use
   void *lethal_ws = nullptr;
   // pinned staging of dpose_map_update for small dirty windows (a 2-D copy out of pageable memory is staged row
@@ -163,14 +160,20 @@ uint64_t window_bytes_host(const dpose_pg *pg, const dpose_map *map, const doubl
 int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses,
                           size_t n, double *d_out, int want_jacobian, cudaStream_t stream,
                           bool hold_planes = false);
-void map_release_cache(dpose_map *map);
-// bitplane.cu: (re)build the lethal bit plane on `stream`
-int bitplane_build(const dpose_map *map, cudaStream_t stream);
-// get_cost_batch_tile.cu: tile plane build and the thread-per-pose batch kernel; *handled = false
-// when the table does not fit its shared-memory layout (the caller then uses the TMA / generic kernel)
-int tileplane_build(const dpose_map *map, cudaStream_t stream);
+// get_cost_batch_tile.cu: the lethal tile plane, the thread-per-pose batch kernel (large batches) and the dispatcher
+std::mutex &map_state_mutex();  // guards the lazily built per-handle state (coefficient images, tile-plane dirty flags)
+int tileplane_ensure(const dpose_map *map, cudaStream_t stream, bool hold_planes);
+int coef_abs_ensure(const dpose_pg *pg, cudaStream_t stream);
 int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
-                        double *d_out, int want_jacobian, cudaStream_t stream, bool hold_planes, bool *handled);
+                        double *d_out, int want_jacobian, cudaStream_t stream, bool hold_planes);
+// get_cost_batch_coop.cu: G lanes per pose, for batches too small to fill the GPU with one thread per pose; used when
+// the batch would get at least DPOSE_COOP_MIN_GROUP lanes per pose
+#ifndef DPOSE_COOP_MIN_GROUP
+#define DPOSE_COOP_MIN_GROUP 4
+#endif
+bool coop_batch_wanted(const dpose_pg *pg, size_t n);
+int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
+                        double *d_out, int want_jacobian, cudaStream_t stream, bool hold_planes);
 // host window geometry shared by the kernel launch code and dpose_pg_window_bytes
 struct WindowRect {
   int x0, y0, x1, y1;  // inclusive cell range, already clipped; empty if x1 < x0

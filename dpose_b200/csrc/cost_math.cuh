@@ -34,18 +34,4 @@ __host__ __device__ inline WindowRect pose_window(const TableGeom &g, double tx,
   return w;
 }
 
-struct BatchArgs {
-  const PatchCoef *coef;
-  TableGeom g;
-  const uint8_t *map;
-  size_t pitch;
-  int size_x, size_y;
-  const double *poses;
-  double *out;
-  size_t n;
-};
-
-// get_cost.cu: generic window-scan kernel (any table size), the fallback of the TMA kernel
-int launch_batch_generic(const BatchArgs &a, int want_jacobian, int device, cudaStream_t stream);
-
 }  // namespace dpose

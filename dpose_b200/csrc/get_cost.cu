@@ -10,13 +10,9 @@
 // f_u = a10 + a11 cy, f_v = a01 + a11 cx:
 //   J_x = -c Sum f_u + s Sum f_v,  J_y = -s Sum f_u - c Sum f_v,  J_theta = Sum (f_u b - f_v a)
 //
-// Two kernels:
-//   k_cost_cells  : one pose, explicit cell list (the reference's call shape); grid-strided,
-//                   fixed-order block reduction, last CTA folds the CTA partials in index order.
-//   k_cost_batch* : many poses against the whole costmap; one warp per pose scans the pose's
-//                   window (axis-aligned bounding box of the valid kernel region, clipped to
-//                   the map), evaluates every lethal cell in it and reduces cost/Su/Sv/Stheta
-//                   with __shfl_xor_sync in a fixed order.
+// k_cost_cells: one pose, explicit cell list (the reference's call shape); grid-strided, fixed-order block
+// reduction, last CTA folds the CTA partials in index order.  The batched kernels (many poses against the whole
+// costmap) live in get_cost_batch_tile.cu / get_cost_batch_coop.cu.
 #include <cmath>
 #include <atomic>
 #include <cstring>
@@ -142,36 +138,6 @@ __global__ void __launch_bounds__(kCellThreads)
   }
 }
 
-// ---- pose batch, generic window scan (any table size) ----------------------------------------
-constexpr int kBatchWarps = 8;
-
-template <bool kJac>
-__global__ void __launch_bounds__(kBatchWarps * 32) k_cost_batch_generic(BatchArgs a) {
-  const int lane = threadIdx.x & 31;
-  const size_t warps_total = (size_t)gridDim.x * kBatchWarps;
-  for (size_t i = (size_t)blockIdx.x * kBatchWarps + (threadIdx.x >> 5); i < a.n; i += warps_total) {
-    const double tx = a.poses[3 * i], ty = a.poses[3 * i + 1], th = a.poses[3 * i + 2];
-    double s, c;
-    sincos(th, &s, &c);
-    const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y);
-    Accum acc = {0.0, 0.0, 0.0, 0.0};
-    for (int y = w.y0; y <= w.y1; ++y) {
-      const uint8_t *row = a.map + (size_t)y * a.pitch;
-      const double dy = (double)y - ty;
-      for (int x = w.x0 + lane; x <= w.x1; x += 32)
-        if (__ldg(row + x) == kLethal)
-          eval_cell<kJac>(a.coef, a.g.rows, a.g.cols, a.g.cx, a.g.cy, c, s, (double)x - tx, dy, acc);
-    }
-    acc.f = warp_sum(acc.f);
-    if (kJac) {
-      acc.su = warp_sum(acc.su);
-      acc.sv = warp_sum(acc.sv);
-      acc.st = warp_sum(acc.st);
-    }
-    if (lane == 0) finish(acc, c, s, a.out + 4 * i);
-  }
-}
-
 struct CellScratch {
   std::mutex mu;
   int device = -1;
@@ -280,20 +246,6 @@ int get_cost_cells(const dpose_pg *pg, const double se2[3], const int2 *d_cells,
 int get_cost_cells_host(const dpose_pg *pg, const double se2[3], const int32_t *cells_xy, size_t n,
                         double *cost, double *J) {
   return cost_cells_impl(pg, se2, nullptr, cells_xy, n, cost, J);
-}
-
-int launch_batch_generic(const BatchArgs &a, int want_jacobian, int device, cudaStream_t stream) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const size_t want = (a.n + kBatchWarps - 1) / kBatchWarps;
-  const size_t cap = (size_t)sms * 8 * 4;  // a few waves of resident CTAs, grid-strided
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
-  if (want_jacobian)
-    k_cost_batch_generic<true><<<grid, kBatchWarps * 32, 0, stream>>>(a);
-  else
-    k_cost_batch_generic<false><<<grid, kBatchWarps * 32, 0, stream>>>(a);
-  DPOSE_LAUNCHED();
-  return DPOSE_OK;
 }
 
 uint64_t window_bytes_host(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n) {

@@ -179,6 +179,7 @@ struct TileArgs {
   uint32_t stride;  // poses a CTA takes per sweep (<= its thread count; a multiple of 32): batches that do not fill
                     // grid x threads whole sweeps are spread evenly over the CTAs instead of leaving some idle
   float clip_thr;   // a strip of the kernel rectangle is clipped per row only if |cos| (|sin|) exceeds this
+  float clip_margin;  // the clipped x-interval is widened by this many cells on both sides (fp32 round-off, see the launch code)
 };
 
 struct Acc4 {
@@ -200,6 +201,12 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 // 85 % to ~60 % busy.  0 keeps every scanned slot (no store predicates).
 #ifndef DPOSE_TILE_COMPACT
 #define DPOSE_TILE_COMPACT 1
+#endif
+#ifndef DPOSE_TILE_THREADS
+#define DPOSE_TILE_THREADS 1024  // largest CTA (A/B builds: 512, 768)
+#endif
+#ifndef DPOSE_TILE_REPLICAS
+#define DPOSE_TILE_REPLICAS 8  // coefficient replicas wanted in shared memory (A/B builds: 1, 4)
 #endif
 // DPOSE_TILE_WALK 1: branch-free row advance in the cell walk (37-instruction loop body, +0.7 % on B200);
 // 0: nested branch (41 instructions)
@@ -261,8 +268,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   }
   __syncthreads();  // barrier initialised before anyone polls it
   {
+    // try_wait suspends for a hardware time slice and returns false on time-out: loop until the bytes have landed.
+    // No trap after a bounded number of polls — a CTA delayed by time-slicing / MPS / a debugger must not take the
+    // whole context down; the copies were issued by this CTA, so completion is guaranteed.
     uint32_t ok = 0;
-    for (uint32_t spin = 0; spin < (1u << 24) && !ok; ++spin)  // bounded: a lost copy must not hang the GPU
+    while (!ok)
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
           "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
@@ -270,7 +280,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           : "=r"(ok)
           : "r"(bar)
           : "memory");
-    if (!ok) __trap();
   }
 
   constexpr int kSlots = kRows + 7;
@@ -311,24 +320,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     }
     // conservative fp32 x-interval of the kernel rectangle per window row y:
     //   0 <= ku0 + s y + c x < cols - 3   and   0 <= kv0 + c y - s x < rows - 3, each linear in y.
-    // All values stay far below 2^22, which the integer extraction in phase 1 relies on.
+    // All values stay below 2^22 (|t| <= 2 win_max^2 and win_max <= 1024, see dpose_pg_create), which the integer
+    // extraction in phase 1 relies on.
     // CLIP INVARIANT (what lets phase 2 drop the bounds test): every cell that survives has k' within one
     // patch of the valid range, so floor(k') is in [-1, dim - 3] and addresses a patch of the table (zeros
-    // outside the valid range).  A clipped strip overshoots by 0.02 |c| cell; a strip left unclipped because
-    // |c| <= clip_thr = 0.5 / win_max varies by at most |c| * window width <= 0.5 cell along a window row,
-    // and every window row crosses the valid rectangle (the window is its bounding box).
+    // outside the valid range).  A clipped strip overshoots by clip_margin |c| cell, where clip_margin (< 0.5 for
+    // every table dpose_pg_create admits) covers the fp32 round-off of the interval ends, which grows with
+    // win_max^2; a strip left unclipped because |c| <= clip_thr = 0.5 / win_max varies by at most
+    // |c| * window width <= 0.5 cell along a window row, and every window row crosses the valid rectangle (the
+    // window is its bounding box).
     float l1 = -1000.f, h1 = 1000.f, d1 = 0.f, l2 = -1000.f, h2 = 1000.f, d2 = 0.f;
     {
       const float cf = (float)c, sf = (float)s, ku0f = (float)ku0, kv0f = (float)kv0;
       if (fabsf(cf) > a.clip_thr) {
         const float inv = rcp_approx(cf);
         const float t0 = -ku0f * inv, t1 = (hi_u - ku0f) * inv;
-        l1 = fminf(t0, t1) - 0.02f, h1 = fmaxf(t0, t1) + 0.02f, d1 = -sf * inv;
+        l1 = fminf(t0, t1) - a.clip_margin, h1 = fmaxf(t0, t1) + a.clip_margin, d1 = -sf * inv;
       }
       if (fabsf(sf) > a.clip_thr) {
         const float inv = rcp_approx(sf);
         const float t0 = kv0f * inv, t1 = (kv0f - hi_v) * inv;
-        l2 = fminf(t0, t1) - 0.02f, h2 = fmaxf(t0, t1) + 0.02f, d2 = cf * inv;
+        l2 = fminf(t0, t1) - a.clip_margin, h2 = fmaxf(t0, t1) + a.clip_margin, d2 = cf * inv;
       }
     }
 
@@ -496,7 +508,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   }
 }
 
-std::mutex g_tile_mu;  // guards the lazily built per-handle state below
 
 template <bool kJac, int kThreads, int kRepShift, int kRows>
 int launch_tile4(const TileArgs &a, int grid, size_t smem_bytes, cudaStream_t stream) {
@@ -529,14 +540,15 @@ int launch_tile1(const TileArgs &a, int threads, int rep_shift, int rows, int gr
   return launch_tile2<kJac, 1024>(a, rep_shift, rows, grid, smem_bytes, stream);
 }
 
-int env_int(const char *name) {
-  const char *e = std::getenv(name);
-  return e ? std::atoi(e) : 0;
-}
-
 }  // namespace
 
-int tileplane_build(const dpose_map *map, cudaStream_t stream) {
+std::mutex &map_state_mutex() {
+  static std::mutex mu;  // guards the lazily built per-handle state: coefficient images, tile-plane dirty flags / events
+  return mu;
+}
+
+// caller holds map_state_mutex()
+static int tileplane_build_locked(const dpose_map *map, cudaStream_t stream) {
   if (!map->d_tiles || map->size_x == 0 || map->size_y == 0) return DPOSE_OK;
   // only the tile rows that cover the dirty map rows (all of them after create / in volatile mode)
   dpose_map *m = const_cast<dpose_map *>(map);
@@ -554,17 +566,52 @@ int tileplane_build(const dpose_map *map, cudaStream_t stream) {
   return DPOSE_OK;
 }
 
-// Returns DPOSE_OK and sets *handled = false if this kernel cannot take the table (shared memory).
+// Makes the lethal tile plane of `map` current for work queued on `stream` afterwards: rebuilds the dirty rows (every
+// row of a volatile map unless hold_planes) in front of it, or orders `stream` behind the rebuild another stream did.
+int tileplane_ensure(const dpose_map *map, cudaStream_t stream, bool hold_planes) {
+  if (!map->d_tiles) return DPOSE_OK;
+  dpose_map *m = const_cast<dpose_map *>(map);
+  std::lock_guard<std::mutex> lock(map_state_mutex());
+  if (!m->tiles_ready) DPOSE_CUDA(cudaEventCreateWithFlags(&m->tiles_ready, cudaEventDisableTiming));
+  if (m->tiles_dirty || (m->is_volatile && !hold_planes)) {
+    DPOSE_TRY(tileplane_build_locked(map, stream));
+    DPOSE_CUDA(cudaEventRecord(m->tiles_ready, stream));
+    m->tiles_dirty = false;
+  } else {
+    DPOSE_CUDA(cudaStreamWaitEvent(stream, m->tiles_ready, 0));  // built on another stream?
+  }
+  return DPOSE_OK;
+}
+
+// The patch polynomials in absolute k' coordinates, one 32-byte record (b00, b10, b01, b11) per patch, zeros outside the
+// valid range: what the cooperative kernels (coop_eval.cuh) gather straight from global memory / L1.  Built on first use.
+int coef_abs_ensure(const dpose_pg *pg, cudaStream_t stream) {
+  dpose_pg *p = const_cast<dpose_pg *>(pg);
+  std::lock_guard<std::mutex> lock(map_state_mutex());
+  if (p->d_coef_abs) return DPOSE_OK;
+  double2 *buf = nullptr;
+  DPOSE_CUDA(cudaMalloc(&buf, sizeof(PatchCoef) * (size_t)pg->rows * pg->cols));
+  k_build_coef_image<<<64, 256, 0, stream>>>(pg->d_coef, buf, nullptr, pg->rows, pg->cols, 0);
+  DPOSE_LAUNCHED();
+  DPOSE_CUDA(cudaStreamSynchronize(stream));  // other streams may use it right after
+  p->d_coef_abs = reinterpret_cast<double *>(buf);
+  return DPOSE_OK;
+}
+
+// fp32 round-off of the clip interval ends grows with win_max^2 (|t| <= 2 win_max^2 before the cancellation): measured
+// worst case 3.5 win_max^2 2^-23 cells (float32 emulation of the exact operation order at angles just above clip_thr);
+// the margin carries twice that plus the 0.02 cell the small tables were tuned with.  dpose_pg_create caps tables at
+// 512 x 512 (win_max <= 724), where margin = 0.52 and margin + error < 1 patch: the CLIP INVARIANT holds.
+static float clip_margin_for(int win_max) { return 0.02f + 8.0f * (float)win_max * (float)win_max * 1.1920929e-7f; }
+
+// Tables with fewer than 4 rows or columns have no valid patch (dpose_core.cpp:181-182 needs 2 <= k_upper <= dim - 2):
+// every cost is 0, like an empty map.  Everything else runs k_cost_batch_tile.
 int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n, double *d_out,
-                        int want_jacobian, cudaStream_t stream, bool hold_planes, bool *handled) {
-  *handled = false;
-  if (!map->d_tiles || pg->rows < 4 || pg->cols < 4) return DPOSE_OK;
+                        int want_jacobian, cudaStream_t stream, bool hold_planes) {
   int sms = 148, smem_optin = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pg->device);
 
-  // tuning overrides (A/B measurements): threads per CTA and coefficient replicas
-  static const int env_threads = env_int("DPOSE_TILE_THREADS"), env_rep = env_int("DPOSE_TILE_REPLICAS");
   // rows kept per chunk
   const int need = std::min(32, pg->win_max);
   const int rows = need <= 20 ? 20 : need <= 28 ? 28 : 32;
@@ -572,9 +619,10 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   // bytes of one replica of the shared-memory image
   const size_t table_bytes = sizeof(PatchCoef) * (size_t)pg->rows * pg->cols;
   const size_t budget = (size_t)smem_optin - 64;
-  // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts)
-  int threads = env_threads == 512 || env_threads == 768 || env_threads == 1024 ? env_threads : 1024;
-  int rep_shift = env_rep == 1 ? 0 : env_rep == 4 ? 2 : 3;  // 8 replicas if they fit (conflict-free LDS.128 gathers)
+  // preference: many threads first (the kernel is issue bound), then replicas (bank conflicts).
+  // A/B builds: -DDPOSE_TILE_THREADS=512|768|1024, -DDPOSE_TILE_REPLICAS=1|4|8
+  int threads = DPOSE_TILE_THREADS;
+  int rep_shift = DPOSE_TILE_REPLICAS == 1 ? 0 : DPOSE_TILE_REPLICAS == 4 ? 2 : 3;  // 8 replicas if they fit (conflict-free LDS.128)
   auto fits = [&](int th, int rs) { return (rs < 0 ? 0 : table_bytes << rs) + (size_t)stored * 4 * th <= budget; };
   const int threads_wanted = threads;
   while (!fits(threads, rep_shift)) {
@@ -591,7 +639,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   }
   // small batches are latency bound: spread them over all SMs with smaller CTAs (the replica count, and with it
   // the cached coefficient image, stays the one chosen for the largest CTA)
-  if (env_threads == 0) {
+  {
     const size_t per_sm = (n + (size_t)sms - 1) / (size_t)sms;
     const int choices[5] = {128, 256, 512, 768, 1024};
     for (int c : choices)
@@ -602,9 +650,8 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   }
 
   dpose_pg *p = const_cast<dpose_pg *>(pg);
-  dpose_map *m = const_cast<dpose_map *>(map);
   {
-    std::lock_guard<std::mutex> lock(g_tile_mu);
+    std::lock_guard<std::mutex> lock(map_state_mutex());
     if (p->coef_image_shift != rep_shift || (rep_shift >= 0 && !p->d_coef_image)) {
       if (p->d_coef_image) {
         DPOSE_CUDA(cudaDeviceSynchronize());
@@ -634,15 +681,8 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
       DPOSE_CUDA(cudaStreamSynchronize(stream));  // other streams may use the image right after
       p->coef_image_shift = rep_shift;
     }
-    if (!m->tiles_ready) DPOSE_CUDA(cudaEventCreateWithFlags(&m->tiles_ready, cudaEventDisableTiming));
-    if (m->tiles_dirty || (m->is_volatile && !hold_planes)) {
-      DPOSE_TRY(tileplane_build(map, stream));
-      DPOSE_CUDA(cudaEventRecord(m->tiles_ready, stream));
-      m->tiles_dirty = false;
-    } else {
-      DPOSE_CUDA(cudaStreamWaitEvent(stream, m->tiles_ready, 0));  // built on another stream?
-    }
   }
+  DPOSE_TRY(tileplane_ensure(map, stream, hold_planes));
 
   TileArgs a;
   a.coef_image = reinterpret_cast<const uint4 *>(p->d_coef_image);
@@ -660,20 +700,33 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.planes = reinterpret_cast<const int4 *>(p->d_coef_hi);
   a.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 31u) == 0;
   a.clip_thr = 0.5f / (float)std::max(pg->win_max, 25);
+  a.clip_margin = clip_margin_for(pg->win_max);
   const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)stored * 4 * threads;
   const size_t want = (n + threads - 1) / threads;
   int grid = (int)std::min<size_t>(want, (size_t)sms);
   a.stride = (uint32_t)threads;
-  static const int env_balance = env_int("DPOSE_TILE_BALANCE");  // 0 (unset): default, 1: off, 2: on (A/B)
-  if (env_balance != 1 && n >= (size_t)sms * 32) {  // every SM gets a CTA, every CTA the same share of every sweep
+  if (n >= (size_t)sms * 32) {  // every SM gets a CTA, every CTA the same share of every sweep
     grid = sms;
     const size_t sweeps = (n + (size_t)grid * threads - 1) / ((size_t)grid * threads);
     const size_t share = (n + (size_t)grid * sweeps - 1) / ((size_t)grid * sweeps);
     a.stride = (uint32_t)std::min<size_t>((size_t)threads, (share + 31) / 32 * 32);
   }
-  *handled = true;
   return want_jacobian ? launch_tile1<true>(a, threads, rep_shift, rows, grid, smem_bytes, stream)
                        : launch_tile1<false>(a, threads, rep_shift, rows, grid, smem_bytes, stream);
+}
+
+int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n, double *d_out,
+                          int want_jacobian, cudaStream_t stream, bool hold_planes) {
+  if (n == 0) return DPOSE_OK;
+  if (pg->device != map->device) return fail(DPOSE_EINVAL, "pose_gradient and map live on different devices");
+  DeviceGuard guard(pg->device);
+  if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
+  if (!map->d_tiles || pg->rows < 4 || pg->cols < 4) {  // empty map / no valid patch: every sum is empty
+    DPOSE_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 4 * n, stream));
+    return DPOSE_OK;
+  }
+  if (coop_batch_wanted(pg, n)) return get_cost_batch_coop(pg, map, d_poses, n, d_out, want_jacobian, stream, hold_planes);
+  return get_cost_batch_tile(pg, map, d_poses, n, d_out, want_jacobian, stream, hold_planes);
 }
 
 }  // namespace dpose

@@ -16,14 +16,10 @@
 #include <mutex>
 #include <new>
 
-#include "common.cuh"
+#include "problem.cuh"
 
 namespace dpose {
 namespace {
-
-struct Reg {
-  double goal[3], norm[3];
-};
 
 struct FinishArgs {
   const double *x;     // n x 3 displacements
@@ -34,14 +30,6 @@ struct FinishArgs {
   Reg regs[2];
   double *f, *grad, *g, *jac;  // any may be null
 };
-
-constexpr double kPi = 3.14159265358979323846;
-
-// angles::normalize_angle (ROS `angles`): fmod(a + pi, 2 pi), result <= 0 ? + pi : - pi
-__host__ __device__ inline double normalize_angle(double a) {
-  const double r = fmod(a + kPi, 2.0 * kPi);
-  return r <= 0.0 ? r + kPi : r - kPi;
-}
 
 __global__ void k_problem_poses(const double *__restrict__ x, size_t n, double ox, double oy, double ot,
                                 double *__restrict__ poses) {
@@ -95,25 +83,6 @@ void reg_init(Reg *r, double w_lin_unscaled, double w_rot_unscaled, const double
 
 using namespace dpose;
 
-struct dpose_problem {
-  const dpose_pg *pg = nullptr;    // borrowed
-  const dpose_map *map = nullptr;  // borrowed
-  dpose_map *crop = nullptr;       // owned: the clamped search box as a map of its own
-  bool ready = false;
-  int32_t search_box[10] = {0};
-  int32_t origin[2] = {0, 0};  // crop origin in map cells
-  double pose[3] = {0, 0, 0};
-  double lin_tol_sq = 1, rot_tol_sq = 1;
-  int n_regs = 0;
-  Reg regs[2];
-  // workspace (grow-only), one call at a time per problem
-  std::mutex mu;
-  cudaStream_t stream = nullptr;
-  size_t cap = 0;
-  double *d_x = nullptr, *d_work = nullptr, *d_res = nullptr;  // 3n, 7n, 9n
-  double *h_stage = nullptr;  // pinned, 12n: x in, then [f | grad | g | jac] out — one copy each way
-};
-
 static int problem_reserve(dpose_problem *p, size_t n) {
   if (!p->stream) DPOSE_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   if (n <= p->cap) return DPOSE_OK;
@@ -151,6 +120,9 @@ void dpose_problem_destroy(dpose_problem *p) {
     DeviceGuard guard(p->pg->device);
     cudaFree(p->d_x);
     cudaFreeHost(p->h_stage);
+    cudaFree(p->d_solve);
+    cudaFreeHost(p->h_solve);
+    cudaFree(p->d_trace);
     if (p->stream) cudaStreamDestroy(p->stream);
   }
   dpose_map_destroy(p->crop);
@@ -164,6 +136,8 @@ int dpose_problem_init(dpose_problem *p, const double start[3], const double goa
   for (int i = 0; i < 3; ++i) p->pose[i] = goal[i];  // :114
   p->lin_tol_sq = std::pow(cfg->lin_tolerance, 2);   // :115-116
   p->rot_tol_sq = std::pow(cfg->rot_tolerance, 2);
+  p->lin_tol = std::abs(cfg->lin_tolerance);
+  p->rot_tol = std::abs(cfg->rot_tolerance);
   int max_coeff = 0;  // :122-123
   for (int i = 0; i < 10; ++i) max_coeff = std::max(max_coeff, std::abs(p->pg->box[i]));
   // :126-133: h is a double, but the ring it is written into is a rectangle<int>: Eigen's comma initialiser converts

@@ -182,6 +182,49 @@ int dpose_problem_eval_batch(dpose_problem *problem, const double *x, size_t n, 
 int dpose_problem_eval_batch_device(const dpose_problem *problem, const double *d_x, size_t n, double *d_work,
                                     double *d_f, double *d_grad_f, double *d_g, double *d_jac_g, void *stream);
 
+/* ---- the goal-tolerance solve, multi-start and device resident --------------------------------------------------
+ * replaces the attempt loop of DposeGoalTolerance::preProcess / preProcessImpl (dpose_goal_tolerance.cpp:376-459):
+ * upstream runs Ipopt from one starting offset per attempt (:378, :430-456), validates the solved pose with
+ * check_footprint (:386-399) and takes the first attempt that passes.  Here all n starting offsets are solved at once
+ * in ONE kernel launch (iterates stay in registers: no host copy, no launch per iteration), validated in a second
+ * one and ranked in a third; one H2D (x0) and one D2H (results) per call.  The evaluated functions are the
+ * reference's f / grad f (:96-110); the constraints (:196-207) are kept by projection; the step rule is a projected
+ * BFGS descent (csrc/solve.cu), since Ipopt itself is not a per-thread algorithm. */
+typedef struct {
+  int max_iter;        /* Ipopt "max_iter" (plugin default 20, dpose_goal_tolerance.cpp:507): evaluations after the first */
+  double tol;          /* Ipopt "tol" (plugin default 5, :504) */
+  double dual_inf_tol; /* Ipopt's default 1: converged when the KKT residual ||x - P(x - grad f)||_inf <= min(tol, dual_inf_tol) */
+  double armijo_c1;    /* sufficient-decrease constant of the line search, default 1e-4 */
+  uint8_t lethal;      /* cost value check_footprint tests, costmap_2d::LETHAL_OBSTACLE (:395-396) */
+} dpose_solver_options;
+void dpose_solver_default_options(dpose_solver_options *opt);
+
+/* per-start status byte */
+#define DPOSE_SOLVE_STATUS_MASK 0x3    /* 1 converged, 2 evaluation budget exhausted, 3 stalled (no descent step left) */
+#define DPOSE_SOLVE_FOOTPRINT_FREE 0x4 /* check_footprint(map, T(goal + x) footprint, lethal) passed (:388-399) */
+#define DPOSE_SOLVE_ACCEPTED 0x8       /* converged and footprint free: what preProcessImpl returns true for */
+
+typedef struct {
+  long long first; /* lowest accepted start index: upstream's choice (attempts are tried in order, :430-447); -1 if none */
+  long long best;  /* accepted start of lowest cost f (ties: lowest index); -1 if none */
+  unsigned long long n_converged, n_accepted;
+  double best_f;
+  double best_pose[3];  /* goal + x of `best`, cells / radians (problem::get_pose after finalize_solution, :283-291) */
+  double first_pose[3]; /* the same for `first` */
+} dpose_solve_summary;
+
+/* uniform_pose_generator (:333-373): n starting offsets, radius ~ U[0, lin_tol), angle ~ U[-pi, pi), yaw ~ U[0, rot_tol)
+ * from one std::mt19937(seed) (upstream seeds from std::random_device); first_zero != 0 makes offset 0 the zero pose
+ * like upstream's attempt 0 (:431).  Host arithmetic. */
+int dpose_sample_offsets(uint32_t seed, double lin_tolerance, double rot_tolerance, size_t n, int first_zero,
+                         double *x0 /* n x 3 */);
+/* x0: n x 3 starting displacements (host).  Outputs (host, any may be NULL): x n x 3 final displacements, f n costs,
+ * status n bytes (flags above), evals n evaluation counts, summary; trace (debug / parity tests): n x (max_iter + 1) x 12
+ * doubles, per evaluation [x_trial(3), f, grad_f(3), g0, g1, alpha, status after the step, 0]. */
+int dpose_problem_solve_batch(dpose_problem *problem, const double *x0, size_t n, const dpose_solver_options *opt,
+                              double *x, double *f, uint8_t *status, int32_t *evals, dpose_solve_summary *summary,
+                              double *trace);
+
 /* ---- world <-> cell poses ------------------------------------------------------------------------
  * replaces to_cell / to_msg (dpose_goal_tolerance.cpp:294-330) for n poses; host arithmetic.  The costmap
  * geometry is costmap_2d::Costmap2D's (getOriginX/Y, getResolution, getSizeInCellsX/Y); yaw <-> quaternion

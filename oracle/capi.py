@@ -42,6 +42,55 @@ class _Problem(C.Structure):
                 ("cells", C.POINTER(C.c_int32)), ("n_cells", C.c_size_t)]
 
 
+class SolverCfg(C.Structure):
+    """oracle_solver_cfg"""
+    _fields_ = [("max_iter", C.c_int), ("kkt_tol", C.c_double), ("c1", C.c_double), ("rho2", C.c_double),
+                ("lin_tol", C.c_double), ("rot_tol", C.c_double)]
+
+
+class SolverState(C.Structure):
+    """oracle_solver_state"""
+    _fields_ = [("x", C.c_double * 3), ("f", C.c_double), ("g", C.c_double * 3), ("H", C.c_double * 6),
+                ("d", C.c_double * 3), ("xt", C.c_double * 3), ("alpha", C.c_double), ("gd", C.c_double),
+                ("n_acc", C.c_int), ("evals", C.c_int), ("status", C.c_int)]
+
+
+TRACE_STRIDE = 12  # doubles per evaluation: x_trial(3), f, grad_f(3), g0, g1, alpha, status after the step, 0
+
+
+def solver_cfg(box, lin_tolerance, rot_tolerance, max_iter=20, tol=5.0, dual_inf_tol=1.0, armijo_c1=1e-4):
+    """the step rule's constants for a footprint whose cost_data box is `box` ((5, 2) ring): rho^2 = the largest
+    squared distance of a box corner from the centre cell (at least 1)"""
+    b = np.asarray(box, np.float64).reshape(5, 2)
+    return SolverCfg(int(max_iter), float(min(tol, dual_inf_tol)), float(armijo_c1),
+                     float(max(1.0, (b ** 2).sum(axis=1).max())), abs(float(lin_tolerance)), abs(float(rot_tolerance)))
+
+
+def solver_replay(cfg, x0, trace_f_grad):
+    """feeds a recorded sequence of (f, grad f) into the restated step rule starting from x0; returns the trial
+    points it asks for (one per evaluation), the status after each step and the final state"""
+    s = SolverState()
+    x0 = np.ascontiguousarray(np.asarray(x0, np.float64).reshape(3))
+    lib().oracle_solver_start(C.byref(s), C.byref(cfg), x0.ctypes.data)
+    trials, statuses = [], []
+    for ft, gt in trace_f_grad:
+        if s.status != 0:
+            break
+        trials.append(np.array(s.xt[:]))
+        g = np.ascontiguousarray(np.asarray(gt, np.float64).reshape(3))
+        lib().oracle_solver_advance(C.byref(s), C.byref(cfg), float(ft), g.ctypes.data)
+        statuses.append(s.status)
+    return np.array(trials).reshape(-1, 3), np.array(statuses, np.int64), s
+
+
+def sample_offsets(seed, lin_tolerance, rot_tolerance, n, first_zero=True):
+    """uniform_pose_generator (dpose_goal_tolerance.cpp:333-373) with std::mt19937(seed), restated"""
+    out = np.zeros((int(n), 3))
+    lib().oracle_sample_offsets(int(seed), float(lin_tolerance), float(rot_tolerance), int(n), int(bool(first_zero)),
+                                out.ctypes.data)
+    return out
+
+
 def build(force=False):
     src_newer = (not os.path.exists(_SO)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
@@ -88,6 +137,11 @@ def lib():
         L.oracle_problem_free.argtypes = [C.POINTER(_Problem)]
         L.oracle_problem_eval_batch.argtypes = [C.POINTER(_CostData), C.POINTER(_Problem), C.c_void_p, C.c_size_t,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_solver_start.argtypes = [C.POINTER(SolverState), C.POINTER(SolverCfg), C.c_void_p]
+        L.oracle_solver_advance.argtypes = [C.POINTER(SolverState), C.POINTER(SolverCfg), C.c_double, C.c_void_p]
+        L.oracle_solve_batch.argtypes = [C.POINTER(_CostData), C.POINTER(_Problem), C.POINTER(SolverCfg), C.c_void_p,
+                                         C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_sample_offsets.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_size_t, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -248,6 +302,18 @@ class Problem:
         lib().oracle_problem_eval_batch(C.byref(self.cd._cd), C.byref(self._p), x.ctypes.data, n, f.ctypes.data,
                                         grad.ctypes.data, g.ctypes.data, jac.ctypes.data, int(nthreads))
         return f, grad, g, jac
+
+    def solve_batch(self, cfg, x0, nthreads=1, trace=False):
+        """the restated step rule on the oracle's own evaluation, n starts: (x, f, status, evals[, trace])"""
+        x0 = np.ascontiguousarray(np.asarray(x0, np.float64).reshape(-1, 3))
+        n = x0.shape[0]
+        x, f = np.empty((n, 3)), np.empty(n)
+        status, evals = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        tr = np.zeros((n, cfg.max_iter + 1, TRACE_STRIDE)) if trace else None
+        lib().oracle_solve_batch(C.byref(self.cd._cd), C.byref(self._p), C.byref(cfg), x0.ctypes.data, n, x.ctypes.data,
+                                 f.ctypes.data, status.ctypes.data, evals.ctypes.data,
+                                 tr.ctypes.data if trace else None, int(nthreads))
+        return (x, f, status, evals, tr) if trace else (x, f, status, evals)
 
     def __del__(self):
         try:

@@ -787,6 +787,219 @@ void oracle_problem_eval_batch(const oracle_cost_data *cd, const oracle_problem 
 
 
 /* ------------------------------------------------------------------------- */
+/* the multi-start solve: step rule restated (see dpose_oracle.h)            */
+/* ------------------------------------------------------------------------- */
+/* Euclidean projection onto {x^2 + y^2 <= lin_tol^2} x {|theta| <= rot_tol}: the feasible set of get_bounds_info
+ * (dpose_goal_tolerance.cpp:196-207) with g0, g1 of eval_g (:238-247) */
+static void solver_project(double p[3], const oracle_solver_cfg *c) {
+  const double r2 = p[0] * p[0] + p[1] * p[1];
+  if (r2 > c->lin_tol * c->lin_tol) {
+    const double sc = c->lin_tol / sqrt(r2);
+    p[0] = p[0] * sc;
+    p[1] = p[1] * sc;
+  }
+  p[2] = fmin(fmax(p[2], -c->rot_tol), c->rot_tol);
+}
+
+/* H = gamma * diag(1, 1, 1 / rho^2) */
+static void solver_h0(oracle_solver_state *s, double gamma, const oracle_solver_cfg *c) {
+  s->H[0] = gamma, s->H[1] = 0.0, s->H[2] = 0.0, s->H[3] = gamma, s->H[4] = 0.0, s->H[5] = gamma / c->rho2;
+}
+
+static void solver_direction(oracle_solver_state *s) { /* d = -(H g) */
+  const double *H = s->H, *g = s->g;
+  s->d[0] = -(H[0] * g[0] + H[1] * g[1] + H[2] * g[2]);
+  s->d[1] = -(H[1] * g[0] + H[3] * g[1] + H[4] * g[2]);
+  s->d[2] = -(H[2] * g[0] + H[4] * g[1] + H[5] * g[2]);
+}
+
+/* first step of a (re)started descent: at most one cell in the metric dx^2 + dy^2 + rho^2 dtheta^2 */
+static double solver_first_alpha(const oracle_solver_state *s, const oracle_solver_cfg *c) {
+  const double nd = sqrt(s->d[0] * s->d[0] + s->d[1] * s->d[1] + c->rho2 * (s->d[2] * s->d[2]));
+  return nd > 1.0 ? 1.0 / nd : 1.0;
+}
+
+/* trial point xt = P(x + alpha d); usable iff it is a descent step of non-negligible length */
+static int solver_trial(oracle_solver_state *s, const oracle_solver_cfg *c) {
+  for (int k = 0; k < 3; ++k) s->xt[k] = s->x[k] + s->alpha * s->d[k];
+  solver_project(s->xt, c);
+  const double e0 = s->xt[0] - s->x[0], e1 = s->xt[1] - s->x[1], e2 = s->xt[2] - s->x[2];
+  s->gd = s->g[0] * e0 + s->g[1] * e1 + s->g[2] * e2;
+  const double step = fmax(fmax(fabs(e0), fabs(e1)), fabs(e2));
+  return s->gd < 0.0 && step > 1e-12;
+}
+
+void oracle_solver_start(oracle_solver_state *s, const oracle_solver_cfg *c, const double x0[3]) {
+  memset(s, 0, sizeof(*s));
+  for (int k = 0; k < 3; ++k) s->xt[k] = x0[k];
+  solver_project(s->xt, c);
+  for (int k = 0; k < 3; ++k) s->x[k] = s->xt[k];
+  s->alpha = 1.0;
+  solver_h0(s, 1.0, c);
+}
+
+void oracle_solver_advance(oracle_solver_state *s, const oracle_solver_cfg *c, double ft, const double gt[3]) {
+  s->evals += 1;
+  int fresh = 1;
+  if (s->evals == 1) { /* the starting point is taken as it is */
+    for (int k = 0; k < 3; ++k) s->x[k] = s->xt[k], s->g[k] = gt[k];
+    s->f = ft;
+    solver_h0(s, 1.0, c);
+    s->n_acc = 0;
+  } else if (ft <= s->f + c->c1 * s->gd) { /* Armijo on the projected arc: accept, BFGS update */
+    const double sx[3] = {s->xt[0] - s->x[0], s->xt[1] - s->x[1], s->xt[2] - s->x[2]};
+    const double y[3] = {gt[0] - s->g[0], gt[1] - s->g[1], gt[2] - s->g[2]};
+    const double sy = sx[0] * y[0] + sx[1] * y[1] + sx[2] * y[2];
+    const double ss = sx[0] * sx[0] + sx[1] * sx[1] + sx[2] * sx[2];
+    const double yy = y[0] * y[0] + y[1] * y[1] + y[2] * y[2];
+    if (sy > 1e-10 * (sqrt(ss) * sqrt(yy))) {
+      if (s->n_acc == 0) solver_h0(s, sy / (y[0] * y[0] + y[1] * y[1] + (y[2] * y[2]) / c->rho2), c);
+      double *H = s->H;
+      const double rho = 1.0 / sy;
+      const double Hy[3] = {H[0] * y[0] + H[1] * y[1] + H[2] * y[2], H[1] * y[0] + H[3] * y[1] + H[4] * y[2],
+                            H[2] * y[0] + H[4] * y[1] + H[5] * y[2]};
+      const double yHy = y[0] * Hy[0] + y[1] * Hy[1] + y[2] * Hy[2];
+      const double cf = (1.0 + rho * yHy) * rho;
+      /* H <- H + cf s s' - rho (Hy s' + s Hy') */
+      static const int ri[6] = {0, 0, 0, 1, 1, 2}, ci[6] = {0, 1, 2, 1, 2, 2};
+      for (int e = 0; e < 6; ++e) {
+        const int i = ri[e], j = ci[e];
+        H[e] = H[e] + cf * (sx[i] * sx[j]) - rho * (Hy[i] * sx[j] + sx[i] * Hy[j]);
+      }
+      s->n_acc += 1;
+    }
+    for (int k = 0; k < 3; ++k) s->x[k] = s->xt[k], s->g[k] = gt[k];
+    s->f = ft;
+  } else { /* shorter step: minimiser of the parabola through f, gd and ft, kept inside [0.1, 0.5] */
+    double t = -s->gd / (2.0 * ((ft - s->f) - s->gd));
+    if (!(t >= 0.1)) t = 0.1;
+    if (t > 0.5) t = 0.5;
+    s->alpha = s->alpha * t;
+    fresh = 0;
+  }
+  if (fresh) {
+    double p[3] = {s->x[0] - s->g[0], s->x[1] - s->g[1], s->x[2] - s->g[2]};
+    solver_project(p, c);
+    const double kkt = fmax(fmax(fabs(s->x[0] - p[0]), fabs(s->x[1] - p[1])), fabs(s->x[2] - p[2]));
+    if (kkt <= c->kkt_tol) {
+      s->status = 1;
+      return;
+    }
+    solver_direction(s);
+    s->alpha = s->n_acc == 0 ? solver_first_alpha(s, c) : 1.0;
+  }
+  if (s->evals > c->max_iter) {
+    s->status = 2;
+    return;
+  }
+  if (solver_trial(s, c)) return;
+  if (fresh && s->n_acc > 0) { /* quasi-Newton direction bent by the projection: restart from the scaled gradient */
+    solver_h0(s, 1.0, c);
+    s->n_acc = 0;
+    solver_direction(s);
+    s->alpha = solver_first_alpha(s, c);
+    if (solver_trial(s, c)) return;
+  }
+  s->status = 3;
+}
+
+int oracle_solve(const oracle_solver_cfg *cfg, oracle_eval_fn eval, void *ctx, const double x0[3], double x[3], double *f,
+                 int *evals, double *trace) {
+  oracle_solver_state s;
+  oracle_solver_start(&s, cfg, x0);
+  while (s.status == 0) {
+    double ft, gt[3], g[2], jac[3];
+    eval(ctx, s.xt, &ft, gt, g, jac);
+    const int slot = s.evals;
+    const double alpha_used = s.alpha, xt[3] = {s.xt[0], s.xt[1], s.xt[2]};
+    oracle_solver_advance(&s, cfg, ft, gt);
+    if (trace) {
+      double *t = trace + 12 * (size_t)slot;
+      t[0] = xt[0], t[1] = xt[1], t[2] = xt[2], t[3] = ft, t[4] = gt[0], t[5] = gt[1], t[6] = gt[2];
+      t[7] = g[0], t[8] = g[1], t[9] = alpha_used, t[10] = (double)s.status, t[11] = 0.0;
+    }
+  }
+  for (int k = 0; k < 3; ++k) x[k] = s.x[k];
+  *f = s.f;
+  if (evals) *evals = s.evals;
+  return s.status;
+}
+
+void oracle_problem_eval_cb(void *ctx, const double x[3], double *f, double grad_f[3], double g[2], double jac_g[3]) {
+  const oracle_problem_ctx *c = (const oracle_problem_ctx *)ctx;
+  oracle_problem_eval(c->cd, c->p, x, f, grad_f, g, jac_g);
+}
+
+void oracle_solve_batch(const oracle_cost_data *cd, const oracle_problem *p, const oracle_solver_cfg *cfg,
+                        const double *x0, size_t n, double *x, double *f, uint8_t *status, int32_t *evals, double *trace,
+                        int nthreads) {
+  oracle_problem_ctx ctx = {cd, p};
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 1 ? nthreads : 1)
+#endif
+  for (long long i = 0; i < (long long)n; ++i) {
+    int ev = 0;
+    const int st = oracle_solve(cfg, oracle_problem_eval_cb, &ctx, x0 + 3 * i, x + 3 * i, f + i, &ev,
+                                trace ? trace + (size_t)i * 12 * (size_t)(cfg->max_iter + 1) : NULL);
+    if (status) status[i] = (uint8_t)st;
+    if (evals) evals[i] = ev;
+  }
+  (void)nthreads;
+}
+
+/* std::mt19937 (32-bit Mersenne twister, the standard's parameters) */
+typedef struct {
+  uint32_t mt[624];
+  int idx;
+} oracle_mt19937;
+static void mt_seed(oracle_mt19937 *m, uint32_t seed) {
+  m->mt[0] = seed;
+  for (int i = 1; i < 624; ++i) m->mt[i] = 1812433253u * (m->mt[i - 1] ^ (m->mt[i - 1] >> 30)) + (uint32_t)i;
+  m->idx = 624;
+}
+static uint32_t mt_next(oracle_mt19937 *m) {
+  if (m->idx >= 624) {
+    for (int i = 0; i < 624; ++i) {
+      const uint32_t y = (m->mt[i] & 0x80000000u) | (m->mt[(i + 1) % 624] & 0x7fffffffu);
+      m->mt[i] = m->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    m->idx = 0;
+  }
+  uint32_t y = m->mt[m->idx++];
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+/* libstdc++ std::uniform_real_distribution<double>(a, b)(mt19937): generate_canonical<double, 53> takes two draws,
+ * sum = r1 + r2 * 2^32 (in double), / 2^64, clamped below 1; then u * (b - a) + a */
+static double mt_uniform(oracle_mt19937 *m, double a, double b) {
+  const double r1 = (double)mt_next(m), r2 = (double)mt_next(m);
+  double u = (r1 + r2 * 4294967296.0) / 18446744073709551616.0;
+  if (u >= 1.0) u = nextafter(1.0, 0.0);
+  return u * (b - a) + a;
+}
+
+void oracle_sample_offsets(uint32_t seed, double lin_tol, double rot_tol, size_t n, int first_zero, double *x0) {
+  oracle_mt19937 m;
+  mt_seed(&m, seed);
+  for (size_t i = 0; i < n; ++i) {
+    if (i == 0 && first_zero) { /* attempt 0 starts at the goal (dpose_goal_tolerance.cpp:431) */
+      x0[0] = x0[1] = x0[2] = 0.0;
+      continue;
+    }
+    const double radius = mt_uniform(&m, 0.0, lin_tol); /* :346-348: radius, angle, yaw in this order */
+    const double pi = 3.14159265358979323846; /* M_PI */
+    const double angle = mt_uniform(&m, -pi, pi);
+    const double yaw = mt_uniform(&m, 0.0, rot_tol);
+    x0[3 * i] = cos(angle) * radius; /* :351-352 */
+    x0[3 * i + 1] = sin(angle) * radius;
+    x0[3 * i + 2] = yaw;
+  }
+}
+
+/* ------------------------------------------------------------------------- */
 /* check_footprint — dpose_costmap.cpp:186-582                                */
 /* ------------------------------------------------------------------------- */
 int oracle_is_inside(uint32_t size_x, uint32_t size_y, const int32_t *fp, int n) { /* :186-199 */

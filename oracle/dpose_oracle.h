@@ -165,6 +165,51 @@ int oracle_check_footprint(const uint8_t *map, uint32_t size_x, uint32_t size_y,
 void oracle_check_footprint_batch(const uint8_t *map, uint32_t size_x, uint32_t size_y, const int32_t *fp_xy, int n,
                                   const double *poses, size_t n_poses, uint8_t cost, uint8_t *ok, int nthreads);
 
+/* ---- the multi-start solve ----------------------------------------------------------------
+ * The reference solves its NLP with Ipopt (dpose_goal_tolerance.cpp:378), which is absent from this image and is not
+ * a per-thread algorithm.  The product's solver (dpose_b200/csrc/solve.cu) is a projected BFGS descent of its own; what
+ * IS the reference's are the functions it evaluates (oracle_problem_eval / the compiled plugin's callbacks), the
+ * constraint set (:196-207), the validation of the solved pose (:386-399) and the sampler of the starting offsets
+ * (:333-373).  Below: an independent C restatement of that step rule, written from the rule's description in
+ * solve.cu's header (not from its code), so that the tests can check (a) every iterate's f / grad f against the
+ * reference's callbacks and (b) every step against this state machine, bit for bit; and a driver that runs the whole
+ * solve on the CPU with ANY evaluation callback — the compiled plugin's for bench.py's reference arm. */
+typedef struct {
+  int max_iter;               /* evaluations after the first */
+  double kkt_tol, c1, rho2;   /* stop tolerance, Armijo constant, squared footprint radius (theta metric) */
+  double lin_tol, rot_tol;    /* the constraint set: x^2 + y^2 <= lin_tol^2, |theta| <= rot_tol */
+} oracle_solver_cfg;
+typedef struct {
+  double x[3], f, g[3];  /* accepted iterate */
+  double H[6];           /* BFGS inverse Hessian approximation, symmetric: 00 01 02 11 12 22 */
+  double d[3], xt[3];    /* search direction at x, trial point to evaluate next */
+  double alpha, gd;      /* step along d, grad f . (xt - x) */
+  int n_acc, evals, status; /* status: 0 running, 1 converged, 2 evaluation budget exhausted, 3 stalled */
+} oracle_solver_state;
+void oracle_solver_start(oracle_solver_state *s, const oracle_solver_cfg *cfg, const double x0[3]);
+/* feeds f / grad f evaluated at s->xt; on return s->xt is the next point to evaluate unless s->status != 0 */
+void oracle_solver_advance(oracle_solver_state *s, const oracle_solver_cfg *cfg, double ft, const double gt[3]);
+/* eval_f + eval_grad_f (+ eval_g, eval_jac_g) at a displacement: the signature of oracle/refshim's ref_problem_eval */
+typedef void (*oracle_eval_fn)(void *ctx, const double x[3], double *f, double grad_f[3], double g[2], double jac_g[3]);
+/* one start, to the end; trace (may be NULL): (max_iter + 1) x 12 doubles, per evaluation
+ * [x_trial(3), f, grad_f(3), g0, g1, alpha, status after the step, 0].  Returns the status. */
+int oracle_solve(const oracle_solver_cfg *cfg, oracle_eval_fn eval, void *ctx, const double x0[3], double x[3], double *f,
+                 int *evals, double *trace);
+/* adapter: ctx for oracle_problem_eval as an oracle_eval_fn */
+typedef struct {
+  const oracle_cost_data *cd;
+  const oracle_problem *p;
+} oracle_problem_ctx;
+void oracle_problem_eval_cb(void *ctx, const double x[3], double *f, double grad_f[3], double g[2], double jac_g[3]);
+/* n starts with the oracle's own problem evaluation (OpenMP over starts) */
+void oracle_solve_batch(const oracle_cost_data *cd, const oracle_problem *p, const oracle_solver_cfg *cfg,
+                        const double *x0, size_t n, double *x, double *f, uint8_t *status, int32_t *evals, double *trace,
+                        int nthreads);
+/* uniform_pose_generator (dpose_goal_tolerance.cpp:333-373) with std::mt19937(seed) and libstdc++'s
+ * std::uniform_real_distribution<double> restated (generate_canonical<double, 53>: two 32-bit draws, low word first);
+ * pinned against the plugin's own uniform_pose_distribution compiled into oracle/_ref */
+void oracle_sample_offsets(uint32_t seed, double lin_tol, double rot_tol, size_t n, int first_zero, double *x0);
+
 /* number of OpenMP threads available (1 if built without OpenMP) */
 int oracle_max_threads(void);
 

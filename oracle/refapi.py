@@ -81,6 +81,8 @@ def lib():
         L.ref_problem_init.argtypes = [vp, vp, vp, vp]
         L.ref_problem_eval_batch.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         L.ref_problem_info.argtypes = [vp] * 8
+        L.ref_sample_offsets.argtypes = [u32, dbl, dbl, sz, vp]
+        L.ref_solve_batch.argtypes = [vp, i32, vp, vp, C.c_uint8, vp, sz, vp, vp, vp, vp, vp]
         L.ref_to_cell.restype = i32
         L.ref_to_cell.argtypes = [u32, u32, dbl, dbl, dbl, vp, vp]
         L.ref_to_msg.restype = i32
@@ -198,12 +200,16 @@ class Problem:
     def __init__(self, footprint, padding, costmap):
         self.map = np.ascontiguousarray(np.asarray(costmap, dtype=np.uint8))  # viewed, not copied: keep it alive
         fp = _i32(footprint).reshape(-1, 2)
+        self._fp, self._padding, self._clones = fp, int(padding), []
         self._h = lib().ref_problem_create(self.map.ctypes.data, self.map.shape[1], self.map.shape[0], fp.ctypes.data,
                                            fp.shape[0], int(padding))
         if not self._h:
             raise RuntimeError("footprint must contain at least three points")
 
     def init(self, start, goal, **cfg):
+        self._start, self._goal, self._cfg = list(start), list(goal), dict(cfg)
+        for c in self._clones:
+            c.init(start, goal, **cfg)
         c = np.array([float(cfg.get(k, 1.0)) for k in CONFIG_KEYS])
         s = np.ascontiguousarray(np.asarray(start, np.float64).reshape(3))
         g = np.ascontiguousarray(np.asarray(goal, np.float64).reshape(3))
@@ -216,6 +222,26 @@ class Problem:
         f, grad, g, jac = np.empty(n), np.empty((n, 3)), np.empty((n, 2)), np.empty((n, 3))
         lib().ref_problem_eval_batch(self._h, x.ctypes.data, n, f.ctypes.data, grad.ctypes.data, g.ctypes.data, jac.ctypes.data)
         return f, grad, g, jac
+
+    def solve_batch(self, cfg, x0, nthreads=1, lethal=254, trace=False):
+        """CPU arm of the multi-start solve: the restated step rule (oracle_solve) on THIS compiled plugin's TNLP callbacks,
+        then preProcessImpl's footprint validation with the reference's check_footprint; one `problem` per thread.
+        cfg: oracle.capi.SolverCfg.  Returns (x, f, status, evals[, trace]) with the product's status encoding."""
+        x0 = np.ascontiguousarray(np.asarray(x0, np.float64).reshape(-1, 3))
+        n = x0.shape[0]
+        nthreads = max(1, int(nthreads))
+        while len(self._clones) < nthreads - 1:  # the callbacks cache cost_ / J_: every thread needs its own problem
+            c = Problem(self._fp, self._padding, self.map)
+            c.init(self._start, self._goal, **self._cfg)
+            self._clones.append(c)
+        hs = (C.c_void_p * nthreads)(*([self._h] + [c._h for c in self._clones[:nthreads - 1]]))
+        x, f = np.empty((n, 3)), np.empty(n)
+        status, evals = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        tr = np.zeros((n, cfg.max_iter + 1, 12)) if trace else None
+        goal = np.ascontiguousarray(np.asarray(self._goal, np.float64).reshape(3))
+        lib().ref_solve_batch(hs, nthreads, goal.ctypes.data, C.byref(cfg), int(lethal), x0.ctypes.data, n, x.ctypes.data,
+                              f.ctypes.data, status.ctypes.data, evals.ctypes.data, tr.ctypes.data if trace else None)
+        return (x, f, status, evals, tr) if trace else (x, f, status, evals)
 
     def info(self):
         """(n, m, nnz_jac_g, index_style), x bounds, g bounds, Jacobian pattern (rows, cols)"""
@@ -232,6 +258,13 @@ class Problem:
                 lib().ref_problem_free(self._h)
         except Exception:
             pass
+
+
+def sample_offsets(seed, lin_tolerance, rot_tolerance, n):
+    """the plugin's uniform_pose_distribution (dpose_goal_tolerance.cpp:333-357) driven by std::mt19937(seed)"""
+    out = np.zeros((int(n), 3))
+    lib().ref_sample_offsets(int(seed), float(lin_tolerance), float(rot_tolerance), int(n), out.ctypes.data)
+    return out
 
 
 def to_cell(world, origin, resolution, size):

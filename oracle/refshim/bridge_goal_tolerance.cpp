@@ -1,16 +1,28 @@
 // bridge_goal_tolerance.cpp — extern "C" access to the reference's dpose_goal_tolerance::problem, for oracle/_ref.
 //
-// TEST INFRASTRUCTURE ONLY (see README.md in this directory).  Compiled together with the reference's
-// dpose_goal_tolerance.cpp (taken from /root/reference where it lies) against the stand-in ROS / Ipopt headers next to
-// it.  There is no Ipopt here: what is exposed is the NLP the plugin hands to Ipopt — problem::init and the TNLP
-// callbacks eval_f / eval_grad_f / eval_g / eval_jac_g / get_bounds_info (dpose_goal_tolerance.cpp:90-292) — and the
-// plugin's two pose conversions (to_cell / to_msg, :293-330).
-#include <dpose_goal_tolerance/dpose_goal_tolerance.hpp>
+// TEST INFRASTRUCTURE ONLY (see README.md in this directory).  This translation unit INCLUDES the reference's
+// dpose_goal_tolerance.cpp from /root/reference where it lies (nothing is copied; -I points there) and is compiled
+// against the stand-in ROS / Ipopt headers next to it — included rather than linked so that the helpers the plugin
+// defines only inside its .cpp (uniform_pose_distribution, :333-357) can be driven too.  There is no Ipopt here: what
+// is exposed is the NLP the plugin hands to Ipopt — problem::init and the TNLP callbacks eval_f / eval_grad_f /
+// eval_g / eval_jac_g / get_bounds_info (dpose_goal_tolerance.cpp:90-292) —, the plugin's two pose conversions
+// (to_cell / to_msg, :293-330), its sampler of starting offsets, and a CPU driver that runs the product's step rule
+// (restated in oracle/dpose_oracle.c) on those callbacks followed by the reference's check_footprint: the reference arm
+// of bench.py --workload cfg4.
+#include <dpose_goal_tolerance.cpp>  // the reference's own source file, unmodified
+
+#include <dpose_core/dpose_costmap.hpp>
+
+#include "../dpose_oracle.h"
 
 #include <tf2/utils.h>
 
 #include <cmath>
 #include <memory>
+#include <random>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdexcept>
 #include <vector>
 
@@ -24,7 +36,8 @@ namespace {
 
 struct holder {
   holder(const uint8_t* map, uint32_t sx, uint32_t sy, const int32_t* fp, int n, unsigned padding) :
-      cm(const_cast<unsigned char*>(map), sx, sy, 1.0), lc(&cm, points(fp, n)) {
+      cm(const_cast<unsigned char*>(map), sx, sy, 1.0), lc(&cm, points(fp, n)), footprint(2, n) {
+    for (int i = 0; i < n; ++i) footprint(0, i) = fp[2 * i], footprint(1, i) = fp[2 * i + 1];
     dpose_core::pose_gradient::parameter param;
     param.padding = padding;
     p.reset(new dpose_goal_tolerance::problem(lc, param));
@@ -37,6 +50,7 @@ struct holder {
   }
   costmap_2d::Costmap2D cm;
   costmap_2d::LayeredCostmap lc;
+  dpose_core::polygon footprint;
   std::unique_ptr<dpose_goal_tolerance::problem> p;
 };
 
@@ -87,6 +101,52 @@ ref_problem_eval(void* h, const double x[3], double* f, double grad_f[3], double
 void
 ref_problem_eval_batch(void* h, const double* x, size_t n, double* f, double* grad_f, double* g, double* jac_g) {
   for (size_t i = 0; i < n; ++i) ref_problem_eval(h, x + 3 * i, f + i, grad_f + 3 * i, g + 2 * i, jac_g + 3 * i);
+}
+
+/// uniform_pose_distribution (:333-357) driven by std::mt19937(seed): n offsets (radius, angle, yaw drawn in the
+/// reference's order)
+void
+ref_sample_offsets(uint32_t seed, double lin_tol, double rot_tol, size_t n, double* out) {
+  dpose_goal_tolerance::DposeGoalToleranceConfig c;
+  c.lin_tolerance = lin_tol, c.rot_tolerance = rot_tol;
+  dpose_goal_tolerance::uniform_pose_distribution dis(c);
+  std::mt19937 gen(seed);
+  for (size_t i = 0; i < n; ++i) {
+    const dpose_goal_tolerance::pose p = dis(gen);
+    out[3 * i] = p.x(), out[3 * i + 1] = p.y(), out[3 * i + 2] = p.z();
+  }
+}
+
+/// preProcessImpl's validation (:386-399) of a solved displacement: footprint moved by T(goal + x) R(theta), rounded,
+/// then the reference's check_footprint against the whole costmap
+static bool
+footprint_free(holder& h, const double goal[3], const double x[3], uint8_t lethal) {
+  const dpose_goal_tolerance::pose g(goal[0] + x[0], goal[1] + x[1], goal[2] + x[2]);
+  Eigen::Isometry2d trans(Eigen::Translation2d(g.x(), g.y()) * Eigen::Rotation2Dd(g.z()));
+  const dpose_core::polygon moved = (trans * h.footprint.cast<double>()).array().round().cast<int>().matrix();
+  return dpose_core::check_footprint(h.cm, moved, lethal);
+}
+
+/// CPU arm of the multi-start solve: the step rule of oracle_solve on the compiled plugin's TNLP callbacks, OpenMP over
+/// starts with one `problem` per thread (the callbacks cache cost_ / J_, :96-110), then the validation above.
+/// status: the product's encoding (low 2 bits status, 0x4 footprint free, 0x8 accepted).
+void
+ref_solve_batch(void** holders, int n_holders, const double goal[3], const oracle_solver_cfg* cfg, uint8_t lethal,
+                const double* x0, size_t n, double* x, double* f, uint8_t* status, int32_t* evals, double* trace) {
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_holders)
+  for (long long i = 0; i < (long long)n; ++i) {
+#ifdef _OPENMP
+    holder* h = static_cast<holder*>(holders[omp_get_thread_num()]);
+#else
+    holder* h = static_cast<holder*>(holders[0]);
+#endif
+    int ev = 0;
+    int st = oracle_solve(cfg, ref_problem_eval, h, x0 + 3 * i, x + 3 * i, f + i, &ev,
+                          trace ? trace + (size_t)i * 12 * (size_t)(cfg->max_iter + 1) : nullptr);
+    const bool free_ = footprint_free(*h, goal, x + 3 * i, lethal);
+    status[i] = (uint8_t)(st | (free_ ? 0x4 : 0) | (st == 1 && free_ ? 0x8 : 0));
+    if (evals) evals[i] = ev;
+  }
 }
 
 /// get_nlp_info + get_bounds_info + the sparsity pattern of eval_jac_g (:183-207, :249-268)

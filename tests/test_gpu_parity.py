@@ -31,6 +31,27 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
+TILE_MIN = 40000  # batches of at least this many poses run the thread-per-pose kernel (k_cost_batch_tile); smaller ones
+                  # the cooperative kernel (k_cost_batch_coop: 148 x 1024 lanes / 4 lanes per pose = 37888)
+
+
+def batch_both(pg, cm, poses, **kw):
+    """the same poses through BOTH batched kernels: as they are (cooperative kernel, G lanes per pose) and padded with
+    NaN poses (empty windows) up to the thread-per-pose kernel's batch size.  The two differ only by the summation
+    order; returns the thread-per-pose result."""
+    poses = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 3))
+    n = len(poses)
+    assert n < TILE_MIN
+    coop = pg.get_cost_batch(cm, poses, **kw)
+    padded = np.full((TILE_MIN, 3), np.nan)
+    padded[:n] = poses
+    full = pg.get_cost_batch(cm, padded, **kw)
+    assert np.all(full[n:] == 0)
+    tile = full[:n]
+    assert np.all(np.abs(coop - tile) <= 1e-12 * np.maximum(1.0, np.abs(tile))), np.abs(coop - tile).max()
+    return tile
+
+
 # ------------------------------------------------------------- precompute ----
 @pytest.mark.parametrize("name", list(fx.FOOTPRINTS))
 def test_tables_bit_exact_vs_cv2_golden(dp, golden_tables, name):
@@ -238,7 +259,7 @@ def test_batch_vs_all_cells_golden(dp, golden_batch, name):
     fp, pad = fx.FOOTPRINTS[name]
     pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
     cm = dp.Costmap(m)
-    out = pg.get_cost_batch(cm, golden_batch[name + ".poses"])
+    out = batch_both(pg, cm, golden_batch[name + ".poses"])
     assert np.all(fx.tol_ok(out, golden_batch[name + ".out"]))
     # equals the list-based GPU path over all lethal cells of the map
     ys, xs = np.nonzero(m == fx.LETHAL)
@@ -257,7 +278,7 @@ def test_batch_config2_vs_oracle(dp, capi, name, n):
     fp, pad = fx.FOOTPRINTS[name]
     pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
     cm = dp.Costmap(m)
-    out = pg.get_cost_batch(cm, poses)
+    out = batch_both(pg, cm, poses)
     oc = capi.CostData(fp, pad)
     nt = capi.max_threads()
     # gate: 100 % against the reference evaluated on translated-equivalent inputs
@@ -277,10 +298,12 @@ def test_batch_config2_vs_oracle(dp, capi, name, n):
     assert fx.tol_ok(out[:, 0], ref[:, 0]).all()  # the cost itself never needs the protocol
     assert (ref[:, 0] > 0).mean() > 0.9  # the workload is not trivially empty
     # determinism and the no-Jacobian variant
-    out2 = pg.get_cost_batch(cm, poses)
+    out2 = batch_both(pg, cm, poses)
     assert np.array_equal(out, out2)
-    out3 = pg.get_cost_batch(cm, poses, jacobian=False)
+    out3 = batch_both(pg, cm, poses, jacobian=False)
     assert np.array_equal(out3[:, 0], out[:, 0]) and np.all(out3[:, 1:] == 0)
+    c1, c2 = pg.get_cost_batch(cm, poses), pg.get_cost_batch(cm, poses[::-1].copy())[::-1]
+    assert np.array_equal(c1, c2)  # cooperative kernel: deterministic, independent of the batch position
 
 
 def test_batch_large_coordinates_protocol(dp, capi):
@@ -297,7 +320,7 @@ def test_batch_large_coordinates_protocol(dp, capi):
     poses = np.stack([rng.uniform(32, size - 32, n), rng.uniform(4750, 5250, n), rng.uniform(-math.pi, math.pi, n)], 1)
     pg = dp.pose_gradient(fx.RECT)
     cm = dp.Costmap(m)
-    out = pg.get_cost_batch(cm, poses)
+    out = batch_both(pg, cm, poses)
     oc = capi.CostData(fx.RECT, 2)
     shifted = oc.get_cost_batch(m, poses, shift=True, nthreads=capi.max_threads())
     assert fx.tol_ok(out, shifted).all()
@@ -321,7 +344,7 @@ def test_batch_border_and_degenerate_poses(dp):
     # paths must agree with std::round.  Exact ties under a rotation (e.g. theta = pi/2 at half-integer
     # positions, where cos is 6e-17 rather than 0) depend on the rounding order of k = C + R^T (p - t) and
     # differ between ANY two evaluation orders, including the reference's own; they are not tested.
-    out = pg.get_cost_batch(cm, poses)
+    out = batch_both(pg, cm, poses)
     for p, o in zip(poses, out):
         c, J = pg.get_cost(p, cells)
         assert fx.tol_ok(o[0], c, rel=1e-12, abs_=1e-12) and np.all(fx.tol_ok(o[1:], J, rel=1e-11, abs_=1e-11)), p
@@ -330,7 +353,7 @@ def test_batch_border_and_degenerate_poses(dp):
     full = dp.Costmap(np.full((64, 48), fx.LETHAL, np.uint8))  # every window cell lethal
     yy, xx = np.mgrid[0:64, 0:48]
     allc = np.stack([xx.ravel(), yy.ravel()], 1).astype(np.int32)
-    o = pg.get_cost_batch(full, poses[:5])
+    o = batch_both(pg, full, poses[:5])
     for p, r in zip(poses[:5], o):
         c, J = pg.get_cost(p, allc)
         assert fx.tol_ok(r[0], c, rel=1e-12, abs_=1e-12) and np.all(fx.tol_ok(r[1:], J, rel=1e-10, abs_=1e-10))
@@ -353,10 +376,62 @@ def test_batch_clip_invariant_on_a_fully_lethal_map(dp, name):
     thetas = [k * math.pi / 2 + sgn * e for k in range(-2, 3) for e in eps for sgn in (-1, 1)]
     poses = np.array([[rng.uniform(100, 220), rng.uniform(100, 220), th] for th in thetas] +
                      [[rng.uniform(-10, 330), rng.uniform(-10, 330), rng.uniform(-4, 4)] for _ in range(200)])
-    out = pg.get_cost_batch(full, poses)
+    out = batch_both(pg, full, poses)
     for p, o in zip(poses, out):
         c, J = pg.get_cost(p, allc)
         assert fx.tol_ok(o[0], c, rel=1e-11, abs_=1e-11) and np.all(fx.tol_ok(o[1:], J, rel=1e-9, abs_=1e-8)), p
+
+
+@pytest.mark.parametrize("half", [(150, 150), (240, 100), (252, 252)])
+def test_batch_clip_invariant_large_tables(dp, half):
+    """The fp32 round-off of the thread-per-pose kernel's window clip grows with the square of the table side (|t| up
+    to 2 win_max^2 before the cancellation): its margin scales with it (clip_margin_for) and dpose_pg_create caps tables
+    at 512 x 512.  Tables of 300 .. 510 cells, a fully lethal map, angles on both sides of clip_thr = 0.5 / win_max
+    where a strip starts to be clipped: a dropped valid cell or a cell that escaped the zero ring shows up against the
+    list kernel (which tests bounds per cell) and against the cooperative kernel (FP64 clip)."""
+    hx, hy = half
+    fp = np.array([[hx, hy], [-hx, hy], [-hx, -hy], [hx, -hy]], np.int32)
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(2))
+    cd = pg.get_data()
+    win_max = math.floor(math.hypot(cd.cols - 3, cd.rows - 3)) + 2
+    thr = 0.5 / win_max
+    side = 2 * max(hx, hy) + 400
+    full = dp.Costmap(np.full((side, side), fx.LETHAL, np.uint8))
+    yy, xx = np.mgrid[0:side, 0:side]
+    allc = dp.cell_vector_device.upload(np.stack([xx.ravel(), yy.ravel()], 1).astype(np.int32))
+    rng = np.random.default_rng(5)
+    eps = [thr * k for k in (0.0, 0.5, 0.999, 1.0, 1.001, 1.01, 1.1, 1.5, 2.0, 4.0)] + [5.2e-4, 1e-3]
+    thetas = [k * math.pi / 2 + sgn * e for k in (-1, 0, 1, 2) for e in eps for sgn in (-1, 1)] + [0.3, 0.78, 2.1, -2.9]
+    c0 = side / 2
+    poses = np.array([[c0 + rng.uniform(-30, 30), c0 + rng.uniform(-30, 30), th] for th in thetas])
+    out = batch_both(pg, full, poses)
+    for p, o in zip(poses, out):
+        c, J = pg.get_cost(p, allc)
+        assert fx.tol_ok(o[0], c, rel=1e-11, abs_=1e-9) and np.all(fx.tol_ok(o[1:], J, rel=1e-9, abs_=1e-6)), (p, o, c, J)
+    with pytest.raises(RuntimeError):  # beyond 512 x 512 cells the table is refused
+        dp.pose_gradient(np.array([[300, 10], [-300, 10], [-300, -10], [300, -10]], np.int32))
+
+
+@pytest.mark.parametrize("n,lanes", [(3000, 32), (9000, 16), (18000, 8), (37000, 4)])
+def test_batch_cooperative_kernel_every_group_size(dp, capi, n, lanes):
+    """the cooperative kernel picks G = 32 / 16 / 8 / 4 lanes per pose by batch size (148 x 1024 lanes per launch):
+    every instantiation against the oracle on translated-equivalent inputs, for a table whose windows fit one chunk
+    and one whose windows span several"""
+    m = fx.bernoulli_map(1200, 1000, 0.10, 21)
+    cm = dp.Costmap(m)
+    for name in ("rect_pad2", "ship_pad10"):
+        k = n if name == "rect_pad2" else max(n // 20, 1000) if lanes > 8 else n // 10
+        fp, pad = fx.FOOTPRINTS[name]
+        pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+        poses = fx.random_poses(n, 1200, 1000, 22, margin=-20.0 if name == "rect_pad2" else 80.0)
+        out = pg.get_cost_batch(cm, poses)
+        sub = np.random.default_rng(n).choice(n, k, replace=False)
+        inside = (np.minimum(poses[sub, 0], 1200 - poses[sub, 0]) > 80) & (np.minimum(poses[sub, 1], 1000 - poses[sub, 1]) > 80)
+        sub = sub[inside]
+        want = capi.CostData(fp, pad).get_cost_batch(m, poses[sub], shift=True, nthreads=capi.max_threads())
+        assert fx.tol_ok(out[sub], want).all() and (want[:, 0] > 0).mean() > 0.9
+        again = pg.get_cost_batch(cm, poses[::-1].copy())[::-1]
+        assert np.array_equal(out, again)  # independent of the batch position
 
 
 def test_batch_sees_map_updates(dp):
@@ -507,7 +582,7 @@ def test_batch_random_footprints_all_table_modes(dp, capi):
         oc = capi.CostData(fp, pad)
         sizes.append((oc.rows, oc.cols))
         poses = fx.random_poses(1200 if radius < 40 else 300, 900, 800, 100 + k, margin=float(2 * radius + 10))
-        out = pg.get_cost_batch(cm, poses)
+        out = batch_both(pg, cm, poses)
         want = oc.get_cost_batch(m, poses, shift=True, nthreads=capi.max_threads())
         ok = fx.tol_ok(out, want)
         assert ok.all(), (fp.tolist(), pad, np.argwhere(~ok)[:4], out[~ok.all(1)][:2], want[~ok.all(1)][:2])
