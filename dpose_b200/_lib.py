@@ -46,6 +46,9 @@ SYMBOLS = {
     "dpose_pg_get_cost_cells_device": (_i, [_vp, _vp, _vp, C.POINTER(_d), _vp]),
     "dpose_pg_get_cost_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
     "dpose_pg_get_cost_batch_device": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "dpose_pg_get_cost_batch_costs": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "dpose_pg_get_cost_sweep": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
+    "dpose_pg_get_cost_sweep_device": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "dpose_pg_get_cost_batch_multi": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _i]),
     "dpose_problem_create": (_i, [_vp, _vp, _pp]),
     "dpose_problem_destroy": (None, [_vp]),

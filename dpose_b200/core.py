@@ -222,6 +222,21 @@ class cost_data:
             pass
 
 
+class _Sweep(C.Structure):
+    """dpose_sweep"""
+    _fields_ = [("x0", C.c_double), ("dx", C.c_double), ("nx", C.c_uint64), ("y0", C.c_double), ("dy", C.c_double),
+                ("ny", C.c_uint64), ("theta0", C.c_double), ("dtheta", C.c_double), ("ntheta", C.c_uint64)]
+
+
+def sweep_poses(x, y, theta):
+    """the lattice of pose_gradient.get_cost_sweep as an (n, 3) array, same bits as the kernel generates"""
+    xs = x[0] + x[1] * np.arange(int(x[2]), dtype=np.float64)
+    ys = y[0] + y[1] * np.arange(int(y[2]), dtype=np.float64)
+    ts = theta[0] + theta[1] * np.arange(int(theta[2]), dtype=np.float64)
+    T, Y, X = np.meshgrid(ts, ys, xs, indexing="ij")
+    return np.stack([X.ravel(), Y.ravel(), T.ravel()], axis=1)
+
+
 class pose_gradient:
     """dpose_core.hpp:133-167."""
 
@@ -268,6 +283,34 @@ class pose_gradient:
         check(lib().dpose_pg_get_cost_batch(self._data._h, costmap._h, p.ctypes.data, p.shape[0],
                                             out.ctypes.data, int(bool(jacobian))))
         return out
+
+    def get_cost_batch_costs(self, costmap, poses, out=None):
+        """cost only: (n, 3) poses -> (n,) costs; 8 bytes per pose travel back instead of 32"""
+        p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+        if out is None:
+            out = np.empty(p.shape[0], dtype=np.float64)
+        assert out.flags.c_contiguous and out.dtype == np.float64 and out.shape == (p.shape[0],)
+        check(lib().dpose_pg_get_cost_batch_costs(self._data._h, costmap._h, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def get_cost_sweep(self, costmap, x, y, theta, jacobian=True, cost_only=False, out=None, d_out=None, stream=0):
+        """a pose LATTICE generated inside the kernel (nothing travels to the device): x, y, theta are (start, step,
+        count) triples; pose i = (x0 + dx ix, y0 + dy iy, theta0 + dtheta it), i = (it ny + iy) nx + ix.
+        Returns (ntheta, ny, nx, 4) results, or (ntheta, ny, nx) costs if cost_only.  d_out: device pointer instead of
+        a host result (asynchronous on `stream`)."""
+        sw = _Sweep(float(x[0]), float(x[1]), int(x[2]), float(y[0]), float(y[1]), int(y[2]), float(theta[0]),
+                    float(theta[1]), int(theta[2]))
+        shape = (sw.ntheta, sw.ny, sw.nx) + (() if cost_only else (4,))
+        if d_out is not None:
+            check(lib().dpose_pg_get_cost_sweep_device(self._data._h, costmap._h, C.byref(sw), C.c_void_p(int(d_out)),
+                                                       int(bool(jacobian)), int(bool(cost_only)), C.c_void_p(int(stream))))
+            return None
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        assert out.flags.c_contiguous and out.dtype == np.float64 and out.size == int(np.prod(shape))
+        check(lib().dpose_pg_get_cost_sweep(self._data._h, costmap._h, C.byref(sw), out.ctypes.data, int(bool(jacobian)),
+                                            int(bool(cost_only))))
+        return out.reshape(shape)
 
     def get_cost_batch_device(self, costmap, d_poses, n, d_out, jacobian=True, stream=0):
         """device pointers (ints), asynchronous on `stream` (a cudaStream_t as int)."""

@@ -38,6 +38,19 @@ static int check_device(int device) {
     return fail(DPOSE_ENODEV, "no CUDA device available (%s); libdpose_b200 has no CPU fallback",
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   if (device < 0 || device >= n) return fail(DPOSE_EINVAL, "device %d out of range [0, %d)", device, n);
+  // once per device: keep freed stream-ordered allocations (results of lethal_cells_within, the per-call workspaces of
+  // check_footprint and the solve) in the device's default pool instead of handing them back to the OS at every
+  // synchronisation — with the default threshold of 0 each call pays a fresh device allocation (~0.4 ms)
+  static std::once_flag once[64];
+  if (device < 64)
+    std::call_once(once[device], [device] {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    });
   return DPOSE_OK;
 }
 
@@ -563,9 +576,17 @@ int dpose_pg_get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, con
 // host buffers: H2D / kernel / D2H chunks on three streams, triple-buffered device staging.  The
 // streams, events and staging buffers live in the pose_gradient handle (created on first use, grown
 // on demand), so a call costs no cudaMalloc / cudaFree; concurrent calls on one handle serialise.
-int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n,
-                            double *out, int want_jacobian) {
-  if (!pg || !map || (n && (!poses || !out))) return fail(DPOSE_EINVAL, "NULL argument");
+// One body for the three host-buffer entry points: pose list or lattice in, n x 4 results or n costs out.
+struct HostBatch {
+  const double *poses = nullptr;      // n x 3, or null with `sweep`
+  const dpose_sweep *sweep = nullptr;
+  size_t n = 0;
+  double *out = nullptr;
+  int want_jacobian = 1, cost_only = 0;
+};
+
+static int batch_host(const dpose_pg *pg, const dpose_map *map, const HostBatch &hb) {
+  const size_t n = hb.n;
   if (n == 0) return DPOSE_OK;
   DPOSE_TRY(check_device(pg->device));
   DeviceGuard guard(pg->device);
@@ -588,16 +609,24 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
     ctx = static_cast<BatchCtx *>(p->batch_ctx);
   }
   std::lock_guard<std::mutex> call_lock(ctx->mu);
+  const size_t ow = hb.cost_only ? 1 : 4;  // doubles per pose that travel back
+  BatchSpec spec;
+  if (hb.sweep) spec.sweep = *hb.sweep;
+  spec.want_jacobian = hb.want_jacobian;
+  spec.cost_only = hb.cost_only;
   if (n <= kZeroCopyPoses) {  // latency path, see kZeroCopyPoses
     DPOSE_TRY(ctx->ensure_zc());
-    std::memcpy(ctx->zc_in(), poses, sizeof(double) * 3 * n);
-    int rc = get_cost_batch_device(pg, map, ctx->zc_in(), n, ctx->zc_out(), want_jacobian, ctx->s_k);
+    if (hb.poses) std::memcpy(ctx->zc_in(), hb.poses, sizeof(double) * 3 * n);
+    spec.d_poses = hb.poses ? ctx->zc_in() : nullptr;
+    spec.n = n;
+    spec.d_out = ctx->zc_out();
+    int rc = get_cost_batch_spec(pg, map, spec, ctx->s_k);
     if (rc == DPOSE_OK) {
       // A stream synchronisation, not a flag polled in the result page: the results are written by every thread of
       // the kernel, and only a synchronisation point guarantees that all of them have reached host memory.
       const cudaError_t e = cudaStreamSynchronize(ctx->s_k);
       if (e != cudaSuccess) rc = fail(DPOSE_ECUDA, "batched get_cost failed: %s", cudaGetErrorString(e));
-      if (rc == DPOSE_OK) std::memcpy(out, ctx->zc_out(), sizeof(double) * 4 * n);
+      if (rc == DPOSE_OK) std::memcpy(hb.out, ctx->zc_out(), sizeof(double) * ow * n);
     }
     if (rc != DPOSE_OK) cudaDeviceSynchronize();
     return rc;
@@ -605,28 +634,27 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
   const size_t chunk = std::min<size_t>(n, kChunkPoses);
   DPOSE_TRY(ctx->reserve(chunk));
   auto body = [&]() -> int {
-    if (n <= chunk) {  // one chunk: in-order on a single stream, no cross-stream events (latency path)
-      DPOSE_CUDA(cudaMemcpyAsync(ctx->d_p[0], poses, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->s_k));
-      DPOSE_TRY(get_cost_batch_device(pg, map, ctx->d_p[0], n, ctx->d_o[0], want_jacobian, ctx->s_k));
-      DPOSE_CUDA(cudaMemcpyAsync(out, ctx->d_o[0], sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, ctx->s_k));
-      DPOSE_CUDA(cudaStreamSynchronize(ctx->s_k));
-      return DPOSE_OK;
-    }
     size_t it = 0;
     for (size_t off = 0; off < n; off += chunk, ++it) {
       const int b = (int)(it % kBuf);
       const size_t m = std::min(chunk, n - off);
       if (it >= kBuf) {  // buffer reuse: its previous D2H must be complete
-        DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->out_done[b], 0));
+        DPOSE_CUDA(cudaStreamWaitEvent(hb.poses ? ctx->s_in : ctx->s_k, ctx->out_done[b], 0));
       }
-      DPOSE_CUDA(cudaMemcpyAsync(ctx->d_p[b], poses + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, ctx->s_in));
-      DPOSE_CUDA(cudaEventRecord(ctx->in_done[b], ctx->s_in));
-      DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_done[b], 0));
-      // volatile maps: the lethal plane is rebuilt for the first chunk only (once per call)
-      DPOSE_TRY(get_cost_batch_device(pg, map, ctx->d_p[b], m, ctx->d_o[b], want_jacobian, ctx->s_k, it > 0));
+      if (hb.poses) {
+        DPOSE_CUDA(cudaMemcpyAsync(ctx->d_p[b], hb.poses + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, ctx->s_in));
+        DPOSE_CUDA(cudaEventRecord(ctx->in_done[b], ctx->s_in));
+        DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_done[b], 0));
+      }
+      spec.d_poses = hb.poses ? ctx->d_p[b] : nullptr;
+      spec.sweep_base = off;
+      spec.n = m;
+      spec.d_out = ctx->d_o[b];
+      spec.hold_planes = it > 0;  // volatile maps: the lethal plane is rebuilt for the first chunk only (once per call)
+      DPOSE_TRY(get_cost_batch_spec(pg, map, spec, ctx->s_k));
       DPOSE_CUDA(cudaEventRecord(ctx->k_done[b], ctx->s_k));
       DPOSE_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->k_done[b], 0));
-      DPOSE_CUDA(cudaMemcpyAsync(out + 4 * off, ctx->d_o[b], sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, ctx->s_out));
+      DPOSE_CUDA(cudaMemcpyAsync(hb.out + ow * off, ctx->d_o[b], sizeof(double) * ow * m, cudaMemcpyDeviceToHost, ctx->s_out));
       DPOSE_CUDA(cudaEventRecord(ctx->out_done[b], ctx->s_out));
     }
     DPOSE_CUDA(cudaStreamSynchronize(ctx->s_out));
@@ -637,6 +665,56 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
   const int rc = body();
   if (rc != DPOSE_OK) cudaDeviceSynchronize();
   return rc;
+}
+
+static int sweep_count(const dpose_sweep *sw, size_t *n) {
+  if (!sw) return fail(DPOSE_EINVAL, "sweep is NULL");
+  const unsigned __int128 total = (unsigned __int128)sw->nx * sw->ny * sw->ntheta;
+  if (total > ((unsigned __int128)1 << 40)) return fail(DPOSE_EINVAL, "sweep lattice too large");
+  *n = (size_t)total;
+  return DPOSE_OK;
+}
+
+int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n,
+                            double *out, int want_jacobian) {
+  if (!pg || !map || (n && (!poses || !out))) return fail(DPOSE_EINVAL, "NULL argument");
+  HostBatch hb;
+  hb.poses = poses, hb.n = n, hb.out = out, hb.want_jacobian = want_jacobian;
+  return batch_host(pg, map, hb);
+}
+
+int dpose_pg_get_cost_batch_costs(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n,
+                                  double *cost) {
+  if (!pg || !map || (n && (!poses || !cost))) return fail(DPOSE_EINVAL, "NULL argument");
+  HostBatch hb;
+  hb.poses = poses, hb.n = n, hb.out = cost, hb.want_jacobian = 0, hb.cost_only = 1;
+  return batch_host(pg, map, hb);
+}
+
+int dpose_pg_get_cost_sweep(const dpose_pg *pg, const dpose_map *map, const dpose_sweep *sweep, double *out,
+                            int want_jacobian, int cost_only) {
+  if (!pg || !map) return fail(DPOSE_EINVAL, "NULL argument");
+  size_t n = 0;
+  DPOSE_TRY(sweep_count(sweep, &n));
+  if (n && !out) return fail(DPOSE_EINVAL, "out is NULL");
+  HostBatch hb;
+  hb.sweep = sweep, hb.n = n, hb.out = out, hb.want_jacobian = want_jacobian, hb.cost_only = cost_only != 0;
+  return batch_host(pg, map, hb);
+}
+
+int dpose_pg_get_cost_sweep_device(const dpose_pg *pg, const dpose_map *map, const dpose_sweep *sweep, double *d_out,
+                                   int want_jacobian, int cost_only, void *stream) {
+  if (!pg || !map) return fail(DPOSE_EINVAL, "NULL argument");
+  size_t n = 0;
+  DPOSE_TRY(sweep_count(sweep, &n));
+  if (n && !d_out) return fail(DPOSE_EINVAL, "d_out is NULL");
+  BatchSpec spec;
+  spec.sweep = *sweep;
+  spec.n = n;
+  spec.d_out = d_out;
+  spec.want_jacobian = want_jacobian;
+  spec.cost_only = cost_only != 0;
+  return get_cost_batch_spec(pg, map, spec, (cudaStream_t)stream);
 }
 
 int dpose_pg_get_cost_batch_multi(dpose_pg *const *pgs, dpose_map *const *maps, int ndev,

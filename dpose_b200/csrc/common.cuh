@@ -155,25 +155,49 @@ int get_cost_cells(const dpose_pg *pg, const double se2[3], const int2 *d_cells,
 int get_cost_cells_host(const dpose_pg *pg, const double se2[3], const int32_t *cells_xy, size_t n,
                         double *cost, double *J);
 uint64_t window_bytes_host(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n);
-// hold_planes: do not rebuild the lethal planes of a volatile map (the host-buffer entry point streams the
-// chunks of ONE call through this function and rebuilds for the first chunk only)
+// What a batched launch evaluates and where the results go.
+struct BatchSpec {
+  const double *d_poses = nullptr;  // n x 3 (x, y, theta), or null: the poses are the lattice `sweep`
+  dpose_sweep sweep = {};           // pose i = (x0 + dx ix, y0 + dy iy, theta0 + dtheta it), i = (it ny + iy) nx + ix
+  size_t sweep_base = 0;            // lattice index of this launch's first pose (chunked host-buffer calls)
+  size_t n = 0;
+  double *d_out = nullptr;          // n x 4 (cost, Jx, Jy, Jtheta), or n costs if cost_only
+  int want_jacobian = 1;
+  int cost_only = 0;
+  // do not rebuild the lethal plane of a volatile map (the host-buffer entry point streams the chunks of ONE call
+  // through this function and rebuilds for the first chunk only)
+  bool hold_planes = false;
+};
+int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream);
 int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses,
                           size_t n, double *d_out, int want_jacobian, cudaStream_t stream,
                           bool hold_planes = false);
+// lattice pose of index gi, the same bits as numpy's x0 + dx * ix (one rounded product, one rounded sum)
+__host__ __device__ inline void sweep_pose(const dpose_sweep &sw, size_t gi, double *x, double *y, double *th) {
+  const size_t ix = gi % sw.nx, r = gi / sw.nx;
+  const size_t iy = r % sw.ny, it = r / sw.ny;
+#ifdef __CUDA_ARCH__
+  *x = __dadd_rn(sw.x0, __dmul_rn(sw.dx, (double)ix));
+  *y = __dadd_rn(sw.y0, __dmul_rn(sw.dy, (double)iy));
+  *th = __dadd_rn(sw.theta0, __dmul_rn(sw.dtheta, (double)it));
+#else
+  *x = sw.x0 + sw.dx * (double)ix;
+  *y = sw.y0 + sw.dy * (double)iy;
+  *th = sw.theta0 + sw.dtheta * (double)it;
+#endif
+}
 // get_cost_batch_tile.cu: the lethal tile plane, the thread-per-pose batch kernel (large batches) and the dispatcher
 std::mutex &map_state_mutex();  // guards the lazily built per-handle state (coefficient images, tile-plane dirty flags)
 int tileplane_ensure(const dpose_map *map, cudaStream_t stream, bool hold_planes);
 int coef_abs_ensure(const dpose_pg *pg, cudaStream_t stream);
-int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
-                        double *d_out, int want_jacobian, cudaStream_t stream, bool hold_planes);
+int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream);
 // get_cost_batch_coop.cu: G lanes per pose, for batches too small to fill the GPU with one thread per pose; used when
 // the batch would get at least DPOSE_COOP_MIN_GROUP lanes per pose
 #ifndef DPOSE_COOP_MIN_GROUP
 #define DPOSE_COOP_MIN_GROUP 4
 #endif
 bool coop_batch_wanted(const dpose_pg *pg, size_t n);
-int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
-                        double *d_out, int want_jacobian, cudaStream_t stream, bool hold_planes);
+int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream);
 // host window geometry shared by the kernel launch code and dpose_pg_window_bytes
 struct WindowRect {
   int x0, y0, x1, y1;  // inclusive cell range, already clipped; empty if x1 < x0

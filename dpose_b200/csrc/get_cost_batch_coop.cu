@@ -16,10 +16,13 @@ constexpr int kCoopThreads = 128;
 
 struct CoopBatchArgs {
   CoopCtx ctx;
-  const double *poses;
+  const double *poses;  // null: lattice poses (sweep, sweep_base)
+  dpose_sweep sweep;
+  size_t sweep_base;
   double *out;
   size_t n;
   int out_aligned;
+  int cost_only;  // out holds n costs instead of n x 4
 };
 
 template <int G, bool kJac>
@@ -29,12 +32,22 @@ __global__ void __launch_bounds__(kCoopThreads) k_cost_batch_coop(CoopBatchArgs 
   const int tid = threadIdx.x, lane = tid & 31, g = lane & (G - 1);
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   constexpr int kPerCta = kCoopThreads / G;
+  // programmatic dependent launch: started while the predecessor in the stream (k_pack_tiles, or the kernel that wrote
+  // the poses) may still be running; nothing of its output is touched before this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (size_t i = (size_t)blockIdx.x * kPerCta + tid / G; i < a.n; i += (size_t)gridDim.x * kPerCta) {
-    const double *pp = a.poses + 3 * i;
-    const double tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
+    double tx, ty, th;
+    if (a.poses) {
+      const double *pp = a.poses + 3 * i;
+      tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
+    } else {
+      sweep_pose(a.sweep, a.sweep_base + i, &tx, &ty, &th);
+    }
     double r[4];
     coop_eval<G, kJac>(a.ctx, tx, ty, th, g, gmask, s_mask + tid, kCoopThreads, r);
-    if (g == 0) {
+    if (g == 0 && a.cost_only) {
+      a.out[i] = r[0];
+    } else if (g == 0) {
       double *o = a.out + 4 * i;
       if (a.out_aligned)
         asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(o), "d"(r[0]), "d"(r[1]), "d"(r[2]), "d"(r[3]) : "memory");
@@ -49,10 +62,19 @@ int launch_coop(const CoopBatchArgs &a, int want_jacobian, int sms, cudaStream_t
   const size_t per_cta = kCoopThreads / G;
   const size_t want = (a.n + per_cta - 1) / per_cta;
   const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sms * 16);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kCoopThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (want_jacobian)
-    k_cost_batch_coop<G, true><<<grid, kCoopThreads, 0, stream>>>(a);
+    DPOSE_CUDA(cudaLaunchKernelEx(&cfg, k_cost_batch_coop<G, true>, a));
   else
-    k_cost_batch_coop<G, false><<<grid, kCoopThreads, 0, stream>>>(a);
+    DPOSE_CUDA(cudaLaunchKernelEx(&cfg, k_cost_batch_coop<G, false>, a));
   DPOSE_LAUNCHED();
   return DPOSE_OK;
 }
@@ -89,18 +111,22 @@ bool coop_batch_wanted(const dpose_pg *pg, size_t n) {
   return coop_group(n, sms) >= DPOSE_COOP_MIN_GROUP;
 }
 
-int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n, double *d_out,
-                        int want_jacobian, cudaStream_t stream, bool hold_planes) {
+int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream) {
+  const size_t n = spec.n;
+  const int want_jacobian = spec.want_jacobian && !spec.cost_only;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
   DPOSE_TRY(coef_abs_ensure(pg, stream));
-  DPOSE_TRY(tileplane_ensure(map, stream, hold_planes));
+  DPOSE_TRY(tileplane_ensure(map, stream, spec.hold_planes));
   CoopBatchArgs a;
   a.ctx = coop_ctx(pg, map);
-  a.poses = d_poses;
-  a.out = d_out;
+  a.poses = spec.d_poses;
+  a.sweep = spec.sweep;
+  a.sweep_base = spec.sweep_base;
+  a.out = spec.d_out;
   a.n = n;
-  a.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 31u) == 0;
+  a.out_aligned = (reinterpret_cast<uintptr_t>(spec.d_out) & 31u) == 0;
+  a.cost_only = spec.cost_only;
   switch (coop_group(n, sms)) {
     case 32: return launch_coop<32>(a, want_jacobian, sms, stream);
     case 16: return launch_coop<16>(a, want_jacobian, sms, stream);

@@ -58,6 +58,9 @@ __device__ __forceinline__ unsigned lethal_bits16(const uint4 v) {
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ map, size_t pitch, uint32_t size_y,
                                                     uint32_t *__restrict__ tiles, uint32_t ntx, uint32_t ty0,
                                                     uint32_t ty1) {
+  // programmatic dependent launch: the batch kernel queued behind this one may start its prologue (staging the
+  // coefficient image) now; it waits for this grid's completion (griddepcontrol.wait) before it reads a tile
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t quads = (ntx + 3) / 4;  // groups of 4 tile columns
   const size_t n_warps = (size_t)quads * (ty1 - ty0);
   const uint32_t lane = threadIdx.x & 31;
@@ -170,8 +173,11 @@ struct TileArgs {
   int size_x, size_y;
   const uint32_t *tiles;
   uint32_t ntx, nty;
-  const double *poses;
+  const double *poses;  // null: lattice poses (sweep, sweep_base)
+  dpose_sweep sweep;
+  size_t sweep_base;
   double *out;
+  int cost_only;  // out holds n costs instead of n x 4
   size_t n;
   cudaTextureObject_t tex_hi;  // texture mode: second halves of the patch polynomials (int4 texels)
   const int4 *planes;          // the same buffer as a plain pointer (DPOSE_TILE_LDG experiment)
@@ -267,7 +273,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     }
   }
   __syncthreads();  // barrier initialised before anyone polls it
-  {
+  // The wait for the image is deferred to the first cell walk: phase 1 of the first pose needs no coefficients, so the
+  // ~109 KB of bulk copies (all 148 CTAs pull the same image out of L2 at once) land behind ~600 instructions of useful
+  // work instead of in front of them — 2-3 us of a 15 us launch on a solver-sized batch.
+  // The barrier is never re-armed, so once phase 0 has completed every later wait returns at its first poll: the wait is
+  // simply issued in front of every walk (3 instructions of ~2600 per pose, no flag register).
+  auto wait_staged = [&]() {
     // try_wait suspends for a hardware time slice and returns false on time-out: loop until the bytes have landed.
     // No trap after a bounded number of polls — a CTA delayed by time-slicing / MPS / a debugger must not take the
     // whole context down; the copies were issued by this CTA, so completion is guaranteed.
@@ -280,7 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
           : "=r"(ok)
           : "r"(bar)
           : "memory");
-  }
+  };
+  // Programmatic dependent launch: this kernel may have been started while its predecessor in the stream (k_pack_tiles
+  // rebuilding the tile plane, or the kernel that wrote the poses) was still running, so that the launch latency and the
+  // staging above overlap it.  Nothing of the predecessor's output is touched before this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   constexpr int kSlots = kRows + 7;
   // DPOSE_TILE_COMPACT 1: only the kRows rows that can belong to a chunk are stored (less shared memory, room
@@ -302,12 +317,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   const float hi_u = (float)a.g.cols - 3.0f, hi_v = (float)a.g.rows - 3.0f;  // 0 <= k' < dim - 3
   const double cx15 = a.g.cx - 1.5, cy15 = a.g.cy - 1.5;
 
-  if ((uint32_t)tid >= a.stride) return;  // no barrier below: threads without poses just leave
+  if ((uint32_t)tid >= a.stride) {  // no barrier below: threads without poses just leave — once the image has landed
+    wait_staged();                  // (a CTA must not exit with bulk copies into its shared memory in flight)
+    return;
+  }
   for (size_t base = (size_t)blockIdx.x * a.stride; base < a.n; base += (size_t)gridDim.x * a.stride) {
     const size_t idx = base + tid;
     if (idx >= a.n) break;
-    const double *pp = a.poses + 3 * idx;
-    const double tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
+    double tx, ty, th;
+    if (a.poses) {
+      const double *pp = a.poses + 3 * idx;
+      tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
+    } else {
+      sweep_pose(a.sweep, a.sweep_base + idx, &tx, &ty, &th);
+    }
     double s, c;
     sincos(th, &s, &c);
     const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y);
@@ -433,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
         const double kuc = fma(c, dcb, fma(s, drb, ku0)), kvc = fma(c, drb, fma(-s, dcb, kv0));
         unsigned mask = 0u;
         int row = 0;
+        wait_staged();
         while (true) {
 #if DPOSE_TILE_WALK == 1
           // branch-free row advance: selects and one predicated load instead of a nested branch
@@ -499,13 +523,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
       jy = -s * acc.su - c * acc.sv;
       jt = acc.st - cy15 * acc.su + cx15 * acc.sv;
     }
-    if (a.out_aligned) {
+    if (a.cost_only) {
+      a.out[idx] = acc.f;
+    } else if (a.out_aligned) {
       stg_result(a.out + 4 * idx, acc.f, jx, jy, jt);
     } else {
       double *o = a.out + 4 * idx;
       o[0] = acc.f, o[1] = jx, o[2] = jy, o[3] = jt;
     }
   }
+  wait_staged();  // a thread that met only empty windows: still no exit before the copies have landed
 }
 
 
@@ -513,7 +540,17 @@ template <bool kJac, int kThreads, int kRepShift, int kRows>
 int launch_tile4(const TileArgs &a, int grid, size_t smem_bytes, cudaStream_t stream) {
   auto kern = k_cost_batch_tile<kJac, kThreads, kRepShift, kRows>;
   DPOSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  kern<<<grid, kThreads, smem_bytes, stream>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DPOSE_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   DPOSE_LAUNCHED();
   return DPOSE_OK;
 }
@@ -606,8 +643,11 @@ static float clip_margin_for(int win_max) { return 0.02f + 8.0f * (float)win_max
 
 // Tables with fewer than 4 rows or columns have no valid patch (dpose_core.cpp:181-182 needs 2 <= k_upper <= dim - 2):
 // every cost is 0, like an empty map.  Everything else runs k_cost_batch_tile.
-int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n, double *d_out,
-                        int want_jacobian, cudaStream_t stream, bool hold_planes) {
+int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream) {
+  const size_t n = spec.n;
+  double *d_out = spec.d_out;
+  const int want_jacobian = spec.want_jacobian && !spec.cost_only;
+  const bool hold_planes = spec.hold_planes;
   int sms = 148, smem_optin = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pg->device);
@@ -693,8 +733,11 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
   a.tiles = map->d_tiles;
   a.ntx = map->tiles_ntx;
   a.nty = map->tiles_nty;
-  a.poses = d_poses;
+  a.poses = spec.d_poses;
+  a.sweep = spec.sweep;
+  a.sweep_base = spec.sweep_base;
   a.out = d_out;
+  a.cost_only = spec.cost_only;
   a.n = n;
   a.tex_hi = (cudaTextureObject_t)p->tex_hi;
   a.planes = reinterpret_cast<const int4 *>(p->d_coef_hi);
@@ -715,18 +758,28 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const double *
                        : launch_tile1<false>(a, threads, rep_shift, rows, grid, smem_bytes, stream);
 }
 
-int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n, double *d_out,
-                          int want_jacobian, cudaStream_t stream, bool hold_planes) {
-  if (n == 0) return DPOSE_OK;
+int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream) {
+  if (spec.n == 0) return DPOSE_OK;
   if (pg->device != map->device) return fail(DPOSE_EINVAL, "pose_gradient and map live on different devices");
   DeviceGuard guard(pg->device);
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
   if (!map->d_tiles || pg->rows < 4 || pg->cols < 4) {  // empty map / no valid patch: every sum is empty
-    DPOSE_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 4 * n, stream));
+    DPOSE_CUDA(cudaMemsetAsync(spec.d_out, 0, sizeof(double) * (spec.cost_only ? 1 : 4) * spec.n, stream));
     return DPOSE_OK;
   }
-  if (coop_batch_wanted(pg, n)) return get_cost_batch_coop(pg, map, d_poses, n, d_out, want_jacobian, stream, hold_planes);
-  return get_cost_batch_tile(pg, map, d_poses, n, d_out, want_jacobian, stream, hold_planes);
+  if (coop_batch_wanted(pg, spec.n)) return get_cost_batch_coop(pg, map, spec, stream);
+  return get_cost_batch_tile(pg, map, spec, stream);
+}
+
+int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n, double *d_out,
+                          int want_jacobian, cudaStream_t stream, bool hold_planes) {
+  BatchSpec spec;
+  spec.d_poses = d_poses;
+  spec.n = n;
+  spec.d_out = d_out;
+  spec.want_jacobian = want_jacobian;
+  spec.hold_planes = hold_planes;
+  return get_cost_batch_spec(pg, map, spec, stream);
 }
 
 }  // namespace dpose

@@ -2,16 +2,23 @@
 //
 // Host: clamp the ring into the map, trace its four edges (integer Bresenham, ROS
 // raytraceLine-compatible) into per-row [xmin, xmax] intervals (to_rays, :106-115).
-// Device: stream compaction over the uint8 grid, two sweeps like the reference
-// (:143-155 count, :167-179 write) with an exclusive scan between them:
-//   k_count : one warp per 2 KB row tile, four aligned 16-byte loads per lane (all in flight before the
-//             first use), byte compare against 254 -> 16-bit lane masks -> popc -> per-tile count
-//   k_scan  : two-level exclusive scan of the tile counts
-//   k_write : same tiling; one warp prefix per 512-byte piece, each lane emits its (x, y)
+// Device: stream compaction.  The reference sweeps the uint8 grid twice (:143-155 count, :167-179 write).  Here the
+// uint8 map is read ONCE — by k_pack_tiles (get_cost_batch_tile.cu: 16-byte coalesced loads, byte compare against 254),
+// and only for the rows that changed since the lethal tile plane was last built (all rows of a volatile map, none of a
+// clean one) — and both sweeps run over that 1-bit-per-cell plane, 1/8 of the bytes and resident in the 126 MB L2:
+//   k_count : one warp per (tile row, chunk of 32 tiles): one 256-bit load per lane = 1 KB of contiguous plane per warp,
+//             each row word clipped to the row's interval, popc, packed butterflies -> the counts of the 8
+//             (row, 1024-cell chunk) units
+//   k_scan  : two-level exclusive scan of the unit counts (row-major order)
+//   k_write : same load; row by row every lane expands its word into x offsets in shared memory, then the warp writes
+//             the unit's (x, y) pairs as consecutive 8-byte stores (full sectors)
+//   k_extract_small : boxes of up to 4096 units (the plugin's search box, a footprint's box) in one launch of one CTA
 // Output order is row-major (y ascending, x ascending) and deterministic.
-// HBM traffic: 2 x box bytes read + 8 B per lethal cell written.
-// Boxes up to 4 M cells (the plugin's search box is ~1e4) size the result by the box and run both sweeps back
-// to back with one synchronisation; larger boxes read the total back before allocating.
+// HBM traffic, 10000 x 10000 map at 10 % lethal: 100 MB read + 12.6 MB written by the pack (if the plane is stale),
+// 2 x 12.6 MB of plane read (L2 hits right after the pack), 80 MB of cells written — §8(d)'s 180 MB plus the plane.
+// The result buffer is sized by the box while that is small (<= 4 M cells), otherwise by what the previous extraction on
+// the same map returned (+25 %): one synchronisation per call; a first call on a large box, or one whose estimate
+// was too small, reads the total back before the write sweep.
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -63,79 +70,88 @@ size_t host_raytrace(const int32_t begin[2], const int32_t end[2], int32_t *out_
 
 namespace {
 
-constexpr int kSub = 4;                  // 512-byte pieces per warp tile: 4 independent 16-byte loads per lane in flight
-constexpr int kTileBytes = 512 * kSub;   // one warp x 4 x 16 B
+// One unit of work = one map row x one chunk of 32 tile columns (1024 cells): a warp, one plane word per lane.
+// A CTA of 8 warps takes the 8 rows of one tile row of one chunk: its 32 tiles are 1 KB of contiguous plane.
+constexpr int kChunkTiles = 32;
 constexpr int kWarpsPerCta = 8;
-constexpr int kScanChunk = 2048;  // tiles per scan CTA (512 threads x 4)
+constexpr int kScanChunk = 2048;  // units per scan CTA (512 threads x 4)
 
 struct RowSpan {
   int xmin, xmax;
 };
 
 struct LethalArgs {
-  const uint8_t *map;
-  size_t pitch;
-  const RowSpan *spans;  // nrows
+  const uint32_t *tiles;  // lethal tile plane (common.cuh)
+  uint32_t ntx;
+  const RowSpan *spans;  // nrows, indexed by y - y_lo
   int y_lo, nrows;
-  int x_base;   // 16-byte aligned
-  int tiles_x;  // tiles per row
-  long long n_tiles;
+  int ty0;        // first tile row (y_lo >> 3)
+  int tx0;        // first tile column of chunk 0
+  int chunks_x;   // chunks per row
+  int n_tile_rows;
+  long long n_units;  // nrows * chunks_x, unit = (y - y_lo) * chunks_x + chunk
 };
 
-// 16 bytes -> bit i set iff byte i == 254 and x_first + i in [xmin, xmax]
-__device__ __forceinline__ unsigned lethal_mask16(const uint4 v, int x_first, int xmin, int xmax) {
-  const unsigned k = 0xFEFEFEFEu;
-  unsigned m = 0;
-  const unsigned w[4] = {v.x, v.y, v.z, v.w};
+// One warp per (tile row, chunk of 32 tile columns): lane l fetches tile tx0 + 32 chunk + l with ONE 256-bit load — the
+// warp's 32 tiles are 1 KB of contiguous plane — and holds the 8 row words of that tile.  Rows outside the box and
+// cells outside a row's interval are masked out.  No shared-memory staging, no block barrier: every warp has its own
+// kilobyte in flight (8 warps per CTA, 8 CTAs per SM: 64 KB of loads in flight per SM).
+struct Tile8 {
+  unsigned w[8];
+};
+__device__ __forceinline__ bool warp_tile(const LethalArgs &a, long long warp_id, int lane, Tile8 *t, int *ty_out, int *chunk_out) {
+  const long long n_warps = (long long)a.n_tile_rows * a.chunks_x;
+  if (warp_id >= n_warps) return false;
+  const int tr = (int)(warp_id / a.chunks_x), chunk = (int)(warp_id - (long long)tr * a.chunks_x);
+  const int ty = a.ty0 + tr, tx = a.tx0 + chunk * kChunkTiles + lane;
+  *ty_out = ty;
+  *chunk_out = chunk;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const unsigned eq = __vcmpeq4(w[i], k) & 0x01010101u;  // bit 0/8/16/24
-    m |= (((eq * 0x00204081u) >> 21) & 0xFu) << (4 * i);
+  for (int r = 0; r < 8; ++r) t->w[r] = 0u;
+  if ((uint32_t)tx < a.ntx) {  // tiles past the plane's width read as zero
+    const uint32_t *p = a.tiles + ((size_t)ty * a.ntx + (size_t)tx) * 8;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(t->w[0]), "=r"(t->w[1]), "=r"(t->w[2]), "=r"(t->w[3]), "=r"(t->w[4]), "=r"(t->w[5]), "=r"(t->w[6]),
+                   "=r"(t->w[7])
+                 : "l"(p));
   }
-  // clip to the row interval
-  const int lo = xmin - x_first, hi = xmax - x_first;  // valid bit range [lo, hi]
-  const unsigned lo_mask = lo <= 0 ? 0xFFFFu : (0xFFFFu << lo) & 0xFFFFu;
-  const unsigned hi_mask = hi >= 15 ? 0xFFFFu : (0xFFFFu >> (15 - hi));
-  return m & lo_mask & hi_mask;
+  const int x0 = tx * 32;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int yr = ty * 8 + r - a.y_lo;
+    unsigned m = 0u;
+    if (yr >= 0 && yr < a.nrows) {
+      const RowSpan sp = a.spans[yr];
+      const int lo = sp.xmin - x0, hi = sp.xmax - x0;  // valid bit range [lo, hi]; an empty interval has xmin > xmax
+      if (!(hi < 0 || lo > 31 || sp.xmin > sp.xmax)) {
+        m = t->w[r];
+        if (lo > 0) m &= 0xffffffffu << lo;
+        if (hi < 31) m &= 0xffffffffu >> (31 - hi);
+      }
+    }
+    t->w[r] = m;
+  }
+  return true;
 }
 
-// the lane's kSub 16-byte pieces of a tile: piece c covers x = x_first + 512 c ... + 15 of row y; all loads are
-// issued before the first use
-__device__ __forceinline__ void tile_lane_masks(const LethalArgs &a, long long tile, int lane, unsigned m[kSub],
-                                                int *x_first, int *y) {
-  const int r = (int)(tile / a.tiles_x), j = (int)(tile - (long long)r * a.tiles_x);
-  const RowSpan s = a.spans[r];
-  const int x0 = a.x_base + j * kTileBytes + lane * 16;
-  *x_first = x0;
-  *y = a.y_lo + r;
-  const uint8_t *row = a.map + (size_t)(a.y_lo + r) * a.pitch;
-  uint4 v[kSub];
-  bool live[kSub];
-#pragma unroll
-  for (int c = 0; c < kSub; ++c) {
-    const int xc = x0 + 512 * c;
-    // xc is 16-byte aligned; a piece that overlaps the span starts below size_x <= pitch (pitch % 16 == 0)
-    live[c] = s.xmin <= s.xmax && xc <= s.xmax && xc + 15 >= s.xmin;
-    v[c] = make_uint4(0u, 0u, 0u, 0u);
-    if (live[c]) v[c] = __ldg(reinterpret_cast<const uint4 *>(row + xc));
-  }
-#pragma unroll
-  for (int c = 0; c < kSub; ++c) m[c] = live[c] ? lethal_mask16(v[c], x0 + 512 * c, s.xmin, s.xmax) : 0u;
-}
-
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_count(LethalArgs a, unsigned *tile_count) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_count(LethalArgs a, unsigned *unit_count) {
   const int lane = threadIdx.x & 31;
-  const long long tile = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (tile >= a.n_tiles) return;
-  int xf, y;
-  unsigned m[kSub];
-  tile_lane_masks(a, tile, lane, m, &xf, &y);
-  unsigned c = 0;
+  Tile8 t;
+  int ty, chunk;
+  if (!warp_tile(a, (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5), lane, &t, &ty, &chunk)) return;
+  // eight counts per lane (each <= 32, their warp sums <= 1024): two per register, four butterflies instead of eight
+  unsigned c[4];
 #pragma unroll
-  for (int k = 0; k < kSub; ++k) c += __popc(m[k]);
+  for (int q = 0; q < 4; ++q) c[q] = __popc(t.w[2 * q]) | (__popc(t.w[2 * q + 1]) << 16);
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-  if (lane == 0) tile_count[tile] = c;
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[q] += __shfl_xor_sync(0xffffffffu, c[q], off);
+  if (lane < 8) {
+    const int yr = ty * 8 + lane - a.y_lo;
+    const unsigned v = (c[lane >> 1] >> ((lane & 1) * 16)) & 0xffffu;
+    if (yr >= 0 && yr < a.nrows) unit_count[(long long)yr * a.chunks_x + chunk] = v;
+  }
 }
 
 // level 1: each CTA turns kScanChunk counts into exclusive prefixes + one chunk total
@@ -215,33 +231,132 @@ __global__ void __launch_bounds__(1024) k_scan_totals(unsigned long long *chunk_
   if (tid == 0) *grand_total = carry;
 }
 
+// Emit, row by row of the warp's tile row: every lane expands its word into x offsets in the warp's staging row
+// (shared memory, 2 bytes per cell), then the warp writes the (x, y) pairs of the unit as consecutive 8-byte stores —
+// full 32-byte sectors instead of the lane-strided scatter of a per-lane emit loop.  `cap`: cells the result buffer
+// holds; a unit that would run past it writes nothing (the host sees total > cap and repeats the sweep with an exact
+// allocation).
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-    k_write(LethalArgs a, const unsigned *tile_prefix, const unsigned long long *chunk_offset, int2 *out) {
-  const int lane = threadIdx.x & 31;
-  const long long tile = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (tile >= a.n_tiles) return;
-  int xf, y;
-  unsigned m[kSub];
-  tile_lane_masks(a, tile, lane, m, &xf, &y);
-  // x ascending inside the tile = piece-major, then lane, then bit: one warp prefix per piece
-  unsigned long long base = chunk_offset[tile / kScanChunk] + tile_prefix[tile];
+    k_write(LethalArgs a, const unsigned *unit_prefix, const unsigned long long *chunk_offset, int2 *out,
+            unsigned long long cap) {
+  __shared__ unsigned short s_stage[kWarpsPerCta][kChunkTiles * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  Tile8 t;
+  int ty, chunk;
+  if (!warp_tile(a, (long long)blockIdx.x * kWarpsPerCta + w, lane, &t, &ty, &chunk)) return;
+  const int xc = (a.tx0 + chunk * kChunkTiles) * 32;
 #pragma unroll
-  for (int k = 0; k < kSub; ++k) {
-    const unsigned c = __popc(m[k]);
+  for (int r = 0; r < 8; ++r) {
+    unsigned m = t.w[r];
+    const unsigned c = __popc(m);
+    unsigned inc = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += v;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) continue;  // warp-uniform (also for rows outside the box)
+    unsigned pos = inc - c;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      s_stage[w][pos++] = (unsigned short)(lane * 32 + b);
+    }
+    __syncwarp();
+    const int y = ty * 8 + r;
+    const long long unit = (long long)(y - a.y_lo) * a.chunks_x + chunk;
+    const unsigned long long base = chunk_offset[unit / kScanChunk] + unit_prefix[unit];
+    if (base + total <= cap)
+      for (unsigned k = lane; k < total; k += 32) out[base + k] = make_int2(xc + (int)s_stage[w][k], y);
+    __syncwarp();  // the staging row is reused by the next row
+  }
+}
+
+// Small boxes (the plugin's search box, a footprint's rotated box): count, scan and emit in ONE launch of one CTA —
+// the multi-kernel pipeline above costs four launches, which is all a 100 x 100 box is.
+constexpr int kSmallUnits = 4096;
+__global__ void __launch_bounds__(1024) k_extract_small(LethalArgs a, int2 *out, unsigned long long cap,
+                                                        unsigned long long *grand_total) {
+  __shared__ unsigned s_count[kSmallUnits];
+  __shared__ unsigned s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto word_of = [&](int u, int *y, int *x0) -> unsigned {
+    const int yr = u / a.chunks_x, chunk = u - yr * a.chunks_x;
+    *y = a.y_lo + yr;
+    const int tx = a.tx0 + chunk * kChunkTiles + lane;
+    *x0 = tx * 32;
+    unsigned m = 0u;
+    if ((uint32_t)tx < a.ntx) m = __ldg(a.tiles + ((size_t)(*y >> 3) * a.ntx + (size_t)tx) * 8 + (*y & 7));
+    const RowSpan sp = a.spans[yr];
+    const int lo = sp.xmin - *x0, hi = sp.xmax - *x0;
+    if (hi < 0 || lo > 31 || sp.xmin > sp.xmax) return 0u;
+    if (lo > 0) m &= 0xffffffffu << lo;
+    if (hi < 31) m &= 0xffffffffu >> (31 - hi);
+    return m;
+  };
+  const int n_units = (int)a.n_units;
+  for (int u = warp; u < n_units; u += 32) {
+    int y, x0;
+    unsigned c = __popc(word_of(u, &y, &x0));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if (lane == 0) s_count[u] = c;
+  }
+  __syncthreads();
+  {  // exclusive scan of s_count[0 .. n_units) in place: 4 per thread, warp scan, scan of the warp sums
+    unsigned v[4];
+    unsigned mine = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = tid * 4 + i < n_units ? s_count[tid * 4 + i] : 0u;
+      mine += v[i];
+    }
+    unsigned inc = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned wv = s_warp[lane];
+      unsigned winc = wv;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, winc, off);
+        if (lane >= off) winc += t;
+      }
+      s_warp[lane] = winc - wv;
+      if (lane == 31) *grand_total = winc;
+    }
+    __syncthreads();
+    unsigned ex = s_warp[warp] + inc - mine;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (tid * 4 + i < n_units) s_count[tid * 4 + i] = ex;
+      ex += v[i];
+    }
+  }
+  __syncthreads();
+  for (int u = warp; u < n_units; u += 32) {
+    int y, x0;
+    unsigned m = word_of(u, &y, &x0);
+    const unsigned c = __popc(m);
     unsigned inc = c;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
       if (lane >= off) inc += t;
     }
-    unsigned long long dst = base + (inc - c);
-    unsigned mk = m[k];
-    while (mk) {
-      const int b = __ffs(mk) - 1;
-      mk &= mk - 1;
-      out[dst++] = make_int2(xf + 512 * k + b, y);
+    unsigned long long dst = (unsigned long long)s_count[u] + (inc - c);
+    while (m) {  // ~3 cells per lane at 10 % density; a staged emit does not pay at this size
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (dst < cap) out[dst] = make_int2(x0 + b, y);
+      ++dst;
     }
-    base += __shfl_sync(0xffffffffu, inc, 31);
   }
 }
 
@@ -261,18 +376,14 @@ struct LethalWs {
   size_t chunks_cap = 0;
   unsigned long long *h_total = nullptr;  // pinned
   float last_kernel_us = 0.f;
+  unsigned long long hint = 0;  // cells the last extraction on this map returned
 
   int init(int device) {
     DPOSE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     DPOSE_CUDA(cudaEventCreate(&ev0));
     DPOSE_CUDA(cudaEventCreate(&ev1));
     DPOSE_CUDA(cudaHostAlloc(&h_total, sizeof(*h_total), cudaHostAllocDefault));
-    // keep freed result buffers in the device's default pool instead of returning them to the OS
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+    (void)device;  // the default pool's release threshold is raised once per device in api.cu (check_device)
     return DPOSE_OK;
   }
   int reserve(size_t rows, size_t tiles, size_t chunks) {
@@ -320,7 +431,7 @@ struct LethalWs {
 };
 
 std::mutex g_ws_mu;  // guards creation of the per-map workspace
-constexpr unsigned long long kSingleSyncCells = 1ull << 22;  // boxes up to 4 M cells: result sized by the box (32 MB)
+constexpr unsigned long long kBoxSizedCells = 1ull << 22;  // boxes up to 4 M cells: result sized by the box (32 MB)
 
 }  // namespace
 
@@ -340,7 +451,7 @@ float lethal_last_kernel_us(const dpose_map *map) {
 int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, size_t *n) {
   *d_cells = nullptr;
   *n = 0;
-  if (map->size_x == 0 || map->size_y == 0) return DPOSE_OK;  // dpose_costmap.cpp:124-125
+  if (map->size_x == 0 || map->size_y == 0 || !map->d_tiles) return DPOSE_OK;  // dpose_costmap.cpp:124-125
   // clamp the ring into the map (:121, :128-129)
   int32_t ring[10];
   for (int i = 0; i < 5; ++i) {
@@ -394,56 +505,76 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
   if (gx_min > gx_max) return DPOSE_OK;  // degenerate ring (all four edges empty)
 
   LethalArgs a;
-  a.map = map->d_data;
-  a.pitch = map->pitch;
+  a.tiles = map->d_tiles;
+  a.ntx = map->tiles_ntx;
   a.y_lo = y_lo;
   a.nrows = nrows;
-  a.x_base = gx_min & ~15;
-  a.tiles_x = (gx_max - a.x_base) / kTileBytes + 1;
-  a.n_tiles = (long long)nrows * a.tiles_x;
-  const int n_chunks = (int)((a.n_tiles + kScanChunk - 1) / kScanChunk);
-  DPOSE_TRY(ws->reserve((size_t)nrows, (size_t)a.n_tiles, (size_t)n_chunks));
+  a.ty0 = y_lo >> 3;
+  a.n_tile_rows = (y_hi >> 3) - a.ty0 + 1;
+  a.tx0 = gx_min >> 5;
+  a.chunks_x = ((gx_max >> 5) - a.tx0) / kChunkTiles + 1;
+  a.n_units = (long long)nrows * a.chunks_x;
+  const int n_chunks = (int)((a.n_units + kScanChunk - 1) / kScanChunk);
+  DPOSE_TRY(ws->reserve((size_t)nrows, (size_t)a.n_units, (size_t)n_chunks));
   a.spans = ws->d_spans;
 
   cudaStream_t st = ws->stream;
   int2 *d_out = nullptr;
   auto body = [&]() -> int {
     DPOSE_CUDA(cudaMemcpyAsync(ws->d_spans, ws->h_spans, sizeof(RowSpan) * nrows, cudaMemcpyHostToDevice, st));
-    const unsigned grid = (unsigned)((a.n_tiles + kWarpsPerCta - 1) / kWarpsPerCta);
     DPOSE_CUDA(cudaEventRecord(ws->ev0, st));
-    k_count<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_count);
-    DPOSE_LAUNCHED();
-    k_scan_chunks<<<n_chunks, 512, 0, st>>>(ws->d_count, ws->d_prefix, ws->d_chunk, a.n_tiles);
-    DPOSE_LAUNCHED();
-    k_scan_totals<<<1, 1024, 0, st>>>(ws->d_chunk, n_chunks, ws->d_chunk + n_chunks);
-    DPOSE_LAUNCHED();
-    DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_chunk + n_chunks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    unsigned long long total;
-    if (box_cells <= kSingleSyncCells) {
-      // small boxes (the plugin's search box): size the result by the box and run both sweeps back to back —
-      // one synchronisation per call instead of a host round trip between the sweeps
-      DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * box_cells, st));
-      k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_chunk, d_out);
+    // the ONE read of the uint8 map: the lethal tile plane, rebuilt for the rows that changed (every row of a volatile
+    // map); a clean plane costs nothing here.  Both sweeps below read the 1-bit plane (1/8 of the map's bytes).
+    DPOSE_TRY(tileplane_ensure(map, st, false));
+    // capacity of the result buffer: the box itself while that is small, else what the last call on this map needed
+    // (+25 %); a first call on a large box sizes the result exactly after the count sweep (one more synchronisation)
+    unsigned long long cap = box_cells <= kBoxSizedCells ? box_cells : (ws->hint ? ws->hint + ws->hint / 4 + 4096 : 0);
+    cap = std::min(cap, box_cells);
+    unsigned long long total = 0;
+    if (a.n_units <= kSmallUnits) {  // one launch: count, scan and emit in one CTA; <= 4 M cells, sized by the box
+      cap = box_cells;
+      DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
+      k_extract_small<<<1, 1024, 0, st>>>(a, d_out, cap, ws->d_chunk);
       DPOSE_LAUNCHED();
+      DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_chunk, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
       DPOSE_CUDA(cudaStreamSynchronize(st));
       total = *ws->h_total;
-      if (total == 0) {  // :157-158
-        cudaFreeAsync(d_out, st);
-        d_out = nullptr;
-        return DPOSE_OK;
-      }
     } else {
-      DPOSE_CUDA(cudaStreamSynchronize(st));
-      total = *ws->h_total;
-      if (total == 0) return DPOSE_OK;  // :157-158
-      DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * total, st));
-      k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_chunk, d_out);
+      const unsigned grid = (unsigned)(((size_t)a.n_tile_rows * a.chunks_x + kWarpsPerCta - 1) / kWarpsPerCta);
+      k_count<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_count);
       DPOSE_LAUNCHED();
-      DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
-      DPOSE_CUDA(cudaStreamSynchronize(st));
+      k_scan_chunks<<<n_chunks, 512, 0, st>>>(ws->d_count, ws->d_prefix, ws->d_chunk, a.n_units);
+      DPOSE_LAUNCHED();
+      k_scan_totals<<<1, 1024, 0, st>>>(ws->d_chunk, n_chunks, ws->d_chunk + n_chunks);
+      DPOSE_LAUNCHED();
+      DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_chunk + n_chunks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      for (int pass = 0; pass < 2; ++pass) {
+        if (!cap) {  // no estimate (or the estimate was too small): read the total back first
+          DPOSE_CUDA(cudaStreamSynchronize(st));
+          total = *ws->h_total;
+          if (total == 0) break;
+          cap = total;
+        }
+        DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
+        k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_chunk, d_out, cap);
+        DPOSE_LAUNCHED();
+        DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
+        DPOSE_CUDA(cudaStreamSynchronize(st));
+        total = *ws->h_total;
+        if (total <= cap) break;
+        cudaFreeAsync(d_out, st);  // the estimate was too small: once more with the exact size
+        d_out = nullptr;
+        cap = 0;
+      }
     }
-    cudaEventElapsedTime(&ws->last_kernel_us, ws->ev0, ws->ev1);  // ms, includes the host round trip for the total
+    ws->hint = total;
+    if (total == 0) {  // :157-158
+      if (d_out) cudaFreeAsync(d_out, st);
+      d_out = nullptr;
+      return DPOSE_OK;
+    }
+    cudaEventElapsedTime(&ws->last_kernel_us, ws->ev0, ws->ev1);  // ms: plane rebuild (if any), both sweeps, the scans
     ws->last_kernel_us *= 1000.f;
     *d_cells = d_out;
     *n = (size_t)total;

@@ -146,6 +146,25 @@ int dpose_pg_get_cost_batch_device(const dpose_pg *pg, const dpose_map *map,
 int dpose_pg_get_cost_batch_multi(dpose_pg *const *pgs, dpose_map *const *maps, int ndev,
                                   const double *poses, size_t n, double *out,
                                   int want_jacobian);
+/* cost only: cost[i] for n poses, 8 bytes per pose back instead of 32 (no Jacobian is formed).  Host buffers. */
+int dpose_pg_get_cost_batch_costs(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n,
+                                  double *cost);
+/* A pose LATTICE instead of a pose list (BASELINE's "pose sweep"): pose i = (x0 + dx ix, y0 + dy iy,
+ * theta0 + dtheta it) with i = (it ny + iy) nx + ix, generated inside the kernel — nothing travels to the device.
+ * out: nx ny ntheta x 4 doubles (or nx ny ntheta costs if cost_only != 0).  Host buffers. */
+typedef struct {
+  double x0, dx;
+  uint64_t nx;
+  double y0, dy;
+  uint64_t ny;
+  double theta0, dtheta;
+  uint64_t ntheta;
+} dpose_sweep;
+int dpose_pg_get_cost_sweep(const dpose_pg *pg, const dpose_map *map, const dpose_sweep *sweep, double *out,
+                            int want_jacobian, int cost_only);
+/* device output buffer, asynchronous on `stream` */
+int dpose_pg_get_cost_sweep_device(const dpose_pg *pg, const dpose_map *map, const dpose_sweep *sweep, double *d_out,
+                                   int want_jacobian, int cost_only, void *stream);
 /* algorithmic window bytes of a pose batch: sum over poses of the
  * number of map cells inside the axis-aligned bounding box of the valid kernel region,
  * clipped to the map.  Host arithmetic. */

@@ -86,10 +86,16 @@ def bench_lethal():
         dev_us = cm.lethal_us()
         xs, ys = ring[:, 0], ring[:, 1]
         box_bytes = int((xs.max() - xs.min() + 1) * (ys.max() - ys.min() + 1))
-        algo = 2 * box_bytes + 8 * n  # two sweeps over the box + the cells written
-        emit(what="lethal_cells_within", box=label, cells=n, call_wall_us=wall * 1e6, device_us=dev_us,
-             algorithmic_bytes=algo, achieved_gbs_device=algo / (dev_us * 1e-6) / 1e9,
-             achieved_gbs_whole_call=algo / wall / 1e9)
+        algo = box_bytes + 8 * n  # the box's map bytes once + 8 B per lethal cell written
+        for volatile in (False, True):  # clean plane (cached 1-bit view) / stale plane (the uint8 map is re-read)
+            cm.set_volatile(volatile)
+            run()
+            wall = best_of(run, 5)
+            dev_us = cm.lethal_us()
+            emit(what="lethal_cells_within", box=label, cells=n, plane="rebuilt from the uint8 map in the call" if volatile
+                 else "clean (cached)", call_wall_us=wall * 1e6, device_us=dev_us, algorithmic_bytes=algo,
+                 achieved_gbs_device=algo / (dev_us * 1e-6) / 1e9, frac_of_hbm_peak=algo / (dev_us * 1e-6) / 1e9 / 6527.5)
+        cm.set_volatile(False)
     # the reference's own perf workload (dpose_core/perf/dpose_core.cpp:73-90): 200 x 200, every 2nd cell lethal
     m = np.zeros((200, 200), np.uint8)
     m.reshape(-1)[::2] = fx.LETHAL
