@@ -1,29 +1,37 @@
 #!/usr/bin/env python
 """bench.py — cost+Jacobian pose evaluations per second on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg5|cfg2|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg5|cfg2|cfg3|cfg4|cfg1]
+                    [--scaling strong|weak]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path (pose_gradient batched get_cost, cost + Jacobian) over one
-batch of synthetic poses.  Default workload = BASELINE config 5: 10000x10000 costmap (0.05 m, 10 %
-lethal), rectangle footprint 1.0x0.6 m (table 17x25), 1e7 uniformly random SE2 poses PER GPU (weak
-scaling: map and table replicated, pose batches sharded by rank, no collective on the data path).
+One "step" = one pass of the hot path over one batch of synthetic input.
 
-value  : poses/s with poses, map and outputs resident in HBM; CUDA events on the launching stream,
-         max over ranks.  Per step the kernel touches 100 MB of map + 240 MB of poses + 320 MB of
-         results (> 126 MB L2), so no explicit L2 flush is needed between iterations.
-e2e    : same metric through the public host-buffer call (dpose_pg_get_cost_batch via ctypes):
-         pinned host poses -> H2D -> kernel -> D2H results, all inside the timed region.
-roofline: algorithmic bytes (24 B pose + 32 B result + |window| map bytes, summed exactly on the
-         host) / average kernel launch time, against the measured HBM copy peak.
-cpu_baseline / --impl reference: the reference's own dpose_core sources as compiled into oracle/_ref
-         (kind "reference"; oracle/refshim/README.md says how), driven per pose as BASELINE defines the
-         batch (rotated box -> lethal_cells_within -> get_cost), OpenMP over poses on all host cores, on a
-         bounded sample of the same workload.  `port_value` beside it is the oracle's C restatement
-         (bit-identical results, leaner data structures, hence faster) on the same sample; when
-         oracle/_ref is absent the port is timed instead and kind says "port".
+Workloads (BASELINE.json `configs`):
+  cfg5 (default)  10000x10000 costmap (0.05 m, 10 % lethal), rectangle footprint 1.0x0.6 m (table 17x25), 1e7 uniformly
+                  random SE2 poses, batched get_cost (cost + Jacobian).  --scaling strong (default, what BASELINE states:
+                  "1e7-pose sweep sharded across 1/2/4/8 B200"): the 1e7 poses are split contiguously over the ranks;
+                  weak: 1e7 poses PER GPU.  On N > 1 the other mode is timed as well and reported under `other_scaling`.
+                  Map and table replicated, no collective on the data path.
+  cfg2 / cfg3     1e5 poses on 2000x2000 / 1e6 poses with the 40-vertex footprint (table 35x55), same call.
+  cfg4            the goal-tolerance solve: 4096 multi-start offsets from the plugin's sampler, max_iter 20, one
+                  dpose_problem_solve_batch per step; value = pose evaluations (solver iterates) per second.
+  cfg1            the reference's own micro-benchmark inputs (dpose_core/perf/dpose_core.cpp:45-71): one pose, 100 cells per
+                  call (latency bound by construction); value = calls per second.
+
+value  : inputs resident in HBM; CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+e2e    : the same metric through the public host-buffer C-ABI call (pinned host buffers, H2D and D2H inside the timed
+         region, host wall clock, max over ranks); `e2e_multi` (N > 1): ONE process driving all N GPUs through
+         dpose_pg_get_cost_batch_multi into one host buffer; `e2e_variants`: the cost-only and lattice-sweep entry points.
+roofline: algorithmic bytes (24 B pose + 32 B result + |window| map bytes, summed exactly on the host) /
+         average launch time, against the measured HBM copy peak.
+cpu_baseline / --impl reference: the reference's own dpose_core sources as compiled into oracle/_ref (kind
+         "reference"; oracle/refshim/README.md says how) on all host threads, on a bounded sample of the same workload;
+         the oracle's C port when oracle/_ref is absent (kind "port").  The in-run baseline is measured by a child
+         process (clean CPU affinity, its own OpenMP pool) so that it equals what `--impl reference` reports.
 """
 import argparse
+import hashlib
 import json
 import math
 import os
@@ -33,11 +41,10 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: NCCL prints its version banner to stdout when NCCL_DEBUG is VERSION or
-# WARN (and logs there for INFO / TRACE); this bench uses NCCL only for the timing barrier / max-reduction, so
-# its logging is switched off.  Must happen before torch / NCCL are loaded.
-if os.environ.get("NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "NONE"
+# stdout carries exactly one JSON line.  NCCL (used only for the timing barrier / reductions) logs to stdout when
+# NCCL_DEBUG asks for it: its log is routed to stderr instead of being silenced, so the launcher can still read it.
+if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -46,23 +53,25 @@ import numpy as np  # noqa: E402
 
 METRIC = "cost+Jacobian pose evals/sec"
 UNIT = "poses/s"
+CFG4 = dict(lin_tolerance=20.0, rot_tolerance=1.0, weight_goal_lin=1, weight_goal_rot=1, weight_start_lin=1,
+            weight_start_rot=1)
+CFG4_START, CFG4_GOAL, CFG4_SEED, CFG4_STARTS = [900.0, 950.0, 0.5], [1000.0, 1000.0, 0.0], 3, 4096
 
 WORKLOADS = {
-    # name: (map side, poses per GPU, footprint fixture, description)
-    "cfg5": (10000, 10_000_000, "rect_pad2",
-             "BASELINE cfg5: 10000x10000 costmap, 10% lethal, rect 1.0x0.6m @0.05m (table 17x25), 1e7 poses/GPU"),
-    "cfg2": (2000, 100_000, "rect_pad2",
-             "BASELINE cfg2: 2000x2000 costmap, 10% lethal, rect footprint, 1e5 poses"),
-    "cfg3": (2000, 1_000_000, "star40_pad2",
+    # name: (kind, map side, poses / starts, footprint fixture, map seed, pose seed, description)
+    "cfg5": ("batch", 10000, 10_000_000, "rect_pad2", 4, 5,
+             "BASELINE cfg5: 10000x10000 costmap, 10% lethal, rect 1.0x0.6m @0.05m (table 17x25), 1e7 random SE2 poses"),
+    "cfg2": ("batch", 2000, 100_000, "rect_pad2", 1, 2,
+             "BASELINE cfg2: 2000x2000 costmap, 10% lethal, rect footprint (table 17x25), 1e5 poses"),
+    "cfg3": ("batch", 2000, 1_000_000, "star40_pad2", 1, 2,
              "BASELINE cfg3: 2000x2000 costmap, 40-vertex star @0.02m (table 35x55), 1e6 poses"),
+    "cfg4": ("solve", 2000, CFG4_STARTS, "rect_pad2", 1, CFG4_SEED,
+             "BASELINE cfg4: goal-tolerance solve, 4096 multi-start offsets (plugin sampler, lin_tol 20 cells, rot_tol 1 rad), "
+             "max_iter 20, 2000x2000 costmap 10% lethal, rect footprint"),
+    "cfg1": ("single", 200, 1, "arrow_pad3", 0, 0,
+             "BASELINE cfg1: dpose_core perf bench (perf/dpose_core.cpp:45-71): arrow footprint pad 3, 10x10 cells, pose 0, "
+             "single-pose get_cost with Jacobian"),
 }
-
-
-def env_int(name, default):
-    try:
-        return int(os.environ.get(name, default))
-    except ValueError:
-        return default
 
 
 def load_peaks():
@@ -73,6 +82,16 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_hash():
+    """hash of the kernel sources: stamps ncu-derived numbers (profiles/traffic.json) so a stale capture is visible"""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "dpose_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def _nvml_handle(local_rank):
@@ -91,7 +110,7 @@ def _nvml_handle(local_rank):
 
 def bind_to_gpu_numa_node(local_rank):
     """run this rank on the CPUs NVML reports as local to its GPU, so that pinned host buffers (first touch) land
-    on the GPU's NUMA node; returns the previous affinity (restored around the CPU baseline)."""
+    on the GPU's NUMA node; returns the previous affinity"""
     try:
         import pynvml
         h = _nvml_handle(local_rank)
@@ -124,9 +143,10 @@ class ClockSampler:
             self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:  # noqa: BLE001
             self.err = f"NVML unavailable: {e}"
-            return
+            return self
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+        return self
 
     def _run(self):
         nv = self.nv
@@ -158,15 +178,9 @@ class ClockSampler:
                 "source": "NVML, 2 ms period, timed region only"}
 
 
-def make_host_workload(side, n_poses, seed_map, seed_pose):
-    import fixtures as fx
-    m = fx.bernoulli_map(side, side, 0.10, seed_map)
-    poses = fx.random_poses(n_poses, side, side, seed_pose)
-    return m, poses
-
-
+# ---- the reference arm (CPU) ----------------------------------------------------------------------------------------
 def cpu_impls(fp, pad):
-    """[(kind, batch_fn)] of the CPU implementations of the path, the one the baseline is quoted on first:
+    """[(kind, batch_fn)] of the CPU implementations of the batched path, the one the baseline is quoted on first:
     the reference's own sources compiled into oracle/_ref when that library is here, then the oracle port"""
     from oracle import capi, refapi
     threads = capi.max_threads()
@@ -178,78 +192,493 @@ def cpu_impls(fp, pad):
     return impls, threads
 
 
-def cpu_reference_rate(fp, pad, host_map, poses, budget_s=12.0):
-    """times the CPU implementation(s) of the path with all host threads on a bounded sample;
-    returns the cpu_baseline object"""
-    impls, threads = cpu_impls(fp, pad)
-    kind, fn = impls[0]
-    probe = min(len(poses), 20000)
-    t0 = time.perf_counter()
-    fn(host_map, poses[:probe])
-    rate = probe / max(time.perf_counter() - t0, 1e-9)
-    n = int(min(len(poses), max(probe, rate * budget_s)))
-    t0 = time.perf_counter()
-    fn(host_map, poses[:n])
-    dt = time.perf_counter() - t0
-    what = ("reference's dpose_core.cpp/dpose_costmap.cpp compiled into oracle/_ref" if kind == "reference"
-            else "oracle port")
-    out = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": kind,
-           "sample": f"first {n} poses of the same workload in {dt:.1f} s "
-                     f"({what}: lethal_cells_within(rotated box)+get_cost per pose, OpenMP)"}
-    if len(impls) > 1:
-        t0 = time.perf_counter()
-        impls[1][1](host_map, poses[:n])
-        out["port_value"] = n / (time.perf_counter() - t0)
-    return out
+def reference_note(kind):
+    return ("the reference's own dpose_core.cpp + dpose_costmap.cpp (+ the plugin's dpose_goal_tolerance.cpp), compiled from "
+            "/root/reference against the stand-in headers of oracle/refshim into oracle/_ref" if kind == "reference" else
+            "CPU restatement of dpose_core (oracle port; oracle/_ref is not present on this box)")
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU path (oracle/_ref, else the oracle port), all host threads,
-    rank 0 only"""
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU path (oracle/_ref, else the oracle port), all host threads, rank 0 only"""
     if rank != 0:
         return 0
     import fixtures as fx
-    side, n_per_gpu, fp_name, desc = WORKLOADS[args.workload]
+    from oracle import capi, refapi
+    kind_w, side, n_units, fp_name, map_seed, pose_seed, desc = WORKLOADS[args.workload]
     fp, pad = fx.FOOTPRINTS[fp_name]
-    impls, threads = cpu_impls(fp, pad)
-    kind, fn = impls[0]
-    host_map = fx.bernoulli_map(side, side, 0.10, 4)
-    # bounded sample per step: sized from a probe so the whole run stays within a few minutes
-    probe_poses = fx.random_poses(20000, side, side, 5)
-    t0 = time.perf_counter()
-    fn(host_map, probe_poses)
-    rate = len(probe_poses) / (time.perf_counter() - t0)
+    budget_s = float(os.environ.get("DPOSE_REF_BUDGET_S", "60"))
     total_steps = args.steps + args.warmup
-    per_step = int(max(20000, min(n_per_gpu, rate * 60.0 / max(total_steps, 1))))
-    poses = fx.random_poses(per_step, side, side, 5)
+    threads = capi.max_threads()
+    extra = {}
+    if kind_w == "batch":
+        impls, threads = cpu_impls(fp, pad)
+        kind, fn = impls[0]
+        host_map = fx.bernoulli_map(side, side, 0.10, map_seed)
+        probe_poses = fx.random_poses(20000, side, side, pose_seed)
+        t0 = time.perf_counter()
+        fn(host_map, probe_poses)
+        rate = len(probe_poses) / (time.perf_counter() - t0)
+        per_step = int(max(20000, min(n_units, rate * budget_s / max(total_steps, 1))))
+        poses = fx.random_poses(per_step, side, side, pose_seed)
+        step = lambda: fn(host_map, poses)  # noqa: E731
+        units = per_step
+        sample = f"{per_step} poses/step of the same workload (bounded sample), {args.steps} steps"
+        how = "per pose lethal_cells_within(rotated box)+get_cost, OpenMP over poses"
+        if len(impls) > 1:
+            t0 = time.perf_counter()
+            impls[1][1](host_map, poses)
+            extra["port_value"] = per_step / (time.perf_counter() - t0)
+    elif kind_w == "solve":
+        host_map = fx.bernoulli_map(side, side, 0.10, map_seed)
+        cd = capi.CostData(fp, pad)
+        scfg = capi.solver_cfg(cd.box, CFG4["lin_tolerance"], CFG4["rot_tolerance"])
+        x0 = capi.sample_offsets(CFG4_SEED, CFG4["lin_tolerance"], CFG4["rot_tolerance"], n_units)
+        if os.environ.get("DPOSE_CPU_BASELINE", "") != "port" and refapi.available():
+            kind = "reference"
+            pr = refapi.Problem(fp, pad, host_map)
+            pr.init(CFG4_START, CFG4_GOAL, **CFG4)
+            solve = lambda: pr.solve_batch(scfg, x0, nthreads=threads)  # noqa: E731
+        else:
+            kind = "port"
+            pr = capi.Problem(cd, host_map)
+            pr.init(CFG4_START, CFG4_GOAL, **CFG4)
+            solve = lambda: pr.solve_batch(scfg, x0, nthreads=threads)  # noqa: E731
+        units = int(solve()[3].sum())  # pose evaluations of one solve (deterministic)
+        step = solve
+        sample = f"the whole workload: {n_units} starts, {units} pose evaluations per solve, {args.steps} solves"
+        how = ("the product's step rule (restated in oracle/dpose_oracle.c) on the plugin's TNLP callbacks eval_f / eval_grad_f "
+               "(finite-difference Jacobian, 7 transforms per cell) + the reference's check_footprint, OpenMP over starts")
+    else:  # single
+        kind = "reference" if os.environ.get("DPOSE_CPU_BASELINE", "") != "port" and refapi.available() else "port"
+        pg = refapi.PoseGradient(fp, pad) if kind == "reference" else capi.CostData(fp, pad)
+        cells = np.array([[x, y] for x in range(10) for y in range(10)], np.int32)
+        reps = 2000
+        step = lambda: [pg.get_cost([0.0, 0.0, 0.0], cells) for _ in range(reps)]  # noqa: E731
+        units = reps
+        threads = 1
+        sample = f"the whole workload: {reps} calls per step, one thread (the reference is single-threaded), through ctypes"
+        how = "pose_gradient::get_cost(se2, cells.begin(), cells.end(), &J) per call"
     for _ in range(args.warmup):
-        fn(host_map, poses)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fn(host_map, poses)
+        step()
     dt = time.perf_counter() - t0
-    value = per_step * args.steps / dt
-    sample = f"{per_step} poses/step of the same workload (bounded sample), {args.steps} steps"
-    cpu_baseline = {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
-    if len(impls) > 1:
-        t0 = time.perf_counter()
-        impls[1][1](host_map, poses)
-        cpu_baseline["port_value"] = per_step / (time.perf_counter() - t0)
-    note = ("the reference's own dpose_core.cpp + dpose_costmap.cpp, compiled from /root/reference against the "
-            "stand-in headers of oracle/refshim into oracle/_ref" if kind == "reference" else
-            "CPU restatement of dpose_core (oracle port; oracle/_ref is not present on this box)")
+    value = units * args.steps / dt
+    cpu_baseline = dict({"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}, **extra)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "poses_per_step": per_step,
-                   "note": note + "; per pose lethal_cells_within(rotated box)+get_cost, OpenMP over poses"},
+        "higher_is_better": True, "scaling": args.scaling or "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "units_per_step": units, "note": reference_note(kind) + "; " + how},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def cpu_baseline_child(workload):
+    """the in-run CPU baseline: `--impl reference` in a child process with this process's ORIGINAL affinity and a fresh
+    OpenMP pool (threads created while this process was bound to the GPU's NUMA node would stay there)"""
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    env.setdefault("DPOSE_REF_BUDGET_S", "12")
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                            "--steps", "3", "--warmup", "1"], env=env, capture_output=True, text=True, timeout=600)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)}
+
+
+# ---- the GPU arm -------------------------------------------------------------------------------------------------------
+def device_map(torch, dev, side, seed):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    return torch.where(torch.rand((side, side), generator=g, device=dev) < 0.10,
+                       torch.tensor(254, dtype=torch.uint8, device=dev),
+                       torch.tensor(0, dtype=torch.uint8, device=dev)).contiguous()
+
+
+def device_poses(torch, dev, n, side, seed, lo=0, hi=None):
+    """rows [lo, hi) of the n x 3 pose batch of `seed` (every rank draws the same stream and keeps its slice)"""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    u = torch.rand((n, 3), generator=g, device=dev, dtype=torch.float64)
+    u = u[lo:hi if hi is not None else n]
+    p = torch.empty_like(u)
+    p[:, 0] = 32.0 + u[:, 0] * (side - 64.0)
+    p[:, 1] = 32.0 + u[:, 1] * (side - 64.0)
+    p[:, 2] = -math.pi + u[:, 2] * (2.0 * math.pi)
+    return p.contiguous()
+
+
+def timed_steps(torch, ranks, stream, step, steps, warmup):
+    """W untimed steps, then exactly K steps bracketed by barrier + synchronize; CUDA events on the launching stream.
+    Returns (this rank's total ms, per-step ms list)"""
+    for _ in range(warmup):
+        step()
+    ranks.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record(stream)
+    for i in range(steps):
+        step()
+        ev[i + 1].record(stream)
+    ranks.barrier()
+    return ev[0].elapsed_time(ev[-1]), [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+
+
+def run_batch(args, ranks, torch, dp, fx):
+    kind_w, side, n_total, fp_name, map_seed, pose_seed, desc = WORKLOADS[args.workload]
+    fp, pad = fx.FOOTPRINTS[fp_name]
+    rank, world, local_rank, dev = ranks.rank, ranks.world, ranks.local_rank, ranks.device
+    scaling = args.scaling or "strong"
+    prev_affinity = bind_to_gpu_numa_node(local_rank)
+    d_map = device_map(torch, dev, side, map_seed)
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad), device=local_rank)
+    cmap = dp.Costmap(device_ptr=d_map.data_ptr(), size_x=side, size_y=side, pitch=side, device=local_rank)
+    # every timed step consumes the raw uint8 costmap: the derived lethal tile plane is rebuilt inside
+    # each batched call (k_pack_tiles in front of the batch kernel), never cached across steps
+    cmap.set_volatile(True)
+    stream = torch.cuda.current_stream()
+
+    def make_mode(mode):
+        if mode == "strong":  # n_total poses in all, this rank's contiguous slice
+            lo, hi = dp.dist.shard_bounds(n_total, rank, world)
+            poses = device_poses(torch, dev, n_total, side, pose_seed, lo, hi)
+        else:  # weak: n_total poses per GPU, rank-specific
+            poses = device_poses(torch, dev, n_total, side, pose_seed + rank)
+        out = torch.zeros((poses.shape[0], 4), device=dev, dtype=torch.float64)
+        return poses, out
+
+    def device_leg(mode):
+        poses, out = make_mode(mode)
+        n = poses.shape[0]
+
+        def step():
+            pg.get_cost_batch_device(cmap, poses.data_ptr(), n, out.data_ptr(), jacobian=True, stream=stream.cuda_stream)
+
+        sampler = ClockSampler(local_rank).start()
+        l0 = dp.launch_count()
+        total_ms, per_ms = timed_steps(torch, ranks, stream, step, args.steps, args.warmup)
+        launches = dp.launch_count() - l0
+        clocks = sampler.stop()
+        value = ranks.sum(n * args.steps) / (ranks.max(total_ms) * 1e-3)
+        return dict(poses=poses, out=out, n=n, value=value, ms_per_step=ranks.max(total_ms) / args.steps, per_ms=per_ms,
+                    launches=launches - 0, clocks=clocks)
+
+    main = device_leg(scaling)
+    d_poses, d_out, n = main["poses"], main["out"], main["n"]
+    other = None
+    if world > 1:
+        om = "weak" if scaling == "strong" else "strong"
+        leg = device_leg(om)
+        other = {"scaling": om, "value": leg["value"], "ms_per_step": leg["ms_per_step"], "poses_per_gpu": leg["n"]}
+        del leg
+
+    # ---- end to end through the host-buffer C ABI call, this rank's shard --------------------------------------------------
+    e2e = e2e_ok = None
+    variants = None
+    if not args.no_e2e:
+        h_poses = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+        h_poses.copy_(d_poses)
+        h_out = torch.empty((n, 4), dtype=torch.float64, pin_memory=True)
+        np_poses, np_out = h_poses.numpy(), h_out.numpy()
+
+        def wall(fn, steps):
+            for _ in range(2):
+                fn()
+            ranks.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+
+        dt = wall(lambda: pg.get_cost_batch(cmap, np_poses, out=np_out), args.steps)
+        e2e_value = ranks.sum(n * args.steps) / ranks.max(dt)
+        e2e_ok = bool(np.array_equal(np_out[:4096], d_out[:4096].cpu().numpy()))
+
+        # what the box's host link gives plain pinned copies of the same sizes: each direction alone, and both at once
+        def copy_ms(pairs):
+            best = 1e30
+            streams = [torch.cuda.Stream() for _ in pairs]
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for s, (dst, src) in zip(streams, pairs):
+                    with torch.cuda.stream(s):
+                        dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            return best * 1e3
+        scratch = torch.empty_like(d_out)
+        h2d_ms = copy_ms([(d_poses, h_poses)])
+        d2h_ms = copy_ms([(h_out, scratch)])
+        bidir_ms = copy_ms([(d_poses, h_poses), (h_out, scratch)])
+        del scratch
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": int(n * 32),
+               "ms_per_step": 1e3 * ranks.max(dt) / args.steps,
+               "pcie_h2d_gbs": n * 24 / (h2d_ms * 1e-3) / 1e9, "pcie_d2h_gbs": n * 32 / (d2h_ms * 1e-3) / 1e9,
+               "pcie_bidirectional_ms_per_step": ranks.max(bidir_ms),
+               "frac_of_bidirectional_copy_floor": ranks.max(bidir_ms) / (1e3 * ranks.max(dt) / args.steps),
+               "host_threads_bound_to_gpu_numa_node": bool(prev_affinity),
+               "timing": "host wall clock around the synchronous C-ABI call (it drives its own streams), max over ranks; "
+                         "bytes are per rank"}
+        # the entry points that move fewer bytes: cost only (8 B/pose back), lattice sweep (nothing in)
+        v_steps = max(3, args.steps // 4)
+        h_cost = torch.empty((n,), dtype=torch.float64, pin_memory=True)
+        dt_c = wall(lambda: pg.get_cost_batch_costs(cmap, np_poses, out=h_cost.numpy()), v_steps)
+        nt = 8
+        nxy = max(1, int(math.isqrt(max(n // nt, 1))))
+        ns = nxy * nxy * nt
+        xs, ys, ts = (32.0, (side - 64.0) / nxy, nxy), (32.0, (side - 64.0) / nxy, nxy), (-math.pi, 2 * math.pi / nt, nt)
+        h_sw = torch.empty((ns, 4), dtype=torch.float64, pin_memory=True)
+        dt_s = wall(lambda: pg.get_cost_sweep(cmap, xs, ys, ts, out=h_sw.numpy()), v_steps)
+        h_swc = torch.empty((ns,), dtype=torch.float64, pin_memory=True)
+        dt_sc = wall(lambda: pg.get_cost_sweep(cmap, xs, ys, ts, cost_only=True, out=h_swc.numpy()), v_steps)
+        variants = {
+            "cost_only": {"value": ranks.sum(n * v_steps) / ranks.max(dt_c), "unit": "cost-only pose evals/s",
+                          "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": int(n * 8)},
+            "sweep": {"value": ranks.sum(ns * v_steps) / ranks.max(dt_s), "unit": UNIT, "poses": ns,
+                      "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(ns * 32),
+                      "lattice": f"{nxy} x {nxy} x {nt} (x, y, theta) generated in the kernel"},
+            "sweep_cost_only": {"value": ranks.sum(ns * v_steps) / ranks.max(dt_sc), "unit": "cost-only pose evals/s",
+                                "poses": ns, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(ns * 8)},
+        }
+        del h_cost, h_sw, h_swc
+
+    # ---- ONE process driving all N GPUs through the in-process multi-GPU entry point (rank 0; the others stay idle) -------
+    e2e_multi = None
+    if world > 1 and not args.no_e2e:
+        ranks.host_barrier()
+        if rank == 0:
+            try:
+                host_map = d_map.cpu().numpy()
+                full = device_poses(torch, dev, n_total, side, pose_seed)
+                hp = torch.empty((n_total, 3), dtype=torch.float64, pin_memory=True)
+                hp.copy_(full)
+                ho = torch.empty((n_total, 4), dtype=torch.float64, pin_memory=True)
+                del full
+                ndev = min(world, torch.cuda.device_count())
+                pgs = [dp.pose_gradient(fp, dp.pose_gradient.parameter(pad), device=i) for i in range(ndev)]
+                maps = [dp.Costmap(host_map, device=i) for i in range(ndev)]
+                for cm in maps:
+                    cm.set_volatile(True)
+                for _ in range(2):
+                    dp.get_cost_batch_multi(pgs, maps, hp.numpy(), out=ho.numpy())
+                m_steps = max(3, args.steps // 4)
+                t0 = time.perf_counter()
+                for _ in range(m_steps):
+                    dp.get_cost_batch_multi(pgs, maps, hp.numpy(), out=ho.numpy())
+                dtm = time.perf_counter() - t0
+                lo, hi = dp.dist.shard_bounds(n_total, 0, world)
+                same = bool(np.array_equal(ho.numpy()[:4096], d_out[:4096].cpu().numpy())) if scaling == "strong" else None
+                single = pg.get_cost_batch(cmap, hp.numpy()[-4096:])
+                e2e_multi = {"value": n_total * m_steps / dtm, "unit": UNIT, "ms_per_step": 1e3 * dtm / m_steps,
+                             "devices": ndev, "poses": n_total, "h2d_bytes_per_step": int(n_total * 24),
+                             "d2h_bytes_per_step": int(n_total * 32),
+                             "first_shard_equals_rank0_device_path": same,
+                             "last_shard_equals_single_gpu_call": bool(np.array_equal(ho.numpy()[-4096:], single)),
+                             "call": "dpose_pg_get_cost_batch_multi from one process (one host thread per device), one "
+                                     "pinned host buffer in, one out"}
+                del pgs, maps, hp, ho
+            except Exception as e:  # noqa: BLE001
+                e2e_multi = {"error": str(e)[:300]}
+        ranks.host_barrier()
+
+    if rank != 0:
+        return None
+
+    # ---- roofline of the step (rank 0's launches) ----------------------------------------------------------------------
+    peak, peak_src = load_peaks()
+    host_poses = d_poses.cpu().numpy()
+    win_bytes = pg.window_bytes(cmap, host_poses)
+    algo_bytes = win_bytes + 56 * n
+    avg_launch_s = statistics.mean(main["per_ms"]) * 1e-3
+    achieved = algo_bytes / avg_launch_s / 1e9
+    traffic, traffic_note, ncu = None, None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj.get(args.workload)
+            ncu = tj.get("ncu_" + args.workload)
+            stamp = tj.get("kernel_source_hash")
+            traffic_note = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, captured on kernel sources " +
+                            str(stamp) + ("" if stamp == kernel_source_hash() else
+                                          f" (STALE: the sources now hash to {kernel_source_hash()})"))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                "kernel": "k_pack_tiles + k_cost_batch_tile (one step)",
+                "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_pose": algo_bytes / n,
+                "avg_launch_ms": avg_launch_s * 1e3,
+                "bound_note": "the contract's roofline is the algorithmic-byte one (HBM); ncu shows the kernel itself is "
+                              "instruction-issue bound — the windows come out of a 12.6 MB L2-resident 1-bit plane, so real "
+                              "DRAM traffic is a tenth of the algorithmic bytes",
+                "ncu": ncu}
+
+    # ---- parity spot check + CPU baseline ------------------------------------------------------------------------------------
+    from oracle import capi
+    oc = capi.CostData(fp, pad)
+    host_map = d_map.cpu().numpy()
+    n_chk = min(4000, n)
+    got = d_out[:n_chk].cpu().numpy()
+    ref = oc.get_cost_batch(host_map, host_poses[:n_chk], shift=True, nthreads=capi.max_threads())
+    ok = fx.tol_ok(got, ref)
+    parity = {"checked_poses": n_chk, "pass_rate_vs_shifted_reference": float(ok.all(axis=1).mean()),
+              "tolerance": "1e-6 + 1e-5*|ref|", "e2e_equals_device_path": e2e_ok}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_child(args.workload)
+
+    l2 = ("inputs larger than L2 (map + poses + results = %d MB/step per GPU), no flush" % ((side * side + 56 * n) // 1_000_000)
+          if side * side + 56 * n > 160_000_000 else
+          "the map is L2-resident by design of this config; poses + results (%d MB/step) stream through" % (56 * n // 1_000_000))
+    return {
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "poses_per_gpu": n, "poses_total": int(n * world) if scaling == "weak" else n_total,
+                   "map": f"{side}x{side} uint8, Bernoulli(0.10)",
+                   "parallelism": f"dp{world} (poses sharded contiguously, map + table replicated, no collective)", "l2": l2},
+        "clocks": main["clocks"], "e2e": e2e, "e2e_multi": e2e_multi, "e2e_variants": variants,
+        "other_scaling": other, "gpu_launches": int(main["launches"]), "roofline": roofline,
+        "cpu_baseline": cpu_baseline, "parity": parity,
+    }
+
+
+def run_solve(args, ranks, torch, dp, fx):
+    """cfg4: every rank solves the same 4096-start problem (replicas only: one solve does not shard)"""
+    kind_w, side, n_starts, fp_name, map_seed, pose_seed, desc = WORKLOADS[args.workload]
+    fp, pad = fx.FOOTPRINTS[fp_name]
+    rank, world, local_rank = ranks.rank, ranks.world, ranks.local_rank
+    host_map = fx.bernoulli_map(side, side, 0.10, map_seed)
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad), device=local_rank)
+    cmap = dp.Costmap(host_map, device=local_rank)
+    pr = dp.problem(pg, cmap)
+    pr.init(CFG4_START, CFG4_GOAL, CFG4)
+    x0 = dp.sample_offsets(CFG4_SEED, CFG4["lin_tolerance"], CFG4["rot_tolerance"], n_starts)
+    for _ in range(max(args.warmup, 3)):
+        out = pr.solve_batch(x0)
+    evals = int(out["evals"].sum())
+    ranks.barrier()
+    sampler = ClockSampler(local_rank).start()
+    l0 = dp.launch_count()
+    dev_us = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = pr.solve_batch(x0)
+        dev_us.append(pr.solve_us())
+    dt = time.perf_counter() - t0
+    launches = dp.launch_count() - l0
+    clocks = sampler.stop()
+    ranks.barrier()
+    value = ranks.sum(evals * args.steps) / (ranks.max(sum(dev_us)) * 1e-6)
+    e2e_value = ranks.sum(evals * args.steps) / ranks.max(dt)
+    if rank != 0:
+        return None
+    # parity of the timed solve's iterates: one traced solve, every iterate against the oracle's evaluation
+    from oracle import capi
+    tr = pr.solve_batch(x0, trace=True)
+    oc = capi.Problem(capi.CostData(fp, pad), host_map)
+    oc.init(CFG4_START, CFG4_GOAL, **CFG4)
+    recs = np.concatenate([tr["trace"][i, :tr["evals"][i]] for i in range(0, n_starts, 8)])
+    f_ref, g_ref, c_ref, _ = oc.eval_batch(recs[:, :3], nthreads=capi.max_threads())
+    parity = {"checked_iterates": int(len(recs)),
+              "pass_rate_f_grad_vs_oracle": float((fx.tol_ok(recs[:, 3], f_ref) & fx.tol_ok(recs[:, 4:7], g_ref).all(axis=1)).mean()),
+              "constraints_bit_exact": bool(np.array_equal(recs[:, 7:9], c_ref)), "tolerance": "1e-6 + 1e-5*|ref|",
+              "same_results_every_solve": bool(np.array_equal(tr["x"], out["x"]))}
+    peak, peak_src = load_peaks()
+    poses_all = np.concatenate([tr["trace"][i, :tr["evals"][i], :3] for i in range(n_starts)]) + np.asarray(CFG4_GOAL)
+    algo_bytes = pg.window_bytes(cmap, poses_all) + 56 * len(poses_all)
+    avg_s = statistics.mean(dev_us) * 1e-6
+    roofline = {"bound": "hbm", "achieved": algo_bytes / avg_s / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": algo_bytes / avg_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "k_solve<32> + k_check_footprint_coop + k_solve_select (one solve)",
+                "algorithmic_bytes_per_launch": int(algo_bytes), "avg_launch_ms": avg_s * 1e3,
+                "bound_note": "latency bound by construction: 4096 starts x <= 21 dependent evaluations each; the figure is "
+                              "reported for completeness, the call latency is the quantity of interest"}
+    cpu_baseline = cpu_baseline_child(args.workload) if world == 1 and not args.no_cpu_baseline else None
+    sm = out["summary"]
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ranks.max(sum(dev_us)) * 1e-3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "starts": n_starts, "pose_evals_per_solve": evals, "solves_per_s_e2e": args.steps / dt,
+                   "converged": sm["n_converged"], "accepted": sm["n_accepted"],
+                   "parallelism": f"{world} independent replicas (a solve does not shard)",
+                   "l2": "the search-box crop (67 x 67 cells) is L1/L2 resident by design of this config",
+                   "note": "Ipopt is absent from this image and is not a per-thread algorithm: the step rule is the "
+                           "product's projected BFGS (csrc/solve.cu); the evaluated functions, the feasible set, the "
+                           "validation and the sampler are the reference's"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_starts * 24),
+                "d2h_bytes_per_step": int(n_starts * (56 + 4 + 2) + 96), "ms_per_step": 1e3 * dt / args.steps,
+                "copies_per_solve": "1 H2D (x0) + 1 D2H (x, f, final pose, evals, status, summary)",
+                "timing": "host wall clock around dpose_problem_solve_batch (host buffers in and out)"},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+    }
+
+
+def run_single(args, ranks, torch, dp, fx):
+    """cfg1: the reference's micro-benchmark call shape — one pose, an explicit list of 100 cells per call"""
+    kind_w, side, _, fp_name, map_seed, pose_seed, desc = WORKLOADS[args.workload]
+    fp, pad = fx.FOOTPRINTS[fp_name]
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad), device=ranks.local_rank)
+    cells = np.array([[x, y] for x in range(10) for y in range(10)], np.int32)  # perf/dpose_core.cpp:33-43
+    pose = [0.0, 0.0, 0.0]
+    reps = 2000
+    for _ in range(max(args.warmup, 3) * 200):
+        pg.get_cost(pose, cells)
+    ranks.barrier()
+    sampler = ClockSampler(ranks.local_rank).start()
+    l0 = dp.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps * reps):
+        c, J = pg.get_cost(pose, cells)
+    dt = time.perf_counter() - t0
+    launches = dp.launch_count() - l0
+    clocks = sampler.stop()
+    value = ranks.sum(args.steps * reps) / ranks.max(dt)
+    if ranks.rank != 0:
+        return None
+    from oracle import capi
+    rc, rJ = capi.CostData(fp, pad).get_cost(pose, cells)
+    peak, peak_src = load_peaks()
+    algo = 24 + 32 + 8 * len(cells)
+    per_call = dt / (args.steps * reps)
+    cpu_baseline = cpu_baseline_child(args.workload) if ranks.world == 1 and not args.no_cpu_baseline else None
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ranks.world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "calls_per_step": reps, "us_per_call": per_call * 1e6,
+                   "parallelism": f"{ranks.world} independent replicas", "l2": "100 cells and a 47x117 table: cache resident",
+                   "note": "one pose per call is launch-latency bound on a GPU (the reference's CPU call takes ~3 us); the "
+                           "batched and solve entry points exist for this reason"},
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(reps * (24 + 8 * len(cells))),
+                "d2h_bytes_per_step": int(reps * 32), "ms_per_step": 1e3 * dt / args.steps,
+                "timing": "the call IS the host-buffer call: cells and pose in, cost and Jacobian out, per call"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": algo / per_call / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / per_call / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel": "k_cost_cells",
+                     "algorithmic_bytes_per_launch": algo, "avg_launch_ms": per_call * 1e3,
+                     "bound_note": "launch-latency bound: 856 bytes per call"},
+        "cpu_baseline": cpu_baseline,
+        "parity": {"cost_and_jacobian_vs_oracle": bool(fx.tol_ok(c, rc) and fx.tol_ok(J, rJ).all()),
+                   "tolerance": "1e-6 + 1e-5*|ref|"},
+    }
 
 
 def main():
@@ -259,190 +688,33 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="batch workloads on N > 1 GPUs: total work fixed (default, BASELINE cfg5) or per-GPU work fixed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
-    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    rank = int(os.environ.get("RANK", 0))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank)
 
     import torch
     import fixtures as fx
     import dpose_b200 as dp
+    import dpose_b200.dist  # noqa: F401
 
     if not torch.cuda.is_available() or dp.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
-    # NUMA: keep this rank (and the pinned host buffers it first-touches) on the CPUs local to its GPU
-    prev_affinity = bind_to_gpu_numa_node(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-
-    side, n_poses, fp_name, desc = WORKLOADS[args.workload]
-    fp, pad = fx.FOOTPRINTS[fp_name]
-    dev = torch.device("cuda", local_rank)
-
-    # ---- synthetic inputs, generated on the device (same map on every rank, rank-specific poses) ----
-    g = torch.Generator(device=dev)
-    g.manual_seed(4)
-    d_map = torch.where(torch.rand((side, side), generator=g, device=dev) < 0.10,
-                        torch.tensor(254, dtype=torch.uint8, device=dev),
-                        torch.tensor(0, dtype=torch.uint8, device=dev)).contiguous()
-    g.manual_seed(5 + rank)
-    u = torch.rand((n_poses, 3), generator=g, device=dev, dtype=torch.float64)
-    d_poses = torch.empty((n_poses, 3), device=dev, dtype=torch.float64)
-    d_poses[:, 0] = 32.0 + u[:, 0] * (side - 64.0)
-    d_poses[:, 1] = 32.0 + u[:, 1] * (side - 64.0)
-    d_poses[:, 2] = -math.pi + u[:, 2] * (2.0 * math.pi)
-    del u
-    d_out = torch.zeros((n_poses, 4), device=dev, dtype=torch.float64)
-    torch.cuda.synchronize()
-
-    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad), device=local_rank)
-    cmap = dp.Costmap(device_ptr=d_map.data_ptr(), size_x=side, size_y=side, pitch=side, device=local_rank)
-    # every timed step consumes the raw uint8 costmap: the derived lethal tile plane is rebuilt inside
-    # each batched call (k_pack_tiles in front of k_cost_batch_tile), never cached across steps
-    cmap.set_volatile(True)
-    stream = torch.cuda.current_stream()
-
-    def step():
-        pg.get_cost_batch_device(cmap, d_poses.data_ptr(), n_poses, d_out.data_ptr(), jacobian=True,
-                                 stream=stream.cuda_stream)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ------------------------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = dp.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record(stream)
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record(stream)
-    barrier()
-    launches = dp.launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    clocks = sampler.stop()
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
-    value = world * n_poses * args.steps / (max_ms * 1e-3)
-
-    # ---- end to end through the host-buffer C ABI call ----------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        h_poses = torch.empty((n_poses, 3), dtype=torch.float64, pin_memory=True)
-        h_poses.copy_(d_poses)
-        h_out = torch.empty((n_poses, 4), dtype=torch.float64, pin_memory=True)
-        np_poses, np_out = h_poses.numpy(), h_out.numpy()
-        e2e_steps = args.steps
-        for _ in range(2):
-            pg.get_cost_batch(cmap, np_poses, out=np_out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            pg.get_cost_batch(cmap, np_poses, out=np_out)  # synchronous: returns with results on the host
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_checksum_ok = bool(np.array_equal(np_out[:4096], d_out[:4096].cpu().numpy()))
-        # context for the e2e figure: what the box's PCIe link gives plain pinned copies of the same sizes
-        def _copy_gbs(dst, src, nbytes):
-            best = 0.0
-            for _ in range(3):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                dst.copy_(src, non_blocking=True)
-                b.record(stream)
-                torch.cuda.synchronize()
-                best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
-            return best
-        h2d_gbs = _copy_gbs(d_poses, h_poses, n_poses * 24)
-        scratch = torch.empty_like(d_out)
-        d2h_gbs = _copy_gbs(h_out, scratch, n_poses * 32)
-        del scratch
-        e2e = {"value": world * n_poses * e2e_steps / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n_poses * 24), "d2h_bytes_per_step": int(n_poses * 32),
-               "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
-               "pcie_h2d_gbs": h2d_gbs, "pcie_d2h_gbs": d2h_gbs,
-               "pcie_bound_ms_per_step": 1e3 * max(n_poses * 24 / (h2d_gbs * 1e9), n_poses * 32 / (d2h_gbs * 1e9)),
-               "host_threads_bound_to_gpu_numa_node": bool(prev_affinity),
-               "timing": "host wall clock around the synchronous C-ABI call (it drives its own streams), max over ranks"}
-    else:
-        e2e_checksum_ok = None
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant (only) kernel ---------------------------------------------------------
-    peak, peak_src = load_peaks()
-    host_poses = d_poses.cpu().numpy()
-    win_bytes = pg.window_bytes(cmap, host_poses)
-    algo_bytes = win_bytes + 56 * n_poses
-    avg_launch_s = statistics.mean(per_launch_ms) * 1e-3
-    achieved = algo_bytes / avg_launch_s / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload)
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_pack_tiles + k_cost_batch_tile (one step)",
-                "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_pose": algo_bytes / n_poses,
-                "avg_launch_ms": avg_launch_s * 1e3}
-
-    # ---- parity spot check + CPU baseline (rank 0, N == 1 only for the baseline) ---------------------------
-    if prev_affinity:  # the CPU baseline may use every core of the box again
-        os.sched_setaffinity(0, prev_affinity)
-    from oracle import capi
-    oc = capi.CostData(fp, pad)
-    host_map = d_map.cpu().numpy()
-    n_chk = 4000
-    got = d_out[:n_chk].cpu().numpy()
-    ref = oc.get_cost_batch(host_map, host_poses[:n_chk], shift=True, nthreads=capi.max_threads())
-    ok = fx.tol_ok(got, ref)
-    parity = {"checked_poses": n_chk, "pass_rate_vs_shifted_reference": float(ok.all(axis=1).mean()),
-              "tolerance": "1e-6 + 1e-5*|ref|", "e2e_equals_device_path": e2e_checksum_ok}
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_reference_rate(fp, pad, host_map, host_poses)
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "poses_per_gpu": n_poses, "map": f"{side}x{side} uint8, Bernoulli(0.10)",
-                   "parallelism": f"dp{world} (poses sharded, map replicated, no collective)",
-                   "l2": "inputs larger than L2 (map+poses+results = 660 MB/step), no flush"
-                   if args.workload == "cfg5" else "map is L2-resident by design of this config"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "cpu_baseline": cpu_baseline, "parity": parity,
-    }
-    print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    ranks = dp.dist.Ranks(backend="nccl", device=torch.device("cuda", local_rank))
+    kind = WORKLOADS[args.workload][0]
+    line = {"batch": run_batch, "solve": run_solve, "single": run_single}[kind](args, ranks, torch, dp, fx)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    ranks.close()
     return 0
 
 

@@ -59,6 +59,7 @@ SYMBOLS = {
     "dpose_solver_default_options": (None, [_vp]),
     "dpose_sample_offsets": (_i, [_u32, _d, _d, _sz, _i, _vp]),
     "dpose_problem_solve_batch": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dpose_problem_solve_us": (_i, [_vp, C.POINTER(C.c_float)]),
     "dpose_world_to_cell": (_i, [_vp, _sz, _d, _d, _d, _u32, _u32, _vp, _vp]),
     "dpose_cell_to_world": (_i, [_vp, _sz, _d, _d, _d, _vp, _vp]),
     "dpose_check_footprint": (_i, [_vp, _vp, _i, C.c_uint8, C.POINTER(_i)]),

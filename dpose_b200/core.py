@@ -441,6 +441,12 @@ class problem:
             out["trace"] = tr
         return out
 
+    def solve_us(self):
+        """device time of the last solve_batch (kernels only), microseconds"""
+        us = C.c_float(0)
+        check(lib().dpose_problem_solve_us(self._h, C.byref(us)))
+        return us.value
+
     # the single-x TNLP callbacks, for callers that keep Ipopt's one-iterate-at-a-time shape
     def eval_f(self, x):
         return float(self.eval_batch([x], want=("f",))["f"][0])

@@ -123,6 +123,8 @@ void dpose_problem_destroy(dpose_problem *p) {
     cudaFree(p->d_solve);
     cudaFreeHost(p->h_solve);
     cudaFree(p->d_trace);
+    if (p->solve_ev0) cudaEventDestroy(p->solve_ev0);
+    if (p->solve_ev1) cudaEventDestroy(p->solve_ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
   }
   dpose_map_destroy(p->crop);

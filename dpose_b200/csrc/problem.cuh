@@ -44,4 +44,6 @@ struct dpose_problem {
   size_t solve_cap = 0, solve_trace_cap = 0;
   unsigned char *d_solve = nullptr, *h_solve = nullptr;
   double *d_trace = nullptr;
+  cudaEvent_t solve_ev0 = nullptr, solve_ev1 = nullptr;
+  float last_solve_us = 0.f;  // device time of the last solve: k_solve + check_footprint + k_solve_select
 };

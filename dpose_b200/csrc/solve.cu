@@ -360,6 +360,12 @@ int dpose_sample_offsets(uint32_t seed, double lin_tolerance, double rot_toleran
   return DPOSE_OK;
 }
 
+int dpose_problem_solve_us(const dpose_problem *p, float *us) {
+  if (!p || !us) return fail(DPOSE_EINVAL, "NULL argument");
+  *us = p->last_solve_us;
+  return DPOSE_OK;
+}
+
 int dpose_problem_solve_batch(dpose_problem *p, const double *x0, size_t n, const dpose_solver_options *opt_in, double *x,
                               double *f, uint8_t *status, int32_t *evals, dpose_solve_summary *summary, double *trace) {
   if (!p || (n && !x0)) return fail(DPOSE_EINVAL, "NULL argument");
@@ -383,6 +389,10 @@ int dpose_problem_solve_batch(dpose_problem *p, const double *x0, size_t n, cons
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
   std::lock_guard<std::mutex> lock(p->mu);
   if (!p->stream) DPOSE_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  if (!p->solve_ev0) {
+    DPOSE_CUDA(cudaEventCreate(&p->solve_ev0));
+    DPOSE_CUDA(cudaEventCreate(&p->solve_ev1));
+  }
   cudaStream_t st = p->stream;
   const Layout lay(n);
   const size_t x0_bytes = sizeof(double) * 3 * n;
@@ -424,6 +434,7 @@ int dpose_problem_solve_batch(dpose_problem *p, const double *x0, size_t n, cons
     } else {
       std::memset(&a.ctx, 0, sizeof(a.ctx));
     }
+    DPOSE_CUDA(cudaEventRecord(p->solve_ev0, st));
     a.x0 = d_x0;
     a.n = n;
     for (int k = 0; k < 3; ++k) a.pose[k] = p->pose[k];
@@ -463,9 +474,12 @@ int dpose_problem_solve_batch(dpose_problem *p, const double *x0, size_t n, cons
     k_solve_select<<<1, 1024, 0, st>>>(a.f, a.x, a.final_pose, a.status, d_ok, n,
                                        reinterpret_cast<dpose_solve_summary *>(d_base + lay.summary));
     DPOSE_LAUNCHED();
+    DPOSE_CUDA(cudaEventRecord(p->solve_ev1, st));
     DPOSE_CUDA(cudaMemcpyAsync(h_base, d_base, lay.total, cudaMemcpyDeviceToHost, st));  // the one D2H of the solve
     if (trace) DPOSE_CUDA(cudaMemcpyAsync(trace, p->d_trace, sizeof(double) * trace_doubles, cudaMemcpyDeviceToHost, st));
     DPOSE_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&p->last_solve_us, p->solve_ev0, p->solve_ev1);
+    p->last_solve_us *= 1000.f;
     if (x) std::memcpy(x, h_base + lay.x, sizeof(double) * 3 * n);
     if (f) std::memcpy(f, h_base + lay.f, sizeof(double) * n);
     if (evals) std::memcpy(evals, h_base + lay.evals, sizeof(int32_t) * n);

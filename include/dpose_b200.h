@@ -244,6 +244,10 @@ int dpose_problem_solve_batch(dpose_problem *problem, const double *x0, size_t n
                               double *x, double *f, uint8_t *status, int32_t *evals, dpose_solve_summary *summary,
                               double *trace);
 
+/* device time of the last dpose_problem_solve_batch on this problem (the solve, validation and ranking kernels,
+ * without the two copies), microseconds */
+int dpose_problem_solve_us(const dpose_problem *problem, float *us);
+
 /* ---- world <-> cell poses ------------------------------------------------------------------------
  * replaces to_cell / to_msg (dpose_goal_tolerance.cpp:294-330) for n poses; host arithmetic.  The costmap
  * geometry is costmap_2d::Costmap2D's (getOriginX/Y, getResolution, getSizeInCellsX/Y); yaw <-> quaternion

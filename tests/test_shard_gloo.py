@@ -1,7 +1,8 @@
-"""N>1 host logic on CPU: two gloo ranks shard a pose batch exactly like the multi-GPU driver
-(one process per device, costmap replicated, no data-path collective), results gathered on rank 0
-equal the single-process evaluation, and the timing reduction is a MAX over ranks.  The compute
-stand-in is the CPU oracle (this is a test; the product path is CUDA-only)."""
+"""N > 1 host logic on CPU: two gloo ranks run the multi-rank plumbing bench.py uses on GPUs (dpose_b200/dist.py:
+contiguous pose shards, barrier around the timed region, max-over-ranks time, whole-job throughput, the CPU-side
+barrier of the one-process-all-GPUs leg) — one process per device, costmap replicated, no data-path collective.  The
+results gathered on rank 0 must equal the single-process evaluation.  The compute stand-in is the CPU oracle (this
+is a test; the product's compute path is CUDA-only and is covered by the -m gpu tests)."""
 import os
 import socket
 import sys
@@ -23,31 +24,36 @@ def _free_port():
 
 
 def _worker(rank, world, port, tmp):
-    import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from dpose_b200.shard import shard_bounds
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from dpose_b200.dist import Ranks, shard_bounds
     from oracle import capi
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ranks = Ranks(backend="gloo")
+    assert (ranks.rank, ranks.world) == (rank, world)
     m = fx.bernoulli_map(300, 300, 0.10, 1)      # replicated costmap
-    poses = fx.random_poses(1001, 300, 300, 2)   # every rank knows the batch, evaluates its slice
+    poses = fx.random_poses(1001, 300, 300, 2)   # strong scaling: every rank draws the batch, keeps its slice
     lo, hi = shard_bounds(len(poses), rank, world)
     oc = capi.CostData(fx.RECT, 2)
+    ranks.barrier()
     part = oc.get_cost_batch(m, poses[lo:hi])
+    ranks.barrier()
+    seconds = 0.25 * (rank + 1)                  # a made-up per-rank duration: the job takes the slowest rank's
+    tmax = ranks.max(seconds)
+    total = ranks.sum(hi - lo)
+    thr = ranks.throughput(hi - lo, seconds)
+    ranks.host_barrier()
     gathered = [None] * world
-    dist.all_gather_object(gathered, (lo, hi, part))
-    t = torch.tensor([float(rank + 1)])
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)     # bench.py's max-over-ranks timing reduction
+    ranks.dist.all_gather_object(gathered, (lo, hi, part))
     if rank == 0:
         out = np.zeros((len(poses), 4))
         covered = np.zeros(len(poses), int)
         for lo_, hi_, p in gathered:
             out[lo_:hi_] = p
             covered[lo_:hi_] += 1
-        np.savez(tmp, out=out, covered=covered, tmax=t.numpy())
-    dist.barrier()
-    dist.destroy_process_group()
+        np.savez(tmp, out=out, covered=covered, tmax=tmax, total=total, thr=thr)
+    ranks.barrier()
+    ranks.close()
 
 
 def test_two_rank_sharding_matches_single_process(tmp_path):
@@ -57,14 +63,26 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), tmp), nprocs=2, join=True)
     r = np.load(tmp)
     assert np.all(r["covered"] == 1)
-    assert r["tmax"][0] == 2.0
+    assert float(r["tmax"]) == 0.5 and float(r["total"]) == 1001 and float(r["thr"]) == 1001 / 0.5
     m = fx.bernoulli_map(300, 300, 0.10, 1)
     poses = fx.random_poses(1001, 300, 300, 2)
     assert np.array_equal(r["out"], capi.CostData(fx.RECT, 2).get_cost_batch(m, poses))
 
 
+def test_single_process_ranks_are_a_no_op():
+    from dpose_b200.dist import Ranks
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        os.environ.pop(k, None)
+    ranks = Ranks(backend="gloo")
+    assert (ranks.rank, ranks.world, ranks.dist) == (0, 1, None)
+    ranks.barrier()
+    ranks.host_barrier()
+    assert ranks.max(3.5) == 3.5 and ranks.sum(7) == 7 and ranks.throughput(10, 2.0) == 5.0
+    ranks.close()
+
+
 def test_shard_bounds_cover_exactly():
-    from dpose_b200.shard import shard_bounds
+    from dpose_b200.dist import shard_bounds
     for n in (0, 1, 7, 8, 1001, 10_000_000):
         for world in (1, 2, 4, 8):
             spans = [shard_bounds(n, r, world) for r in range(world)]
