@@ -277,13 +277,11 @@ void dpose_pg_destroy(dpose_pg *pg) {
   if (!pg) return;
   {
     DeviceGuard guard(pg->device);
-    cudaFree(pg->d_cost);
-    cudaFree(pg->d_coef);
+    if (pg->d_cost) cudaFreeAsync(pg->d_cost, nullptr);  // one stream-ordered allocation: [cost | coef] (precompute.cu)
     cudaFree(pg->d_coef_image);
     if (pg->tex_hi) cudaDestroyTextureObject((cudaTextureObject_t)pg->tex_hi);
     cudaFree(pg->d_coef_hi);
     cudaFree(pg->d_coef_abs);
-    cudaFree(pg->d_arena);
     pg_release_batch_ctx(pg);
   }
   delete pg;

@@ -84,9 +84,6 @@ struct dpose_pg {
   std::vector<int32_t> h_edt_sq;
   std::vector<uint8_t> h_outline, h_mask;
   float precompute_us = 0.f;
-  // device arena of the precompute (footprint + intermediate images) and the offsets dpose_pg_stages reads
-  void *d_arena = nullptr;
-  size_t o_outline = 0, o_mask = 0, o_d2 = 0, o_pre = 0;
   // batched kernel geometry: side of the largest window (cells) any pose can touch
   int win_max = 0;
   // replicated, bank-interleaved copy of d_coef for the thread-per-pose kernel (get_cost_batch_tile.cu),

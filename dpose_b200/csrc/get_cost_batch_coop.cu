@@ -16,9 +16,7 @@ constexpr int kCoopThreads = 128;
 
 struct CoopBatchArgs {
   CoopCtx ctx;
-  const double *poses;  // null: lattice poses (sweep, sweep_base)
-  dpose_sweep sweep;
-  size_t sweep_base;
+  const double *poses;
   double *out;
   size_t n;
   int out_aligned;
@@ -36,13 +34,8 @@ __global__ void __launch_bounds__(kCoopThreads) k_cost_batch_coop(CoopBatchArgs 
   // the poses) may still be running; nothing of its output is touched before this point
   asm volatile("griddepcontrol.wait;" ::: "memory");
   for (size_t i = (size_t)blockIdx.x * kPerCta + tid / G; i < a.n; i += (size_t)gridDim.x * kPerCta) {
-    double tx, ty, th;
-    if (a.poses) {
-      const double *pp = a.poses + 3 * i;
-      tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
-    } else {
-      sweep_pose(a.sweep, a.sweep_base + i, &tx, &ty, &th);
-    }
+    const double *pp = a.poses + 3 * i;
+    const double tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
     double r[4];
     coop_eval<G, kJac>(a.ctx, tx, ty, th, g, gmask, s_mask + tid, kCoopThreads, r);
     if (g == 0 && a.cost_only) {
@@ -121,8 +114,6 @@ int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   CoopBatchArgs a;
   a.ctx = coop_ctx(pg, map);
   a.poses = spec.d_poses;
-  a.sweep = spec.sweep;
-  a.sweep_base = spec.sweep_base;
   a.out = spec.d_out;
   a.n = n;
   a.out_aligned = (reinterpret_cast<uintptr_t>(spec.d_out) & 31u) == 0;

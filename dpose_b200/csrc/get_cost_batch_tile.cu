@@ -173,9 +173,7 @@ struct TileArgs {
   int size_x, size_y;
   const uint32_t *tiles;
   uint32_t ntx, nty;
-  const double *poses;  // null: lattice poses (sweep, sweep_base)
-  dpose_sweep sweep;
-  size_t sweep_base;
+  const double *poses;
   double *out;
   int cost_only;  // out holds n costs instead of n x 4
   size_t n;
@@ -191,6 +189,15 @@ struct TileArgs {
 struct Acc4 {
   double f, su, sv, st;
 };
+
+// lattice poses of a sweep, gi = base .. base + n (see sweep_pose, common.cuh)
+__global__ void __launch_bounds__(256) k_sweep_poses(dpose_sweep sw, size_t base, size_t n, double *__restrict__ poses) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x, y, th;
+  sweep_pose(sw, base + i, &x, &y, &th);
+  poses[3 * i] = x, poses[3 * i + 1] = y, poses[3 * i + 2] = th;
+}
 
 // index of the most significant set bit (x != 0): one FLO, no bit reversal
 __device__ __forceinline__ int top_bit(unsigned x) {
@@ -324,13 +331,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   for (size_t base = (size_t)blockIdx.x * a.stride; base < a.n; base += (size_t)gridDim.x * a.stride) {
     const size_t idx = base + tid;
     if (idx >= a.n) break;
-    double tx, ty, th;
-    if (a.poses) {
-      const double *pp = a.poses + 3 * idx;
-      tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
-    } else {
-      sweep_pose(a.sweep, a.sweep_base + idx, &tx, &ty, &th);
-    }
+    const double *pp = a.poses + 3 * idx;
+    const double tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
     double s, c;
     sincos(th, &s, &c);
     const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y);
@@ -734,8 +736,6 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   a.ntx = map->tiles_ntx;
   a.nty = map->tiles_nty;
   a.poses = spec.d_poses;
-  a.sweep = spec.sweep;
-  a.sweep_base = spec.sweep_base;
   a.out = d_out;
   a.cost_only = spec.cost_only;
   a.n = n;
@@ -766,6 +766,28 @@ int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   if (!map->d_tiles || pg->rows < 4 || pg->cols < 4) {  // empty map / no valid patch: every sum is empty
     DPOSE_CUDA(cudaMemsetAsync(spec.d_out, 0, sizeof(double) * (spec.cost_only ? 1 : 4) * spec.n, stream));
     return DPOSE_OK;
+  }
+  if (!spec.d_poses) {
+    // a pose lattice: k_sweep_poses writes a slab of poses (<= 2^20, 24 MB, L2 resident) that the batch kernel launched
+    // right behind it consumes — the generation stays out of the hot kernels (measured: generating in-kernel cost the
+    // thread-per-pose kernel 4 % through register pressure), nothing crosses PCIe, and the slab never reaches HBM hot
+    constexpr size_t kSlab = (size_t)1 << 20;
+    double *d_slab = nullptr;
+    DPOSE_CUDA(cudaMallocAsync(&d_slab, sizeof(double) * 3 * std::min(spec.n, kSlab), stream));
+    int rc = DPOSE_OK;
+    for (size_t off = 0; off < spec.n && rc == DPOSE_OK; off += kSlab) {
+      BatchSpec part = spec;
+      part.n = std::min(kSlab, spec.n - off);
+      part.sweep_base = spec.sweep_base + off;
+      part.d_poses = d_slab;
+      part.d_out = spec.d_out + (spec.cost_only ? 1 : 4) * off;
+      part.hold_planes = spec.hold_planes || off > 0;
+      k_sweep_poses<<<(unsigned)((part.n + 255) / 256), 256, 0, stream>>>(spec.sweep, part.sweep_base, part.n, d_slab);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      rc = coop_batch_wanted(pg, part.n) ? get_cost_batch_coop(pg, map, part, stream) : get_cost_batch_tile(pg, map, part, stream);
+    }
+    cudaFreeAsync(d_slab, stream);
+    return rc;
   }
   if (coop_batch_wanted(pg, spec.n)) return get_cost_batch_coop(pg, map, spec, stream);
   return get_cost_batch_tile(pg, map, spec, stream);

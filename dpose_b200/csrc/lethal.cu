@@ -5,20 +5,21 @@
 // Device: stream compaction.  The reference sweeps the uint8 grid twice (:143-155 count, :167-179 write).  Here the
 // uint8 map is read ONCE — by k_pack_tiles (get_cost_batch_tile.cu: 16-byte coalesced loads, byte compare against 254),
 // and only for the rows that changed since the lethal tile plane was last built (all rows of a volatile map, none of a
-// clean one) — and both sweeps run over that 1-bit-per-cell plane, 1/8 of the bytes and resident in the 126 MB L2:
-//   k_count : one warp per (tile row, chunk of 32 tiles): one 256-bit load per lane = 1 KB of contiguous plane per warp,
-//             each row word clipped to the row's interval, popc, packed butterflies -> the counts of the 8
-//             (row, 1024-cell chunk) units
-//   k_scan  : two-level exclusive scan of the unit counts (row-major order)
-//   k_write : same load; row by row every lane expands its word into x offsets in shared memory, then the warp writes
-//             the unit's (x, y) pairs as consecutive 8-byte stores (full sectors)
-//   k_extract_small : boxes of up to 4096 units (the plugin's search box, a footprint's box) in one launch of one CTA
+// clean one) — and the compaction itself is ONE pass over that 1-bit-per-cell plane (1/8 of the bytes, L2 resident):
+//   k_extract : a CTA owns one tile row (8 map rows).  Its warps fetch the row's tiles with 256-bit loads (one tile per
+//               lane = 1 KB of contiguous plane per warp), clip every row word to the row's interval and count; the
+//               CTA scans its (row, 1024-cell chunk) counts in row-major order and obtains its global offset by a
+//               decoupled look-back over the aggregates the CTAs before it have published (single-pass chained scan:
+//               no count kernel, no scan kernels, no second read); then, row by row, every lane expands its word into
+//               x offsets in shared memory and the warp writes the row's (x, y) pairs as consecutive 8-byte stores.
+//               CTAs take their tile row from a ticket counter, so a CTA only ever waits for CTAs that already run.
+//   k_extract_small : boxes of up to 4096 units (the plugin's search box, a footprint's box) in one CTA, no look-back
 // Output order is row-major (y ascending, x ascending) and deterministic.
 // HBM traffic, 10000 x 10000 map at 10 % lethal: 100 MB read + 12.6 MB written by the pack (if the plane is stale),
-// 2 x 12.6 MB of plane read (L2 hits right after the pack), 80 MB of cells written — §8(d)'s 180 MB plus the plane.
+// 12.6 MB of plane read (L2 hits right after the pack), 80 MB of cells written — §8(d)'s 180 MB plus the plane.
 // The result buffer is sized by the box while that is small (<= 4 M cells), otherwise by what the previous extraction on
 // the same map returned (+25 %): one synchronisation per call; a first call on a large box, or one whose estimate
-// was too small, reads the total back before the write sweep.
+// was too small, runs the pass once to learn the total and once more to write.
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -74,7 +75,6 @@ namespace {
 // A CTA of 8 warps takes the 8 rows of one tile row of one chunk: its 32 tiles are 1 KB of contiguous plane.
 constexpr int kChunkTiles = 32;
 constexpr int kWarpsPerCta = 8;
-constexpr int kScanChunk = 2048;  // units per scan CTA (512 threads x 4)
 
 struct RowSpan {
   int xmin, xmax;
@@ -134,142 +134,158 @@ __device__ __forceinline__ bool warp_tile(const LethalArgs &a, long long warp_id
   return true;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_count(LethalArgs a, unsigned *unit_count) {
-  const int lane = threadIdx.x & 31;
-  Tile8 t;
-  int ty, chunk;
-  if (!warp_tile(a, (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5), lane, &t, &ty, &chunk)) return;
-  // eight counts per lane (each <= 32, their warp sums <= 1024): two per register, four butterflies instead of eight
-  unsigned c[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) c[q] = __popc(t.w[2 * q]) | (__popc(t.w[2 * q + 1]) << 16);
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) c[q] += __shfl_xor_sync(0xffffffffu, c[q], off);
-  if (lane < 8) {
-    const int yr = ty * 8 + lane - a.y_lo;
-    const unsigned v = (c[lane >> 1] >> ((lane & 1) * 16)) & 0xffffu;
-    if (yr >= 0 && yr < a.nrows) unit_count[(long long)yr * a.chunks_x + chunk] = v;
-  }
+// status word of a CTA in the chained scan: [epoch : 22][flag : 2][value : 40].  The epoch tags the call, so the array is
+// never cleared between calls (a stale word of an earlier call reads as "nothing published yet").
+constexpr unsigned long long kFlagAggregate = 1ull, kFlagInclusive = 2ull;
+__device__ __forceinline__ unsigned long long pack_status(unsigned epoch, unsigned long long flag, unsigned long long v) {
+  return ((unsigned long long)epoch << 42) | (flag << 40) | (v & ((1ull << 40) - 1ull));
 }
 
-// level 1: each CTA turns kScanChunk counts into exclusive prefixes + one chunk total
-__global__ void __launch_bounds__(512) k_scan_chunks(const unsigned *tile_count, unsigned *tile_prefix,
-                                                     unsigned long long *chunk_total, long long n_tiles) {
-  __shared__ unsigned warp_sum[16];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long base = (long long)blockIdx.x * kScanChunk + tid * 4;
-  unsigned v[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = base + i < n_tiles ? tile_count[base + i] : 0u;
-  const unsigned mine = v[0] + v[1] + v[2] + v[3];
-  unsigned inc = mine;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
-    if (lane >= off) inc += t;
-  }
-  if (lane == 31) warp_sum[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    unsigned w = lane < 16 ? warp_sum[lane] : 0u;
-    unsigned winc = w;
-#pragma unroll
-    for (int off = 1; off < 16; off <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, winc, off);
-      if (lane >= off) winc += t;
-    }
-    if (lane < 16) warp_sum[lane] = winc - w;  // exclusive
-    if (lane == 15) chunk_total[blockIdx.x] = winc;
-  }
-  __syncthreads();
-  unsigned ex = warp_sum[warp] + inc - mine;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (base + i < n_tiles) tile_prefix[base + i] = ex;
-    ex += v[i];
-  }
-}
+struct ExtractArgs {
+  LethalArgs box;
+  unsigned long long *status;   // one word per tile row of the box
+  unsigned long long *ticket;   // monotonically increasing over the workspace's lifetime
+  unsigned long long ticket_base;
+  unsigned epoch;               // 1 .. 2^22 - 1
+  int2 *out;
+  unsigned long long cap;       // cells `out` holds; 0: count only
+  unsigned long long *grand_total;
+};
 
-// level 2: exclusive scan of the chunk totals (one CTA, sequential over 1024-wide slabs)
-__global__ void __launch_bounds__(1024) k_scan_totals(unsigned long long *chunk_total, int n_chunks,
-                                                      unsigned long long *grand_total) {
-  __shared__ unsigned long long warp_sum[32];
-  __shared__ unsigned long long carry;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry = 0ull;
-  __syncthreads();
-  for (int base = 0; base < n_chunks; base += 1024) {
-    const int i = base + tid;
-    const unsigned long long mine = i < n_chunks ? chunk_total[i] : 0ull;
-    unsigned long long inc = mine;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, off);
-      if (lane >= off) inc += t;
-    }
-    if (lane == 31) warp_sum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      const unsigned long long w = warp_sum[lane];
-      unsigned long long winc = w;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, off);
-        if (lane >= off) winc += t;
-      }
-      warp_sum[lane] = winc - w;
-    }
-    __syncthreads();
-    const unsigned long long ex = carry + warp_sum[warp] + inc - mine;
-    if (i < n_chunks) chunk_total[i] = ex;
-    __syncthreads();
-    if (tid == 1023) carry = ex + mine;
-    __syncthreads();
-  }
-  if (tid == 0) *grand_total = carry;
-}
-
-// Emit, row by row of the warp's tile row: every lane expands its word into x offsets in the warp's staging row
-// (shared memory, 2 bytes per cell), then the warp writes the (x, y) pairs of the unit as consecutive 8-byte stores —
-// full 32-byte sectors instead of the lane-strided scatter of a per-lane emit loop.  `cap`: cells the result buffer
-// holds; a unit that would run past it writes nothing (the host sees total > cap and repeats the sweep with an exact
-// allocation).
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-    k_write(LethalArgs a, const unsigned *unit_prefix, const unsigned long long *chunk_offset, int2 *out,
-            unsigned long long cap) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
+  extern __shared__ unsigned s_cnt[];  // [8][chunks_x] unit counts, then their exclusive prefixes (row-major)
   __shared__ unsigned short s_stage[kWarpsPerCta][kChunkTiles * 32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  Tile8 t;
-  int ty, chunk;
-  if (!warp_tile(a, (long long)blockIdx.x * kWarpsPerCta + w, lane, &t, &ty, &chunk)) return;
-  const int xc = (a.tx0 + chunk * kChunkTiles) * 32;
+  __shared__ unsigned s_part[32];
+  __shared__ unsigned long long s_base;
+  __shared__ unsigned s_tr;
+  const LethalArgs &a = e.box;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int cx = a.chunks_x, n_units = 8 * cx;
+  if (tid == 0) s_tr = (unsigned)(atomicAdd(e.ticket, 1ull) - e.ticket_base);  // tile rows in the order CTAs start
+  __syncthreads();
+  const int tr = (int)s_tr;
+  // ---- counts of this tile row's units -----------------------------------------------------------------------------
+  for (int chunk = w; chunk < cx; chunk += kWarpsPerCta) {
+    Tile8 t;
+    int ty, ch;
+    warp_tile(a, (long long)tr * cx + chunk, lane, &t, &ty, &ch);
+    unsigned c[4];  // eight counts per lane (each <= 32, warp sums <= 1024): two per register, four butterflies
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    unsigned m = t.w[r];
-    const unsigned c = __popc(m);
-    unsigned inc = c;
+    for (int q = 0; q < 4; ++q) c[q] = __popc(t.w[2 * q]) | (__popc(t.w[2 * q + 1]) << 16);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[q] += __shfl_xor_sync(0xffffffffu, c[q], off);
+    if (lane < 8) s_cnt[lane * cx + chunk] = (c[lane >> 1] >> ((lane & 1) * 16)) & 0xffffu;
+  }
+  __syncthreads();
+  // ---- exclusive scan of the n_units counts (row-major = output order); total of the tile row -----------------------------
+  {
+    const int per = (n_units + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32);
+    const int lo = tid * per, hi = min(lo + per, n_units);
+    unsigned mine = 0;
+    for (int k = lo; k < hi; ++k) mine += s_cnt[k];
+    unsigned inc = mine;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const unsigned v = __shfl_up_sync(0xffffffffu, inc, off);
       if (lane >= off) inc += v;
     }
-    const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
-    if (total == 0) continue;  // warp-uniform (also for rows outside the box)
-    unsigned pos = inc - c;
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      s_stage[w][pos++] = (unsigned short)(lane * 32 + b);
+    if (lane == 31) s_part[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      const unsigned pv = lane < kWarpsPerCta ? s_part[lane] : 0u;
+      unsigned pinc = pv;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, pinc, off);
+        if (lane >= off) pinc += v;
+      }
+      if (lane < kWarpsPerCta) s_part[lane] = pinc - pv;
+      if (lane == kWarpsPerCta - 1) s_part[31] = pinc;  // total of the tile row
     }
-    __syncwarp();
-    const int y = ty * 8 + r;
-    const long long unit = (long long)(y - a.y_lo) * a.chunks_x + chunk;
-    const unsigned long long base = chunk_offset[unit / kScanChunk] + unit_prefix[unit];
-    if (base + total <= cap)
-      for (unsigned k = lane; k < total; k += 32) out[base + k] = make_int2(xc + (int)s_stage[w][k], y);
-    __syncwarp();  // the staging row is reused by the next row
+    __syncthreads();
+    unsigned ex = s_part[w] + inc - mine;
+    for (int k = lo; k < hi; ++k) {
+      const unsigned v = s_cnt[k];
+      s_cnt[k] = ex;
+      ex += v;
+    }
+  }
+  // ---- global offset: publish the aggregate, look back over the tile rows before this one -----------------------------
+  if (w == 0) {
+    const unsigned long long total = s_part[31];
+    volatile unsigned long long *st = e.status;
+    if (lane == 0) {
+      st[tr] = pack_status(e.epoch, tr == 0 ? kFlagInclusive : kFlagAggregate, total);
+      __threadfence();
+    }
+    unsigned long long prefix = 0;
+    int j = tr - 1;  // look back 32 predecessors at a time
+    while (j >= 0) {
+      const int k = j - lane;
+      unsigned long long word = 0;
+      bool ready = true;
+      if (k >= 0) {
+        do {
+          word = st[k];
+          ready = (unsigned)(word >> 42) == e.epoch && ((word >> 40) & 3ull) != 0ull;
+        } while (!ready);
+      }
+      const bool incl = k >= 0 && ((word >> 40) & 3ull) == kFlagInclusive;
+      const unsigned m_incl = __ballot_sync(0xffffffffu, incl);
+      const int stop = m_incl ? __ffs(m_incl) - 1 : 31;  // nearest predecessor with an inclusive prefix
+      unsigned long long v = (k >= 0 && lane <= stop) ? (word & ((1ull << 40) - 1ull)) : 0ull;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      prefix += v;
+      if (m_incl) break;
+      j -= 32;
+    }
+    if (lane == 0) {
+      if (tr > 0) {
+        st[tr] = pack_status(e.epoch, kFlagInclusive, prefix + total);
+        __threadfence();
+      }
+      s_base = prefix;
+      if (tr == a.n_tile_rows - 1) *e.grand_total = prefix + total;
+    }
+  }
+  __syncthreads();
+  if (e.cap == 0) return;  // count only
+  // ---- emit, row by row: x offsets staged in shared memory, then consecutive 8-byte stores ----------------------------
+  const unsigned long long base_tr = s_base;
+  for (int chunk = w; chunk < cx; chunk += kWarpsPerCta) {
+    Tile8 t;
+    int ty, ch;
+    warp_tile(a, (long long)tr * cx + chunk, lane, &t, &ty, &ch);  // the same kilobyte again: an L1 / L2 hit
+    const int xc = (a.tx0 + chunk * kChunkTiles) * 32;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      unsigned m = t.w[r];
+      const unsigned c = __popc(m);
+      unsigned inc = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += v;
+      }
+      const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+      if (total == 0) continue;  // warp-uniform (also for rows outside the box)
+      unsigned pos = inc - c;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        s_stage[w][pos++] = (unsigned short)(lane * 32 + b);
+      }
+      __syncwarp();
+      const unsigned long long base = base_tr + s_cnt[r * cx + chunk];
+      if (base + total <= e.cap) {
+        const int y = ty * 8 + r;
+        for (unsigned k = lane; k < total; k += 32) e.out[base + k] = make_int2(xc + (int)s_stage[w][k], y);
+      }
+      __syncwarp();  // the staging row is reused by the next row
+    }
   }
 }
 
@@ -370,10 +386,10 @@ struct LethalWs {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   RowSpan *d_spans = nullptr, *h_spans = nullptr;  // h_spans pinned
   size_t rows_cap = 0;
-  unsigned *d_count = nullptr, *d_prefix = nullptr;
-  size_t tiles_cap = 0;
-  unsigned long long *d_chunk = nullptr;  // n_chunks + 1 (last = grand total)
-  size_t chunks_cap = 0;
+  unsigned long long *d_status = nullptr;  // chained-scan status words, one per tile row (+ [cap]: ticket, [cap+1]: total)
+  size_t status_cap = 0;
+  unsigned epoch = 0;
+  unsigned long long tickets = 0;  // tickets handed out so far (the device counter is never reset)
   unsigned long long *h_total = nullptr;  // pinned
   float last_kernel_us = 0.f;
   unsigned long long hint = 0;  // cells the last extraction on this map returned
@@ -386,7 +402,7 @@ struct LethalWs {
     (void)device;  // the default pool's release threshold is raised once per device in api.cu (check_device)
     return DPOSE_OK;
   }
-  int reserve(size_t rows, size_t tiles, size_t chunks) {
+  int reserve(size_t rows, size_t tile_rows) {
     if (rows > rows_cap) {
       cudaFree(d_spans);
       cudaFreeHost(h_spans);
@@ -397,32 +413,24 @@ struct LethalWs {
       DPOSE_CUDA(cudaHostAlloc(&h_spans, sizeof(RowSpan) * cap, cudaHostAllocDefault));
       rows_cap = cap;
     }
-    if (tiles > tiles_cap) {
-      cudaFree(d_count);
-      cudaFree(d_prefix);
-      d_count = d_prefix = nullptr;
-      tiles_cap = 0;
-      const size_t cap = tiles + tiles / 2 + 1024;
-      DPOSE_CUDA(cudaMalloc(&d_count, sizeof(unsigned) * cap));
-      DPOSE_CUDA(cudaMalloc(&d_prefix, sizeof(unsigned) * cap));
-      tiles_cap = cap;
-    }
-    if (chunks + 1 > chunks_cap) {
-      cudaFree(d_chunk);
-      d_chunk = nullptr;
-      chunks_cap = 0;
-      const size_t cap = chunks + chunks / 2 + 16;
-      DPOSE_CUDA(cudaMalloc(&d_chunk, sizeof(unsigned long long) * cap));
-      chunks_cap = cap;
+    if (tile_rows > status_cap) {
+      cudaFree(d_status);
+      d_status = nullptr;
+      status_cap = 0;
+      const size_t cap = tile_rows + tile_rows / 2 + 64;
+      DPOSE_CUDA(cudaMalloc(&d_status, sizeof(unsigned long long) * (cap + 2)));
+      DPOSE_CUDA(cudaMemset(d_status, 0, sizeof(unsigned long long) * (cap + 2)));
+      DPOSE_CUDA(cudaStreamSynchronize(nullptr));  // the memset is asynchronous; its users run on a non-blocking stream
+      status_cap = cap;
+      epoch = 0;
+      tickets = 0;
     }
     return DPOSE_OK;
   }
   void release() {
     cudaFree(d_spans);
     cudaFreeHost(h_spans);
-    cudaFree(d_count);
-    cudaFree(d_prefix);
-    cudaFree(d_chunk);
+    cudaFree(d_status);
     cudaFreeHost(h_total);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -485,7 +493,7 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
     ws = static_cast<LethalWs *>(m->lethal_ws);
   }
   std::lock_guard<std::mutex> call_lock(ws->mu);
-  DPOSE_TRY(ws->reserve((size_t)nrows, 0, 0));
+  DPOSE_TRY(ws->reserve((size_t)nrows, 0));
   RowSpan *spans = ws->h_spans;
   for (int r = 0; r < nrows; ++r) spans[r] = RowSpan{INT_MAX, INT_MIN};
   for (int e = 0; e < 4; ++e)  // to_rays (:106-115)
@@ -514,9 +522,10 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
   a.tx0 = gx_min >> 5;
   a.chunks_x = ((gx_max >> 5) - a.tx0) / kChunkTiles + 1;
   a.n_units = (long long)nrows * a.chunks_x;
-  const int n_chunks = (int)((a.n_units + kScanChunk - 1) / kScanChunk);
-  DPOSE_TRY(ws->reserve((size_t)nrows, (size_t)a.n_units, (size_t)n_chunks));
+  if (a.chunks_x > 4096) return fail(DPOSE_EINVAL, "box wider than 4 M cells");  // 32 B of shared memory per chunk
+  DPOSE_TRY(ws->reserve((size_t)nrows, (size_t)a.n_tile_rows));
   a.spans = ws->d_spans;
+  unsigned long long *d_ticket = ws->d_status + ws->status_cap, *d_total = d_ticket + 1;
 
   cudaStream_t st = ws->stream;
   int2 *d_out = nullptr;
@@ -524,48 +533,63 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
     DPOSE_CUDA(cudaMemcpyAsync(ws->d_spans, ws->h_spans, sizeof(RowSpan) * nrows, cudaMemcpyHostToDevice, st));
     DPOSE_CUDA(cudaEventRecord(ws->ev0, st));
     // the ONE read of the uint8 map: the lethal tile plane, rebuilt for the rows that changed (every row of a volatile
-    // map); a clean plane costs nothing here.  Both sweeps below read the 1-bit plane (1/8 of the map's bytes).
+    // map); a clean plane costs nothing here.  The compaction below reads the 1-bit plane (1/8 of the map's bytes).
     DPOSE_TRY(tileplane_ensure(map, st, false));
     // capacity of the result buffer: the box itself while that is small, else what the last call on this map needed
-    // (+25 %); a first call on a large box sizes the result exactly after the count sweep (one more synchronisation)
+    // (+25 %); a first call on a large box runs the pass count-only first (one more launch and synchronisation)
     unsigned long long cap = box_cells <= kBoxSizedCells ? box_cells : (ws->hint ? ws->hint + ws->hint / 4 + 4096 : 0);
     cap = std::min(cap, box_cells);
     unsigned long long total = 0;
-    if (a.n_units <= kSmallUnits) {  // one launch: count, scan and emit in one CTA; <= 4 M cells, sized by the box
+    if (a.n_units <= kSmallUnits) {  // one CTA: count, scan and emit; <= 4 M cells, sized by the box
       cap = box_cells;
       DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
-      k_extract_small<<<1, 1024, 0, st>>>(a, d_out, cap, ws->d_chunk);
+      k_extract_small<<<1, 1024, 0, st>>>(a, d_out, cap, d_total);
       DPOSE_LAUNCHED();
-      DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_chunk, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
       DPOSE_CUDA(cudaStreamSynchronize(st));
       total = *ws->h_total;
     } else {
-      const unsigned grid = (unsigned)(((size_t)a.n_tile_rows * a.chunks_x + kWarpsPerCta - 1) / kWarpsPerCta);
-      k_count<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_count);
-      DPOSE_LAUNCHED();
-      k_scan_chunks<<<n_chunks, 512, 0, st>>>(ws->d_count, ws->d_prefix, ws->d_chunk, a.n_units);
-      DPOSE_LAUNCHED();
-      k_scan_totals<<<1, 1024, 0, st>>>(ws->d_chunk, n_chunks, ws->d_chunk + n_chunks);
-      DPOSE_LAUNCHED();
-      DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_chunk + n_chunks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-      for (int pass = 0; pass < 2; ++pass) {
-        if (!cap) {  // no estimate (or the estimate was too small): read the total back first
-          DPOSE_CUDA(cudaStreamSynchronize(st));
-          total = *ws->h_total;
-          if (total == 0) break;
-          cap = total;
+      const size_t dyn = sizeof(unsigned) * 8 * (size_t)a.chunks_x;
+      if (dyn > ((size_t)24 << 10))
+        DPOSE_CUDA(cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      auto pass = [&](unsigned long long capacity) -> int {
+        if (++ws->epoch >= (1u << 22)) {  // the epoch tag is about to wrap: start over from a cleared array
+          DPOSE_CUDA(cudaMemsetAsync(ws->d_status, 0, sizeof(unsigned long long) * ws->status_cap, st));
+          ws->epoch = 1;
         }
-        DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
-        k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_chunk, d_out, cap);
+        ExtractArgs e;
+        e.box = a;
+        e.status = ws->d_status;
+        e.ticket = d_ticket;
+        e.ticket_base = ws->tickets;
+        e.epoch = ws->epoch;
+        e.out = d_out;
+        e.cap = capacity;
+        e.grand_total = d_total;
+        k_extract<<<(unsigned)a.n_tile_rows, kWarpsPerCta * 32, dyn, st>>>(e);
         DPOSE_LAUNCHED();
+        ws->tickets += (unsigned long long)a.n_tile_rows;
+        DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
         DPOSE_CUDA(cudaStreamSynchronize(st));
         total = *ws->h_total;
-        if (total <= cap) break;
-        cudaFreeAsync(d_out, st);  // the estimate was too small: once more with the exact size
-        d_out = nullptr;
-        cap = 0;
+        return DPOSE_OK;
+      };
+      if (!cap) {  // no estimate yet: learn the total
+        DPOSE_TRY(pass(0));
+        cap = total;
+      }
+      if (cap) {
+        DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
+        DPOSE_TRY(pass(cap));
+        if (total > cap) {  // the estimate was too small: once more with the exact size
+          cudaFreeAsync(d_out, st);
+          d_out = nullptr;
+          cap = total;
+          DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
+          DPOSE_TRY(pass(cap));
+        }
       }
     }
     ws->hint = total;
@@ -574,7 +598,7 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       d_out = nullptr;
       return DPOSE_OK;
     }
-    cudaEventElapsedTime(&ws->last_kernel_us, ws->ev0, ws->ev1);  // ms: plane rebuild (if any), both sweeps, the scans
+    cudaEventElapsedTime(&ws->last_kernel_us, ws->ev0, ws->ev1);  // ms: plane rebuild (if any) + the compaction pass(es)
     ws->last_kernel_us *= 1000.f;
     *d_cells = d_out;
     *n = (size_t)total;

@@ -7,10 +7,15 @@
 //                        right (the rule of cv::polylines / cv::fillPoly's outline)
 //   2. even-odd fill   : one warp per scanline, 16.16 fixed-point edge crossings,
 //                        ballot-compacted and rank-sorted inside the warp
-//   3. exact EDT       : column pass (one thread per column, two sweeps), then a row pass
-//                        where each warp owns 32 output pixels and scans the row's parabolas
-//                        g(i)^2 + (x-i)^2 tile by tile, broadcasting candidates with
-//                        __shfl_sync and skipping tiles that cannot beat the current best.
+//   3. exact EDT       : column pass (one thread per column, two sweeps), then the row pass
+//                        d2(x) = min_i g(i)^2 + (x - i)^2 in one of two exact integer forms:
+//                        tables up to kScanCols columns — each warp owns 32 output pixels and scans the
+//                        row's parabolas tile by tile, broadcasting candidates with __shfl_sync and
+//                        skipping tiles that cannot beat the current best (a handful of tiles: lowest
+//                        latency); wider tables — Meijster's lower envelope, one thread per row: a
+//                        forward scan keeps the stack of parabolas that own a piece of the row (their
+//                        indices s and the first column t each one wins), a backward scan reads the
+//                        winners off, O(cols) per row instead of O(cols^2 / 32).
 //                        All integer -> squared distances are exact (bit-exact gate).
 //   4. cost shaping    : sqrt, outside *= -0.01f, global min (warp shuffles + one smem
 //                        atomic), shift, separable [1 2 1]/4 blur with REFLECT_101 borders.
@@ -18,6 +23,10 @@
 //                        compiler cannot contract it; the table is bit-identical to OpenCV's.
 //   5. patch tables    : FP64 bilinear coefficients per interpolation patch (the
 //                        reference-consistent form of "gradient tables").
+#include <algorithm>
+#include <cstring>
+#include <new>
+
 #include "common.cuh"
 
 namespace dpose {
@@ -28,14 +37,19 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kInfG = 1 << 20;   // "no outline pixel in this column"
 constexpr int kBigD2 = 1 << 29;  // its square stand-in; (x-i)^2 < 2^30 keeps sums in int32
 
+constexpr int kScanCols = 160;   // widest table whose row pass is the warp-shuffle scan (B200: crossover ~150-200)
+constexpr int kParamVerts = 64;  // footprints up to this many vertices travel in the kernel parameters
+
 struct PrecomputeArgs {
-  const int2 *fp;  // shifted footprint vertices
+  const int2 *fp;  // shifted footprint vertices (null: fp_param)
+  int2 fp_param[kParamVerts];
   int n;
   int rows, cols;
   uint8_t *outline, *mask;
   int *g;              // column-pass distances
   int *d2;             // squared EDT
   float *pre, *tmp, *cost;
+  float *cost_host;  // mapped pinned copy of the table for the caller (or null)
   PatchCoef *coef;
   long long *scratch;  // kWarps * 2 * n crossings
 };
@@ -86,6 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rows = p.rows, cols = p.cols, np = rows * cols, n = p.n;
   __shared__ unsigned s_maxmag;
+  auto vertex = [&](int e) { return p.fp ? p.fp[e] : p.fp_param[e]; };
 
   // ---- phase 0: white images ---------------------------------------------------------
   for (int i = tid; i < np; i += kThreads) {
@@ -97,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
 
   // ---- phase 1: outline (polylines == fillPoly's outline) ------------------------------
   for (int e = tid; e < n; e += kThreads) {
-    const int2 a = p.fp[e == 0 ? n - 1 : e - 1], b = p.fp[e];
+    const int2 a = vertex(e == 0 ? n - 1 : e - 1), b = vertex(e);
     draw_edge(p.outline, p.mask, cols, rows, a.x, a.y, b.x, b.y);
   }
   __syncthreads();
@@ -112,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
         bool active = false;
         long long x = 0;
         if (e < n) {
-          const int2 a = p.fp[e == 0 ? n - 1 : e - 1], b = p.fp[e];
+          const int2 a = vertex(e == 0 ? n - 1 : e - 1), b = vertex(e);
           if (a.y != b.y) {
             const long long dx = ((long long)(b.x - a.x) * 65536) / (long long)(b.y - a.y);
             const int y0 = a.y < b.y ? a.y : b.y, y1 = a.y < b.y ? b.y : a.y;
@@ -165,8 +180,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
   }
   __syncthreads();
 
-  // ---- phase 3b: EDT row pass, warp-shuffle scan over the row's parabolas ----------------
-  {
+  // ---- phase 3b: EDT row pass ----------------------------------------------------------------------
+  if (cols <= kScanCols) {  // warp-shuffle scan over the row's parabolas
     const int segs = (cols + 31) / 32;
     for (int item = warp; item < rows * segs; item += kWarps) {
       const int y = item / segs, s = item - y * segs;
@@ -189,6 +204,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
         }
       }
       if (x < cols) p.d2[y * cols + x] = best;
+    }
+  } else {  // Meijster's lower envelope, one thread per row
+    // the stacks live in the (still unused) float scratch images, [q][row] so that the threads of a warp, whose stack
+    // depths stay close, touch neighbouring words; the top of the stack is carried in registers
+    int *st_s = reinterpret_cast<int *>(p.pre), *st_t = reinterpret_cast<int *>(p.tmp);
+    for (int y = tid; y < rows; y += kThreads) {
+      const int *gr = p.g + y * cols;
+      auto g2_of = [&](int i) {
+        const int gi = gr[i];
+        return gi >= kInfG ? kBigD2 : gi * gi;
+      };
+      int q = 0, s_top = 0, t_top = 0, g2_top = g2_of(0);
+      st_s[y] = 0, st_t[y] = 0;
+      for (int u = 1; u < cols; ++u) {
+        const int g2u = g2_of(u);
+        // pop every parabola that u beats already at the column where it starts to own the row
+        while (q >= 0) {
+          const int a = t_top - s_top, b = t_top - u;
+          if (a * a + g2_top <= b * b + g2u) break;
+          --q;
+          if (q >= 0) {
+            s_top = st_s[q * rows + y];
+            t_top = st_t[q * rows + y];
+            g2_top = g2_of(s_top);
+          }
+        }
+        if (q < 0) {
+          q = 0, s_top = u, t_top = 0, g2_top = g2u;
+          st_s[y] = u, st_t[y] = 0;
+        } else {
+          // first column where u is strictly better than s_top: 1 + floor((u^2 - s^2 + g2u - g2s) / (2 (u - s)));
+          // the numerator is >= 0 here (s_top still wins at t_top >= 0) and < 2^31 (|g2| <= 2^29, u < 2^9)
+          const int w = 1 + (u * u - s_top * s_top + g2u - g2_top) / (2 * (u - s_top));
+          if (w < cols) {
+            ++q;
+            s_top = u, t_top = w, g2_top = g2u;
+            st_s[q * rows + y] = u, st_t[q * rows + y] = w;
+          }
+        }
+      }
+      for (int u = cols - 1; u >= 0; --u) {
+        const int dxi = u - s_top;
+        p.d2[y * cols + u] = dxi * dxi + g2_top;
+        if (u == t_top && q > 0) {
+          --q;
+          s_top = st_s[q * rows + y];
+          t_top = st_t[q * rows + y];
+          g2_top = g2_of(s_top);
+        }
+      }
     }
   }
   __syncthreads();
@@ -230,7 +295,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
     const float a = p.tmp[reflect101(y - 1, rows) * cols + x];
     const float b = p.tmp[i];
     const float c = p.tmp[reflect101(y + 1, rows) * cols + x];
-    p.cost[i] = __fadd_rn(__fmul_rn(__fadd_rn(a, c), 0.25f), __fmul_rn(b, 0.5f));
+    const float v = __fadd_rn(__fmul_rn(__fadd_rn(a, c), 0.25f), __fmul_rn(b, 0.5f));
+    p.cost[i] = v;
+    if (p.cost_host) p.cost_host[i] = v;  // straight into the caller's (mapped pinned) copy: no copy back
   }
   __syncthreads();
 
@@ -252,75 +319,162 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
 
 }  // namespace
 
-// One device arena holds the footprint and every intermediate image; it stays with the handle so that
-// dpose_pg_stages can download the intermediates on demand (they are a debugging / parity aid, like the
-// /tmp/*.jpg dumps of the reference's assert-enabled build, dpose_core.cpp:76,85,135).
-int precompute_run(dpose_pg *pg, const int32_t *fp_xy, int n) {
-  const int rows = pg->rows, cols = pg->cols;
-  const size_t np = (size_t)rows * cols;
-  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  const size_t o_fp = 0, o_outline = o_fp + up(sizeof(int2) * n), o_mask = o_outline + up(np),
-               o_g = o_mask + up(np), o_d2 = o_g + up(sizeof(int) * np), o_pre = o_d2 + up(sizeof(int) * np),
-               o_tmp = o_pre + up(sizeof(float) * np), o_scratch = o_tmp + up(sizeof(float) * np),
-               total = o_scratch + up(sizeof(long long) * kWarps * 2 * (size_t)n);
+// Device memory of one construction: the persistent part (cost table + patch coefficients) and a scratch arena with
+// the footprint and every intermediate image, both from the stream-ordered pool (no cudaMalloc after the first call
+// of a process).  The scratch is freed as soon as the kernel has run; dpose_pg_stages — a debugging / parity aid, like
+// the /tmp/*.jpg dumps of the reference's assert-enabled build (dpose_core.cpp:76,85,135) — re-runs the kernel on a
+// scratch arena of its own and downloads the intermediates from there.
+namespace {
+
+struct Arena {
+  size_t o_fp, o_outline, o_mask, o_g, o_d2, o_pre, o_tmp, o_scratch, total;
+  Arena(size_t np, int n) {
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    o_fp = 0;
+    o_outline = o_fp + up(sizeof(int2) * (size_t)n);
+    o_mask = o_outline + up(np);
+    o_g = o_mask + up(np);
+    o_d2 = o_g + up(sizeof(int) * np);
+    o_pre = o_d2 + up(sizeof(int) * np);
+    o_tmp = o_pre + up(sizeof(float) * np);
+    o_scratch = o_tmp + up(sizeof(float) * np);
+    total = o_scratch + up(sizeof(long long) * kWarps * 2 * (size_t)n);
+  }
+};
+
+// per host thread: timing events and a mapped pinned page the kernel writes small tables into (grow-only)
+struct ThreadCtx {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  auto body = [&]() -> int {
-    DPOSE_CUDA(cudaMalloc(&pg->d_arena, total));
-    DPOSE_CUDA(cudaMalloc(&pg->d_cost, sizeof(float) * np));
-    DPOSE_CUDA(cudaMalloc(&pg->d_coef, sizeof(PatchCoef) * np));
-    unsigned char *base = static_cast<unsigned char *>(pg->d_arena);
-    DPOSE_CUDA(cudaMemcpy(base + o_fp, fp_xy, sizeof(int2) * n, cudaMemcpyHostToDevice));
-    DPOSE_CUDA(cudaEventCreate(&e0));
-    DPOSE_CUDA(cudaEventCreate(&e1));
-    PrecomputeArgs a;
-    a.fp = reinterpret_cast<const int2 *>(base + o_fp);
-    a.n = n;
-    a.rows = rows;
-    a.cols = cols;
-    a.outline = base + o_outline;
-    a.mask = base + o_mask;
-    a.g = reinterpret_cast<int *>(base + o_g);
-    a.d2 = reinterpret_cast<int *>(base + o_d2);
-    a.pre = reinterpret_cast<float *>(base + o_pre);
-    a.tmp = reinterpret_cast<float *>(base + o_tmp);
-    a.cost = pg->d_cost;
-    a.coef = pg->d_coef;
-    a.scratch = reinterpret_cast<long long *>(base + o_scratch);
-    pg->o_outline = o_outline, pg->o_mask = o_mask, pg->o_d2 = o_d2, pg->o_pre = o_pre;
-    DPOSE_CUDA(cudaEventRecord(e0));
-    k_precompute<<<1, kThreads>>>(a);
-    DPOSE_LAUNCHED();
-    DPOSE_CUDA(cudaEventRecord(e1));
+  float *h_table = nullptr;
+  size_t cap = 0;
+  int device = -1;
+};
+
+int launch_precompute(const dpose_pg *pg, const int32_t *fp_xy, int n, unsigned char *base, const Arena &ar, float *d_cost,
+                      PatchCoef *d_coef, float *cost_host, cudaEvent_t e0, cudaEvent_t e1) {
+  PrecomputeArgs a;
+  a.n = n;
+  if (n <= kParamVerts) {
+    a.fp = nullptr;
+    for (int i = 0; i < n; ++i) a.fp_param[i] = make_int2(fp_xy[2 * i], fp_xy[2 * i + 1]);
+  } else {
+    DPOSE_CUDA(cudaMemcpyAsync(base + ar.o_fp, fp_xy, sizeof(int2) * n, cudaMemcpyHostToDevice, nullptr));
+    a.fp = reinterpret_cast<const int2 *>(base + ar.o_fp);
+  }
+  a.rows = pg->rows;
+  a.cols = pg->cols;
+  a.outline = base + ar.o_outline;
+  a.mask = base + ar.o_mask;
+  a.g = reinterpret_cast<int *>(base + ar.o_g);
+  a.d2 = reinterpret_cast<int *>(base + ar.o_d2);
+  a.pre = reinterpret_cast<float *>(base + ar.o_pre);
+  a.tmp = reinterpret_cast<float *>(base + ar.o_tmp);
+  a.cost = d_cost;
+  a.cost_host = cost_host;
+  a.coef = d_coef;
+  a.scratch = reinterpret_cast<long long *>(base + ar.o_scratch);
+  if (e0) DPOSE_CUDA(cudaEventRecord(e0, nullptr));
+  k_precompute<<<1, kThreads>>>(a);
+  DPOSE_LAUNCHED();
+  if (e1) DPOSE_CUDA(cudaEventRecord(e1, nullptr));
+  return DPOSE_OK;
+}
+
+}  // namespace
+
+int precompute_run(dpose_pg *pg, const int32_t *fp_xy, int n) {
+  const size_t np = (size_t)pg->rows * pg->cols;
+  const Arena ar(np, n);
+  thread_local ThreadCtx tc;
+  if (tc.device != pg->device) {  // a thread that moves between devices rebuilds its context (rare)
+    if (tc.e0) cudaEventDestroy(tc.e0);
+    if (tc.e1) cudaEventDestroy(tc.e1);
+    if (tc.h_table) cudaFreeHost(tc.h_table);
+    tc = ThreadCtx();
+    DPOSE_CUDA(cudaEventCreate(&tc.e0));
+    DPOSE_CUDA(cudaEventCreate(&tc.e1));
+    tc.device = pg->device;
+  }
+  constexpr size_t kZeroCopyTable = (size_t)1 << 16;  // tables up to 64 K cells land in mapped pinned memory
+  if (np <= kZeroCopyTable && tc.cap < np) {
+    if (tc.h_table) cudaFreeHost(tc.h_table);
+    tc.h_table = nullptr;
+    tc.cap = 0;
+    const size_t cap = std::max<size_t>(np, 4096);
+    DPOSE_CUDA(cudaHostAlloc(&tc.h_table, sizeof(float) * cap, cudaHostAllocMapped));
+    tc.cap = cap;
+  }
+  try {
     pg->h_cost.resize(np);
-    DPOSE_CUDA(cudaMemcpy(pg->h_cost.data(), pg->d_cost, sizeof(float) * np, cudaMemcpyDeviceToHost));
+  } catch (const std::bad_alloc &) {
+    return fail(DPOSE_ENOMEM, "out of host memory");
+  }
+  unsigned char *scratch = nullptr;
+  auto body = [&]() -> int {
+    // persistent: [cost | pad | coef] in one stream-ordered allocation
+    const size_t o_coef = (sizeof(float) * np + 255) & ~(size_t)255;
+    unsigned char *keep = nullptr;
+    DPOSE_CUDA(cudaMallocAsync(&keep, o_coef + sizeof(PatchCoef) * np, nullptr));
+    pg->d_cost = reinterpret_cast<float *>(keep);
+    pg->d_coef = reinterpret_cast<PatchCoef *>(keep + o_coef);
+    DPOSE_CUDA(cudaMallocAsync(&scratch, ar.total, nullptr));
+    float *cost_host = np <= kZeroCopyTable ? tc.h_table : nullptr;
+    DPOSE_TRY(launch_precompute(pg, fp_xy, n, scratch, ar, pg->d_cost, pg->d_coef, cost_host, tc.e0, tc.e1));
+    if (!cost_host)
+      DPOSE_CUDA(cudaMemcpyAsync(pg->h_cost.data(), pg->d_cost, sizeof(float) * np, cudaMemcpyDeviceToHost, nullptr));
+    DPOSE_CUDA(cudaFreeAsync(scratch, nullptr));
+    scratch = nullptr;
+    DPOSE_CUDA(cudaStreamSynchronize(nullptr));
+    if (cost_host) std::memcpy(pg->h_cost.data(), cost_host, sizeof(float) * np);
     float ms = 0.f;
-    DPOSE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    DPOSE_CUDA(cudaEventElapsedTime(&ms, tc.e0, tc.e1));
     pg->precompute_us = ms * 1000.f;
     return DPOSE_OK;
   };
   const int rc = body();
-  if (e0) cudaEventDestroy(e0);
-  if (e1) cudaEventDestroy(e1);
+  if (scratch) cudaFreeAsync(scratch, nullptr);
   return rc;
 }
 
-// downloads the intermediate images on first request
+// the intermediate images: the kernel once more, on a scratch arena of its own, downloaded on first request
 int precompute_fetch_stages(dpose_pg *pg) {
-  if (!pg->h_edt_sq.empty() || !pg->d_arena) return DPOSE_OK;
+  if (!pg->h_edt_sq.empty()) return DPOSE_OK;
   const size_t np = (size_t)pg->rows * pg->cols;
+  const int n = (int)(pg->footprint.size() / 2);
   DeviceGuard guard(pg->device);
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
-  const unsigned char *base = static_cast<const unsigned char *>(pg->d_arena);
-  pg->h_pre_blur.resize(np);
-  pg->h_outline.resize(np);
-  pg->h_mask.resize(np);
-  std::vector<int32_t> d2(np);
-  DPOSE_CUDA(cudaMemcpy(pg->h_pre_blur.data(), base + pg->o_pre, sizeof(float) * np, cudaMemcpyDeviceToHost));
-  DPOSE_CUDA(cudaMemcpy(d2.data(), base + pg->o_d2, sizeof(int) * np, cudaMemcpyDeviceToHost));
-  DPOSE_CUDA(cudaMemcpy(pg->h_outline.data(), base + pg->o_outline, np, cudaMemcpyDeviceToHost));
-  DPOSE_CUDA(cudaMemcpy(pg->h_mask.data(), base + pg->o_mask, np, cudaMemcpyDeviceToHost));
-  pg->h_edt_sq.swap(d2);  // last: h_edt_sq non-empty marks "fetched"
-  return DPOSE_OK;
+  std::vector<int32_t> shifted(pg->footprint);  // dpose_core.cpp:128
+  for (int i = 0; i < n; ++i) {
+    shifted[2 * i] += pg->center[0];
+    shifted[2 * i + 1] += pg->center[1];
+  }
+  const Arena ar(np, n);
+  unsigned char *scratch = nullptr;
+  std::vector<int32_t> d2;
+  auto body = [&]() -> int {
+    try {
+      pg->h_pre_blur.resize(np);
+      pg->h_outline.resize(np);
+      pg->h_mask.resize(np);
+      d2.resize(np);
+    } catch (const std::bad_alloc &) {
+      return fail(DPOSE_ENOMEM, "out of host memory");
+    }
+    const size_t o_cost = ar.total, o_coef = (o_cost + sizeof(float) * np + 255) & ~(size_t)255;
+    DPOSE_CUDA(cudaMallocAsync(&scratch, o_coef + sizeof(PatchCoef) * np, nullptr));
+    DPOSE_TRY(launch_precompute(pg, shifted.data(), n, scratch, ar, reinterpret_cast<float *>(scratch + o_cost),
+                                reinterpret_cast<PatchCoef *>(scratch + o_coef), nullptr, nullptr, nullptr));
+    DPOSE_CUDA(cudaMemcpyAsync(pg->h_pre_blur.data(), scratch + ar.o_pre, sizeof(float) * np, cudaMemcpyDeviceToHost, nullptr));
+    DPOSE_CUDA(cudaMemcpyAsync(d2.data(), scratch + ar.o_d2, sizeof(int) * np, cudaMemcpyDeviceToHost, nullptr));
+    DPOSE_CUDA(cudaMemcpyAsync(pg->h_outline.data(), scratch + ar.o_outline, np, cudaMemcpyDeviceToHost, nullptr));
+    DPOSE_CUDA(cudaMemcpyAsync(pg->h_mask.data(), scratch + ar.o_mask, np, cudaMemcpyDeviceToHost, nullptr));
+    DPOSE_CUDA(cudaStreamSynchronize(nullptr));
+    return DPOSE_OK;
+  };
+  const int rc = body();
+  if (scratch) cudaFreeAsync(scratch, nullptr);
+  if (rc == DPOSE_OK) pg->h_edt_sq.swap(d2);  // last: h_edt_sq non-empty marks "fetched"
+  return rc;
 }
 
 }  // namespace dpose
