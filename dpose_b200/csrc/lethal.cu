@@ -6,20 +6,23 @@
 // uint8 map is read ONCE — by k_pack_tiles (get_cost_batch_tile.cu: 16-byte coalesced loads, byte compare against 254),
 // and only for the rows that changed since the lethal tile plane was last built (all rows of a volatile map, none of a
 // clean one) — and the compaction itself is ONE pass over that 1-bit-per-cell plane (1/8 of the bytes, L2 resident):
-//   k_extract : a CTA owns one tile row (8 map rows).  Its warps fetch the row's tiles with 256-bit loads (one tile per
-//               lane = 1 KB of contiguous plane per warp), clip every row word to the row's interval and count; the
-//               CTA scans its (row, 1024-cell chunk) counts in row-major order and obtains its global offset by a
-//               decoupled look-back over the aggregates the CTAs before it have published (single-pass chained scan:
-//               no count kernel, no scan kernels, no second read); then, row by row, every lane expands its word into
-//               x offsets in shared memory and the warp writes the row's (x, y) pairs as consecutive 8-byte stores.
-//               CTAs take their tile row from a ticket counter, so a CTA only ever waits for CTAs that already run.
+//   k_extract<false> : a CTA owns one tile row (8 map rows).  Its warps fetch the row's tiles with 256-bit loads (one
+//               tile per lane = 1 KB of contiguous plane per warp), clip every row word to the row's interval and count;
+//               the tile row's total goes to totals[], to its group of 64 tile rows and to the grand total (2 atomics)
+//   k_extract<true>  : the counts again (L2 hot), scanned inside the CTA in row-major order; the CTA's global offset is
+//               summed on the fly from the group totals and the tile-row totals before it (two short reads: no scan
+//               kernel, no look-back chain); then, row by row, every lane expands its word into x offsets in shared
+//               memory and the warp writes the row's (x, y) pairs as consecutive 8-byte stores.
+//               (A single-pass chained scan with decoupled look-back was built and measured first: 77 us against 58 us
+//               for count / scan / write — with 1 KB of input per warp the look-back over ~1000 resident CTAs costs more
+//               than the second, L2-resident read of the plane.)
 //   k_extract_small : boxes of up to 4096 units (the plugin's search box, a footprint's box) in one CTA, no look-back
 // Output order is row-major (y ascending, x ascending) and deterministic.
 // HBM traffic, 10000 x 10000 map at 10 % lethal: 100 MB read + 12.6 MB written by the pack (if the plane is stale),
 // 12.6 MB of plane read (L2 hits right after the pack), 80 MB of cells written — §8(d)'s 180 MB plus the plane.
 // The result buffer is sized by the box while that is small (<= 4 M cells), otherwise by what the previous extraction on
 // the same map returned (+25 %): one synchronisation per call; a first call on a large box, or one whose estimate
-// was too small, runs the pass once to learn the total and once more to write.
+// was too small, reads the total back before the write pass.
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -134,36 +137,39 @@ __device__ __forceinline__ bool warp_tile(const LethalArgs &a, long long warp_id
   return true;
 }
 
-// status word of a CTA in the chained scan: [epoch : 22][flag : 2][value : 40].  The epoch tags the call, so the array is
-// never cleared between calls (a stale word of an earlier call reads as "nothing published yet").
-constexpr unsigned long long kFlagAggregate = 1ull, kFlagInclusive = 2ull;
-__device__ __forceinline__ unsigned long long pack_status(unsigned epoch, unsigned long long flag, unsigned long long v) {
-  return ((unsigned long long)epoch << 42) | (flag << 40) | (v & ((1ull << 40) - 1ull));
-}
+// The compaction over the tile plane, two launches of the same kernel body.  A CTA owns one tile row of the box (8 map
+// rows x chunks_x chunks of 1024 cells); its warps fetch the row's tiles with 256-bit loads (one tile per lane = 1 KB
+// of contiguous plane per warp), clip every row word to the row's interval and count the (row, chunk) units.
+//   kWrite = false : the tile row's total goes to totals[tr], to its group of 64 tile rows (one atomic) and to the grand
+//                    total (one atomic): 2 atomics per CTA instead of a scan kernel
+//   kWrite = true  : the counts again (the plane is L2 / L1 hot), an in-CTA scan of the units in row-major order, the
+//                    CTA's global offset summed on the fly from the group totals before its group and the tile-row
+//                    totals before it inside the group (two short coalesced reads — no look-back chain, no scan
+//                    kernel), then the emit: row by row every lane expands its word into x offsets in shared memory and
+//                    the warp writes the row's (x, y) pairs as consecutive 8-byte stores (full sectors).
+// `cap`: cells the result buffer holds; a unit that would run past it writes nothing (the host sees total > cap and
+// repeats the write pass with an exact allocation).
+constexpr int kGroup = 64;  // tile rows per group total
 
 struct ExtractArgs {
   LethalArgs box;
-  unsigned long long *status;   // one word per tile row of the box
-  unsigned long long *ticket;   // monotonically increasing over the workspace's lifetime
-  unsigned long long ticket_base;
-  unsigned epoch;               // 1 .. 2^22 - 1
+  unsigned *totals;              // one per tile row of the box
+  unsigned long long *groups;    // one per kGroup tile rows; [n_groups] = grand total
+  int n_groups;
   int2 *out;
-  unsigned long long cap;       // cells `out` holds; 0: count only
-  unsigned long long *grand_total;
+  unsigned long long cap;
 };
 
+template <bool kWrite>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
   extern __shared__ unsigned s_cnt[];  // [8][chunks_x] unit counts, then their exclusive prefixes (row-major)
-  __shared__ unsigned short s_stage[kWarpsPerCta][kChunkTiles * 32];
+  __shared__ unsigned short s_stage[kWrite ? kWarpsPerCta : 1][kChunkTiles * 32];
   __shared__ unsigned s_part[32];
-  __shared__ unsigned long long s_base;
-  __shared__ unsigned s_tr;
+  __shared__ unsigned long long s_red[kWarpsPerCta];
   const LethalArgs &a = e.box;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int cx = a.chunks_x, n_units = 8 * cx;
-  if (tid == 0) s_tr = (unsigned)(atomicAdd(e.ticket, 1ull) - e.ticket_base);  // tile rows in the order CTAs start
-  __syncthreads();
-  const int tr = (int)s_tr;
+  const int tr = blockIdx.x;
   // ---- counts of this tile row's units -----------------------------------------------------------------------------
   for (int chunk = w; chunk < cx; chunk += kWarpsPerCta) {
     Tile8 t;
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
   // ---- exclusive scan of the n_units counts (row-major = output order); total of the tile row -----------------------------
   {
     const int per = (n_units + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32);
-    const int lo = tid * per, hi = min(lo + per, n_units);
+    const int lo = min(tid * per, n_units), hi = min(lo + per, n_units);
     unsigned mine = 0;
     for (int k = lo; k < hi; ++k) mine += s_cnt[k];
     unsigned inc = mine;
@@ -205,56 +211,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
       if (lane == kWarpsPerCta - 1) s_part[31] = pinc;  // total of the tile row
     }
     __syncthreads();
-    unsigned ex = s_part[w] + inc - mine;
-    for (int k = lo; k < hi; ++k) {
-      const unsigned v = s_cnt[k];
-      s_cnt[k] = ex;
-      ex += v;
+    if (kWrite) {
+      unsigned ex = s_part[w] + inc - mine;
+      for (int k = lo; k < hi; ++k) {
+        const unsigned v = s_cnt[k];
+        s_cnt[k] = ex;
+        ex += v;
+      }
     }
   }
-  // ---- global offset: publish the aggregate, look back over the tile rows before this one -----------------------------
-  if (w == 0) {
-    const unsigned long long total = s_part[31];
-    volatile unsigned long long *st = e.status;
-    if (lane == 0) {
-      st[tr] = pack_status(e.epoch, tr == 0 ? kFlagInclusive : kFlagAggregate, total);
-      __threadfence();
-    }
-    unsigned long long prefix = 0;
-    int j = tr - 1;  // look back 32 predecessors at a time
-    while (j >= 0) {
-      const int k = j - lane;
-      unsigned long long word = 0;
-      bool ready = true;
-      if (k >= 0) {
-        do {
-          word = st[k];
-          ready = (unsigned)(word >> 42) == e.epoch && ((word >> 40) & 3ull) != 0ull;
-        } while (!ready);
+  if (!kWrite) {
+    if (tid == 0) {
+      const unsigned total = s_part[31];
+      e.totals[tr] = total;
+      if (total) {
+        atomicAdd(&e.groups[tr / kGroup], (unsigned long long)total);
+        atomicAdd(&e.groups[e.n_groups], (unsigned long long)total);
       }
-      const bool incl = k >= 0 && ((word >> 40) & 3ull) == kFlagInclusive;
-      const unsigned m_incl = __ballot_sync(0xffffffffu, incl);
-      const int stop = m_incl ? __ffs(m_incl) - 1 : 31;  // nearest predecessor with an inclusive prefix
-      unsigned long long v = (k >= 0 && lane <= stop) ? (word & ((1ull << 40) - 1ull)) : 0ull;
+    }
+    return;
+  }
+  // ---- global offset of this tile row: group totals before its group + tile-row totals before it inside the group --------
+  {
+    const int g = tr / kGroup;
+    unsigned long long v = 0;
+    for (int k = tid; k < g; k += kWarpsPerCta * 32) v += e.groups[k];
+    const int k2 = g * kGroup + tid;
+    if (tid < kGroup && k2 < tr) v += e.totals[k2];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      prefix += v;
-      if (m_incl) break;
-      j -= 32;
-    }
-    if (lane == 0) {
-      if (tr > 0) {
-        st[tr] = pack_status(e.epoch, kFlagInclusive, prefix + total);
-        __threadfence();
-      }
-      s_base = prefix;
-      if (tr == a.n_tile_rows - 1) *e.grand_total = prefix + total;
-    }
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[w] = v;
   }
   __syncthreads();
-  if (e.cap == 0) return;  // count only
+  unsigned long long base_tr = 0;
+#pragma unroll
+  for (int k = 0; k < kWarpsPerCta; ++k) base_tr += s_red[k];
   // ---- emit, row by row: x offsets staged in shared memory, then consecutive 8-byte stores ----------------------------
-  const unsigned long long base_tr = s_base;
   for (int chunk = w; chunk < cx; chunk += kWarpsPerCta) {
     Tile8 t;
     int ty, ch;
@@ -386,10 +378,9 @@ struct LethalWs {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   RowSpan *d_spans = nullptr, *h_spans = nullptr;  // h_spans pinned
   size_t rows_cap = 0;
-  unsigned long long *d_status = nullptr;  // chained-scan status words, one per tile row (+ [cap]: ticket, [cap+1]: total)
-  size_t status_cap = 0;
-  unsigned epoch = 0;
-  unsigned long long tickets = 0;  // tickets handed out so far (the device counter is never reset)
+  unsigned *d_totals = nullptr;            // one per tile row of the box
+  unsigned long long *d_groups = nullptr;  // one per 64 tile rows, + the grand total
+  size_t totals_cap = 0;
   unsigned long long *h_total = nullptr;  // pinned
   float last_kernel_us = 0.f;
   unsigned long long hint = 0;  // cells the last extraction on this map returned
@@ -413,24 +404,23 @@ struct LethalWs {
       DPOSE_CUDA(cudaHostAlloc(&h_spans, sizeof(RowSpan) * cap, cudaHostAllocDefault));
       rows_cap = cap;
     }
-    if (tile_rows > status_cap) {
-      cudaFree(d_status);
-      d_status = nullptr;
-      status_cap = 0;
+    if (tile_rows > totals_cap) {
+      cudaFree(d_totals);
+      cudaFree(d_groups);
+      d_totals = nullptr, d_groups = nullptr;
+      totals_cap = 0;
       const size_t cap = tile_rows + tile_rows / 2 + 64;
-      DPOSE_CUDA(cudaMalloc(&d_status, sizeof(unsigned long long) * (cap + 2)));
-      DPOSE_CUDA(cudaMemset(d_status, 0, sizeof(unsigned long long) * (cap + 2)));
-      DPOSE_CUDA(cudaStreamSynchronize(nullptr));  // the memset is asynchronous; its users run on a non-blocking stream
-      status_cap = cap;
-      epoch = 0;
-      tickets = 0;
+      DPOSE_CUDA(cudaMalloc(&d_totals, sizeof(unsigned) * cap));
+      DPOSE_CUDA(cudaMalloc(&d_groups, sizeof(unsigned long long) * (cap / kGroup + 2)));
+      totals_cap = cap;
     }
     return DPOSE_OK;
   }
   void release() {
     cudaFree(d_spans);
     cudaFreeHost(h_spans);
-    cudaFree(d_status);
+    cudaFree(d_totals);
+    cudaFree(d_groups);
     cudaFreeHost(h_total);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -525,7 +515,8 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
   if (a.chunks_x > 4096) return fail(DPOSE_EINVAL, "box wider than 4 M cells");  // 32 B of shared memory per chunk
   DPOSE_TRY(ws->reserve((size_t)nrows, (size_t)a.n_tile_rows));
   a.spans = ws->d_spans;
-  unsigned long long *d_ticket = ws->d_status + ws->status_cap, *d_total = d_ticket + 1;
+  const int n_groups = (a.n_tile_rows + kGroup - 1) / kGroup;
+  unsigned long long *d_total = ws->d_groups + n_groups;
 
   cudaStream_t st = ws->stream;
   int2 *d_out = nullptr;
@@ -536,7 +527,7 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
     // map); a clean plane costs nothing here.  The compaction below reads the 1-bit plane (1/8 of the map's bytes).
     DPOSE_TRY(tileplane_ensure(map, st, false));
     // capacity of the result buffer: the box itself while that is small, else what the last call on this map needed
-    // (+25 %); a first call on a large box runs the pass count-only first (one more launch and synchronisation)
+    // (+25 %); a first call on a large box reads the total back before the write pass (one more synchronisation)
     unsigned long long cap = box_cells <= kBoxSizedCells ? box_cells : (ws->hint ? ws->hint + ws->hint / 4 + 4096 : 0);
     cap = std::min(cap, box_cells);
     unsigned long long total = 0;
@@ -551,45 +542,40 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       total = *ws->h_total;
     } else {
       const size_t dyn = sizeof(unsigned) * 8 * (size_t)a.chunks_x;
-      if (dyn > ((size_t)24 << 10))
-        DPOSE_CUDA(cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      auto pass = [&](unsigned long long capacity) -> int {
-        if (++ws->epoch >= (1u << 22)) {  // the epoch tag is about to wrap: start over from a cleared array
-          DPOSE_CUDA(cudaMemsetAsync(ws->d_status, 0, sizeof(unsigned long long) * ws->status_cap, st));
-          ws->epoch = 1;
+      if (dyn > ((size_t)16 << 10)) {
+        DPOSE_CUDA(cudaFuncSetAttribute(k_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        DPOSE_CUDA(cudaFuncSetAttribute(k_extract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      }
+      ExtractArgs e;
+      e.box = a;
+      e.totals = ws->d_totals;
+      e.groups = ws->d_groups;
+      e.n_groups = n_groups;
+      e.out = nullptr;
+      e.cap = 0;
+      DPOSE_CUDA(cudaMemsetAsync(ws->d_groups, 0, sizeof(unsigned long long) * (n_groups + 1), st));
+      k_extract<false><<<(unsigned)a.n_tile_rows, kWarpsPerCta * 32, dyn, st>>>(e);
+      DPOSE_LAUNCHED();
+      DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!cap) {  // no estimate (or it was too small): the exact total first
+          DPOSE_CUDA(cudaStreamSynchronize(st));
+          total = *ws->h_total;
+          if (total == 0) break;
+          cap = total;
         }
-        ExtractArgs e;
-        e.box = a;
-        e.status = ws->d_status;
-        e.ticket = d_ticket;
-        e.ticket_base = ws->tickets;
-        e.epoch = ws->epoch;
+        DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
         e.out = d_out;
-        e.cap = capacity;
-        e.grand_total = d_total;
-        k_extract<<<(unsigned)a.n_tile_rows, kWarpsPerCta * 32, dyn, st>>>(e);
+        e.cap = cap;
+        k_extract<true><<<(unsigned)a.n_tile_rows, kWarpsPerCta * 32, dyn, st>>>(e);
         DPOSE_LAUNCHED();
-        ws->tickets += (unsigned long long)a.n_tile_rows;
-        DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
         DPOSE_CUDA(cudaStreamSynchronize(st));
         total = *ws->h_total;
-        return DPOSE_OK;
-      };
-      if (!cap) {  // no estimate yet: learn the total
-        DPOSE_TRY(pass(0));
-        cap = total;
-      }
-      if (cap) {
-        DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
-        DPOSE_TRY(pass(cap));
-        if (total > cap) {  // the estimate was too small: once more with the exact size
-          cudaFreeAsync(d_out, st);
-          d_out = nullptr;
-          cap = total;
-          DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
-          DPOSE_TRY(pass(cap));
-        }
+        if (total <= cap) break;
+        cudaFreeAsync(d_out, st);
+        d_out = nullptr;
+        cap = 0;
       }
     }
     ws->hint = total;

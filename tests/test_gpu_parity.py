@@ -97,14 +97,17 @@ def test_tables_bit_exact_vs_oracle_random_polygons(dp, capi):
     assert checked == 120
 
 
-def test_large_table_exact(dp, capi):
-    # a table larger than any fixture: exercises multi-tile EDT row scans
-    fp = np.array([[150, 0], [40, 90], [-120, 60], [-160, -10], [-20, -100], [90, -70]], np.int32)
-    o = capi.CostData(fp, 7)
-    cd = dp.cost_data(fp, 7)
+@pytest.mark.parametrize("scale,pad", [(1.0, 7), (0.45, 3), (1.5, 10)])
+def test_large_table_exact(dp, capi, scale, pad):
+    # tables larger than any fixture: 325 x 215 and 500 x 325 cells run the Meijster lower-envelope row pass (wider than
+    # 160 columns), 150 x 97 the multi-tile warp-shuffle scan; squared distances bit-exact either way
+    fp = np.round(np.array([[150, 0], [40, 90], [-120, 60], [-160, -10], [-20, -100], [90, -70]]) * scale).astype(np.int32)
+    o = capi.CostData(fp, pad)
+    cd = dp.cost_data(fp, pad)
     d2, outline, mask, pre = cd.stages()
     assert np.array_equal(d2, o.edt_sq) and np.array_equal(mask, o.mask)
     assert np.array_equal(bits(cd.get_data()), bits(o.cost))
+    assert np.array_equal(bits(dp.cost_data(fp, pad).get_data()), bits(o.cost))  # a second handle: pooled scratch reused
 
 
 @pytest.mark.parametrize("shift", [(10, 0), (4, 5), (-4, -5), (0, -9)])
@@ -410,7 +413,10 @@ def test_batch_clip_invariant_large_tables(dp, half):
     out = batch_both(pg, full, poses, rel=1e-10)  # 1e5 .. 2.5e5 terms per sum
     for p, o in zip(poses, out):
         c, J = pg.get_cost(p, allc)
-        assert fx.tol_ok(o[0], c, rel=1e-11, abs_=1e-9) and np.all(fx.tol_ok(o[1:], J, rel=1e-9, abs_=1e-6)), (p, o, c, J)
+        # 1e5 .. 2.6e5 cells per sum: a Jacobian entry can vanish by symmetry while its terms are ~ cost / cell x lever arm
+        # each, so the rounding of the two summation orders is measured against cost x table side
+        j_abs = 1e-14 * abs(c) * max(cd.rows, cd.cols)
+        assert fx.tol_ok(o[0], c, rel=1e-11, abs_=1e-9) and np.all(fx.tol_ok(o[1:], J, rel=1e-9, abs_=j_abs)), (p, o, c, J)
     with pytest.raises(RuntimeError):  # beyond 512 x 512 cells the table is refused
         dp.pose_gradient(np.array([[300, 10], [-300, 10], [-300, -10], [300, -10]], np.int32))
 
