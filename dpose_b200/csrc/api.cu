@@ -332,7 +332,7 @@ static int map_create_impl(const uint8_t *data, uint32_t size_x, uint32_t size_y
   m->device = device;
   m->size_x = size_x;
   m->size_y = size_y;
-  m->pitch = ((size_t)size_x + 15) & ~(size_t)15;
+  m->pitch = ((size_t)size_x + 31) & ~(size_t)31;  // 32-byte rows: k_pack_tiles reads a tile row with one 256-bit load
   auto body = [&]() -> int {
     DeviceGuard guard(device);
     if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", device);

@@ -107,7 +107,7 @@ struct dpose_pg {
 struct dpose_map {
   int device = 0;
   uint32_t size_x = 0, size_y = 0;
-  size_t pitch = 0;  // bytes, multiple of 16
+  size_t pitch = 0;  // bytes, multiple of 32 (pad bytes are zero)
   uint8_t *d_data = nullptr;
   // lethal tile plane (get_cost_batch_tile.cu): bit = (cell == 254), in 32 x 8 cell tiles of 32 bytes: word
   // ((ty * tiles_ntx + tx) * 8 + (y & 7)), bit x & 31; tiles_ntx includes one zero pad tile per tile row.

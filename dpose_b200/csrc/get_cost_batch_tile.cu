@@ -53,8 +53,14 @@ __device__ __forceinline__ unsigned lethal_bits16(const uint4 v) {
   return n0 | (n1 << 4) | (n2 << 8) | (n3 << 12);
 }
 
-// One thread per plane word.  Lane l of a warp handles row (l >> 2) of tile column 4 * warp + (l & 3):
-// the warp reads 8 map rows x 128 contiguous bytes and writes 4 tiles = 128 contiguous bytes.
+__device__ __forceinline__ unsigned lethal_bits32(const uint32_t v[8]) {
+  const uint4 lo = make_uint4(v[0], v[1], v[2], v[3]), hi = make_uint4(v[4], v[5], v[6], v[7]);
+  return lethal_bits16(lo) | (lethal_bits16(hi) << 16);
+}
+
+// One thread per plane word.  Lane l of a warp handles row (l >> 2) of tile column 4 * warp + (l & 3): the warp reads
+// 8 map rows x 128 contiguous bytes (one 256-bit load per lane) and writes 4 tiles = 128 contiguous bytes.  Two warp
+// items per iteration, both loads issued before the first compare: 64 bytes in flight per thread.
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ map, size_t pitch, uint32_t size_y,
                                                     uint32_t *__restrict__ tiles, uint32_t ntx, uint32_t ty0,
                                                     uint32_t ty1) {
@@ -65,20 +71,33 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ 
   const size_t n_warps = (size_t)quads * (ty1 - ty0);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t r = lane >> 2, j = lane & 3;
-  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps;
-       w += ((size_t)gridDim.x * blockDim.x) >> 5) {
-    const uint32_t byr = (uint32_t)(w / quads), bx = (uint32_t)(w - (size_t)byr * quads) * 4 + j;
-    const uint32_t by = ty0 + byr;
-    if (bx >= ntx) continue;
+  const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 5;
+  auto locate = [&](size_t w, uint32_t *by, uint32_t *bx) {
+    const uint32_t byr = (uint32_t)(w / quads);
+    *bx = (uint32_t)(w - (size_t)byr * quads) * 4 + j;
+    *by = ty0 + byr;
+  };
+  auto fetch = [&](uint32_t by, uint32_t bx, uint32_t v[8]) {  // pitch % 32 == 0 and the pad bytes of the device copy are zero
     const uint32_t y = by * 8 + r;
     const size_t x = (size_t)bx * 32;
-    unsigned out = 0u;
-    if (y < size_y) {  // pitch % 16 == 0 and the pad bytes of the device copy are zero
-      const uint8_t *row = map + (size_t)y * pitch;
-      if (x < pitch) out = lethal_bits16(__ldg(reinterpret_cast<const uint4 *>(row + x)));
-      if (x + 16 < pitch) out |= lethal_bits16(__ldg(reinterpret_cast<const uint4 *>(row + x + 16))) << 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0u;
+    if (bx < ntx && y < size_y && x < pitch)
+      asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "l"(map + (size_t)y * pitch + x));
+  };
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps; w += 2 * stride) {
+    uint32_t by0, bx0, by1 = 0, bx1 = 0, v0[8], v1[8];
+    const bool two = w + stride < n_warps;
+    locate(w, &by0, &bx0);
+    fetch(by0, bx0, v0);
+    if (two) {
+      locate(w + stride, &by1, &bx1);
+      fetch(by1, bx1, v1);
     }
-    tiles[((size_t)by * ntx + bx) * 8 + r] = out;
+    if (bx0 < ntx) tiles[((size_t)by0 * ntx + bx0) * 8 + r] = lethal_bits32(v0);
+    if (two && bx1 < ntx) tiles[((size_t)by1 * ntx + bx1) * 8 + r] = lethal_bits32(v1);
   }
 }
 

@@ -88,6 +88,7 @@ struct LethalArgs {
   uint32_t ntx;
   const RowSpan *spans;  // nrows, indexed by y - y_lo
   int y_lo, nrows;
+  int in_x0, in_x1;  // columns every row's interval contains (max of xmin, min of xmax; empty if in_x0 > in_x1)
   int ty0;        // first tile row (y_lo >> 3)
   int tx0;        // first tile column of chunk 0
   int chunks_x;   // chunks per row
@@ -102,13 +103,9 @@ struct LethalArgs {
 struct Tile8 {
   unsigned w[8];
 };
-__device__ __forceinline__ bool warp_tile(const LethalArgs &a, long long warp_id, int lane, Tile8 *t, int *ty_out, int *chunk_out) {
-  const long long n_warps = (long long)a.n_tile_rows * a.chunks_x;
-  if (warp_id >= n_warps) return false;
-  const int tr = (int)(warp_id / a.chunks_x), chunk = (int)(warp_id - (long long)tr * a.chunks_x);
+__device__ __forceinline__ void warp_tile(const LethalArgs &a, int tr, int chunk, int lane, Tile8 *t, int *ty_out) {
   const int ty = a.ty0 + tr, tx = a.tx0 + chunk * kChunkTiles + lane;
   *ty_out = ty;
-  *chunk_out = chunk;
 #pragma unroll
   for (int r = 0; r < 8; ++r) t->w[r] = 0u;
   if ((uint32_t)tx < a.ntx) {  // tiles past the plane's width read as zero
@@ -118,6 +115,10 @@ __device__ __forceinline__ bool warp_tile(const LethalArgs &a, long long warp_id
                    "=r"(t->w[7])
                  : "l"(p));
   }
+  // interior of the box (warp-uniform test): all 8 rows belong to it and every row's interval covers the chunk's 1024
+  // columns — nothing to clip.  Nearly every unit of a large box takes this path.
+  const int xc = (a.tx0 + chunk * kChunkTiles) * 32;
+  if (ty * 8 >= a.y_lo && ty * 8 + 7 < a.y_lo + a.nrows && xc >= a.in_x0 && xc + kChunkTiles * 32 - 1 <= a.in_x1) return;
   const int x0 = tx * 32;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
@@ -134,7 +135,6 @@ __device__ __forceinline__ bool warp_tile(const LethalArgs &a, long long warp_id
     }
     t->w[r] = m;
   }
-  return true;
 }
 
 // The compaction over the tile plane, two launches of the same kernel body.  A CTA owns one tile row of the box (8 map
@@ -162,19 +162,20 @@ struct ExtractArgs {
 
 template <bool kWrite>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
-  extern __shared__ unsigned s_cnt[];  // [8][chunks_x] unit counts, then their exclusive prefixes (row-major)
-  __shared__ unsigned short s_stage[kWrite ? kWarpsPerCta : 1][kChunkTiles * 32];
+  // dynamic: [8][chunks_x] unit counts (then their exclusive prefixes, row-major) | per warp 1024 staged x offsets
+  extern __shared__ unsigned s_cnt[];
   __shared__ unsigned s_part[32];
   __shared__ unsigned long long s_red[kWarpsPerCta];
   const LethalArgs &a = e.box;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n_warps = blockDim.x >> 5, n_thr = blockDim.x;  // 1 .. kWarpsPerCta warps, chosen by the host
   const int cx = a.chunks_x, n_units = 8 * cx;
   const int tr = blockIdx.x;
   // ---- counts of this tile row's units -----------------------------------------------------------------------------
-  for (int chunk = w; chunk < cx; chunk += kWarpsPerCta) {
+  for (int chunk = w; chunk < cx; chunk += n_warps) {
     Tile8 t;
-    int ty, ch;
-    warp_tile(a, (long long)tr * cx + chunk, lane, &t, &ty, &ch);
+    int ty;
+    warp_tile(a, tr, chunk, lane, &t, &ty);
     unsigned c[4];  // eight counts per lane (each <= 32, warp sums <= 1024): two per register, four butterflies
 #pragma unroll
     for (int q = 0; q < 4; ++q) c[q] = __popc(t.w[2 * q]) | (__popc(t.w[2 * q + 1]) << 16);
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
   __syncthreads();
   // ---- exclusive scan of the n_units counts (row-major = output order); total of the tile row -----------------------------
   {
-    const int per = (n_units + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32);
+    const int per = (n_units + n_thr - 1) / n_thr;
     const int lo = min(tid * per, n_units), hi = min(lo + per, n_units);
     unsigned mine = 0;
     for (int k = lo; k < hi; ++k) mine += s_cnt[k];
@@ -200,15 +201,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
     if (lane == 31) s_part[w] = inc;
     __syncthreads();
     if (w == 0) {
-      const unsigned pv = lane < kWarpsPerCta ? s_part[lane] : 0u;
+      const unsigned pv = lane < n_warps ? s_part[lane] : 0u;
       unsigned pinc = pv;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const unsigned v = __shfl_up_sync(0xffffffffu, pinc, off);
         if (lane >= off) pinc += v;
       }
-      if (lane < kWarpsPerCta) s_part[lane] = pinc - pv;
-      if (lane == kWarpsPerCta - 1) s_part[31] = pinc;  // total of the tile row
+      if (lane < n_warps) s_part[lane] = pinc - pv;
+      if (lane == 31) s_part[31] = pinc;  // total of the tile row
     }
     __syncthreads();
     if (kWrite) {
@@ -235,23 +236,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
   {
     const int g = tr / kGroup;
     unsigned long long v = 0;
-    for (int k = tid; k < g; k += kWarpsPerCta * 32) v += e.groups[k];
-    const int k2 = g * kGroup + tid;
-    if (tid < kGroup && k2 < tr) v += e.totals[k2];
+    for (int k = tid; k < g; k += n_thr) v += e.groups[k];
+    for (int k2 = g * kGroup + tid; k2 < tr; k2 += n_thr) v += e.totals[k2];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (lane == 0) s_red[w] = v;
   }
   __syncthreads();
   unsigned long long base_tr = 0;
-#pragma unroll
-  for (int k = 0; k < kWarpsPerCta; ++k) base_tr += s_red[k];
-  // ---- emit, row by row: x offsets staged in shared memory, then consecutive 8-byte stores ----------------------------
-  for (int chunk = w; chunk < cx; chunk += kWarpsPerCta) {
+  for (int k = 0; k < n_warps; ++k) base_tr += s_red[k];
+  // ---- emit, row by row: x offsets staged in shared memory, then consecutive stores ------------------------------------
+  unsigned short *stage = reinterpret_cast<unsigned short *>(s_cnt + n_units) + w * (kChunkTiles * 32);
+  const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(stage);
+  for (int chunk = w; chunk < cx; chunk += n_warps) {
     Tile8 t;
-    int ty, ch;
-    warp_tile(a, (long long)tr * cx + chunk, lane, &t, &ty, &ch);  // the same kilobyte again: an L1 / L2 hit
+    int ty;
+    warp_tile(a, tr, chunk, lane, &t, &ty);  // the same kilobyte again: an L1 / L2 hit
     const int xc = (a.tx0 + chunk * kChunkTiles) * 32;
+    const unsigned xl = (unsigned)(lane * 32);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       unsigned m = t.w[r];
@@ -264,17 +266,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
       }
       const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
       if (total == 0) continue;  // warp-uniform (also for rows outside the box)
-      unsigned pos = inc - c;
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        s_stage[w][pos++] = (unsigned short)(lane * 32 + b);
+      uint32_t sp = stage_u32 + 2u * (inc - c);
+      m = __brev(m);  // lowest x first with one FLO per bit
+      while (m) {     // ~3 set bits per lane at 10 % density
+        const unsigned b = (unsigned)__clz(m);
+        m ^= 0x80000000u >> b;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sp), "h"((unsigned short)(xl + b)) : "memory");
+        sp += 2u;
       }
       __syncwarp();
       const unsigned long long base = base_tr + s_cnt[r * cx + chunk];
       if (base + total <= e.cap) {
         const int y = ty * 8 + r;
-        for (unsigned k = lane; k < total; k += 32) e.out[base + k] = make_int2(xc + (int)s_stage[w][k], y);
+        int2 *o = e.out + base + lane;
+        const unsigned short *q = stage + lane;
+        for (unsigned k = lane; k < total; k += 32, o += 32, q += 32) *o = make_int2(xc + (int)*q, y);
       }
       __syncwarp();  // the staging row is reused by the next row
     }
@@ -493,13 +499,17 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       s.xmax = std::max(s.xmax, x);
     });
   int gx_min = INT_MAX, gx_max = INT_MIN;
+  int in_x0 = INT_MIN, in_x1 = INT_MAX;  // the columns every row's interval contains
   unsigned long long box_cells = 0;  // cells inside the row intervals: an upper bound of the result size
-  for (int r = 0; r < nrows; ++r)
+  for (int r = 0; r < nrows; ++r) {
     if (spans[r].xmin <= spans[r].xmax) {
       gx_min = std::min(gx_min, spans[r].xmin);
       gx_max = std::max(gx_max, spans[r].xmax);
       box_cells += (unsigned long long)(spans[r].xmax - spans[r].xmin + 1);
     }
+    in_x0 = std::max(in_x0, spans[r].xmin);
+    in_x1 = std::min(in_x1, spans[r].xmax);
+  }
   if (gx_min > gx_max) return DPOSE_OK;  // degenerate ring (all four edges empty)
 
   LethalArgs a;
@@ -507,6 +517,8 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
   a.ntx = map->tiles_ntx;
   a.y_lo = y_lo;
   a.nrows = nrows;
+  a.in_x0 = in_x0;
+  a.in_x1 = in_x1;
   a.ty0 = y_lo >> 3;
   a.n_tile_rows = (y_hi >> 3) - a.ty0 + 1;
   a.tx0 = gx_min >> 5;
@@ -541,10 +553,14 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       DPOSE_CUDA(cudaStreamSynchronize(st));
       total = *ws->h_total;
     } else {
-      const size_t dyn = sizeof(unsigned) * 8 * (size_t)a.chunks_x;
-      if (dyn > ((size_t)16 << 10)) {
-        DPOSE_CUDA(cudaFuncSetAttribute(k_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        DPOSE_CUDA(cudaFuncSetAttribute(k_extract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      // warps per CTA: every warp one or two of the tile row's chunks, and CTAs small enough that the whole grid is
+      // resident at once when it can be (1250 tile rows of a 10000-row map: 5 warps -> 12 CTAs per SM, one wave)
+      const int warps = std::min(kWarpsPerCta, std::max(1, (a.chunks_x + 1) / 2));
+      const size_t dyn_cnt = sizeof(unsigned) * 8 * (size_t)a.chunks_x;
+      const size_t dyn_wr = dyn_cnt + (size_t)warps * kChunkTiles * 32 * sizeof(unsigned short);
+      if (dyn_wr > ((size_t)40 << 10)) {
+        DPOSE_CUDA(cudaFuncSetAttribute(k_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_cnt));
+        DPOSE_CUDA(cudaFuncSetAttribute(k_extract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_wr));
       }
       ExtractArgs e;
       e.box = a;
@@ -554,7 +570,7 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       e.out = nullptr;
       e.cap = 0;
       DPOSE_CUDA(cudaMemsetAsync(ws->d_groups, 0, sizeof(unsigned long long) * (n_groups + 1), st));
-      k_extract<false><<<(unsigned)a.n_tile_rows, kWarpsPerCta * 32, dyn, st>>>(e);
+      k_extract<false><<<(unsigned)a.n_tile_rows, warps * 32, dyn_cnt, st>>>(e);
       DPOSE_LAUNCHED();
       DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       for (int attempt = 0; attempt < 2; ++attempt) {
@@ -567,7 +583,7 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
         DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
         e.out = d_out;
         e.cap = cap;
-        k_extract<true><<<(unsigned)a.n_tile_rows, kWarpsPerCta * 32, dyn, st>>>(e);
+        k_extract<true><<<(unsigned)a.n_tile_rows, warps * 32, dyn_wr, st>>>(e);
         DPOSE_LAUNCHED();
         DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
         DPOSE_CUDA(cudaStreamSynchronize(st));

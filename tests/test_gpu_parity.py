@@ -484,7 +484,7 @@ def test_sweep_device_entry_and_argument_checks(dp):
     assert np.array_equal(d_out.cpu().numpy(), want)
     assert lib().dpose_pg_get_cost_sweep(pg._data._h, cm._h, None, None, 1, 0) == 1  # DPOSE_EINVAL
     with pytest.raises(dp.DposeError):
-        pg.get_cost_sweep(cm, (0, 1, 1 << 30), (0, 1, 1 << 30), (0, 1, 4), out=np.empty(1))
+        pg.get_cost_sweep(cm, (0, 1, 1 << 30), (0, 1, 1 << 30), (0, 1, 4), d_out=d_out.data_ptr())  # 2^62 poses: refused
 
 
 def test_batch_sees_map_updates(dp):
