@@ -5,21 +5,17 @@
 // Device: stream compaction.  The reference sweeps the uint8 grid twice (:143-155 count, :167-179 write).  Here the
 // uint8 map is read ONCE — by k_pack_tiles (get_cost_batch_tile.cu: 16-byte coalesced loads, byte compare against 254),
 // and only for the rows that changed since the lethal tile plane was last built (all rows of a volatile map, none of a
-// clean one) — and the compaction itself is ONE pass over that 1-bit-per-cell plane (1/8 of the bytes, L2 resident):
-//   k_extract<false> : a CTA owns one tile row (8 map rows).  Its warps fetch the row's tiles with 256-bit loads (one
-//               tile per lane = 1 KB of contiguous plane per warp), clip every row word to the row's interval and count;
-//               the tile row's total goes to totals[], to its group of 64 tile rows and to the grand total (2 atomics)
-//   k_extract<true>  : the counts again (L2 hot), scanned inside the CTA in row-major order; the CTA's global offset is
-//               summed on the fly from the group totals and the tile-row totals before it (two short reads: no scan
-//               kernel, no look-back chain); then, row by row, every lane expands its word into x offsets in shared
-//               memory and the warp writes the row's (x, y) pairs as consecutive 8-byte stores.
-//               (A single-pass chained scan with decoupled look-back was built and measured first: 77 us against 58 us
-//               for count / scan / write — with 1 KB of input per warp the look-back over ~1000 resident CTAs costs more
-//               than the second, L2-resident read of the plane.)
+// clean one) — and the compaction itself runs over that 1-bit-per-cell plane (1/8 of the bytes, L2 resident):
+//   k_count : one warp per (tile row, chunk of 32 tiles): one 256-bit load per lane = 1 KB of contiguous plane per warp,
+//             each row word clipped to the row's interval (interior units skip the clip), popc, packed butterflies ->
+//             the counts of the 8 (row, 1024-cell chunk) units
+//   k_scan  : exclusive scan of the unit counts in row-major order, both levels in one launch (last-CTA pattern)
+//   k_write : same load (L2 hot); row by row every lane expands its word into x offsets in shared memory, then the warp
+//             writes the unit's (x, y) pairs as consecutive 8-byte stores (full sectors)
 //   k_extract_small : boxes of up to 4096 units (the plugin's search box, a footprint's box) in one CTA, no look-back
 // Output order is row-major (y ascending, x ascending) and deterministic.
 // HBM traffic, 10000 x 10000 map at 10 % lethal: 100 MB read + 12.6 MB written by the pack (if the plane is stale),
-// 12.6 MB of plane read (L2 hits right after the pack), 80 MB of cells written — §8(d)'s 180 MB plus the plane.
+// 2 x 12.6 MB of plane read (L2 hits right after the pack), 80 MB of cells written — §8(d)'s 180 MB plus the plane.
 // The result buffer is sized by the box while that is small (<= 4 M cells), otherwise by what the previous extraction on
 // the same map returned (+25 %): one synchronisation per call; a first call on a large box, or one whose estimate
 // was too small, reads the total back before the write pass.
@@ -137,153 +133,180 @@ __device__ __forceinline__ void warp_tile(const LethalArgs &a, int tr, int chunk
   }
 }
 
-// The compaction over the tile plane, two launches of the same kernel body.  A CTA owns one tile row of the box (8 map
-// rows x chunks_x chunks of 1024 cells); its warps fetch the row's tiles with 256-bit loads (one tile per lane = 1 KB
-// of contiguous plane per warp), clip every row word to the row's interval and count the (row, chunk) units.
-//   kWrite = false : the tile row's total goes to totals[tr], to its group of 64 tile rows (one atomic) and to the grand
-//                    total (one atomic): 2 atomics per CTA instead of a scan kernel
-//   kWrite = true  : the counts again (the plane is L2 / L1 hot), an in-CTA scan of the units in row-major order, the
-//                    CTA's global offset summed on the fly from the group totals before its group and the tile-row
-//                    totals before it inside the group (two short coalesced reads — no look-back chain, no scan
-//                    kernel), then the emit: row by row every lane expands its word into x offsets in shared memory and
-//                    the warp writes the row's (x, y) pairs as consecutive 8-byte stores (full sectors).
+// The compaction over the tile plane: count, scan, write.  A warp owns one (tile row, chunk of 1024 cells) — 8 units, one
+// per map row — and never synchronises with another warp:
+//   k_count : 256-bit loads (one tile per lane = 1 KB of contiguous plane per warp), every row word clipped to the row's
+//             interval (skipped for interior units), popc, packed butterflies -> unit_count[(row, chunk)]
+//   k_scan  : exclusive scan of the unit counts in row-major order (the output order): 2048 units per CTA; the CTA that
+//             finishes last (ticket) scans the CTA totals, so one launch does both levels
+//   k_write : the same load (L2 hot); the 8 units' offsets are fetched up front by 8 lanes; then, row by row, every lane
+//             expands its word into x offsets in shared memory and the warp writes the row's (x, y) pairs as consecutive
+//             8-byte stores (full sectors)
+// (Two other shapes were built and measured on the full 10000 x 10000 map, clean plane: a single-pass chained scan with
+// decoupled look-back — 77 us, the look-back over ~1000 resident CTAs costs more than a second L2-resident read of
+// 12.6 MB — and a CTA-per-tile-row totals pass + write pass with the offset summed on the fly — 61 us, two block
+// barriers and a block scan per 8 KB of input.)
 // `cap`: cells the result buffer holds; a unit that would run past it writes nothing (the host sees total > cap and
 // repeats the write pass with an exact allocation).
-constexpr int kGroup = 64;  // tile rows per group total
+constexpr int kScanUnits = 2048;  // units per scan CTA (512 threads x 4)
 
-struct ExtractArgs {
-  LethalArgs box;
-  unsigned *totals;              // one per tile row of the box
-  unsigned long long *groups;    // one per kGroup tile rows; [n_groups] = grand total
-  int n_groups;
-  int2 *out;
-  unsigned long long cap;
-};
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_count(LethalArgs a, unsigned *unit_count) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (wid >= (long long)a.n_tile_rows * a.chunks_x) return;
+  const int tr = (int)(wid / a.chunks_x), chunk = (int)(wid - (long long)tr * a.chunks_x);
+  Tile8 t;
+  int ty;
+  warp_tile(a, tr, chunk, lane, &t, &ty);
+  unsigned c[4];  // eight counts per lane (each <= 32, warp sums <= 1024): two per register, four butterflies
+#pragma unroll
+  for (int q = 0; q < 4; ++q) c[q] = __popc(t.w[2 * q]) | (__popc(t.w[2 * q + 1]) << 16);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[q] += __shfl_xor_sync(0xffffffffu, c[q], off);
+  if (lane < 8) {
+    const int yr = ty * 8 + lane - a.y_lo;
+    if (yr >= 0 && yr < a.nrows) unit_count[(long long)yr * a.chunks_x + chunk] = (c[lane >> 1] >> ((lane & 1) * 16)) & 0xffffu;
+  }
+}
 
-template <bool kWrite>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_extract(ExtractArgs e) {
-  // dynamic: [8][chunks_x] unit counts (then their exclusive prefixes, row-major) | per warp 1024 staged x offsets
-  extern __shared__ unsigned s_cnt[];
-  __shared__ unsigned s_part[32];
-  __shared__ unsigned long long s_red[kWarpsPerCta];
-  const LethalArgs &a = e.box;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int n_warps = blockDim.x >> 5, n_thr = blockDim.x;  // 1 .. kWarpsPerCta warps, chosen by the host
-  const int cx = a.chunks_x, n_units = 8 * cx;
-  const int tr = blockIdx.x;
-  // ---- counts of this tile row's units -----------------------------------------------------------------------------
-  for (int chunk = w; chunk < cx; chunk += n_warps) {
-    Tile8 t;
-    int ty;
-    warp_tile(a, tr, chunk, lane, &t, &ty);
-    unsigned c[4];  // eight counts per lane (each <= 32, warp sums <= 1024): two per register, four butterflies
+// both scan levels in one launch: every CTA turns kScanUnits counts into exclusive prefixes and a CTA total; the CTA
+// whose ticket is the last one then scans the totals in place (exclusive) and publishes the grand total
+__global__ void __launch_bounds__(512) k_scan(const unsigned *unit_count, unsigned *unit_prefix, unsigned long long *cta_total,
+                                              unsigned *ticket, long long n_units, unsigned long long *grand_total) {
+  __shared__ unsigned warp_sum[16];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long base = (long long)blockIdx.x * kScanUnits + tid * 4;
+  unsigned v[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) c[q] = __popc(t.w[2 * q]) | (__popc(t.w[2 * q + 1]) << 16);
+  for (int i = 0; i < 4; ++i) v[i] = base + i < n_units ? unit_count[base + i] : 0u;
+  const unsigned mine = v[0] + v[1] + v[2] + v[3];
+  unsigned inc = mine;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += t;
+  }
+  if (lane == 31) warp_sum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < 16 ? warp_sum[lane] : 0u;
+    unsigned winc = w;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) c[q] += __shfl_xor_sync(0xffffffffu, c[q], off);
-    if (lane < 8) s_cnt[lane * cx + chunk] = (c[lane >> 1] >> ((lane & 1) * 16)) & 0xffffu;
+    for (int off = 1; off < 16; off <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, winc, off);
+      if (lane >= off) winc += t;
+    }
+    if (lane < 16) warp_sum[lane] = winc - w;  // exclusive
+    if (lane == 15) {
+      cta_total[blockIdx.x] = winc;
+      __threadfence();
+      s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
   }
   __syncthreads();
-  // ---- exclusive scan of the n_units counts (row-major = output order); total of the tile row -----------------------------
+  unsigned ex = warp_sum[warp] + inc - mine;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (base + i < n_units) unit_prefix[base + i] = ex;
+    ex += v[i];
+  }
+  if (!s_last) return;
+  // last CTA: exclusive scan of the gridDim.x totals (a 10000 x 10000 map has 49 of them), 512 at a time
+  __threadfence();
+  __shared__ unsigned long long s_w[16];
+  __shared__ unsigned long long s_carry;
+  if (tid == 0) s_carry = 0ull;
+  __syncthreads();
+  volatile unsigned long long *tot = cta_total;
+  for (int b0 = 0; b0 < (int)gridDim.x; b0 += 512) {
+    const int i = b0 + tid;
+    const unsigned long long m = i < (int)gridDim.x ? tot[i] : 0ull;
+    unsigned long long s = m;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, s, off);
+      if (lane >= off) s += t;
+    }
+    if (lane == 31) s_w[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long w = lane < 16 ? s_w[lane] : 0ull;
+      unsigned long long ws = w;
+#pragma unroll
+      for (int off = 1; off < 16; off <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, ws, off);
+        if (lane >= off) ws += t;
+      }
+      if (lane < 16) s_w[lane] = ws - w;
+    }
+    __syncthreads();
+    const unsigned long long exc = s_carry + s_w[warp] + s - m;
+    if (i < (int)gridDim.x) tot[i] = exc;
+    __syncthreads();
+    if (tid == 511) s_carry = exc + m;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *grand_total = s_carry;
+    *ticket = 0u;  // ready for the next call
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+    k_write(LethalArgs a, const unsigned *unit_prefix, const unsigned long long *cta_offset, int2 *out, unsigned long long cap) {
+  __shared__ unsigned short s_stage[kWarpsPerCta][kChunkTiles * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long wid = (long long)blockIdx.x * kWarpsPerCta + w;
+  if (wid >= (long long)a.n_tile_rows * a.chunks_x) return;
+  const int tr = (int)(wid / a.chunks_x), chunk = (int)(wid - (long long)tr * a.chunks_x);
+  Tile8 t;
+  int ty;
+  warp_tile(a, tr, chunk, lane, &t, &ty);
+  // offsets of the 8 units, fetched by lanes 0..7 before the row loop (two dependent loads once, not once per row)
+  unsigned long long my_base = 0;
   {
-    const int per = (n_units + n_thr - 1) / n_thr;
-    const int lo = min(tid * per, n_units), hi = min(lo + per, n_units);
-    unsigned mine = 0;
-    for (int k = lo; k < hi; ++k) mine += s_cnt[k];
-    unsigned inc = mine;
+    const int yr = ty * 8 + (lane & 7) - a.y_lo;
+    if (lane < 8 && yr >= 0 && yr < a.nrows) {
+      const long long unit = (long long)yr * a.chunks_x + chunk;
+      my_base = cta_offset[unit / kScanUnits] + unit_prefix[unit];
+    }
+  }
+  const int xc = (a.tx0 + chunk * kChunkTiles) * 32;
+  const unsigned xl = (unsigned)(lane * 32);
+  unsigned short *stage = s_stage[w];
+  const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(stage);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    unsigned m = t.w[r];
+    const unsigned c = __popc(m);
+    unsigned inc = c;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const unsigned v = __shfl_up_sync(0xffffffffu, inc, off);
       if (lane >= off) inc += v;
     }
-    if (lane == 31) s_part[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-      const unsigned pv = lane < n_warps ? s_part[lane] : 0u;
-      unsigned pinc = pv;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, pinc, off);
-        if (lane >= off) pinc += v;
-      }
-      if (lane < n_warps) s_part[lane] = pinc - pv;
-      if (lane == 31) s_part[31] = pinc;  // total of the tile row
+    const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+    const unsigned long long base = __shfl_sync(0xffffffffu, my_base, r);
+    if (total == 0) continue;  // warp-uniform (also for rows outside the box)
+    uint32_t sp = stage_u32 + 2u * (inc - c);
+    m = __brev(m);  // lowest x first with one FLO per bit
+    while (m) {     // ~3 set bits per lane at 10 % density
+      const unsigned b = (unsigned)__clz(m);
+      m ^= 0x80000000u >> b;
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(sp), "h"((unsigned short)(xl + b)) : "memory");
+      sp += 2u;
     }
-    __syncthreads();
-    if (kWrite) {
-      unsigned ex = s_part[w] + inc - mine;
-      for (int k = lo; k < hi; ++k) {
-        const unsigned v = s_cnt[k];
-        s_cnt[k] = ex;
-        ex += v;
-      }
+    __syncwarp();
+    if (base + total <= cap) {
+      const int y = ty * 8 + r;
+      int2 *o = out + base + lane;
+      const unsigned short *q = stage + lane;
+      for (unsigned k = lane; k < total; k += 32, o += 32, q += 32) *o = make_int2(xc + (int)*q, y);
     }
-  }
-  if (!kWrite) {
-    if (tid == 0) {
-      const unsigned total = s_part[31];
-      e.totals[tr] = total;
-      if (total) {
-        atomicAdd(&e.groups[tr / kGroup], (unsigned long long)total);
-        atomicAdd(&e.groups[e.n_groups], (unsigned long long)total);
-      }
-    }
-    return;
-  }
-  // ---- global offset of this tile row: group totals before its group + tile-row totals before it inside the group --------
-  {
-    const int g = tr / kGroup;
-    unsigned long long v = 0;
-    for (int k = tid; k < g; k += n_thr) v += e.groups[k];
-    for (int k2 = g * kGroup + tid; k2 < tr; k2 += n_thr) v += e.totals[k2];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) s_red[w] = v;
-  }
-  __syncthreads();
-  unsigned long long base_tr = 0;
-  for (int k = 0; k < n_warps; ++k) base_tr += s_red[k];
-  // ---- emit, row by row: x offsets staged in shared memory, then consecutive stores ------------------------------------
-  unsigned short *stage = reinterpret_cast<unsigned short *>(s_cnt + n_units) + w * (kChunkTiles * 32);
-  const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(stage);
-  for (int chunk = w; chunk < cx; chunk += n_warps) {
-    Tile8 t;
-    int ty;
-    warp_tile(a, tr, chunk, lane, &t, &ty);  // the same kilobyte again: an L1 / L2 hit
-    const int xc = (a.tx0 + chunk * kChunkTiles) * 32;
-    const unsigned xl = (unsigned)(lane * 32);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      unsigned m = t.w[r];
-      const unsigned c = __popc(m);
-      unsigned inc = c;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, inc, off);
-        if (lane >= off) inc += v;
-      }
-      const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
-      if (total == 0) continue;  // warp-uniform (also for rows outside the box)
-      uint32_t sp = stage_u32 + 2u * (inc - c);
-      m = __brev(m);  // lowest x first with one FLO per bit
-      while (m) {     // ~3 set bits per lane at 10 % density
-        const unsigned b = (unsigned)__clz(m);
-        m ^= 0x80000000u >> b;
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sp), "h"((unsigned short)(xl + b)) : "memory");
-        sp += 2u;
-      }
-      __syncwarp();
-      const unsigned long long base = base_tr + s_cnt[r * cx + chunk];
-      if (base + total <= e.cap) {
-        const int y = ty * 8 + r;
-        int2 *o = e.out + base + lane;
-        const unsigned short *q = stage + lane;
-        for (unsigned k = lane; k < total; k += 32, o += 32, q += 32) *o = make_int2(xc + (int)*q, y);
-      }
-      __syncwarp();  // the staging row is reused by the next row
-    }
+    __syncwarp();  // the staging row is reused by the next row
   }
 }
 
@@ -384,9 +407,10 @@ struct LethalWs {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   RowSpan *d_spans = nullptr, *h_spans = nullptr;  // h_spans pinned
   size_t rows_cap = 0;
-  unsigned *d_totals = nullptr;            // one per tile row of the box
-  unsigned long long *d_groups = nullptr;  // one per 64 tile rows, + the grand total
-  size_t totals_cap = 0;
+  unsigned *d_count = nullptr, *d_prefix = nullptr;  // per (row, chunk) unit
+  size_t units_cap = 0;
+  unsigned long long *d_cta = nullptr;  // per scan CTA: total, then exclusive offset; [n] = grand total, [n + 1] = ticket
+  size_t cta_cap = 0;
   unsigned long long *h_total = nullptr;  // pinned
   float last_kernel_us = 0.f;
   unsigned long long hint = 0;  // cells the last extraction on this map returned
@@ -399,7 +423,7 @@ struct LethalWs {
     (void)device;  // the default pool's release threshold is raised once per device in api.cu (check_device)
     return DPOSE_OK;
   }
-  int reserve(size_t rows, size_t tile_rows) {
+  int reserve(size_t rows, size_t units) {
     if (rows > rows_cap) {
       cudaFree(d_spans);
       cudaFreeHost(h_spans);
@@ -410,23 +434,35 @@ struct LethalWs {
       DPOSE_CUDA(cudaHostAlloc(&h_spans, sizeof(RowSpan) * cap, cudaHostAllocDefault));
       rows_cap = cap;
     }
-    if (tile_rows > totals_cap) {
-      cudaFree(d_totals);
-      cudaFree(d_groups);
-      d_totals = nullptr, d_groups = nullptr;
-      totals_cap = 0;
-      const size_t cap = tile_rows + tile_rows / 2 + 64;
-      DPOSE_CUDA(cudaMalloc(&d_totals, sizeof(unsigned) * cap));
-      DPOSE_CUDA(cudaMalloc(&d_groups, sizeof(unsigned long long) * (cap / kGroup + 2)));
-      totals_cap = cap;
+    if (units > units_cap) {
+      cudaFree(d_count);
+      cudaFree(d_prefix);
+      d_count = d_prefix = nullptr;
+      units_cap = 0;
+      const size_t cap = units + units / 2 + 1024;
+      DPOSE_CUDA(cudaMalloc(&d_count, sizeof(unsigned) * cap));
+      DPOSE_CUDA(cudaMalloc(&d_prefix, sizeof(unsigned) * cap));
+      units_cap = cap;
+    }
+    const size_t ctas = (units + kScanUnits - 1) / kScanUnits;
+    if (ctas + 2 > cta_cap) {
+      cudaFree(d_cta);
+      d_cta = nullptr;
+      cta_cap = 0;
+      const size_t cap = ctas + ctas / 2 + 16;
+      DPOSE_CUDA(cudaMalloc(&d_cta, sizeof(unsigned long long) * cap));
+      DPOSE_CUDA(cudaMemset(d_cta, 0, sizeof(unsigned long long) * cap));  // the ticket starts at 0
+      DPOSE_CUDA(cudaStreamSynchronize(nullptr));  // the memset is asynchronous; its users run on a non-blocking stream
+      cta_cap = cap;
     }
     return DPOSE_OK;
   }
   void release() {
     cudaFree(d_spans);
     cudaFreeHost(h_spans);
-    cudaFree(d_totals);
-    cudaFree(d_groups);
+    cudaFree(d_count);
+    cudaFree(d_prefix);
+    cudaFree(d_cta);
     cudaFreeHost(h_total);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -525,10 +561,12 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
   a.chunks_x = ((gx_max >> 5) - a.tx0) / kChunkTiles + 1;
   a.n_units = (long long)nrows * a.chunks_x;
   if (a.chunks_x > 4096) return fail(DPOSE_EINVAL, "box wider than 4 M cells");  // 32 B of shared memory per chunk
-  DPOSE_TRY(ws->reserve((size_t)nrows, (size_t)a.n_tile_rows));
+  DPOSE_TRY(ws->reserve((size_t)nrows, (size_t)a.n_units));
   a.spans = ws->d_spans;
-  const int n_groups = (a.n_tile_rows + kGroup - 1) / kGroup;
-  unsigned long long *d_total = ws->d_groups + n_groups;
+  // the ticket lives at a fixed slot (the end of the array) so that it survives calls with different CTA counts
+  const int n_scan = (int)((a.n_units + kScanUnits - 1) / kScanUnits);
+  unsigned long long *d_total = ws->d_cta + (ws->cta_cap - 2);
+  unsigned *d_ticket = reinterpret_cast<unsigned *>(ws->d_cta + (ws->cta_cap - 1));
 
   cudaStream_t st = ws->stream;
   int2 *d_out = nullptr;
@@ -553,24 +591,10 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       DPOSE_CUDA(cudaStreamSynchronize(st));
       total = *ws->h_total;
     } else {
-      // warps per CTA: every warp one or two of the tile row's chunks, and CTAs small enough that the whole grid is
-      // resident at once when it can be (1250 tile rows of a 10000-row map: 5 warps -> 12 CTAs per SM, one wave)
-      const int warps = std::min(kWarpsPerCta, std::max(1, (a.chunks_x + 1) / 2));
-      const size_t dyn_cnt = sizeof(unsigned) * 8 * (size_t)a.chunks_x;
-      const size_t dyn_wr = dyn_cnt + (size_t)warps * kChunkTiles * 32 * sizeof(unsigned short);
-      if (dyn_wr > ((size_t)40 << 10)) {
-        DPOSE_CUDA(cudaFuncSetAttribute(k_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_cnt));
-        DPOSE_CUDA(cudaFuncSetAttribute(k_extract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_wr));
-      }
-      ExtractArgs e;
-      e.box = a;
-      e.totals = ws->d_totals;
-      e.groups = ws->d_groups;
-      e.n_groups = n_groups;
-      e.out = nullptr;
-      e.cap = 0;
-      DPOSE_CUDA(cudaMemsetAsync(ws->d_groups, 0, sizeof(unsigned long long) * (n_groups + 1), st));
-      k_extract<false><<<(unsigned)a.n_tile_rows, warps * 32, dyn_cnt, st>>>(e);
+      const unsigned grid = (unsigned)(((size_t)a.n_tile_rows * a.chunks_x + kWarpsPerCta - 1) / kWarpsPerCta);
+      k_count<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_count);
+      DPOSE_LAUNCHED();
+      k_scan<<<n_scan, 512, 0, st>>>(ws->d_count, ws->d_prefix, ws->d_cta, d_ticket, a.n_units, d_total);
       DPOSE_LAUNCHED();
       DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       for (int attempt = 0; attempt < 2; ++attempt) {
@@ -581,9 +605,7 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
           cap = total;
         }
         DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
-        e.out = d_out;
-        e.cap = cap;
-        k_extract<true><<<(unsigned)a.n_tile_rows, warps * 32, dyn_wr, st>>>(e);
+        k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_cta, d_out, cap);
         DPOSE_LAUNCHED();
         DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
         DPOSE_CUDA(cudaStreamSynchronize(st));

@@ -5,6 +5,7 @@
 //   ./test_dpose_core_shim              everything (needs a GPU)
 // Each block names the upstream test it restates (paths relative to dpose_core/test/).
 #include <dpose_core/dpose_costmap.hpp>
+#include <dpose_core/dpose_solve.hpp>
 
 #include <cmath>
 #include <cstdio>
@@ -339,6 +340,42 @@ test_batch() {
   }
 }
 
+// ---- the multi-start solve: preProcess's attempt loop (dpose_goal_tolerance.cpp:430-456) in one call ---------------------
+static void
+test_solve() {
+  const int side = 300;
+  costmap_2d::Costmap2D map(side, side, 0.05, 0, 0);
+  for (int y = 145; y < 156; ++y)
+    for (int x = 145; x < 156; ++x) map.setCost(x, y, costmap_2d::LETHAL_OBSTACLE);  // a block on the goal
+  const polygon rect = make_polygon({{10, 6}, {-10, 6}, {-10, -6}, {10, -6}});
+  const pose_gradient pg(rect, {2});
+  const device_costmap dmap(map.getCharMap(), side, side, side);
+  multi_start_problem pr(pg, dmap);
+  const dpose_gt_config cfg = {20.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+  pr.init(pose_gradient::pose(100, 100, 0), pose_gradient::pose(150, 150, 0), cfg);
+  const auto res = pr.solve(256, 9);
+  CHECK(res.x.size() == 3 * 256 && res.f.size() == 256);
+  CHECK(res.accepted() && res.summary.n_accepted > 0);
+  {  // attempt 0 starts at the goal, where the footprint collides with the block
+    polygon at_goal(2, 4);
+    for (int k = 0; k < 4; ++k) at_goal(0, k) = 150 + rect(0, k), at_goal(1, k) = 150 + rect(1, k);
+    CHECK(!check_footprint(map, at_goal, costmap_2d::LETHAL_OBSTACLE));
+  }
+  for (size_t i = 0; i < 256; ++i) {
+    // every accepted start is one the upstream validation accepts (:386-399): transform, round, check_footprint
+    const double px = 150 + res.x[3 * i], py = 150 + res.x[3 * i + 1], pt = res.x[3 * i + 2];
+    polygon moved(2, 4);
+    for (int k = 0; k < 4; ++k) {
+      moved(0, k) = (int)std::round(px + std::cos(pt) * rect(0, k) - std::sin(pt) * rect(1, k));
+      moved(1, k) = (int)std::round(py + std::sin(pt) * rect(0, k) + std::cos(pt) * rect(1, k));
+    }
+    const bool free_ = check_footprint(map, moved, costmap_2d::LETHAL_OBSTACLE);
+    CHECK(free_ == ((res.status[i] & DPOSE_SOLVE_FOOTPRINT_FREE) != 0));
+    CHECK(res.x[3 * i] * res.x[3 * i] + res.x[3 * i + 1] * res.x[3 * i + 1] <= 400.0 * (1 + 1e-12));
+    CHECK(std::abs(res.x[3 * i + 2]) <= 1.0);
+  }
+}
+
 int
 main(int argc, char** argv) {
   const bool cpu_only = argc > 1 && !std::strcmp(argv[1], "--cpu-only");
@@ -354,6 +391,7 @@ main(int argc, char** argv) {
     test_lethal();
     test_check_footprint();
     test_batch();
+    test_solve();
   } else {
     // without a device the constructors must fail loudly, not fall back to a CPU path
     int ndev = 0;

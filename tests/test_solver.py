@@ -199,7 +199,7 @@ def test_solve_batch_acceptance_happens_and_is_the_references(dp):
     x0 = dp.sample_offsets(9, CFG["lin_tolerance"], CFG["rot_tolerance"], 512)
     out = pr.solve_batch(x0)
     st = out["status"]
-    assert not (st[0] & dp.SOLVE_FOOTPRINT_FREE)  # attempt 0 starts in collision and is pushed out or stays rejected
+    assert not capi.check_footprint_batch(m, fp, np.array([goal]), nthreads=1)[0]  # attempt 0 starts in collision
     assert out["summary"]["n_accepted"] > 0 and out["summary"]["first"] >= 0
     poses = out["x"] + np.asarray(goal)
     free = capi.check_footprint_batch(m, fp, poses, nthreads=2).astype(bool)
