@@ -47,6 +47,27 @@ extern std::atomic<uint64_t> g_launches;
     DPOSE_CUDA(cudaGetLastError());               \
   } while (0)
 
+// Launch with programmatic stream serialisation allowed: the kernel may start while its predecessor in the stream is
+// still draining (the launch latency and the prologue overlap it).  The kernel must execute griddepcontrol.wait before
+// it touches anything the predecessor wrote; predecessors call griddepcontrol.launch_dependents as early as they like.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define DPOSE_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define DPOSE_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;

@@ -561,17 +561,7 @@ template <bool kJac, int kThreads, int kRepShift, int kRows>
 int launch_tile4(const TileArgs &a, int grid, size_t smem_bytes, cudaStream_t stream) {
   auto kern = k_cost_batch_tile<kJac, kThreads, kRepShift, kRows>;
   DPOSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol.wait in the kernel
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  DPOSE_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  DPOSE_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem_bytes, stream, a));  // see griddepcontrol.wait
   DPOSE_LAUNCHED();
   return DPOSE_OK;
 }

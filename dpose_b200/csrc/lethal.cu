@@ -151,6 +151,8 @@ __device__ __forceinline__ void warp_tile(const LethalArgs &a, int tr, int chunk
 constexpr int kScanUnits = 2048;  // units per scan CTA (512 threads x 4)
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_count(LethalArgs a, unsigned *unit_count) {
+  DPOSE_PDL_WAIT();     // behind k_pack_tiles (or the copy of the row intervals)
+  DPOSE_PDL_TRIGGER();  // k_scan may queue up
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (wid >= (long long)a.n_tile_rows * a.chunks_x) return;
@@ -177,6 +179,8 @@ __global__ void __launch_bounds__(512) k_scan(const unsigned *unit_count, unsign
                                               unsigned *ticket, long long n_units, unsigned long long *grand_total) {
   __shared__ unsigned warp_sum[16];
   __shared__ bool s_last;
+  DPOSE_PDL_WAIT();
+  DPOSE_PDL_TRIGGER();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long base = (long long)blockIdx.x * kScanUnits + tid * 4;
   unsigned v[4];
@@ -264,7 +268,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
   const int tr = (int)(wid / a.chunks_x), chunk = (int)(wid - (long long)tr * a.chunks_x);
   Tile8 t;
   int ty;
-  warp_tile(a, tr, chunk, lane, &t, &ty);
+  warp_tile(a, tr, chunk, lane, &t, &ty);  // the plane and the intervals are older than k_scan: fetched before the wait
+  DPOSE_PDL_WAIT();
   // offsets of the 8 units, fetched by lanes 0..7 before the row loop (two dependent loads once, not once per row)
   unsigned long long my_base = 0;
   {
@@ -592,22 +597,25 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
       total = *ws->h_total;
     } else {
       const unsigned grid = (unsigned)(((size_t)a.n_tile_rows * a.chunks_x + kWarpsPerCta - 1) / kWarpsPerCta);
-      k_count<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_count);
+      DPOSE_CUDA(launch_pdl(k_count, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, a, ws->d_count));
       DPOSE_LAUNCHED();
-      k_scan<<<n_scan, 512, 0, st>>>(ws->d_count, ws->d_prefix, ws->d_cta, d_ticket, a.n_units, d_total);
+      DPOSE_CUDA(launch_pdl(k_scan, dim3((unsigned)n_scan), dim3(512), 0, st, (const unsigned *)ws->d_count, ws->d_prefix,
+                            ws->d_cta, d_ticket, a.n_units, d_total));
       DPOSE_LAUNCHED();
-      DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       for (int attempt = 0; attempt < 2; ++attempt) {
         if (!cap) {  // no estimate (or it was too small): the exact total first
+          DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
           DPOSE_CUDA(cudaStreamSynchronize(st));
           total = *ws->h_total;
           if (total == 0) break;
           cap = total;
         }
         DPOSE_CUDA(cudaMallocAsync(&d_out, sizeof(int2) * cap, st));
-        k_write<<<grid, kWarpsPerCta * 32, 0, st>>>(a, ws->d_prefix, ws->d_cta, d_out, cap);
+        DPOSE_CUDA(launch_pdl(k_write, dim3(grid), dim3(kWarpsPerCta * 32), 0, st, a, (const unsigned *)ws->d_prefix,
+                              (const unsigned long long *)ws->d_cta, d_out, cap));
         DPOSE_LAUNCHED();
         DPOSE_CUDA(cudaEventRecord(ws->ev1, st));
+        DPOSE_CUDA(cudaMemcpyAsync(ws->h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         DPOSE_CUDA(cudaStreamSynchronize(st));
         total = *ws->h_total;
         if (total <= cap) break;
