@@ -41,10 +41,18 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line.  NCCL (used only for the timing barrier / reductions) logs to stdout when
-# NCCL_DEBUG asks for it: its log is routed to stderr instead of being silenced, so the launcher can still read it.
-if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+# stdout carries exactly one JSON line.  NCCL (used only for the timing barrier / reductions) prints its version banner
+# and, when NCCL_DEBUG asks for it, its log to stdout: nothing is silenced — file descriptor 1 is pointed at stderr
+# for the whole run (so the launcher still sees NCCL's lines, there) and the JSON line is written to the real stdout
+# at the very end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_line(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -276,7 +284,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -479,14 +487,14 @@ def run_batch(args, ranks, torch, dp, fx):
                 for _ in range(m_steps):
                     dp.get_cost_batch_multi(pgs, maps, hp.numpy(), out=ho.numpy())
                 dtm = time.perf_counter() - t0
-                lo, hi = dp.dist.shard_bounds(n_total, 0, world)
                 same = bool(np.array_equal(ho.numpy()[:4096], d_out[:4096].cpu().numpy())) if scaling == "strong" else None
-                single = pg.get_cost_batch(cmap, hp.numpy()[-4096:])
+                lo, hi = dp.dist.shard_bounds(n_total, ndev - 1, ndev)  # the last device's shard, once more on device 0
+                single = pg.get_cost_batch(cmap, hp.numpy()[lo:hi])
                 e2e_multi = {"value": n_total * m_steps / dtm, "unit": UNIT, "ms_per_step": 1e3 * dtm / m_steps,
                              "devices": ndev, "poses": n_total, "h2d_bytes_per_step": int(n_total * 24),
                              "d2h_bytes_per_step": int(n_total * 32),
                              "first_shard_equals_rank0_device_path": same,
-                             "last_shard_equals_single_gpu_call": bool(np.array_equal(ho.numpy()[-4096:], single)),
+                             "last_shard_equals_single_gpu_call": bool(np.array_equal(ho.numpy()[lo:hi], single)),
                              "call": "dpose_pg_get_cost_batch_multi from one process (one host thread per device), one "
                                      "pinned host buffer in, one out"}
                 del pgs, maps, hp, ho
@@ -713,7 +721,7 @@ def main():
     kind = WORKLOADS[args.workload][0]
     line = {"batch": run_batch, "solve": run_solve, "single": run_single}[kind](args, ranks, torch, dp, fx)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     ranks.close()
     return 0
 
