@@ -58,46 +58,49 @@ __device__ __forceinline__ unsigned lethal_bits32(const uint32_t v[8]) {
   return lethal_bits16(lo) | (lethal_bits16(hi) << 16);
 }
 
-// One thread per plane word.  Lane l of a warp handles row (l >> 2) of tile column 4 * warp + (l & 3): the warp reads
-// 8 map rows x 128 contiguous bytes (one 256-bit load per lane) and writes 4 tiles = 128 contiguous bytes.  Two warp
-// items per iteration, both loads issued before the first compare: 64 bytes in flight per thread.
+// A CTA of 8 warps packs blocks of 8 map rows x 1024 columns (32 tiles = 1 KB of plane): warp w reads row w of the
+// block as ONE contiguous kilobyte (a 256-bit load per lane — long DRAM bursts instead of eight 128-byte pieces of eight
+// different rows), every lane turns its 32 bytes into one plane word, the words are transposed through shared memory
+// and leave as one coalesced kilobyte of tiles.  Two blocks per iteration, both loads issued before the first compare:
+// 64 bytes in flight per thread.
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ map, size_t pitch, uint32_t size_y,
                                                     uint32_t *__restrict__ tiles, uint32_t ntx, uint32_t ty0,
                                                     uint32_t ty1) {
   // programmatic dependent launch: the batch kernel queued behind this one may start its prologue (staging the
   // coefficient image) now; it waits for this grid's completion (griddepcontrol.wait) before it reads a tile
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const uint32_t quads = (ntx + 3) / 4;  // groups of 4 tile columns
-  const size_t n_warps = (size_t)quads * (ty1 - ty0);
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t r = lane >> 2, j = lane & 3;
-  const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 5;
-  auto locate = [&](size_t w, uint32_t *by, uint32_t *bx) {
-    const uint32_t byr = (uint32_t)(w / quads);
-    *bx = (uint32_t)(w - (size_t)byr * quads) * 4 + j;
-    *by = ty0 + byr;
-  };
-  auto fetch = [&](uint32_t by, uint32_t bx, uint32_t v[8]) {  // pitch % 32 == 0 and the pad bytes of the device copy are zero
-    const uint32_t y = by * 8 + r;
-    const size_t x = (size_t)bx * 32;
+  __shared__ uint32_t s_words[2][32][9];  // [block of the pair][tile][row], padded: conflict-free both ways
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t chunks = (ntx + 31) / 32;  // blocks per tile row
+  const size_t n_blocks = (size_t)chunks * (ty1 - ty0);
+  auto fetch = [&](size_t blk, uint32_t v[8]) {  // pitch % 32 == 0 and the pad bytes of the device copy are zero
+    const uint32_t tr = (uint32_t)(blk / chunks), c = (uint32_t)(blk - (size_t)tr * chunks);
+    const uint32_t y = (ty0 + tr) * 8 + w;
+    const size_t x = ((size_t)c * 32 + lane) * 32;
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = 0u;
-    if (bx < ntx && y < size_y && x < pitch)
+    if (y < size_y && x < pitch)
       asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                    : "l"(map + (size_t)y * pitch + x));
   };
-  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps; w += 2 * stride) {
-    uint32_t by0, bx0, by1 = 0, bx1 = 0, v0[8], v1[8];
-    const bool two = w + stride < n_warps;
-    locate(w, &by0, &bx0);
-    fetch(by0, bx0, v0);
-    if (two) {
-      locate(w + stride, &by1, &bx1);
-      fetch(by1, bx1, v1);
-    }
-    if (bx0 < ntx) tiles[((size_t)by0 * ntx + bx0) * 8 + r] = lethal_bits32(v0);
-    if (two && bx1 < ntx) tiles[((size_t)by1 * ntx + bx1) * 8 + r] = lethal_bits32(v1);
+  auto store = [&](size_t blk, int which) {  // thread t writes word t of the block's kilobyte: tile t >> 3, row t & 7
+    const uint32_t tr = (uint32_t)(blk / chunks), c = (uint32_t)(blk - (size_t)tr * chunks);
+    const uint32_t tile = c * 32 + (threadIdx.x >> 3);
+    if (tile < ntx) tiles[((size_t)(ty0 + tr) * ntx + tile) * 8 + (threadIdx.x & 7)] = s_words[which][threadIdx.x >> 3][threadIdx.x & 7];
+  };
+  for (size_t blk = blockIdx.x; blk < n_blocks; blk += 2 * (size_t)gridDim.x) {
+    const size_t blk2 = blk + gridDim.x;
+    const bool two = blk2 < n_blocks;
+    uint32_t v0[8], v1[8];
+    fetch(blk, v0);
+    if (two) fetch(blk2, v1);
+    s_words[0][lane][w] = lethal_bits32(v0);
+    if (two) s_words[1][lane][w] = lethal_bits32(v1);
+    __syncthreads();
+    store(blk, 0);
+    if (two) store(blk2, 1);
+    __syncthreads();
   }
 }
 
@@ -606,9 +609,8 @@ static int tileplane_build_locked(const dpose_map *map, cudaStream_t stream) {
   m->tiles_dirty_hi = 0;
   if (hi <= lo) return DPOSE_OK;
   const uint32_t ty0 = lo / 8, ty1 = (hi + 7) / 8;
-  const uint32_t quads = (map->tiles_ntx + 3) / 4;
-  const size_t n_warps = (size_t)quads * (ty1 - ty0);
-  const unsigned grid = (unsigned)std::min<size_t>((n_warps + 7) / 8, (size_t)148 * 32);
+  const size_t n_blocks = (size_t)((map->tiles_ntx + 31) / 32) * (ty1 - ty0);
+  const unsigned grid = (unsigned)std::min<size_t>((n_blocks + 1) / 2, (size_t)148 * 8);
   k_pack_tiles<<<grid, 256, 0, stream>>>(map->d_data, map->pitch, map->size_y, map->d_tiles, map->tiles_ntx, ty0, ty1);
   DPOSE_LAUNCHED();
   return DPOSE_OK;

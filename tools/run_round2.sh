@@ -1,0 +1,27 @@
+# usage: bash tools/run_round2.sh <tag>   (under gpurun, one GPU): smoke, GPU tests, every bench workload + reference arms,
+# side kernels, ncu launch lists and full captures of the dominant kernels.  Everything lands in gpurun_out/r2_<tag>_*.
+tag=${1:-vx}; O=gpurun_out/r2_${tag}
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1700 python -m pytest tests -m gpu -q 2>&1 | tail -3 | tee ${O}_gpu_tests.log
+for w in cfg5 cfg2 cfg3 cfg4 cfg1; do
+  timeout 600 python bench.py --workload $w > ${O}_bench_$w.json 2>> ${O}_bench.err; cut -c1-160 ${O}_bench_$w.json
+done
+for w in cfg5 cfg4; do
+  timeout 600 python bench.py --impl reference --workload $w --steps 3 --warmup 1 > ${O}_bench_${w}_reference_arm.json 2>> ${O}_bench.err
+done
+timeout 900 python tools/bench_kernels.py > ${O}_side_kernels.jsonl 2>> ${O}_bench.err
+timeout 600 python tools/bench_solver.py > ${O}_solver.jsonl 2>> ${O}_bench.err
+# launch lists (a number printed under ncu is never a bench value)
+B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+for w in cfg5 cfg2 cfg4; do
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${O}_launches_$w.csv $B --workload $w > /dev/null 2>&1
+done
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${O}_launches_lethal.csv python tools/lethal_only.py > /dev/null 2>&1
+# full captures of the dominant kernels
+ncu --set full --clock-control none --import-source on -k regex:k_cost_batch_tile -s 3 -c 1 -f -o ${O}_tile_cfg5 $B --workload cfg5 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_cost_batch_tile -s 3 -c 1 -f -o ${O}_tile_cfg2 $B --workload cfg2 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_cost_batch_tile -s 3 -c 1 -f -o ${O}_tile_cfg3 $B --workload cfg3 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_solve -s 6 -c 1 -f -o ${O}_solve_cfg4 $B --workload cfg4 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:k_pack_tiles|k_count|k_scan|k_write" -s 8 -c 4 -f -o ${O}_lethal python tools/lethal_only.py > /dev/null 2>&1
+ls -la gpurun_out/*.ncu-rep | tail -8
