@@ -18,10 +18,20 @@ for w in cfg5 cfg2 cfg4; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${O}_launches_$w.csv $B --workload $w > /dev/null 2>&1
 done
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${O}_launches_lethal.csv python tools/lethal_only.py > /dev/null 2>&1
-# full captures of the dominant kernels
-ncu --set full --clock-control none --import-source on -k regex:k_cost_batch_tile -s 3 -c 1 -f -o ${O}_tile_cfg5 $B --workload cfg5 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_cost_batch_tile -s 3 -c 1 -f -o ${O}_tile_cfg2 $B --workload cfg2 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_cost_batch_tile -s 3 -c 1 -f -o ${O}_tile_cfg3 $B --workload cfg3 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_solve -s 6 -c 1 -f -o ${O}_solve_cfg4 $B --workload cfg4 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:k_pack_tiles|k_count|k_scan|k_write" -s 8 -c 4 -f -o ${O}_lethal python tools/lethal_only.py > /dev/null 2>&1
-ls -la gpurun_out/*.ncu-rep | tail -8
+# full captures of the dominant kernels; summarised on the box (the .ncu-rep files are too big to travel back together)
+cap() {  # cap <name> <kernel regex> <skip> <count> <command...>
+  name=$1; pat=$2; skip=$3; cnt=$4; shift 4
+  ncu --set full --clock-control none --import-source on -k "regex:$pat" -s $skip -c $cnt -f -o ${O}_$name "$@" > /dev/null 2>&1
+  python tools/ncu_metrics.py ${O}_$name.ncu-rep > ${O}_${name}_metrics.txt 2>&1
+  ncu -i ${O}_$name.ncu-rep --page source --csv --print-source cuda,sass > ${O}_$name.src.csv 2>/dev/null
+  python tools/ncu_lines.py ${O}_$name.src.csv 45 > ${O}_${name}_lines.txt 2>&1
+  rm -f ${O}_$name.src.csv
+  if [ "$name" != "tile_cfg5" ]; then rm -f ${O}_$name.ncu-rep; fi
+}
+cap tile_cfg5 k_cost_batch_tile 3 1 $B --workload cfg5
+cap tile_cfg2 k_cost_batch_tile 3 1 $B --workload cfg2
+cap tile_cfg3 k_cost_batch_tile 3 1 $B --workload cfg3
+cap solve_cfg4 k_solve 6 1 $B --workload cfg4
+cap coop_4096 k_cost_batch_coop 20 1 python tools/bench_solver.py batch
+cap lethal "k_pack_tiles|k_count|k_scan|k_write" 8 4 python tools/lethal_only.py
+du -sh gpurun_out; ls gpurun_out | head -60
