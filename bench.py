@@ -92,13 +92,11 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def kernel_source_hash():
-    """hash of the kernel sources: stamps ncu-derived numbers (profiles/traffic.json) so a stale capture is visible"""
+def kernel_source_hash(files=("dpose_b200/csrc/get_cost_batch_tile.cu", "dpose_b200/csrc/cost_math.cuh")):
+    """hash of the batch kernel's sources: stamps ncu-derived numbers (profiles/traffic.json) so a stale capture is visible"""
     h = hashlib.sha256()
-    csrc = os.path.join(ROOT, "dpose_b200", "csrc")
-    for f in sorted(os.listdir(csrc)):
-        if f.endswith((".cu", ".cuh")):
-            h.update(open(os.path.join(csrc, f), "rb").read())
+    for f in files:
+        h.update(open(os.path.join(ROOT, f), "rb").read())
     return h.hexdigest()[:16]
 
 
@@ -519,10 +517,9 @@ def run_batch(args, ranks, torch, dp, fx):
             tj = json.load(open(tpath))
             traffic = tj.get(args.workload)
             ncu = tj.get("ncu_" + args.workload)
-            stamp = tj.get("kernel_source_hash")
+            stamp, now = tj.get("kernel_source_hash"), kernel_source_hash(tj.get("hashed_files") or ())
             traffic_note = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, captured on kernel sources " +
-                            str(stamp) + ("" if stamp == kernel_source_hash() else
-                                          f" (STALE: the sources now hash to {kernel_source_hash()})"))
+                            str(stamp) + ("" if stamp == now else f" (STALE: the sources now hash to {now})"))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

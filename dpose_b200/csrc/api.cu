@@ -218,7 +218,19 @@ int dpose_cell_to_world(const double *cells, size_t n, double origin_x, double o
 }
 
 // ---- pose_gradient / cost_data ----------------------------------------------------------------
+static int pg_create_impl(const int32_t *fp, int n, uint32_t padding, int device, dpose_pg **out);
+
 int dpose_pg_create(const int32_t *fp, int n, uint32_t padding, int device, dpose_pg **out) {
+  try {  // no exception crosses the C ABI
+    return pg_create_impl(fp, n, padding, device, out);
+  } catch (const std::bad_alloc &) {
+    return fail(DPOSE_ENOMEM, "out of host memory");
+  } catch (const std::exception &e) {
+    return fail(DPOSE_ECUDA, "dpose_pg_create: %s", e.what());
+  }
+}
+
+static int pg_create_impl(const int32_t *fp, int n, uint32_t padding, int device, dpose_pg **out) {
   if (!out) return fail(DPOSE_EINVAL, "out is NULL");
   *out = nullptr;
   if (n < 3 || !fp) return fail(DPOSE_EINVAL, "footprint must contain at least three points");
@@ -722,21 +734,28 @@ int dpose_pg_get_cost_batch_multi(dpose_pg *const *pgs, dpose_map *const *maps, 
     if (!pgs[d] || !maps[d]) return fail(DPOSE_EINVAL, "NULL handle for shard %d", d);
   if (ndev == 1) return dpose_pg_get_cost_batch(pgs[0], maps[0], poses, n, out, want_jacobian);
   // contiguous shards, one host thread per device, no collective
-  std::vector<int> rcs((size_t)ndev, DPOSE_OK);
-  std::vector<std::string> errs((size_t)ndev);
   std::vector<std::thread> th;
-  const size_t per = (n + ndev - 1) / ndev;
-  for (int d = 0; d < ndev; ++d) {
-    const size_t lo = std::min(n, per * d), hi = std::min(n, per * (d + 1));
-    th.emplace_back([&, d, lo, hi]() {
-      rcs[d] = dpose_pg_get_cost_batch(pgs[d], maps[d], poses + 3 * lo, hi - lo, out + 4 * lo, want_jacobian);
-      if (rcs[d] != DPOSE_OK) errs[d] = last_error();
-    });
+  try {
+    std::vector<int> rcs((size_t)ndev, DPOSE_OK);
+    std::vector<std::string> errs((size_t)ndev);
+    const size_t per = (n + ndev - 1) / ndev;
+    for (int d = 0; d < ndev; ++d) {
+      const size_t lo = std::min(n, per * d), hi = std::min(n, per * (d + 1));
+      th.emplace_back([&, d, lo, hi]() {
+        rcs[d] = dpose_pg_get_cost_batch(pgs[d], maps[d], poses + 3 * lo, hi - lo, out + 4 * lo, want_jacobian);
+        if (rcs[d] != DPOSE_OK) errs[d] = last_error();
+      });
+    }
+    for (auto &t : th) t.join();
+    th.clear();
+    for (int d = 0; d < ndev; ++d)
+      if (rcs[d] != DPOSE_OK) return fail(rcs[d], "shard %d: %s", d, errs[d].c_str());
+    return DPOSE_OK;
+  } catch (const std::exception &e) {  // thread creation / allocation failed: no exception crosses the C ABI
+    for (auto &t : th)
+      if (t.joinable()) t.join();
+    return fail(DPOSE_ENOMEM, "dpose_pg_get_cost_batch_multi: %s", e.what());
   }
-  for (auto &t : th) t.join();
-  for (int d = 0; d < ndev; ++d)
-    if (rcs[d] != DPOSE_OK) return fail(rcs[d], "shard %d: %s", d, errs[d].c_str());
-  return DPOSE_OK;
 }
 
 int dpose_pg_window_bytes(const dpose_pg *pg, const dpose_map *map, const double *poses, size_t n,

@@ -121,10 +121,8 @@ int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   switch (coop_group(n, sms)) {
     case 32: return launch_coop<32>(a, want_jacobian, sms, stream);
     case 16: return launch_coop<16>(a, want_jacobian, sms, stream);
-    case 8: return launch_coop<8>(a, want_jacobian, sms, stream);
-    case 4: return launch_coop<4>(a, want_jacobian, sms, stream);
-    default: return launch_coop<2>(a, want_jacobian, sms, stream);
-  }
+    default: return launch_coop<8>(a, want_jacobian, sms, stream);  // DPOSE_COOP_MIN_GROUP: smaller groups lose to
+  }                                                                 // the thread-per-pose kernel
 }
 
 }  // namespace dpose

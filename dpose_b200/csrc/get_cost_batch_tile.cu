@@ -44,18 +44,23 @@ namespace dpose {
 namespace {
 
 // ---- tile plane ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned lethal_bits16(const uint4 v) {
-  const unsigned k = 0xFEFEFEFEu;
-  const unsigned e0 = __vcmpeq4(v.x, k) & 0x01010101u, e1 = __vcmpeq4(v.y, k) & 0x01010101u;
-  const unsigned e2 = __vcmpeq4(v.z, k) & 0x01010101u, e3 = __vcmpeq4(v.w, k) & 0x01010101u;
-  const unsigned n0 = (e0 * 0x00204081u) >> 21 & 0xFu, n1 = (e1 * 0x00204081u) >> 21 & 0xFu;
-  const unsigned n2 = (e2 * 0x00204081u) >> 21 & 0xFu, n3 = (e3 * 0x00204081u) >> 21 & 0xFu;
-  return n0 | (n1 << 4) | (n2 << 8) | (n3 << 12);
+// 4 bytes -> 4 bits (bit j set iff byte j == 254).  The SIMD-in-a-word byte compare of older architectures
+// (__vcmpeq4) is emulated on sm_100 and made k_pack_tiles instruction bound (ncu: issue slots 66 % busy, "math pipe
+// throttle" the top stall); exact zero-byte detection needs three logic ops: z = v ^ 0xFEFEFEFE is zero exactly in the
+// lethal bytes, (z & 0x7F..) + 0x7F.. carries into bit 7 of every byte whose low 7 bits are non-zero without ever
+// crossing a byte, so ~(that | z) & 0x80.. flags the zero bytes.  One multiply gathers the four flags (bits 7, 15, 23,
+// 31 land on bits 28 .. 31; no other partial product reaches them).
+__device__ __forceinline__ unsigned lethal_nibble(unsigned v) {
+  const unsigned z = v ^ 0xFEFEFEFEu;
+  const unsigned t = ((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z;
+  const unsigned m = ~t & 0x80808080u;
+  return (m * 0x00204081u) >> 28;
 }
-
 __device__ __forceinline__ unsigned lethal_bits32(const uint32_t v[8]) {
-  const uint4 lo = make_uint4(v[0], v[1], v[2], v[3]), hi = make_uint4(v[4], v[5], v[6], v[7]);
-  return lethal_bits16(lo) | (lethal_bits16(hi) << 16);
+  unsigned out = 0u;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out |= lethal_nibble(v[k]) << (4 * k);
+  return out;
 }
 
 // A CTA of 8 warps packs blocks of 8 map rows x 1024 columns (32 tiles = 1 KB of plane): warp w reads row w of the

@@ -31,8 +31,8 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-TILE_MIN = 40000  # batches of at least this many poses run the thread-per-pose kernel (k_cost_batch_tile); smaller ones
-                  # the cooperative kernel (k_cost_batch_coop: 148 x 1024 lanes / 4 lanes per pose = 37888)
+TILE_MIN = 40000  # batches of at least this many poses run the thread-per-pose kernel (k_cost_batch_tile); batches up to
+                  # 148 x 1024 lanes / 8 lanes per pose = 18944 poses the cooperative kernel (k_cost_batch_coop)
 
 
 def batch_both(pg, cm, poses, rel=1e-12, **kw):
@@ -421,15 +421,15 @@ def test_batch_clip_invariant_large_tables(dp, half):
         dp.pose_gradient(np.array([[300, 10], [-300, 10], [-300, -10], [300, -10]], np.int32))
 
 
-@pytest.mark.parametrize("n,lanes", [(3000, 32), (9000, 16), (18000, 8), (37000, 4)])
+@pytest.mark.parametrize("n,lanes", [(3000, 32), (9000, 16), (18000, 8), (19000, 1)])
 def test_batch_cooperative_kernel_every_group_size(dp, capi, n, lanes):
-    """the cooperative kernel picks G = 32 / 16 / 8 / 4 lanes per pose by batch size (148 x 1024 lanes per launch):
-    every instantiation against the oracle on translated-equivalent inputs, for a table whose windows fit one chunk
-    and one whose windows span several"""
+    """the cooperative kernel picks G = 32 / 16 / 8 lanes per pose by batch size (148 x 1024 lanes per launch; from
+    18945 poses on the thread-per-pose kernel takes over): every instantiation against the oracle on
+    translated-equivalent inputs, for a table whose windows fit one chunk and one whose windows span several"""
     m = fx.bernoulli_map(1200, 1000, 0.10, 21)
     cm = dp.Costmap(m)
     for name in ("rect_pad2", "ship_pad10"):
-        k = n if name == "rect_pad2" else max(n // 20, 1000) if lanes > 8 else n // 10
+        k = n if name == "rect_pad2" else max(n // 20, 1000)
         fp, pad = fx.FOOTPRINTS[name]
         pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
         poses = fx.random_poses(n, 1200, 1000, 22, margin=-20.0 if name == "rect_pad2" else 80.0)

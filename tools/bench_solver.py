@@ -2,7 +2,7 @@
 """Side measurements of the small-batch paths (run under gpurun, one GPU), one JSON line each:
 
   solve     : dpose_problem_solve_batch, BASELINE config 4 (4096 starts, max_iter 20) — wall time per call
-  batch     : device time of one batched get_cost launch for n = 1e3 .. 1e5 poses (cooperative kernel below 37889
+  batch     : device time of one batched get_cost launch for n = 1e3 .. 1e5 poses (cooperative kernel up to 18944
               poses, thread-per-pose kernel above), clean map (no plane rebuild) and volatile map
 """
 import json
