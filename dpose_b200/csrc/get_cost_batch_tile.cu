@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ 
   __shared__ uint32_t s_words[2][32][9];  // [block of the pair][tile][row], padded: conflict-free both ways
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t chunks = (ntx + 31) / 32;  // blocks per tile row
-  const size_t n_blocks = (size_t)chunks * (ty1 - ty0);
-  auto fetch = [&](size_t blk, uint32_t v[8]) {  // pitch % 32 == 0 and the pad bytes of the device copy are zero
-    const uint32_t tr = (uint32_t)(blk / chunks), c = (uint32_t)(blk - (size_t)tr * chunks);
+  const uint32_t n_blocks = chunks * (ty1 - ty0);  // < 2^32: the host checks (32-bit index arithmetic: a 64-bit
+                                                   // division per block was a third of this kernel's instructions)
+  auto fetch = [&](uint32_t blk, uint32_t v[8]) {  // pitch % 32 == 0 and the pad bytes of the device copy are zero
+    const uint32_t tr = blk / chunks, c = blk - tr * chunks;
     const uint32_t y = (ty0 + tr) * 8 + w;
     const size_t x = ((size_t)c * 32 + lane) * 32;
 #pragma unroll
@@ -89,13 +90,13 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ 
                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                    : "l"(map + (size_t)y * pitch + x));
   };
-  auto store = [&](size_t blk, int which) {  // thread t writes word t of the block's kilobyte: tile t >> 3, row t & 7
-    const uint32_t tr = (uint32_t)(blk / chunks), c = (uint32_t)(blk - (size_t)tr * chunks);
+  auto store = [&](uint32_t blk, int which) {  // thread t writes word t of the block's kilobyte: tile t >> 3, row t & 7
+    const uint32_t tr = blk / chunks, c = blk - tr * chunks;
     const uint32_t tile = c * 32 + (threadIdx.x >> 3);
     if (tile < ntx) tiles[((size_t)(ty0 + tr) * ntx + tile) * 8 + (threadIdx.x & 7)] = s_words[which][threadIdx.x >> 3][threadIdx.x & 7];
   };
-  for (size_t blk = blockIdx.x; blk < n_blocks; blk += 2 * (size_t)gridDim.x) {
-    const size_t blk2 = blk + gridDim.x;
+  for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += 2 * gridDim.x) {
+    const uint32_t blk2 = blk + gridDim.x;
     const bool two = blk2 < n_blocks;
     uint32_t v0[8], v1[8];
     fetch(blk, v0);
@@ -615,6 +616,7 @@ static int tileplane_build_locked(const dpose_map *map, cudaStream_t stream) {
   if (hi <= lo) return DPOSE_OK;
   const uint32_t ty0 = lo / 8, ty1 = (hi + 7) / 8;
   const size_t n_blocks = (size_t)((map->tiles_ntx + 31) / 32) * (ty1 - ty0);
+  if (n_blocks >= ((size_t)1 << 31)) return fail(DPOSE_EINVAL, "costmap too large for the tile plane (more than 2^44 cells)");
   const unsigned grid = (unsigned)std::min<size_t>((n_blocks + 1) / 2, (size_t)148 * 8);
   k_pack_tiles<<<grid, 256, 0, stream>>>(map->d_data, map->pitch, map->size_y, map->d_tiles, map->tiles_ntx, ty0, ty1);
   DPOSE_LAUNCHED();
