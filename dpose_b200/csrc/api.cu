@@ -21,6 +21,18 @@ std::string &last_error() {
   return e;
 }
 
+const DeviceInfo &device_info(int device) {
+  static DeviceInfo info[64];
+  static std::once_flag once[64];
+  const int d = device >= 0 && device < 64 ? device : 0;
+  std::call_once(once[d], [d] {
+    cudaDeviceGetAttribute(&info[d].sms, cudaDevAttrMultiProcessorCount, d);
+    cudaDeviceGetAttribute(&info[d].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d);
+    cudaGetLastError();
+  });
+  return info[d];
+}
+
 int fail(int code, const char *fmt, ...) {
   char buf[1024];
   va_list ap;

@@ -68,6 +68,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 #define DPOSE_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define DPOSE_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 
+// device attributes the launch code needs on every call, queried once per device
+struct DeviceInfo {
+  int sms = 148, smem_optin = 0;
+};
+const DeviceInfo &device_info(int device);  // api.cu
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;

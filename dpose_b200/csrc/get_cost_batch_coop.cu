@@ -99,16 +99,13 @@ CoopCtx coop_ctx(const dpose_pg *pg, const dpose_map *map) {
 }
 
 bool coop_batch_wanted(const dpose_pg *pg, size_t n) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
-  return coop_group(n, sms) >= DPOSE_COOP_MIN_GROUP;
+  return coop_group(n, device_info(pg->device).sms) >= DPOSE_COOP_MIN_GROUP;
 }
 
 int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream) {
   const size_t n = spec.n;
   const int want_jacobian = spec.want_jacobian && !spec.cost_only;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
+  const int sms = device_info(pg->device).sms;
   DPOSE_TRY(coef_abs_ensure(pg, stream));
   DPOSE_TRY(tileplane_ensure(map, stream, spec.hold_planes));
   CoopBatchArgs a;

@@ -569,7 +569,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
 template <bool kJac, int kThreads, int kRepShift, int kRows>
 int launch_tile4(const TileArgs &a, int grid, size_t smem_bytes, cudaStream_t stream) {
   auto kern = k_cost_batch_tile<kJac, kThreads, kRepShift, kRows>;
-  DPOSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  // the opt-in shared-memory size is a per-device property of the function: raised once per (instantiation, device)
+  static std::atomic<size_t> raised[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || raised[dev].load(std::memory_order_relaxed) < smem_bytes) {
+    DPOSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (dev >= 0 && dev < 64) raised[dev].store(smem_bytes, std::memory_order_relaxed);
+  }
   DPOSE_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem_bytes, stream, a));  // see griddepcontrol.wait
   DPOSE_LAUNCHED();
   return DPOSE_OK;
@@ -668,9 +675,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   double *d_out = spec.d_out;
   const int want_jacobian = spec.want_jacobian && !spec.cost_only;
   const bool hold_planes = spec.hold_planes;
-  int sms = 148, smem_optin = 0;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
-  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pg->device);
+  const int sms = device_info(pg->device).sms, smem_optin = device_info(pg->device).smem_optin;
 
   // rows kept per chunk
   const int need = std::min(32, pg->win_max);

@@ -50,6 +50,7 @@ struct PrecomputeArgs {
   int *d2;             // squared EDT
   float *pre, *tmp, *cost;
   float *cost_host;  // mapped pinned copy of the table for the caller (or null)
+  int want_stages;   // kSmem only: copy outline / mask / d2 / pre-blur table out to their global images at the end
   PatchCoef *coef;
   long long *scratch;  // kWarps * 2 * n crossings
 };
@@ -96,16 +97,44 @@ __device__ void draw_edge(uint8_t *a, uint8_t *b, int cols, int rows, int x1, in
   }
 }
 
+// kSmem: every intermediate image lives in shared memory (18 bytes per pixel + the fill's scratch: tables up to ~11 000
+// pixels, i.e. all of the reference's fixtures).  The phases are separated by block barriers and chained through these
+// images, so with the images in global memory every phase starts with an L2 round trip per access (the CTA's own stores
+// invalidate its L1 lines); in shared memory the same accesses cost ~30 cycles.  Only the table, the coefficients and
+// — on request — the debug stages leave the SM.
+template <bool kSmem>
 __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rows = p.rows, cols = p.cols, np = rows * cols, n = p.n;
   __shared__ unsigned s_maxmag;
-  auto vertex = [&](int e) { return p.fp ? p.fp[e] : p.fp_param[e]; };
+  uint8_t *outline = p.outline, *mask = p.mask;
+  int *g = p.g, *d2 = p.d2;
+  float *pre = p.pre, *tmp = p.tmp;
+  long long *scratch = p.scratch;
+  if (kSmem) {  // same order as smem_bytes() below
+    const size_t np4 = ((size_t)np + 3) & ~(size_t)3;
+    g = reinterpret_cast<int *>(s_dyn);
+    d2 = g + np4;
+    pre = reinterpret_cast<float *>(d2 + np4);
+    tmp = pre + np4;
+    scratch = reinterpret_cast<long long *>(tmp + np4);
+    outline = reinterpret_cast<uint8_t *>(scratch + (size_t)kWarps * 2 * n);
+    mask = outline + np4;
+  }
+  // vertices that travelled in the kernel parameters go to shared memory first: the parameters live in the constant
+  // bank, which serves one address per warp access — lanes reading different vertices (the fill takes one edge per lane)
+  // serialise 32-fold (the 40-vertex footprint lost 7 us that way)
+  __shared__ int2 s_fp[kParamVerts];
+  if (!p.fp)
+    for (int e = tid; e < n; e += kThreads) s_fp[e] = p.fp_param[e];
+  const int2 *verts = p.fp ? p.fp : s_fp;
+  auto vertex = [&](int e) { return verts[e]; };
 
   // ---- phase 0: white images ---------------------------------------------------------
   for (int i = tid; i < np; i += kThreads) {
-    p.outline[i] = 255;
-    p.mask[i] = 255;
+    outline[i] = 255;
+    mask[i] = 255;
   }
   if (tid == 0) s_maxmag = 0u;
   __syncthreads();
@@ -113,13 +142,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
   // ---- phase 1: outline (polylines == fillPoly's outline) ------------------------------
   for (int e = tid; e < n; e += kThreads) {
     const int2 a = vertex(e == 0 ? n - 1 : e - 1), b = vertex(e);
-    draw_edge(p.outline, p.mask, cols, rows, a.x, a.y, b.x, b.y);
+    draw_edge(outline, mask, cols, rows, a.x, a.y, b.x, b.y);
   }
   __syncthreads();
 
   // ---- phase 2: even-odd scanline fill into mask ---------------------------------------
   {
-    long long *xs = p.scratch + (size_t)warp * 2 * n, *sorted = xs + n;
+    long long *xs = scratch + (size_t)warp * 2 * n, *sorted = xs + n;
     for (int y = warp; y < rows; y += kWarps) {
       int na = 0;
       for (int e0 = 0; e0 < n; e0 += 32) {
@@ -157,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
         if (x1 < cols && x2 >= 0) {
           x1 = x1 < 0 ? 0 : x1;
           x2 = x2 >= cols ? cols - 1 : x2;
-          for (int x = x1 + lane; x <= x2; x += 32) p.mask[y * cols + x] = 0;
+          for (int x = x1 + lane; x <= x2; x += 32) mask[y * cols + x] = 0;
         }
       }
       __syncwarp();
@@ -169,13 +198,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
   for (int x = tid; x < cols; x += kThreads) {
     int last = -1;
     for (int y = 0; y < rows; ++y) {
-      if (p.outline[y * cols + x] == 0) last = y;
-      p.g[y * cols + x] = last < 0 ? kInfG : y - last;
+      if (outline[y * cols + x] == 0) last = y;
+      g[y * cols + x] = last < 0 ? kInfG : y - last;
     }
     last = -1;
     for (int y = rows - 1; y >= 0; --y) {
-      if (p.outline[y * cols + x] == 0) last = y;
-      if (last >= 0 && last - y < p.g[y * cols + x]) p.g[y * cols + x] = last - y;
+      if (outline[y * cols + x] == 0) last = y;
+      if (last >= 0 && last - y < g[y * cols + x]) g[y * cols + x] = last - y;
     }
   }
   __syncthreads();
@@ -186,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
     for (int item = warp; item < rows * segs; item += kWarps) {
       const int y = item / segs, s = item - y * segs;
       const int x = s * 32 + lane;
-      const int *gr = p.g + y * cols;
+      const int *gr = g + y * cols;
       int best = 0x7fffffff;
       for (int t = 0; t < segs; ++t) {
         // smallest |x - i| between this segment and tile t
@@ -203,14 +232,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
           best = min(best, dxi * dxi + cand);
         }
       }
-      if (x < cols) p.d2[y * cols + x] = best;
+      if (x < cols) d2[y * cols + x] = best;
     }
   } else {  // Meijster's lower envelope, one thread per row
     // the stacks live in the (still unused) float scratch images, [q][row] so that the threads of a warp, whose stack
     // depths stay close, touch neighbouring words; the top of the stack is carried in registers
-    int *st_s = reinterpret_cast<int *>(p.pre), *st_t = reinterpret_cast<int *>(p.tmp);
+    int *st_s = reinterpret_cast<int *>(pre), *st_t = reinterpret_cast<int *>(tmp);
     for (int y = tid; y < rows; y += kThreads) {
-      const int *gr = p.g + y * cols;
+      const int *gr = g + y * cols;
       auto g2_of = [&](int i) {
         const int gi = gr[i];
         return gi >= kInfG ? kBigD2 : gi * gi;
@@ -246,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
       }
       for (int u = cols - 1; u >= 0; --u) {
         const int dxi = u - s_top;
-        p.d2[y * cols + u] = dxi * dxi + g2_top;
+        d2[y * cols + u] = dxi * dxi + g2_top;
         if (u == t_top && q > 0) {
           --q;
           s_top = st_s[q * rows + y];
@@ -262,8 +291,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
   {
     unsigned mag = 0u;
     for (int i = tid; i < np; i += kThreads) {
-      const float d = __fsqrt_rn(__int2float_rn(p.d2[i]));
-      const float o = p.mask[i] != 0 ? __fmul_rn(d, -0.01f) : 0.0f;
+      const float d = __fsqrt_rn(__int2float_rn(d2[i]));
+      const float o = mask[i] != 0 ? __fmul_rn(d, -0.01f) : 0.0f;
       mag = max(mag, __float_as_uint(o) & 0x7fffffffu);
     }
 #pragma unroll
@@ -275,26 +304,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
 
   // ---- phase 4b: shift ----------------------------------------------------------------------
   for (int i = tid; i < np; i += kThreads) {
-    const float d = __fsqrt_rn(__int2float_rn(p.d2[i]));
-    const float v = p.mask[i] != 0 ? __fmul_rn(d, -0.01f) : d;
-    p.pre[i] = __fsub_rn(v, mn);
+    const float d = __fsqrt_rn(__int2float_rn(d2[i]));
+    const float v = mask[i] != 0 ? __fmul_rn(d, -0.01f) : d;
+    pre[i] = __fsub_rn(v, mn);
   }
   __syncthreads();
 
   // ---- phase 4c: blur rows then columns ([0.25 0.5 0.25], BORDER_REFLECT_101) -----------------
   for (int i = tid; i < np; i += kThreads) {
     const int y = i / cols, x = i - y * cols;
-    const float a = p.pre[y * cols + reflect101(x - 1, cols)];
-    const float b = p.pre[i];
-    const float c = p.pre[y * cols + reflect101(x + 1, cols)];
-    p.tmp[i] = __fadd_rn(__fmul_rn(__fadd_rn(a, c), 0.25f), __fmul_rn(b, 0.5f));
+    const float a = pre[y * cols + reflect101(x - 1, cols)];
+    const float b = pre[i];
+    const float c = pre[y * cols + reflect101(x + 1, cols)];
+    tmp[i] = __fadd_rn(__fmul_rn(__fadd_rn(a, c), 0.25f), __fmul_rn(b, 0.5f));
   }
   __syncthreads();
   for (int i = tid; i < np; i += kThreads) {
     const int y = i / cols, x = i - y * cols;
-    const float a = p.tmp[reflect101(y - 1, rows) * cols + x];
-    const float b = p.tmp[i];
-    const float c = p.tmp[reflect101(y + 1, rows) * cols + x];
+    const float a = tmp[reflect101(y - 1, rows) * cols + x];
+    const float b = tmp[i];
+    const float c = tmp[reflect101(y + 1, rows) * cols + x];
     const float v = __fadd_rn(__fmul_rn(__fadd_rn(a, c), 0.25f), __fmul_rn(b, 0.5f));
     p.cost[i] = v;
     if (p.cost_host) p.cost_host[i] = v;  // straight into the caller's (mapped pinned) copy: no copy back
@@ -315,6 +344,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_precompute(PrecomputeArgs p) {
     }
     p.coef[i] = c;
   }
+  if (kSmem && p.want_stages) {  // debug / parity aid: the intermediate images leave the SM only on request
+    for (int i = tid; i < np; i += kThreads) {
+      p.outline[i] = outline[i];
+      p.mask[i] = mask[i];
+      p.d2[i] = d2[i];
+      p.pre[i] = pre[i];
+    }
+  }
+}
+
+// shared-memory bytes of the kSmem variant (layout in the kernel)
+size_t smem_bytes(size_t np, int n) {
+  const size_t np4 = (np + 3) & ~(size_t)3;
+  return 16 * np4 + sizeof(long long) * kWarps * 2 * (size_t)n + 2 * np4;
 }
 
 }  // namespace
@@ -351,7 +394,7 @@ struct ThreadCtx {
 };
 
 int launch_precompute(const dpose_pg *pg, const int32_t *fp_xy, int n, unsigned char *base, const Arena &ar, float *d_cost,
-                      PatchCoef *d_coef, float *cost_host, cudaEvent_t e0, cudaEvent_t e1) {
+                      PatchCoef *d_coef, float *cost_host, bool want_stages, cudaEvent_t e0, cudaEvent_t e1) {
   PrecomputeArgs a;
   a.n = n;
   if (n <= kParamVerts) {
@@ -373,8 +416,17 @@ int launch_precompute(const dpose_pg *pg, const int32_t *fp_xy, int n, unsigned 
   a.cost_host = cost_host;
   a.coef = d_coef;
   a.scratch = reinterpret_cast<long long *>(base + ar.o_scratch);
+  a.want_stages = want_stages ? 1 : 0;
+  const int smem_optin = device_info(pg->device).smem_optin;
+  const size_t dyn = smem_bytes((size_t)pg->rows * pg->cols, n);
   if (e0) DPOSE_CUDA(cudaEventRecord(e0, nullptr));
-  k_precompute<<<1, kThreads>>>(a);
+  if (dyn + 2048 <= (size_t)smem_optin) {
+    if (dyn > ((size_t)40 << 10))
+      DPOSE_CUDA(cudaFuncSetAttribute(k_precompute<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    k_precompute<true><<<1, kThreads, dyn>>>(a);
+  } else {
+    k_precompute<false><<<1, kThreads>>>(a);
+  }
   DPOSE_LAUNCHED();
   if (e1) DPOSE_CUDA(cudaEventRecord(e1, nullptr));
   return DPOSE_OK;
@@ -419,7 +471,7 @@ int precompute_run(dpose_pg *pg, const int32_t *fp_xy, int n) {
     pg->d_coef = reinterpret_cast<PatchCoef *>(keep + o_coef);
     DPOSE_CUDA(cudaMallocAsync(&scratch, ar.total, nullptr));
     float *cost_host = np <= kZeroCopyTable ? tc.h_table : nullptr;
-    DPOSE_TRY(launch_precompute(pg, fp_xy, n, scratch, ar, pg->d_cost, pg->d_coef, cost_host, tc.e0, tc.e1));
+    DPOSE_TRY(launch_precompute(pg, fp_xy, n, scratch, ar, pg->d_cost, pg->d_coef, cost_host, false, tc.e0, tc.e1));
     if (!cost_host)
       DPOSE_CUDA(cudaMemcpyAsync(pg->h_cost.data(), pg->d_cost, sizeof(float) * np, cudaMemcpyDeviceToHost, nullptr));
     DPOSE_CUDA(cudaFreeAsync(scratch, nullptr));
@@ -463,7 +515,7 @@ int precompute_fetch_stages(dpose_pg *pg) {
     const size_t o_cost = ar.total, o_coef = (o_cost + sizeof(float) * np + 255) & ~(size_t)255;
     DPOSE_CUDA(cudaMallocAsync(&scratch, o_coef + sizeof(PatchCoef) * np, nullptr));
     DPOSE_TRY(launch_precompute(pg, shifted.data(), n, scratch, ar, reinterpret_cast<float *>(scratch + o_cost),
-                                reinterpret_cast<PatchCoef *>(scratch + o_coef), nullptr, nullptr, nullptr));
+                                reinterpret_cast<PatchCoef *>(scratch + o_coef), nullptr, true, nullptr, nullptr));
     DPOSE_CUDA(cudaMemcpyAsync(pg->h_pre_blur.data(), scratch + ar.o_pre, sizeof(float) * np, cudaMemcpyDeviceToHost, nullptr));
     DPOSE_CUDA(cudaMemcpyAsync(d2.data(), scratch + ar.o_d2, sizeof(int) * np, cudaMemcpyDeviceToHost, nullptr));
     DPOSE_CUDA(cudaMemcpyAsync(pg->h_outline.data(), scratch + ar.o_outline, np, cudaMemcpyDeviceToHost, nullptr));

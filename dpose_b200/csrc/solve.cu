@@ -420,8 +420,7 @@ int dpose_problem_solve_batch(dpose_problem *p, const double *x0, size_t n, cons
   double *d_x0 = reinterpret_cast<double *>(d_base + align_up(lay.total, 16));
   double *h_x0 = reinterpret_cast<double *>(h_base + align_up(lay.total, 16));
 
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pg->device);
+  const int sms = device_info(pg->device).sms;
   SolveArgs a;
   a.has_map = p->crop && p->crop->d_tiles && pg->rows >= 4 && pg->cols >= 4;
   auto body = [&]() -> int {
