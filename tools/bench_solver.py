@@ -94,7 +94,45 @@ def bench_batch():
                  poses_per_s=n / us * 1e6)
 
 
+def bench_shard():
+    """one rank's share of BASELINE cfg5 under strong scaling on 8 GPUs: 1.25e6 poses on the 10000 x 10000 volatile
+    map — device time per step and the host time it takes to queue a step"""
+    import torch
+    fp, pad = fx.FOOTPRINTS["rect_pad2"]
+    side = 10000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4)
+    d_map = torch.where(torch.rand((side, side), generator=g, device="cuda") < 0.10,
+                        torch.tensor(254, dtype=torch.uint8, device="cuda"),
+                        torch.tensor(0, dtype=torch.uint8, device="cuda")).contiguous()
+    pg = dp.pose_gradient(fp, dp.pose_gradient.parameter(pad))
+    cm = dp.Costmap(device_ptr=d_map.data_ptr(), size_x=side, size_y=side, pitch=side)
+    for volatile in (True, False):
+        cm.set_volatile(volatile)
+        for n in (1_250_000, 2_500_000, 5_000_000, 10_000_000):
+            u = torch.rand((n, 3), generator=g, device="cuda", dtype=torch.float64)
+            poses = torch.stack([32 + u[:, 0] * (side - 64), 32 + u[:, 1] * (side - 64), -3.14159 + u[:, 2] * 6.28318], 1).contiguous()
+            out = torch.zeros((n, 4), dtype=torch.float64, device="cuda")
+            st = torch.cuda.current_stream()
+            for _ in range(5):
+                pg.get_cost_batch_device(cm, poses.data_ptr(), n, out.data_ptr(), stream=st.cuda_stream)
+            torch.cuda.synchronize()
+            reps = 20
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record(st)
+            for _ in range(reps):
+                pg.get_cost_batch_device(cm, poses.data_ptr(), n, out.data_ptr(), stream=st.cuda_stream)
+            b.record(st)
+            issue = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) * 1e3 / reps
+            emit(what="one rank's shard of cfg5 (device time per step, back to back)", poses=n, volatile_map=volatile,
+                 us_per_step=us, host_issue_us_per_step=issue / reps * 1e6, poses_per_s=n / us * 1e6)
+            del poses, out, u
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["solve", "batch"]
     for w in which:
-        {"solve": bench_solve, "batch": bench_batch}[w]()
+        {"solve": bench_solve, "batch": bench_batch, "shard": bench_shard}[w]()
