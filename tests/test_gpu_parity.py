@@ -240,6 +240,33 @@ def test_lethal_random_boxes_vs_oracle(dp, capi):
     assert np.array_equal(dev.numpy(), capi.lethal_cells_within(m, ring))
 
 
+def test_lethal_large_boxes_capacity_estimates(dp, capi):
+    """boxes of more than 4 M cells size their result by what the previous extraction on the map returned (+25 %): a
+    first call (no estimate), a call whose estimate is far too small (the write pass is repeated with the exact size),
+    one whose estimate is too large, and a volatile map — all bit-exact against the oracle"""
+    side = 3000
+    rng = np.random.default_rng(17)
+    m = np.zeros((side, side), np.uint8)
+    m[:, : side // 2][rng.random((side, side // 2)) < 0.01] = fx.LETHAL
+    m[:, side // 2:][rng.random((side, side - side // 2)) < 0.30] = fx.LETHAL
+    m[::7, ::5] = 253  # near misses: only 254 is lethal
+    cm = dp.Costmap(m)
+    left = fx.to_rectangle((0, 0), (side // 2 - 1, side - 1))          # 4.5 M cells, 1 % lethal
+    full = fx.to_rectangle((0, 0), (side - 1, side - 1))                # 9 M cells, mostly the dense half
+    tilted = fx.rotated_ring(fx.to_rectangle((-1300, -1100), (1300, 1100)), (1500.0, 1500.0, 0.6))
+    for ring in (left, full, left, tilted, full):
+        got = dp.lethal_cells_within(cm, ring)
+        want = capi.lethal_cells_within(m, ring)
+        assert got.shape == want.shape and np.array_equal(got, want)
+    cm.set_volatile(True)
+    assert np.array_equal(dp.lethal_cells_within(cm, tilted), capi.lethal_cells_within(m, tilted))
+    m2 = m.copy()
+    m2[1000:1200, 100:900] = fx.LETHAL
+    cm.set_volatile(False)
+    cm.update(m2[1000:1200, 100:900], 100, 1000)  # dirty rows only: the plane is rebuilt for rows 1000 .. 1199
+    assert np.array_equal(dp.lethal_cells_within(cm, full), capi.lethal_cells_within(m2, full))
+
+
 def test_lethal_perf_bench_workload(dp, capi):  # dpose_core/perf/dpose_core.cpp:73-90
     m = np.zeros((200, 200), np.uint8)
     m.reshape(-1)[::2] = fx.LETHAL
