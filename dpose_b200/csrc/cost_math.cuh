@@ -11,26 +11,36 @@ struct TableGeom {
 };
 
 // axis-aligned bounding box (inclusive integer cells) of the valid kernel region
-// [1.5, cols-1.5) x [1.5, rows-1.5) mapped into the map by p = t + R(theta)(k - C)
+// [1.5, cols-1.5) x [1.5, rows-1.5) mapped into the map by p = t + R(theta)(k - C), widened by 1e-7 cell.
+// Centre / half-extent form: the box of a rotated rectangle is its rotated centre -+ (|c| hu + |s| hv, |s| hu + |c| hv) —
+// 16 FP64 operations and no floating-point min / max (a double fmin is a compare, two selects and NaN fix-ups on the
+// GPU; the corner form needed twelve of them per pose).  Conversions saturate, the clamps are integer.
 __host__ __device__ inline WindowRect pose_window(const TableGeom &g, double tx, double ty, double c,
                                                   double s, int size_x, int size_y) {
-  const double au0 = 1.5 - g.cx, au1 = (double)g.cols - 1.5 - g.cx;
-  const double av0 = 1.5 - g.cy, av1 = (double)g.rows - 1.5 - g.cy;
-  const double xa = c * au0, xb = c * au1, xc = -s * av0, xd = -s * av1;
-  const double ya = s * au0, yb = s * au1, yc = c * av0, yd = c * av1;
+  const double hu = 0.5 * ((double)g.cols - 3.0), hv = 0.5 * ((double)g.rows - 3.0);  // half extents of the valid region
+  const double mu = 0.5 * (double)g.cols - g.cx, mv = 0.5 * (double)g.rows - g.cy;    // its centre relative to C
   const double eps = 1e-7;
-  const double xmin = tx + fmin(xa, xb) + fmin(xc, xd) - eps, xmax = tx + fmax(xa, xb) + fmax(xc, xd) + eps;
-  const double ymin = ty + fmin(ya, yb) + fmin(yc, yd) - eps, ymax = ty + fmax(ya, yb) + fmax(yc, yd) + eps;
+  const double px = tx + fma(c, mu, -s * mv), py = ty + fma(s, mu, c * mv);
+  const double hx = fma(fabs(c), hu, fabs(s) * hv) + eps, hy = fma(fabs(s), hu, fabs(c) * hv) + eps;
+  const double xmin = px - hx, xmax = px + hx, ymin = py - hy, ymax = py + hy;
   WindowRect w;
   w.x0 = w.y0 = 0;
   w.x1 = w.y1 = -1;  // empty; also the answer for NaN poses and windows off the map
-  if (!(xmax >= 0.0) || !(ymax >= 0.0) || !(xmin <= (double)size_x - 1.0) || !(ymin <= (double)size_y - 1.0))
-    return w;
-  // clamped in floating point, so the int casts cannot overflow
-  w.x0 = (int)ceil(fmax(xmin, 0.0));
-  w.y0 = (int)ceil(fmax(ymin, 0.0));
-  w.x1 = (int)floor(fmin(xmax, (double)size_x - 1.0));
-  w.y1 = (int)floor(fmin(ymax, (double)size_y - 1.0));
+  const double t = xmin + ymin;
+  if (t != t) return w;  // a NaN anywhere in the pose (or opposite infinities) ends up here
+#ifdef __CUDA_ARCH__
+  // cvt.rpi / cvt.rmi saturate to the int range, so windows far off the map come out empty after the clamps
+  w.x0 = max(__double2int_ru(xmin), 0);
+  w.y0 = max(__double2int_ru(ymin), 0);
+  w.x1 = min(__double2int_rd(xmax), size_x - 1);
+  w.y1 = min(__double2int_rd(ymax), size_y - 1);
+#else
+  // the same values on the host (clamped in floating point, so the int casts cannot overflow)
+  w.x0 = (int)ceil(fmin(fmax(xmin, 0.0), 2147483647.0));
+  w.y0 = (int)ceil(fmin(fmax(ymin, 0.0), 2147483647.0));
+  w.x1 = (int)floor(fmax(fmin(xmax, (double)size_x - 1.0), -2147483648.0));
+  w.y1 = (int)floor(fmax(fmin(ymax, (double)size_y - 1.0), -2147483648.0));
+#endif
   return w;
 }
 

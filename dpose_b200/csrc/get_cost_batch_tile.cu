@@ -235,7 +235,10 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 }
 
 // DPOSE_TILE_CVT: how the walk turns a bit / row index into a double.
-//   0: 2^52 trick (one DADD on the FP64 pipe + register-pair set-up), 1: I2F.F64 (conversion pipe)
+//   0: 2^52 trick (one DADD on the FP64 pipe + register-pair set-up), 1: I2F.F64 (conversion pipe: with the two FLO of
+//   an iteration that is 4 x 8 issue cycles on the 4-lane XU, as busy as the FP64 pipe), 2: no conversion at all — the
+//   index x < 32 is planted into the top five mantissa bits of 1.0 by an integer multiply-add on the high word
+//   (1 + x / 32, exact), and the walk's FMAs run on 32 c, 32 s with the constant terms folded into the chunk origin.
 // DPOSE_TILE_COMPACT 1 stores only the rows that can belong to a chunk: less shared memory, so that 8
 // coefficient replicas (conflict-free LDS.128 gathers) fit next to 1024 threads' row masks.  Measured on B200
 // (cfg5): 9.26e9 poses/s against 8.89e9 for "every slot stored, 4 replicas"; the L1/shared data pipe drops from
@@ -249,8 +252,6 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 #ifndef DPOSE_TILE_REPLICAS
 #define DPOSE_TILE_REPLICAS 8  // coefficient replicas wanted in shared memory (A/B builds: 1, 4)
 #endif
-// DPOSE_TILE_WALK 1: branch-free row advance in the cell walk (37-instruction loop body, +0.7 % on B200);
-// 0: nested branch (41 instructions)
 // Big tables (the coefficient image fits shared memory only once: kRepShift == 0) run in "texture mode": shared
 // memory holds the (b00, b10) halves twice (same bytes as one full copy, half the bank conflicts) and the
 // (b01, b11) halves are fetched through the texture unit from a plain global array, which takes those gathers
@@ -267,18 +268,24 @@ __device__ __forceinline__ int top_bit(unsigned x) {
 #ifndef DPOSE_TILE_CHECK
 #define DPOSE_TILE_CHECK 0
 #endif
-#ifndef DPOSE_TILE_WALK
-#define DPOSE_TILE_WALK 1
-#endif
 #ifndef DPOSE_TILE_CVT
-#define DPOSE_TILE_CVT 1
+#define DPOSE_TILE_CVT 2
 #endif
-__device__ __forceinline__ double index_to_double(int x) {
+__device__ __forceinline__ double index_to_double(int x, int zero) {  // zero: an opaque 0 (CVT 2: the low word)
 #if DPOSE_TILE_CVT == 0
   return small_int_to_double(x);
+#elif DPOSE_TILE_CVT == 2
+  return __hiloint2double(0x3FF00000 + (x << 15), zero);  // 1 + x / 32 for 0 <= x < 32
 #else
   return (double)x;
 #endif
+}
+// m without its most significant set bit, b = top_bit(m) (b = -1 for m == 0: m stays 0): AND with a mask of the b low bits
+// (BMSK) — no materialised 1 to shift
+__device__ __forceinline__ unsigned clear_top(unsigned m, int b) {
+  unsigned r;
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(b));
+  return m & r;
 }
 
 // kRepShift: log2 of the coefficient replicas; kRows: rows of a chunk (>= min(32, largest window height)).  A
@@ -347,8 +354,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   // Kernel coordinates are carried as k' = k + 0.5 - 2 = k - 1.5: floor(k') = k_upper - 2 (k_upper = round(k),
   // dpose_core.cpp:177), frac(k') = c_rel (:193), and the bounds test (:181-182) becomes
   // 0 <= floor(k') <= dim - 4.  The patch of k_upper = (2, 2) therefore sits at the base address.
-  const uint32_t my_coef =
+  uint32_t my_coef =
       coef_u32 + ((uint32_t)lane & ((1u << kLoShift) - 1u)) * 16u + (uint32_t)(2 * cols + 2) * kPatchStride;
+  uint32_t colstride = (uint32_t)cols * kPatchStride;  // bytes between the images of two table rows
+  asm volatile("" : "+r"(my_coef), "+r"(colstride));  // two registers: nothing of either is re-derived inside the cell walk
   const float hi_u = (float)a.g.cols - 3.0f, hi_v = (float)a.g.rows - 3.0f;  // 0 <= k' < dim - 3
   const double cx15 = a.g.cx - 1.5, cy15 = a.g.cy - 1.5;
 
@@ -398,9 +407,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     }
 
     Acc4 acc = {0.0, 0.0, 0.0, 0.0};
-    for (int rb = 0; rb < H; rb += 32) {
+#if DPOSE_TILE_CVT == 2
+    const double cw = 32.0 * c, sw = 32.0 * s;
+#endif
+    // low words of the walk's index doubles: opaque zeros that stay in the low halves of two register pairs, so that
+    // an index costs one integer instruction on the high half (a literal 0 is re-materialised in every iteration)
+    int zero_x = (int)(a.stride >> 31), zero_y = (int)(a.ntx >> 31);  // both 0 (stride <= 1024, ntx < 2^31)
+    asm volatile("" : "+r"(zero_x), "+r"(zero_y));
+    // kRows < 32: every window of the table fits one 32 x 32 chunk — the chunk loops and what they keep alive across
+    // the cell walk (the clip intervals, the window, its origin in kernel coordinates) drop out at compile time
+    constexpr bool kSingle = kRows < 32;
+    int rb = 0;
+    if (H > 0 && W > 0) do {
       const int hc = min(32, H - rb), ys = w.y0 + rb;
-      for (int cb = 0; cb < W; cb += 32) {
+      int cb = 0;
+      do {
         const int wc = min(32, W - cb), xs = w.x0 + cb;
         const int off = ys & 7;  // chunk row i sits in row slot i + off of the chunk's tile rows
         // ---- phase 1: row masks of this chunk; branch-free per slot, every slot is stored ---------------------
@@ -482,35 +503,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
         // re-derives it from threadIdx and the kernel arguments inside the walk (measured: +20 % instructions)
         uint32_t srow = smem_u32(DPOSE_TILE_COMPACT ? s_mask : s_mask + off * kThreads);
         asm volatile("" : "+r"(srow));
+#if DPOSE_TILE_CVT == 2
+        // X = 1 + b / 32, Y = 1 + row / 32 (index_to_double): c b + s row = cw X + sw Y - cw - sw with cw = 32 c, sw = 32 s
+        // (exact scalings); the constants ride on the chunk origin: cb / 32 - 1 and rb / 32 - 1 are exact integers
+        const double dcb = (double)((cb >> 5) - 1), drb = (double)((rb >> 5) - 1);
+        const double kuc = fma(cw, dcb, fma(sw, drb, ku0)), kvc = fma(cw, drb, fma(-sw, dcb, kv0));
+#else
         const double dcb = (double)cb, drb = (double)rb;
         const double kuc = fma(c, dcb, fma(s, drb, ku0)), kvc = fma(c, drb, fma(-s, dcb, kv0));
-        unsigned mask = 0u;
-        int row = 0;
-        wait_staged();
-        while (true) {
-#if DPOSE_TILE_WALK == 1
-          // branch-free row advance: selects and one predicated load instead of a nested branch
-          if ((mask | rowmask) == 0u) break;
-          const bool adv = mask == 0u;
-          const int r2 = top_bit(rowmask);  // -1 when no row is left; then adv is false and nothing below uses it
-          row = adv ? r2 : row;
-          rowmask = adv ? rowmask ^ shl_clamp(1u, (unsigned)r2) : rowmask;
-          if (adv) mask = lds_u32(srow + (uint32_t)row * (uint32_t)(kThreads * 4));
-#else
-          if (mask == 0u) {
-            if (rowmask == 0u) break;
-            row = top_bit(rowmask);
-            rowmask ^= 1u << row;
-            mask = lds_u32(srow + (uint32_t)row * (uint32_t)(kThreads * 4));
-          }
 #endif
-          const int b = top_bit(mask);
-          mask ^= 1u << b;
-          const double X = index_to_double(b), Y = index_to_double(row);
-          const double ku = fma(c, X, fma(s, Y, kuc));
-          const double kv = fma(c, Y, fma(-s, X, kvc));
+        wait_staged();
+        // One cell = bit b of window row `row`.  gather: k' of the cell, its patch, the two 16-byte halves of the patch
+        // polynomial; accumulate: value and derivatives.  Split so that the loop below can put the selection of the next
+        // cell between the two.
+        struct Cell {
+          double ku, kv, b00, b10, b01, b11;
+        };
+        auto gather = [&](int b, int row) {
+          Cell q;
+          const double X = index_to_double(b, zero_x), Y = index_to_double(row, zero_y);
+#if DPOSE_TILE_CVT == 2
+          q.ku = fma(cw, X, fma(sw, Y, kuc));
+          q.kv = fma(cw, Y, fma(-sw, X, kvc));
+#else
+          q.ku = fma(c, X, fma(s, Y, kuc));
+          q.kv = fma(c, Y, fma(-s, X, kvc));
+#endif
           const double M = 6755399441055744.0;  // 1.5 * 2^52: adding it (rounding down) floors to an integer
-          const int ux = __double2loint(__dadd_rd(ku, M)), uy = __double2loint(__dadd_rd(kv, M));  // k_upper - 2
+          const int ux = __double2loint(__dadd_rd(q.ku, M)), uy = __double2loint(__dadd_rd(q.kv, M));  // k_upper - 2
           // no bounds test (dpose_core.cpp:181-182): out-of-range patches are zero, see the clip invariant
           const int pidx = uy * cols + ux;
 #if DPOSE_TILE_CHECK
@@ -518,35 +538,81 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
               ux > cols - 3 || uy < -2 || uy > a.g.rows - 3)
             __trap();
 #endif
-          const uint32_t addr = my_coef + (uint32_t)pidx * kPatchStride;
-          double b00, b10, b01, b11;
+          // shared-memory modes: two multiply-adds on registers (base + uy * row stride + ux * patch stride)
+          const uint32_t addr = kTex ? my_coef + (uint32_t)pidx * kPatchStride
+                                     : my_coef + (uint32_t)uy * colstride + (uint32_t)ux * kPatchStride;
           if (kGlobal) {
             const int4 t = DPOSE_TILE_LDG ? __ldg(a.planes + (a.g.rows * cols + pidx + 2 * cols + 2))
                                           : tex1Dfetch<int4>(a.tex_hi, a.g.rows * cols + pidx + 2 * cols + 2);
-            b00 = __hiloint2double(t.y, t.x);
-            b10 = __hiloint2double(t.w, t.z);
+            q.b00 = __hiloint2double(t.y, t.x);
+            q.b10 = __hiloint2double(t.w, t.z);
           } else {
-            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b00), "=d"(b10) : "r"(addr));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.b00), "=d"(q.b10) : "r"(addr));
           }
           if (kTex) {
             const int4 t = DPOSE_TILE_LDG ? __ldg(a.planes + (pidx + 2 * cols + 2)) : tex1Dfetch<int4>(a.tex_hi, pidx + 2 * cols + 2);
-            b01 = __hiloint2double(t.y, t.x);
-            b11 = __hiloint2double(t.w, t.z);
+            q.b01 = __hiloint2double(t.y, t.x);
+            q.b11 = __hiloint2double(t.w, t.z);
           } else {
-            asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(b01), "=d"(b11) : "r"(addr), "n"(kHalfOff));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(q.b01), "=d"(q.b11) : "r"(addr), "n"(kHalfOff));
           }
-          const double fv = fma(b11, ku, b01);  // df/dkv
-          acc.f += fma(kv, fv, fma(b10, ku, b00));
+          return q;
+        };
+        auto accumulate = [&](const Cell &q) {
+          const double fv = fma(q.b11, q.ku, q.b01);  // df/dkv
+          acc.f += fma(q.kv, fv, fma(q.b10, q.ku, q.b00));
           if (kJac) {
-            const double fu = fma(b11, kv, b10);  // df/dku
+            const double fu = fma(q.b11, q.kv, q.b10);  // df/dku
             acc.su += fu;
             acc.sv += fv;
-            acc.st = fma(fu, kv, acc.st);  // Sum(fu * kv' - fv * ku'); center terms folded in below
-            acc.st = fma(-fv, ku, acc.st);
+            acc.st = fma(fu, q.kv, acc.st);  // Sum(fu * kv' - fv * ku'); center terms folded in below
+            acc.st = fma(-fv, q.ku, acc.st);
+          }
+        };
+        auto row_mask = [&](int row) { return lds_u32(srow + (uint32_t)row * (uint32_t)(kThreads * 4)); };
+        // The row advance is branch-free in both forms: selects and one predicated load (a nested branch measured slower).
+        if (!kTex) {
+          // Rotated loop: the selection of the NEXT cell (row advance = an LDS of the next row's mask, then a
+          // find-leading-one) sits between the gathers of this cell's polynomial and the arithmetic that consumes them, so
+          // that the two latency chains of an iteration overlap inside one warp instead of following each other
+          // (+1 % at cfg5; the texture modes lose 3 % with it — their gathers are long enough to cover everything).
+          if (rowmask != 0u) {
+            int row = top_bit(rowmask);
+            rowmask = clear_top(rowmask, row);
+            unsigned mask = row_mask(row);
+            int b = top_bit(mask);
+            while (true) {
+              mask = clear_top(mask, b);
+              const Cell q = gather(b, row);
+              const bool more = (mask | rowmask) != 0u;
+              const bool adv = mask == 0u && rowmask != 0u;
+              const int r2 = top_bit(rowmask);
+              row = adv ? r2 : row;
+              rowmask = adv ? clear_top(rowmask, r2) : rowmask;
+              if (adv) mask = row_mask(row);
+              b = top_bit(mask);
+              accumulate(q);
+              if (!more) break;
+            }
+          }
+        } else {
+          unsigned mask = 0u;
+          int row = 0;
+          while ((mask | rowmask) != 0u) {
+            const bool adv = mask == 0u;
+            const int r2 = top_bit(rowmask);  // -1 when no row is left; then adv is false and nothing below uses it
+            row = adv ? r2 : row;
+            rowmask = adv ? clear_top(rowmask, r2) : rowmask;
+            if (adv) mask = row_mask(row);
+            const int b = top_bit(mask);
+            mask = clear_top(mask, b);
+            accumulate(gather(b, row));
           }
         }
-      }
-    }
+        cb += 32;
+      } while (!kSingle && cb < W);
+      rb += 32;
+    } while (!kSingle && rb < H);
     double jx = 0.0, jy = 0.0, jt = 0.0;
     if (kJac) {
       jx = -c * acc.su + s * acc.sv;
