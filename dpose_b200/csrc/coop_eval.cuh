@@ -46,11 +46,6 @@ struct CoopK {
 };
 
 namespace coop_detail {
-__device__ __forceinline__ int top_bit(unsigned x) {
-  int r;
-  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
-  return r;
-}
 __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned n) {  // PTX shifts clamp the amount to 32
   unsigned r;
   asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
@@ -115,6 +110,9 @@ __device__ __forceinline__ void coop_eval(const CoopCtx &a, double tx, double ty
   }
 
   double f = 0.0, su = 0.0, sv = 0.0, st = 0.0;
+  const double cw = __dmul_rn(32.0, c), sw = __dmul_rn(32.0, s);  // exact
+  int zero_x = (int)(a.ntx >> 31), zero_y = (int)(a.nty >> 31);   // 0, but not to the compiler (see unit_plus_32nd)
+  asm volatile("" : "+r"(zero_x), "+r"(zero_y));
   for (int rb = 0; rb < H; rb += 32) {
     const int hc = min(32, H - rb), ys = w.y0 + rb;
     for (int cb = 0; cb < W; cb += 32) {
@@ -147,23 +145,26 @@ __device__ __forceinline__ void coop_eval(const CoopCtx &a, double tx, double ty
         }
       }
       // ---- phase 2: walk the set bits of this lane's rows, highest slot / highest bit first ------------------------------
-      const double dcb = (double)cb, drb = (double)rb;
-      const double kuc = fma(c, dcb, fma(s, drb, ku0)), kvc = fma(c, drb, fma(-s, dcb, kv0));
+      // the bit / row index enters as X = 1 + b / 32, Y = 1 + row / 32 (unit_plus_32nd, cost_math.cuh: no int -> double
+      // conversion): c b + s row = cw X + sw Y - cw - sw, the constants ride on the chunk origin (cb / 32 - 1 and
+      // rb / 32 - 1 are exact integers)
+      const double dcb = (double)((cb >> 5) - 1), drb = (double)((rb >> 5) - 1);
+      const double kuc = fma(cw, dcb, fma(sw, drb, ku0)), kvc = fma(cw, drb, fma(-sw, dcb, kv0));
       unsigned mask = 0u;
       int row = 0;
       while (true) {
         if ((mask | local) == 0u) break;
         if (mask == 0u) {
           const int k = top_bit(local);
-          local ^= 1u << k;
+          local = clear_top(local, k);
           mask = s_mask[k * stride];
           row = g + k * G - off;
         }
         const int b = top_bit(mask);
-        mask ^= 1u << b;
-        const double X = (double)b, Y = (double)row;
-        const double ku = fma(c, X, fma(s, Y, kuc));
-        const double kv = fma(c, Y, fma(-s, X, kvc));
+        mask = clear_top(mask, b);
+        const double X = unit_plus_32nd(b, zero_x), Y = unit_plus_32nd(row, zero_y);
+        const double ku = fma(cw, X, fma(sw, Y, kuc));
+        const double kv = fma(cw, Y, fma(-sw, X, kvc));
         const double M = 6755399441055744.0;  // 1.5 * 2^52: adding it (rounding down) floors to an integer
         const int ux = __double2loint(__dadd_rd(ku, M)), uy = __double2loint(__dadd_rd(kv, M));  // k_upper - 2
         // no bounds test (dpose_core.cpp:181-182): records outside the valid range are zero, see the clip invariant

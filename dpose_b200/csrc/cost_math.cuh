@@ -44,4 +44,28 @@ __host__ __device__ inline WindowRect pose_window(const TableGeom &g, double tx,
   return w;
 }
 
+#ifdef __CUDACC__
+// ---- bit walking (device) --------------------------------------------------------------------------------
+// index of the most significant set bit (-1 for 0): one FLO, no bit reversal
+__device__ __forceinline__ int top_bit(unsigned x) {
+  int r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+// m without its most significant set bit, b = top_bit(m) (b = -1 for m == 0: m stays 0): AND with a mask of the b low bits
+// (BMSK) — no materialised 1 to shift
+__device__ __forceinline__ unsigned clear_top(unsigned m, int b) {
+  unsigned r;
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(b));
+  return m & r;
+}
+// 1 + x / 32 for 0 <= x < 32 as a double without the conversion pipe: x is planted into the top five mantissa bits of 1.0 by
+// one integer instruction on the high word.  `zero` must be a 0 the compiler cannot see through (it becomes the low word;
+// a literal is re-materialised in every loop iteration).  A cell walk that needs c * x + s * y uses
+//   (32 c) X + (32 s) Y - 32 c - 32 s,  X = unit_plus_32nd(x), Y = unit_plus_32nd(y)
+// with the constants folded into its origin (32 c, 32 s exact).  I2F.F64 runs on the 4-lane conversion pipe, 8 issue
+// cycles per warp instruction — as many as four DFMAs.
+__device__ __forceinline__ double unit_plus_32nd(int x, int zero) { return __hiloint2double(0x3FF00000 + (x << 15), zero); }
+#endif
+
 }  // namespace dpose

@@ -227,13 +227,6 @@ __global__ void __launch_bounds__(256) k_sweep_poses(dpose_sweep sw, size_t base
   poses[3 * i] = x, poses[3 * i + 1] = y, poses[3 * i + 2] = th;
 }
 
-// index of the most significant set bit (x != 0): one FLO, no bit reversal
-__device__ __forceinline__ int top_bit(unsigned x) {
-  int r;
-  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
-  return r;
-}
-
 // DPOSE_TILE_CVT: how the walk turns a bit / row index into a double.
 //   0: 2^52 trick (one DADD on the FP64 pipe + register-pair set-up), 1: I2F.F64 (conversion pipe: with the two FLO of
 //   an iteration that is 4 x 8 issue cycles on the 4-lane XU, as busy as the FP64 pipe), 2: no conversion at all — the
@@ -275,17 +268,10 @@ __device__ __forceinline__ double index_to_double(int x, int zero) {  // zero: a
 #if DPOSE_TILE_CVT == 0
   return small_int_to_double(x);
 #elif DPOSE_TILE_CVT == 2
-  return __hiloint2double(0x3FF00000 + (x << 15), zero);  // 1 + x / 32 for 0 <= x < 32
+  return unit_plus_32nd(x, zero);
 #else
   return (double)x;
 #endif
-}
-// m without its most significant set bit, b = top_bit(m) (b = -1 for m == 0: m stays 0): AND with a mask of the b low bits
-// (BMSK) — no materialised 1 to shift
-__device__ __forceinline__ unsigned clear_top(unsigned m, int b) {
-  unsigned r;
-  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(b));
-  return m & r;
 }
 
 // kRepShift: log2 of the coefficient replicas; kRows: rows of a chunk (>= min(32, largest window height)).  A
@@ -344,7 +330,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   // for 8 coefficient replicas at 1024 threads); 0: every scanned slot is stored (no store predicates)
   constexpr int kStored = DPOSE_TILE_COMPACT ? kRows : kSlots;
   (void)kStored;
-  uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + tid;  // [row * kThreads], row < kStored
+  // [row * kThreads], -1 <= row < kStored: row -1 is a guard the rotated cell loop may read (never use) when it runs out
+  // of rows — its last row advance is not predicated on "a row is left"
+  uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + a.coef_bytes) + kThreads + tid;
   constexpr bool kTex = kRepShift <= 0;             // texture mode, see above
   constexpr bool kGlobal = kRepShift < 0;           // nothing of the table in shared memory
   constexpr int kLoShift = kTex ? 1 : kRepShift;    // log2 replicas of what lives in shared memory
@@ -584,8 +572,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
             while (true) {
               mask = clear_top(mask, b);
               const Cell q = gather(b, row);
-              const bool more = (mask | rowmask) != 0u;
-              const bool adv = mask == 0u && rowmask != 0u;
+              // (when nothing is left, adv still holds: r2 = -1, the guard row is read and the loop ends)
+              const bool adv = mask == 0u;
+              const bool more = !adv || rowmask != 0u;
               const int r2 = top_bit(rowmask);
               row = adv ? r2 : row;
               rowmask = adv ? clear_top(rowmask, r2) : rowmask;
@@ -754,7 +743,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   // A/B builds: -DDPOSE_TILE_THREADS=512|768|1024, -DDPOSE_TILE_REPLICAS=1|4|8
   int threads = DPOSE_TILE_THREADS;
   int rep_shift = DPOSE_TILE_REPLICAS == 1 ? 0 : DPOSE_TILE_REPLICAS == 4 ? 2 : 3;  // 8 replicas if they fit (conflict-free LDS.128)
-  auto fits = [&](int th, int rs) { return (rs < 0 ? 0 : table_bytes << rs) + (size_t)stored * 4 * th <= budget; };
+  auto fits = [&](int th, int rs) { return (rs < 0 ? 0 : table_bytes << rs) + (size_t)(stored + 1) * 4 * th <= budget; };  // + guard row
   const int threads_wanted = threads;
   while (!fits(threads, rep_shift)) {
     if (rep_shift == 3)
@@ -833,7 +822,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   a.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 31u) == 0;
   a.clip_thr = 0.5f / (float)std::max(pg->win_max, 25);
   a.clip_margin = clip_margin_for(pg->win_max);
-  const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)stored * 4 * threads;
+  const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)(stored + 1) * 4 * threads;
   const size_t want = (n + threads - 1) / threads;
   int grid = (int)std::min<size_t>(want, (size_t)sms);
   a.stride = (uint32_t)threads;
