@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ 
 // in the kernel.
 // image[((patch * 2 + half) * R + rep)] (16 bytes each), patch = k_upper.y * cols + k_upper.x
 __global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *__restrict__ image,
-                                   double2 *__restrict__ hi_only, int rows, int cols, int rep_shift) {
+                                   double2 *__restrict__ hi_only, int rows, int cols, int rep_shift, int planes) {
   const int n_patches = rows * cols;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_patches; i += gridDim.x * blockDim.x) {
     const int uy = i / cols, ux = i - uy * cols;
@@ -143,8 +143,13 @@ __global__ void k_build_coef_image(const PatchCoef *__restrict__ coef, double2 *
         for (int r = 0; r < (1 << rep_shift); ++r) image[((size_t)i << rep_shift) + r] = lo;
     } else {
       for (int r = 0; r < (1 << rep_shift); ++r) {
-        image[(((size_t)i * 2 + 0) << rep_shift) + r] = lo;
-        image[(((size_t)i * 2 + 1) << rep_shift) + r] = hi;
+        if (planes) {  // two planes of 16-byte halves (the two-replica mode, see kPlanes in the kernel)
+          image[((size_t)i << rep_shift) + r] = lo;
+          image[(((size_t)n_patches + i) << rep_shift) + r] = hi;
+        } else {
+          image[(((size_t)i * 2 + 0) << rep_shift) + r] = lo;
+          image[(((size_t)i * 2 + 1) << rep_shift) + r] = hi;
+        }
       }
     }
   }
@@ -336,8 +341,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   constexpr bool kTex = kRepShift <= 0;             // texture mode, see above
   constexpr bool kGlobal = kRepShift < 0;           // nothing of the table in shared memory
   constexpr int kLoShift = kTex ? 1 : kRepShift;    // log2 replicas of what lives in shared memory
-  constexpr uint32_t kPatchStride = (kTex ? 16u : 32u) << kLoShift, kHalfOff = 16u << kLoShift;
+  // Two replicas (kRepShift == 1): the halves live in two PLANES, plane[(patch * 2 + rep)] — the 16-byte bank group of a
+  // gather is then (patch & 3) * 2 + rep, eight classes for the eight lanes of an LDS.128 phase.  Interleaved halves
+  // would leave four ((patch & 1) * 4 + half * 2 + rep with half fixed per instruction): measured on the 35 x 55 table,
+  // 84.7 M bank conflicts for 165 M wavefronts, the LSU data pipe 89 % busy.  With 4 / 8 replicas the interleaved form
+  // is conflict-free per replica and its second half sits at an immediate offset.
+  constexpr bool kPlanes = kRepShift == 1;
+  constexpr uint32_t kPatchStride = (kTex || kPlanes ? 16u : 32u) << kLoShift, kHalfOff = 16u << kLoShift;
   (void)kHalfOff;
+  const uint32_t plane_off = a.coef_bytes / 2;  // kPlanes: bytes between the two planes
+  (void)plane_off;
   const int cols = a.g.cols;
   // Kernel coordinates are carried as k' = k + 0.5 - 2 = k - 1.5: floor(k') = k_upper - 2 (k_upper = round(k),
   // dpose_core.cpp:177), frac(k') = c_rel (:193), and the bounds test (:181-182) becomes
@@ -542,7 +555,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
             q.b01 = __hiloint2double(t.y, t.x);
             q.b11 = __hiloint2double(t.w, t.z);
           } else {
-            asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(q.b01), "=d"(q.b11) : "r"(addr), "n"(kHalfOff));
+            if (kPlanes)
+              asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.b01), "=d"(q.b11) : "r"(addr + plane_off));
+            else
+              asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(q.b01), "=d"(q.b11) : "r"(addr), "n"(kHalfOff));
           }
           return q;
         };
@@ -646,6 +662,7 @@ template <bool kJac, int kThreads>
 int launch_tile2(const TileArgs &a, int rep_shift, int rows, int grid, size_t smem_bytes, cudaStream_t stream) {
   if (rep_shift < 0) return launch_tile3<kJac, kThreads, -1>(a, rows, grid, smem_bytes, stream);
   if (rep_shift == 0) return launch_tile3<kJac, kThreads, 0>(a, rows, grid, smem_bytes, stream);
+  if (rep_shift == 1) return launch_tile3<kJac, kThreads, 1>(a, rows, grid, smem_bytes, stream);
   if (rep_shift == 2) return launch_tile3<kJac, kThreads, 2>(a, rows, grid, smem_bytes, stream);
   return launch_tile3<kJac, kThreads, 3>(a, rows, grid, smem_bytes, stream);
 }
@@ -710,7 +727,7 @@ int coef_abs_ensure(const dpose_pg *pg, cudaStream_t stream) {
   if (p->d_coef_abs) return DPOSE_OK;
   double2 *buf = nullptr;
   DPOSE_CUDA(cudaMalloc(&buf, sizeof(PatchCoef) * (size_t)pg->rows * pg->cols));
-  k_build_coef_image<<<64, 256, 0, stream>>>(pg->d_coef, buf, nullptr, pg->rows, pg->cols, 0);
+  k_build_coef_image<<<64, 256, 0, stream>>>(pg->d_coef, buf, nullptr, pg->rows, pg->cols, 0, 0);
   DPOSE_LAUNCHED();
   DPOSE_CUDA(cudaStreamSynchronize(stream));  // other streams may use it right after
   p->d_coef_abs = reinterpret_cast<double *>(buf);
@@ -744,18 +761,23 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   int threads = DPOSE_TILE_THREADS;
   int rep_shift = DPOSE_TILE_REPLICAS == 1 ? 0 : DPOSE_TILE_REPLICAS == 4 ? 2 : 3;  // 8 replicas if they fit (conflict-free LDS.128)
   auto fits = [&](int th, int rs) { return (rs < 0 ? 0 : table_bytes << rs) + (size_t)(stored + 1) * 4 * th <= budget; };  // + guard row
-  const int threads_wanted = threads;
-  while (!fits(threads, rep_shift)) {
-    if (rep_shift == 3)
-      rep_shift = 2;
-    else if (rep_shift == 2)
-      rep_shift = 0;
-    else if (threads > 512) {
-      threads -= 256;
-    } else {  // the table does not fit shared memory even once: both halves through the texture unit
-      rep_shift = -1;
-      threads = threads_wanted;
+  // candidates in order of preference: replicas first at full width, then two full replicas on a narrower CTA (shared
+  // memory only: the texture path's latency is what bounds the single-replica mode), then the texture modes
+  {
+    const int want_shift = rep_shift, want_threads = threads;
+    const int cand[][2] = {{want_threads, want_shift}, {want_threads, 2}, {want_threads, 1}, {768, 1}, {want_threads, 0}, {768, 0}, {512, 0}};
+    bool found = false;
+    for (const auto &cd : cand) {
+      if (cd[0] > want_threads || cd[1] > want_shift) continue;
+#ifdef DPOSE_TILE_NO_REP2
+      if (cd[1] == 1) continue;
+#endif
+      if (fits(cd[0], cd[1])) {
+        threads = cd[0], rep_shift = cd[1], found = true;
+        break;
+      }
     }
+    if (!found) rep_shift = -1, threads = want_threads;  // not even once: both halves through the texture unit
   }
   // small batches are latency bound: spread them over all SMs with smaller CTAs (the replica count, and with it
   // the cached coefficient image, stays the one chosen for the largest CTA)
@@ -796,7 +818,7 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
       }
       k_build_coef_image<<<64, 256, 0, stream>>>(pg->d_coef, reinterpret_cast<double2 *>(p->d_coef_image),
                                                  tex_mode ? reinterpret_cast<double2 *>(p->d_coef_hi) : nullptr, pg->rows,
-                                                 pg->cols, tex_mode ? 1 : rep_shift);
+                                                 pg->cols, tex_mode ? 1 : rep_shift, rep_shift == 1);
       DPOSE_LAUNCHED();
       DPOSE_CUDA(cudaStreamSynchronize(stream));  // other streams may use the image right after
       p->coef_image_shift = rep_shift;

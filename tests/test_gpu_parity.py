@@ -659,9 +659,9 @@ def test_full_size_properties_cfg5(dp):
 
 
 def test_batch_random_footprints_all_table_modes(dp, capi):
-    """random footprints from a few cells to 150 cells across: the tile kernel's 8-replica, 4-replica, single-replica
-    (texture) and no-shared-memory (both halves through the texture unit) modes, multi-chunk windows included, against
-    the oracle on translated-equivalent inputs"""
+    """random footprints from a few cells to 150 cells across: the tile kernel's 8-replica, 4-replica, 2-replica (two planes
+    of halves), single-replica (texture) and no-shared-memory (both halves through the texture unit) modes, multi-chunk
+    windows included, against the oracle on translated-equivalent inputs"""
     rng = np.random.default_rng(99)
     m = fx.bernoulli_map(900, 800, 0.05, 13)
     cm = dp.Costmap(m)
@@ -684,3 +684,4 @@ def test_batch_random_footprints_all_table_modes(dp, capi):
         assert ok.all(), (fp.tolist(), pad, np.argwhere(~ok)[:4], out[~ok.all(1)][:2], want[~ok.all(1)][:2])
         assert (want[:, 0] > 0).mean() > 0.5
     assert min(r * c for r, c in sizes) < 400 and max(r * c for r, c in sizes) > 8000  # from 8 replicas to no shared-memory copy at all
+    assert any(760 <= r * c <= 1519 for r, c in sizes)  # the 2-replica mode (star40's 35 x 55 table runs it on 768 threads)
