@@ -327,20 +327,23 @@ def device_poses(torch, dev, n, side, seed, lo=0, hi=None):
 
 
 def timed_steps(torch, ranks, stream, step, steps, warmup):
-    """W untimed steps, then exactly K steps bracketed by barrier + synchronize; CUDA events on the launching stream.
-    Returns (this rank's total ms, per-step ms list)"""
+    """W untimed steps, then exactly K steps bracketed by barrier + synchronize; two CUDA events on the launching stream
+    around the K steps (an event record between the steps is a stream operation of its own: it breaks the programmatic
+    launch chain between a step's last kernel and the next step's first and costs 2-4 us per step, a fifth of a
+    20 us step).  Returns (this rank's total ms, per-step ms list — the mean repeated —, host seconds to queue the steps)"""
     for _ in range(warmup):
         step()
     ranks.barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    ev[0].record(stream)
+    e0.record(stream)
     for i in range(steps):
         step()
-        ev[i + 1].record(stream)
+    e1.record(stream)
     issue_s = time.perf_counter() - t0  # host time to QUEUE the K steps: if it approaches the device time the run is launch bound
     ranks.barrier()
-    return ev[0].elapsed_time(ev[-1]), [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)], issue_s
+    total = e0.elapsed_time(e1)
+    return total, [total / steps] * steps, issue_s
 
 
 def run_batch(args, ranks, torch, dp, fx):

@@ -71,8 +71,11 @@ __device__ __forceinline__ unsigned lethal_bits32(const uint32_t v[8]) {
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint8_t *__restrict__ map, size_t pitch, uint32_t size_y,
                                                     uint32_t *__restrict__ tiles, uint32_t ntx, uint32_t ty0,
                                                     uint32_t ty1) {
-  // programmatic dependent launch: the batch kernel queued behind this one may start its prologue (staging the
-  // coefficient image) now; it waits for this grid's completion (griddepcontrol.wait) before it reads a tile
+  // Programmatic dependent launch, both ways.  This grid may have been set up while its predecessor in the stream (the
+  // batch kernel of the previous call, still reading the plane this grid overwrites, or the caller's kernel that wrote the
+  // map) was running: wait for that grid's completion before touching anything.  The batch kernel queued behind this one
+  // may start its prologue (staging the coefficient image) now; it waits for this grid's completion before it reads a tile.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ uint32_t s_words[2][32][9];  // [block of the pair][tile][row], padded: conflict-free both ways
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -329,6 +332,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   // rebuilding the tile plane, or the kernel that wrote the poses) was still running, so that the launch latency and the
   // staging above overlap it.  Nothing of the predecessor's output is touched before this point.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // ... and whatever is queued behind this kernel with the same launch attribute (the plane rebuild of the next call, an
+  // extraction) may be set up while this grid runs; those kernels wait for its completion themselves.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   constexpr int kSlots = kRows + 7;
   // DPOSE_TILE_COMPACT 1: only the kRows rows that can belong to a chunk are stored (less shared memory, room
@@ -697,7 +703,8 @@ static int tileplane_build_locked(const dpose_map *map, cudaStream_t stream) {
   const size_t n_blocks = (size_t)((map->tiles_ntx + 31) / 32) * (ty1 - ty0);
   if (n_blocks >= ((size_t)1 << 31)) return fail(DPOSE_EINVAL, "costmap too large for the tile plane (more than 2^44 cells)");
   const unsigned grid = (unsigned)std::min<size_t>((n_blocks + 1) / 2, (size_t)148 * 8);
-  k_pack_tiles<<<grid, 256, 0, stream>>>(map->d_data, map->pitch, map->size_y, map->d_tiles, map->tiles_ntx, ty0, ty1);
+  DPOSE_CUDA(launch_pdl(k_pack_tiles, dim3(grid), dim3(256), 0, stream, map->d_data, map->pitch, map->size_y, map->d_tiles,
+                        map->tiles_ntx, ty0, ty1));  // see griddepcontrol.wait in the kernel
   DPOSE_LAUNCHED();
   return DPOSE_OK;
 }
