@@ -550,8 +550,9 @@ def run_batch(args, ranks, torch, dp, fx):
                 "algorithmic_bytes_per_launch": int(algo_bytes), "bytes_per_pose": algo_bytes / n,
                 "avg_launch_ms": avg_launch_s * 1e3,
                 "bound_note": "the contract's roofline is the algorithmic-byte one (HBM); ncu shows the kernel itself is "
-                              "instruction-issue bound — the windows come out of a 12.6 MB L2-resident 1-bit plane, so real "
-                              "DRAM traffic is a tenth of the algorithmic bytes",
+                              "bound by instruction issue and its two half-rate pipes (FP64 in the cell walk, ALU in the row scan) "
+                              "— the windows come out of an L2-resident 1-bit plane, so real DRAM traffic is a tenth of the "
+                              "algorithmic bytes",
                 "ncu": ncu}
 
     # ---- parity spot check + CPU baseline ------------------------------------------------------------------------------------

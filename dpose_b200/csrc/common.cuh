@@ -216,11 +216,16 @@ int tileplane_ensure(const dpose_map *map, cudaStream_t stream, bool hold_planes
 int coef_abs_ensure(const dpose_pg *pg, cudaStream_t stream);
 int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream);
 // get_cost_batch_coop.cu: G lanes per pose, for batches too small to fill the GPU with one thread per pose; used when
-// the batch would get at least DPOSE_COOP_MIN_GROUP lanes per pose
-// (B200, 17 x 25 table, device time per launch: 4096 poses 7.8 us with 32 lanes per pose, 9000 poses 9.3 us with 16,
-// 18 000 poses 11.2 us with 8; 37 000 poses 15.3 us with 4 against 10.9 us for one thread per pose at 40 000)
+// the batch would get at least DPOSE_COOP_MIN_GROUP lanes per pose.
+// B200, 17 x 25 table, clean plane, device time per launch (profiles/r2_ab_tile_walk.txt, runs v28 / v29):
+//   poses              1000   4096   9000   18000
+//   G lanes per pose   6.1    7.1    8.4    10.3  us   (G = 32, 32, 16, 8)
+//   one thread/pose    6.5    6.7    6.7    6.7   us
+// Since the thread-per-pose kernel lost its staging wait and its conversion-pipe traffic it wins from a few thousand poses
+// on (round 2 started with the crossover at 18 944 poses): the cooperative BATCH kernel is kept for G = 32 only
+// (<= 4736 poses); coop_eval itself is what k_solve runs on.
 #ifndef DPOSE_COOP_MIN_GROUP
-#define DPOSE_COOP_MIN_GROUP 8
+#define DPOSE_COOP_MIN_GROUP 32
 #endif
 bool coop_batch_wanted(const dpose_pg *pg, size_t n);
 int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream);

@@ -115,11 +115,14 @@ int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   a.n = n;
   a.out_aligned = (reinterpret_cast<uintptr_t>(spec.d_out) & 31u) == 0;
   a.cost_only = spec.cost_only;
+  // only G = 32 is launched (DPOSE_COOP_MIN_GROUP, common.cuh); an A/B build with a smaller minimum gets 16 / 8 too
   switch (coop_group(n, sms)) {
-    case 32: return launch_coop<32>(a, want_jacobian, sms, stream);
+#if DPOSE_COOP_MIN_GROUP <= 16
     case 16: return launch_coop<16>(a, want_jacobian, sms, stream);
-    default: return launch_coop<8>(a, want_jacobian, sms, stream);  // DPOSE_COOP_MIN_GROUP: smaller groups lose to
-  }                                                                 // the thread-per-pose kernel
+    case 8: return launch_coop<8>(a, want_jacobian, sms, stream);
+#endif
+    default: return launch_coop<32>(a, want_jacobian, sms, stream);
+  }
 }
 
 }  // namespace dpose

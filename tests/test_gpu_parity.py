@@ -31,8 +31,8 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-TILE_MIN = 40000  # batches of at least this many poses run the thread-per-pose kernel (k_cost_batch_tile); batches up to
-                  # 148 x 1024 lanes / 8 lanes per pose = 18944 poses the cooperative kernel (k_cost_batch_coop)
+TILE_MIN = 40000  # batches of at least this many poses run the thread-per-pose kernel (k_cost_batch_tile) in every build;
+                  # batches up to 148 x 1024 lanes / 32 lanes per pose = 4736 poses the cooperative kernel (k_cost_batch_coop)
 
 
 def batch_both(pg, cm, poses, rel=1e-12, **kw):
@@ -450,9 +450,10 @@ def test_batch_clip_invariant_large_tables(dp, half):
 
 @pytest.mark.parametrize("n,lanes", [(3000, 32), (9000, 16), (18000, 8), (19000, 1)])
 def test_batch_cooperative_kernel_every_group_size(dp, capi, n, lanes):
-    """the cooperative kernel picks G = 32 / 16 / 8 lanes per pose by batch size (148 x 1024 lanes per launch; from
-    18945 poses on the thread-per-pose kernel takes over): every instantiation against the oracle on
-    translated-equivalent inputs, for a table whose windows fit one chunk and one whose windows span several"""
+    """batch sizes on both sides of the kernel switch (up to 4736 poses: cooperative kernel with 32 lanes per pose; above:
+    thread-per-pose kernel on CTAs of 128 ... 1024 threads — an A/B build with a smaller DPOSE_COOP_MIN_GROUP runs the
+    16- and 8-lane instantiations on the same sizes): against the oracle on translated-equivalent inputs, for a table
+    whose windows fit one chunk and one whose windows span several"""
     m = fx.bernoulli_map(1200, 1000, 0.10, 21)
     cm = dp.Costmap(m)
     for name in ("rect_pad2", "ship_pad10"):

@@ -47,8 +47,9 @@ for w in ("cfg5", "cfg2", "cfg3"):
                        "thread_inst_per_inst": m["smsp__thread_inst_executed_per_inst_executed.ratio"][0],
                        "warp_instructions": m["smsp__inst_executed.sum"][0],
                        "fp64_pipe_pct": m["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][0],
+                       "alu_pipe_pct": m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"][0],
                        "xu_pipe_pct": m["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"][0],
-                       "limiter": "instruction issue"}
+                       "limiter": "instruction issue + the two half-rate pipes (FP64 in the cell walk, ALU in phase 1)"}
 json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 n = 0
 for f in glob.glob(G + "*"):

@@ -46,7 +46,7 @@ rep["R2_CFG4_CPU"] = f"{r4['ms_per_step']:.1f}"
 sol = lines("r2_solver.jsonl")
 s64 = [x for x in sol if x.get("what") == "solve_batch" and x.get("starts") == 65536][0]
 rep["R2_CFG4_64K"] = f"{s64['call_us'] / 1e3:.2f}"
-coop = [x for x in sol if x.get("what", "").startswith("batch launch") and not x["volatile_map"] and x["poses"] <= 18000]
+coop = [x for x in sol if x.get("what", "").startswith("batch launch") and not x["volatile_map"]]
 rep["R2_COOP_TABLE"] = ", ".join(f"{x['poses']} poses {x['us_per_call']:.1f} µs" for x in coop)
 side = lines("r2_side_kernels.jsonl")
 let = [x for x in side if x.get("what") == "lethal_cells_within" and x.get("box", "").startswith("full")]
@@ -86,8 +86,8 @@ rep["R2_TILE_COUNTERS"] = (f"ncu of this round's build: {t['kernel_ms']:.3f} ms 
                            f"{t['warps_active_pct']:.1f} % of the warp slots occupied, "
                            f"`smsp__thread_inst_executed_per_inst_executed` = {t['thread_inst_per_inst']:.2f} of 32 "
                            f"({100 * t['thread_inst_per_inst'] / 32:.0f} % of the lanes do work in the average instruction: the "
-                           f"divergence of the cell walk and of the window-chunk loops), FP64 pipe {t['fp64_pipe_pct']:.0f} %, "
-                           f"XU (int → double conversions) {t['xu_pipe_pct']:.0f} %, "
+                           f"divergence of the cell walk), FP64 pipe {t['fp64_pipe_pct']:.0f} %, ALU pipe {t.get('alu_pipe_pct', 0):.0f} %, "
+                           f"XU (find-leading-one, conversions) {t['xu_pipe_pct']:.0f} %, "
                            f"{t['warp_instructions'] / 1e7:.1f} warp instructions per pose")
 path = os.path.join(ROOT, "DESIGN.md")
 s = open(os.path.join(ROOT, "tools", "DESIGN.template.md")).read()  # the document with R2_* placeholders

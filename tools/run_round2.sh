@@ -26,6 +26,11 @@ cap() {  # cap <name> <kernel regex> <skip> <count> <command...>
   ncu -i ${O}_$name.ncu-rep --page source --csv --print-source cuda,sass > ${O}_$name.src.csv 2>/dev/null
   python tools/ncu_lines.py ${O}_$name.src.csv 45 > ${O}_${name}_lines.txt 2>&1
   rm -f ${O}_$name.src.csv
+  case $name in tile_*)  # the cell walk, instruction by instruction (executions, active threads, stall samples and reasons)
+    ncu -i ${O}_$name.ncu-rep --page source --csv --print-source sass > ${O}_$name.sass.csv 2>/dev/null
+    python tools/ncu_sass_loop.py ${O}_$name.sass.csv DADD.RM 14 26 > ${O}_${name}_sass_loop.txt 2>&1
+    rm -f ${O}_$name.sass.csv;;
+  esac
   if [ "$name" != "tile_cfg5" ]; then rm -f ${O}_$name.ncu-rep; fi
 }
 cap tile_cfg5 k_cost_batch_tile 3 1 $B --workload cfg5
