@@ -177,8 +177,18 @@ __device__ __forceinline__ void advance(State &s, const SolveArgs &a, double ft,
   s.status = kStalled;
 }
 
+// Occupancy: uncapped the kernel takes 126 registers (4 CTAs = 512 lanes per SM), and a group size chosen for 1024 lanes
+// per SM put 4096 starts x 32 lanes into 1.7 waves.  Capped at 96 registers (5 CTAs = 640 lanes per SM; the spilled
+// words are solver state touched once per evaluation) with G chosen for the lanes that are really resident, 4096 starts
+// run as ONE wave of 16-lane groups: 156 -> 119 us of device time per solve (profiles/r2_ab_tile_walk.txt, runs v30 / v31).
+#ifndef DPOSE_SOLVE_MIN_CTAS
+#define DPOSE_SOLVE_MIN_CTAS 5
+#endif
+#ifndef DPOSE_SOLVE_LANES_PER_SM
+#define DPOSE_SOLVE_LANES_PER_SM (DPOSE_SOLVE_MIN_CTAS * 128)
+#endif
 template <int G>
-__global__ void __launch_bounds__(kSolveThreads) k_solve(SolveArgs a) {
+__global__ void __launch_bounds__(kSolveThreads, DPOSE_SOLVE_MIN_CTAS) k_solve(SolveArgs a) {
   constexpr int K = CoopK<G>::value;
   __shared__ uint32_t s_mask[K * kSolveThreads];
   const int tid = threadIdx.x, lane = tid & 31, g = lane & (G - 1);
@@ -310,7 +320,7 @@ struct Layout {
 
 int solve_group(size_t n, int sms) {
   int G = 32;
-  while (G > 2 && n * (size_t)G > (size_t)sms * 1024) G >>= 1;
+  while (G > 2 && n * (size_t)G > (size_t)sms * DPOSE_SOLVE_LANES_PER_SM) G >>= 1;
   return G;
 }
 
