@@ -216,8 +216,7 @@ struct TileArgs {
   cudaTextureObject_t tex_hi;  // texture mode: second halves of the patch polynomials (int4 texels)
   const int4 *planes;          // the same buffer as a plain pointer (DPOSE_TILE_LDG experiment)
   int out_aligned;  // out is 32-byte aligned: one 256-bit store per result
-  uint32_t stride;  // poses a CTA takes per sweep (<= its thread count; a multiple of 32): batches that do not fill
-                    // grid x threads whole sweeps are spread evenly over the CTAs instead of leaving some idle
+  unsigned long long per_cta;  // CTA c owns the poses [c per_cta, (c + 1) per_cta) (a multiple of 32; equal shares)
   float clip_thr;   // a strip of the kernel rectangle is clipped per row only if |cos| (|sin|) exceeds this
   float clip_margin;  // the clipped x-interval is widened by this many cells on both sides (fp32 round-off, see the launch code)
 };
@@ -289,7 +288,9 @@ template <bool kJac, int kThreads, int kRepShift, int kRows>
 __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ unsigned s_next;  // next 32-pose group of this CTA's share
   const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_next = 0u;  // published by the barrier below
 
   // ---- stage the replicated coefficient image with TMA bulk copies -----------------------------------------
   const uint32_t coef_u32 = smem_u32(smem);
@@ -368,13 +369,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   const float hi_u = (float)a.g.cols - 3.0f, hi_v = (float)a.g.rows - 3.0f;  // 0 <= k' < dim - 3
   const double cx15 = a.g.cx - 1.5, cy15 = a.g.cy - 1.5;
 
-  if ((uint32_t)tid >= a.stride) {  // no barrier below: threads without poses just leave — once the image has landed
-    wait_staged();                  // (a CTA must not exit with bulk copies into its shared memory in flight)
-    return;
-  }
-  for (size_t base = (size_t)blockIdx.x * a.stride; base < a.n; base += (size_t)gridDim.x * a.stride) {
-    const size_t idx = base + tid;
-    if (idx >= a.n) break;
+  // The CTA owns a contiguous share of the batch and its WARPS draw 32-pose groups from it through a shared-memory
+  // counter: a warp's poses differ by +-12 % in cost, so with a static deal (the same lanes sweep after sweep) the warp
+  // that drew the heaviest poses finished ~10 us after the SM's average (tools/sweep_timing.py: 15.6 us of fixed cost per
+  // launch with random poses, 5.2 us with identical ones) — a tenth of an 8-GPU shard's step.  Which warp evaluates a
+  // pose changes nothing in its result.
+  const size_t cta_base = (size_t)blockIdx.x * (size_t)a.per_cta;
+  const size_t cta_end = min(a.n, cta_base + (size_t)a.per_cta);
+  // The draw sits at the top of the loop, where the warp is converged anyway (at the end of a pose the lanes leave the
+  // cell walk one by one: a shuffle there costs a second reconvergence), and it is made when the previous group is DONE:
+  // a group drawn ahead is a group no idle warp can take (measured on the 35 x 55 table, where a group is 80 us of a
+  // warp's time: -2.2 %).  Dealing a single-wave batch statically instead (no draw) gains 1.7 % at 1e5 poses and costs
+  // the large batches 0.5 - 2 % through the extra loop state (profiles/r2_ab_tile_walk.txt, runs v33 - v37): one form.
+  for (;;) {
+    unsigned grp = 0u;
+    if (lane == 0) grp = atomicAdd(&s_next, 1u);
+    grp = __shfl_sync(0xffffffffu, grp, 0);
+    const size_t gbase = cta_base + (size_t)grp * 32u;
+    if (gbase >= cta_end) break;  // warp-uniform
+    const size_t idx = gbase + (size_t)lane;
+    if (idx >= cta_end) continue;  // the ragged last group (the next draw ends the loop)
     const double *pp = a.poses + 3 * idx;
     const double tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
     double s, c;
@@ -419,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
 #endif
     // low words of the walk's index doubles: opaque zeros that stay in the low halves of two register pairs, so that
     // an index costs one integer instruction on the high half (a literal 0 is re-materialised in every iteration)
-    int zero_x = (int)(a.stride >> 31), zero_y = (int)(a.ntx >> 31);  // both 0 (stride <= 1024, ntx < 2^31)
+    int zero_x = (int)(a.per_cta >> 48), zero_y = (int)(a.ntx >> 31);  // both 0 (per_cta <= n < 2^48, ntx < 2^31)
     asm volatile("" : "+r"(zero_x), "+r"(zero_y));
     // kRows < 32: every window of the table fits one 32 x 32 chunk — the chunk loops and what they keep alive across
     // the cell walk (the clip intervals, the window, its origin in kernel coordinates) drop out at compile time
@@ -854,13 +868,8 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   const size_t smem_bytes = (size_t)a.coef_bytes + (size_t)(stored + 1) * 4 * threads;
   const size_t want = (n + threads - 1) / threads;
   int grid = (int)std::min<size_t>(want, (size_t)sms);
-  a.stride = (uint32_t)threads;
-  if (n >= (size_t)sms * 32) {  // every SM gets a CTA, every CTA the same share of every sweep
-    grid = sms;
-    const size_t sweeps = (n + (size_t)grid * threads - 1) / ((size_t)grid * threads);
-    const size_t share = (n + (size_t)grid * sweeps - 1) / ((size_t)grid * sweeps);
-    a.stride = (uint32_t)std::min<size_t>((size_t)threads, (share + 31) / 32 * 32);
-  }
+  if (n >= (size_t)sms * 32) grid = sms;  // every SM gets a CTA
+  a.per_cta = ((n + (size_t)grid - 1) / (size_t)grid + 31) / 32 * 32;  // equal contiguous shares, whole groups
   return want_jacobian ? launch_tile1<true>(a, threads, rep_shift, rows, grid, smem_bytes, stream)
                        : launch_tile1<false>(a, threads, rep_shift, rows, grid, smem_bytes, stream);
 }
