@@ -80,7 +80,7 @@ for n, d in ((1, d1),) + tuple((n, line(f"r2_bench_cfg5_n{n}.json")) for n in (2
 rep["R2_SCALING_TABLE"] = "\n\n" + "\n".join(rows) + "\n"
 if os.path.exists(os.path.join(P, "r2_bench_cfg5_n8.json")):
     d8 = line("r2_bench_cfg5_n8.json")
-    rep["R2_PACK_SHARE_N8"] = f"{100 * 0.050 / d8['ms_per_step']:.0f} %"
+    rep["R2_PACK_SHARE_N8"] = f"{100 * 0.052 / d8['ms_per_step']:.0f} %"
 t = json.load(open(os.path.join(P, "traffic.json")))["ncu_cfg5"]
 rep["R2_TILE_COUNTERS"] = (f"ncu of this round's build: {t['kernel_ms']:.3f} ms per launch, issue slots {t['issue_active_pct']:.1f} % busy, "
                            f"{t['warps_active_pct']:.1f} % of the warp slots occupied, "
