@@ -333,9 +333,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
   // rebuilding the tile plane, or the kernel that wrote the poses) was still running, so that the launch latency and the
   // staging above overlap it.  Nothing of the predecessor's output is touched before this point.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // ... and whatever is queued behind this kernel with the same launch attribute (the plane rebuild of the next call, an
-  // extraction) may be set up while this grid runs; those kernels wait for its completion themselves.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // (This kernel does NOT trigger its own dependents early.  Measured: with griddepcontrol.launch_dependents here, the
+  // plane rebuild of the next call is set up while this grid runs and its CTAs then sit on freed SMs waiting — a volatile-map
+  // step got 2 us (1e5 poses) to 7 us (1.25e6 poses) SLOWER, profiles/r2_ab_tile_walk.txt run v39.)
 
   constexpr int kSlots = kRows + 7;
   // DPOSE_TILE_COMPACT 1: only the kRows rows that can belong to a chunk are stored (less shared memory, room
