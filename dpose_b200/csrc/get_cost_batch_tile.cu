@@ -1,11 +1,13 @@
 // get_cost_batch_tile.cu — batched get_cost(poses[]) for B200 (sm_100a), one THREAD per pose.
 //
-// Why this shape.  The warp-per-pose kernel (get_cost_batch.cu) spends ~355 warp instructions and 78
+// Why this shape.  A warp-per-pose kernel (round 1's first design) spent ~355 warp instructions and 78
 // shared-memory wavefronts per pose (ncu, profiles/r1_v2_*): a pose has only ~31 valid lethal cells, so
 // warp-wide scans, prefix sums, compaction queues and shuffle reductions cost more than the
 // arithmetic.  Here every lane owns a pose: nothing is exchanged between lanes, there is no barrier
 // in the main loop and no reduction at all — a pose's sum is accumulated by one thread in a fixed
-// (row-major) order, so the result is deterministic and independent of the batch position.
+// (row-major) order, so the result is deterministic and independent of the batch position.  A CTA owns a contiguous
+// share of the batch; its warps draw 32-pose groups from a shared-memory counter (which warp evaluates a pose changes
+// nothing in its result, and the kernel no longer ends with the warp that was dealt the heaviest poses).
 //
 // Data layout.
 //   * lethal plane in 32 x 8 cell tiles (tileplane, below): one tile = 8 rows x 32 bits = 32 bytes =
@@ -17,6 +19,8 @@
 //     eight lanes of an LDS.128 phase hit eight different 16-byte bank groups whatever patches
 //     they address — random gathers become conflict-free.  The replicated image is built once per
 //     pose_gradient in global memory and staged by a TMA bulk copy (cp.async.bulk -> UBLKCP) per CTA.
+//     Tables that fit only twice keep two replicas with the halves in two planes (kPlanes), tables that fit once
+//     fetch the second halves through the texture unit, larger ones both halves.
 //   * per-thread row masks in shared memory, [row][thread] (a thread only touches its own column:
 //     conflict-free, no synchronisation).
 //
@@ -30,7 +34,7 @@
 //            patch; two LDS.128 fetch its bilinear polynomial in absolute k' coordinates (so no per-cell
 //            fraction); f, f_u, f_v by FMA; accumulate.  There is no bounds test (dpose_core.cpp:181-182):
 //            patches outside the valid range are zero and the clip keeps every cell within one patch of
-//            it (CLIP INVARIANT in the kernel) — the loop body is branch-free, 37 instructions, 15 FP64.
+//            it (CLIP INVARIANT in the kernel) — the loop body is branch-free, 33 instructions, 15 FP64.
 // Tensor cores are not used: there is no dense contraction on this path.
 //
 // Algorithmic bytes per pose: 24 (pose) + 32 (result) + |window| map bytes.
