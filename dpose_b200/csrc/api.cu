@@ -636,6 +636,7 @@ static int batch_host(const dpose_pg *pg, const dpose_map *map, const HostBatch 
   if (hb.sweep) spec.sweep = *hb.sweep;
   spec.want_jacobian = hb.want_jacobian;
   spec.cost_only = hb.cost_only;
+  spec.call_n = n;
   if (n <= kZeroCopyPoses) {  // latency path, see kZeroCopyPoses
     DPOSE_TRY(ctx->ensure_zc());
     if (hb.poses) std::memcpy(ctx->zc_in(), hb.poses, sizeof(double) * 3 * n);

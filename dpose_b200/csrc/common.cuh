@@ -191,6 +191,10 @@ struct BatchSpec {
   // do not rebuild the lethal plane of a volatile map (the host-buffer entry point streams the chunks of ONE call
   // through this function and rebuilds for the first chunk only)
   bool hold_planes = false;
+  // poses of the whole CALL this launch is a part of (0: the launch is the call).  The kernel is chosen by it, not by
+  // the size of a staging chunk / lattice slab: the cooperative kernel sums a pose's cells in another order, and the
+  // bits of a pose must not depend on where a chunk boundary falls (a 131 073-pose call used to run its last pose there)
+  size_t call_n = 0;
 };
 int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream);
 int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses,

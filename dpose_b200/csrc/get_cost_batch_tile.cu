@@ -887,6 +887,7 @@ int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpe
     DPOSE_CUDA(cudaMemsetAsync(spec.d_out, 0, sizeof(double) * (spec.cost_only ? 1 : 4) * spec.n, stream));
     return DPOSE_OK;
   }
+  const size_t call_n = spec.call_n ? spec.call_n : spec.n;  // the kernel follows the size of the whole call
   if (!spec.d_poses) {
     // a pose lattice: k_sweep_poses writes a slab of poses (<= 2^20, 24 MB, L2 resident) that the batch kernel launched
     // right behind it consumes — the generation stays out of the hot kernels (measured: generating in-kernel cost the
@@ -904,12 +905,12 @@ int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpe
       part.hold_planes = spec.hold_planes || off > 0;
       k_sweep_poses<<<(unsigned)((part.n + 255) / 256), 256, 0, stream>>>(spec.sweep, part.sweep_base, part.n, d_slab);
       g_launches.fetch_add(1, std::memory_order_relaxed);
-      rc = coop_batch_wanted(pg, part.n) ? get_cost_batch_coop(pg, map, part, stream) : get_cost_batch_tile(pg, map, part, stream);
+      rc = coop_batch_wanted(pg, call_n) ? get_cost_batch_coop(pg, map, part, stream) : get_cost_batch_tile(pg, map, part, stream);
     }
     cudaFreeAsync(d_slab, stream);
     return rc;
   }
-  if (coop_batch_wanted(pg, spec.n)) return get_cost_batch_coop(pg, map, spec, stream);
+  if (coop_batch_wanted(pg, call_n)) return get_cost_batch_coop(pg, map, spec, stream);
   return get_cost_batch_tile(pg, map, spec, stream);
 }
 

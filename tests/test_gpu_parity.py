@@ -471,6 +471,29 @@ def test_batch_cooperative_kernel_every_group_size(dp, capi, n, lanes):
         assert np.array_equal(out, again)  # independent of the batch position
 
 
+def test_batch_ragged_sizes_bit_equal(dp):
+    """the thread-per-pose kernel deals 32-pose groups to its warps through a per-CTA counter: batch sizes on both sides of
+    every boundary of that deal (one group per CTA, one group per warp, ragged last groups, shares that are not whole
+    groups, empty shares of the last CTAs) must reproduce, bit for bit, the prefix of one large batch — a pose's result
+    does not depend on the batch size, its position or the warp that evaluated it"""
+    m = fx.bernoulli_map(900, 700, 0.10, 5)
+    pg = dp.pose_gradient(fx.RECT)
+    cm = dp.Costmap(m)
+    big = 148 * 1024 * 2 + 4129
+    poses = fx.random_poses(big, 900, 700, 77, margin=20.0)
+    ref = pg.get_cost_batch(cm, poses)
+    assert (ref[:, 0] > 0).mean() > 0.8
+    # (up to 148 * 32 = 4736 poses the cooperative kernel runs: another summation order)
+    # 131 073 and 2 x 131 072 + 4736: the host-buffer call stages 131 072-pose chunks, and the kernel follows the size of the CALL —
+    # a last chunk of 1 or 4736 poses must not fall to the cooperative kernel
+    for n in (4737, 4738, 4769, 9473, 20001, 148 * 128 + 31, 131072, 131073, 148 * 1024 - 1, 148 * 1024, 148 * 1024 + 1,
+              148 * 1024 + 32 * 148 + 5, 2 * 131072 + 4736, big - 1):
+        out = pg.get_cost_batch(cm, poses[:n])
+        assert np.array_equal(out, ref[:n]), n
+    tail = pg.get_cost_batch(cm, poses[-5000:])  # other positions, other warps
+    assert np.array_equal(tail, ref[-5000:])
+
+
 @pytest.mark.parametrize("nx,ny,nt", [(40, 30, 7), (300, 200, 5), (1, 1, 1), (1200, 700, 3)])
 def test_sweep_and_cost_only_entry_points(dp, nx, ny, nt):
     """the lattice entry point generates its poses inside the kernel (x0 + dx ix: one rounded product, one rounded sum,
