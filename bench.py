@@ -12,7 +12,10 @@ Workloads (BASELINE.json `configs`):
                   random SE2 poses, batched get_cost (cost + Jacobian).  --scaling strong (default, what BASELINE states:
                   "1e7-pose sweep sharded across 1/2/4/8 B200"): the 1e7 poses are split contiguously over the ranks;
                   weak: 1e7 poses PER GPU.  On N > 1 the other mode is timed as well and reported under `other_scaling`.
-                  Map and table replicated, no collective on the data path.
+                  Map and table replicated, no collective on the data path.  Strong scaling orders the job's poses by map
+                  row at set-up: a rank's slice is a stripe of the map, the rank passes the stripe's rows to
+                  the call (dpose_pg_get_cost_batch_device_rows) and the per-step rebuild of the volatile map's lethal plane
+                  shards with the poses; `list_order` is the same job unordered through the plain call.
   cfg2 / cfg3     1e5 poses on 2000x2000 / 1e6 poses with the 40-vertex footprint (table 35x55), same call.
   cfg4            the goal-tolerance solve: 4096 multi-start offsets from the plugin's sampler, max_iter 20, one
                   dpose_problem_solve_batch per step; value = pose evaluations (solver iterates) per second.
@@ -372,27 +375,45 @@ def run_batch(args, ranks, torch, dp, fx):
     cmap.set_volatile(True)
     stream = torch.cuda.current_stream()
 
-    def make_mode(mode):
+    # Strong scaling (BASELINE cfg5: "1e7-pose sweep sharded across 1/2/4/8 B200"): the job is the SAME 1e7 poses at every N,
+    # ordered by map row once at set-up ("pre-sorted by map tile so each GPU's slice touches a compact
+    # region"); a rank's contiguous slice is then a stripe of the map, and with N > 1 it tells the call so
+    # (dpose_pg_get_cost_batch_device_rows): the rebuild of the volatile map's lethal plane — the part of the step that
+    # did not shard — covers the stripe + the footprint's reach, 1 / N of the map.  `list_order` in the line is the same
+    # leg on the unordered list with the plain call (every rank re-reads the whole map).
+    srank, sworld = (int(v) for v in args.as_rank.split("/")) if args.as_rank else (rank, world)
+
+    def job_poses(order):
+        full = device_poses(torch, dev, n_total, side, pose_seed)
+        if order == "row":
+            full = full[torch.argsort(full[:, 1], stable=True)].contiguous()
+        return full
+
+    def make_mode(mode, order="row"):
+        band = None
         if mode == "strong":  # n_total poses in all, this rank's contiguous slice
-            lo, hi = dp.dist.shard_bounds(n_total, rank, world)
-            poses = device_poses(torch, dev, n_total, side, pose_seed, lo, hi)
+            lo, hi = dp.dist.shard_bounds(n_total, srank, sworld)
+            poses = job_poses(order)[lo:hi].contiguous()
+            if sworld > 1 and order == "row":
+                band = dp.dist.row_band(float(poses[:, 1].min()), float(poses[:, 1].max()), pg.reach(), side)
         else:  # weak: n_total poses per GPU, rank-specific
             poses = device_poses(torch, dev, n_total, side, pose_seed + rank)
         out = torch.zeros((poses.shape[0], 4), device=dev, dtype=torch.float64)
-        return poses, out
+        torch.cuda.empty_cache()
+        return poses, out, band
 
-    def device_leg(mode):
-        poses, out = make_mode(mode)
+    def device_leg(mode, order="row"):
+        poses, out, band = make_mode(mode, order)
         n = poses.shape[0]
 
         def step():
-            pg.get_cost_batch_device(cmap, poses.data_ptr(), n, out.data_ptr(), jacobian=True, stream=stream.cuda_stream)
+            pg.get_cost_batch_device(cmap, poses.data_ptr(), n, out.data_ptr(), jacobian=True, stream=stream.cuda_stream, rows=band)
 
         sampler = ClockSampler(local_rank).start()
         total_ms, per_ms, issue_s, reps, launches = timed_steps(torch, ranks, stream, step, args.steps, args.warmup, dp.launch_count)
         clocks = sampler.stop()
         value = ranks.sum(n * args.steps) / (ranks.max(total_ms) * 1e-3)
-        return dict(poses=poses, out=out, n=n, value=value, ms_per_step=ranks.max(total_ms) / args.steps, per_ms=per_ms,
+        return dict(poses=poses, out=out, n=n, value=value, ms_per_step=ranks.max(total_ms) / args.steps, per_ms=per_ms, band=band,
                     launches=launches, clocks=clocks, host_issue_ms_per_step=1e3 * ranks.max(issue_s) / args.steps, reps=reps)
 
     main = device_leg(scaling)
@@ -405,12 +426,18 @@ def run_batch(args, ranks, torch, dp, fx):
              "note": "lethal tile plane cached between steps (no k_pack_tiles in the step); `value` rebuilds it every step"}
     del leg
     cmap.set_volatile(True)
-    other = None
+    other = list_order = None
     if world > 1:
         om = "weak" if scaling == "strong" else "strong"
         leg = device_leg(om)
         other = {"scaling": om, "value": leg["value"], "ms_per_step": leg["ms_per_step"], "poses_per_gpu": leg["n"],
                  "host_issue_ms_per_step": leg["host_issue_ms_per_step"]}
+        del leg
+    if scaling == "strong":
+        leg = device_leg("strong", order="list")
+        list_order = {"value": leg["value"], "ms_per_step": leg["ms_per_step"],
+                      "note": "the same 1e7 poses in list order, contiguous slices, the plain call: every rank's slice spans "
+                              "the whole map, so every rank rebuilds the whole lethal plane of the volatile map in its step"}
         del leg
 
     # ---- end to end through the host-buffer C ABI call, this rank's shard --------------------------------------------------
@@ -500,7 +527,7 @@ def run_batch(args, ranks, torch, dp, fx):
         if rank == 0:
             try:
                 host_map = d_map.cpu().numpy()
-                full = device_poses(torch, dev, n_total, side, pose_seed)
+                full = job_poses("row") if scaling == "strong" else device_poses(torch, dev, n_total, side, pose_seed)
                 hp = torch.empty((n_total, 3), dtype=torch.float64, pin_memory=True)
                 hp.copy_(full)
                 ho = torch.empty((n_total, 4), dtype=torch.float64, pin_memory=True)
@@ -584,14 +611,19 @@ def run_batch(args, ranks, torch, dp, fx):
           "the map is L2-resident by design of this config; poses + results (%d MB/step) stream through" % (56 * n // 1_000_000))
     return {
         "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "host_issue_ms_per_step": main["host_issue_ms_per_step"],
-        "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "reps_ms_per_step": main["reps"],
+        "host_issue_ms_per_step": main["host_issue_ms_per_step"], "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "poses_per_gpu": n, "poses_total": int(n * world) if scaling == "weak" else n_total,
                    "map": f"{side}x{side} uint8, Bernoulli(0.10)",
-                   "parallelism": f"dp{world} (poses sharded contiguously, map + table replicated, no collective)", "l2": l2},
+                   "parallelism": f"dp{world} (poses sharded contiguously, map + table replicated, no collective)", "l2": l2,
+                   "pose_order": ("ordered by map row at set-up (untimed): a rank's contiguous slice is a stripe of the map"
+                                  + (f"; this rank's call is restricted to map rows [{main['band'][0]}, {main['band'][1]}) = its "
+                                     "stripe + the footprint's reach (dpose_pg_get_cost_batch_device_rows), so the per-step "
+                                     "rebuild of the volatile map's lethal plane shards with the poses" if main["band"] else
+                                     "; one rank: the plain call on the whole map")) if scaling == "strong" else "list order"},
         "clocks": main["clocks"], "e2e": e2e, "e2e_multi": e2e_multi, "e2e_variants": variants,
-        "other_scaling": other, "clean_map": clean, "gpu_launches": int(main["launches"]), "roofline": roofline,
+        "other_scaling": other, "list_order": list_order, "clean_map": clean, "gpu_launches": int(main["launches"]), "roofline": roofline,
         "cpu_baseline": cpu_baseline, "parity": parity,
     }
 
@@ -731,6 +763,9 @@ def main():
                     help="batch workloads on N > 1 GPUs: total work fixed (default, BASELINE cfg5) or per-GPU work fixed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--as-rank", default=None, metavar="R/W",
+                    help="development aid: time, in ONE process on one GPU, the strong-scaling shard rank R of W would own "
+                         "(value and ms_per_step are then that shard's, not a job's)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -88,6 +88,13 @@ class Costmap:
         change behind the library's back); bench.py times with this ON"""
         check(lib().dpose_map_set_volatile(self._h, int(bool(flag))))
 
+    def device_ptr(self):
+        """(device pointer, pitch) of the library's copy of the map: a producer on the device (a costmap layer kernel)
+        writes here; mark the map volatile, or the lethal plane will not follow (dpose_map_device_ptr)"""
+        p, pitch = C.c_void_p(), C.c_size_t(0)
+        check(lib().dpose_map_device_ptr(self._h, C.byref(p), C.byref(pitch)))
+        return int(p.value), int(pitch.value)
+
     def update(self, window, x0, y0):
         """re-upload a dirty window (rows [y0, y0+h), columns [x0, x0+w))"""
         w = np.ascontiguousarray(np.asarray(window, dtype=np.uint8))
@@ -312,11 +319,24 @@ class pose_gradient:
                                             int(bool(cost_only))))
         return out.reshape(shape)
 
-    def get_cost_batch_device(self, costmap, d_poses, n, d_out, jacobian=True, stream=0):
-        """device pointers (ints), asynchronous on `stream` (a cudaStream_t as int)."""
-        check(lib().dpose_pg_get_cost_batch_device(self._data._h, costmap._h, C.c_void_p(int(d_poses)), int(n),
-                                                   C.c_void_p(int(d_out)), int(bool(jacobian)),
-                                                   C.c_void_p(int(stream))))
+    def get_cost_batch_device(self, costmap, d_poses, n, d_out, jacobian=True, stream=0, rows=None):
+        """device pointers (ints), asynchronous on `stream` (a cudaStream_t as int).
+        rows = (row_lo, row_hi): only lethal cells of these map rows count, and only these rows of a volatile map are
+        re-read in front of the launch — for callers that shard their poses by map row (see `reach`, dist.row_band)."""
+        if rows is None:
+            check(lib().dpose_pg_get_cost_batch_device(self._data._h, costmap._h, C.c_void_p(int(d_poses)), int(n),
+                                                       C.c_void_p(int(d_out)), int(bool(jacobian)),
+                                                       C.c_void_p(int(stream))))
+        else:
+            check(lib().dpose_pg_get_cost_batch_device_rows(self._data._h, costmap._h, C.c_void_p(int(d_poses)), int(n),
+                                                            C.c_void_p(int(d_out)), int(bool(jacobian)),
+                                                            C.c_void_p(int(stream)), int(rows[0]), int(rows[1])))
+
+    def reach(self):
+        """rows / columns around a pose beyond which no cell contributes to its cost (dpose_pg_reach)"""
+        r = C.c_uint32(0)
+        check(lib().dpose_pg_reach(self._data._h, C.byref(r)))
+        return int(r.value)
 
     def window_bytes(self, costmap, poses):
         p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))

@@ -595,6 +595,22 @@ int dpose_pg_get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, con
   return get_cost_batch_device(pg, map, d_poses, n, d_out, want_jacobian, (cudaStream_t)stream);
 }
 
+int dpose_pg_reach(const dpose_pg *pg, uint32_t *reach) {
+  if (!pg || !reach) return fail(DPOSE_EINVAL, "NULL argument");
+  double r2 = 0.0;  // farthest corner of the table from its centre (the valid region, :181-182, lies 1.5 cells inside)
+  for (int i = 0; i < 4; ++i) r2 = std::max(r2, (double)pg->box[2 * i] * pg->box[2 * i] + (double)pg->box[2 * i + 1] * pg->box[2 * i + 1]);
+  *reach = (uint32_t)std::ceil(std::sqrt(r2)) + 1u;
+  return DPOSE_OK;
+}
+
+int dpose_pg_get_cost_batch_device_rows(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n,
+                                        double *d_out, int want_jacobian, void *stream, uint32_t row_lo, uint32_t row_hi) {
+  if (!pg || !map || (n && (!d_poses || !d_out))) return fail(DPOSE_EINVAL, "NULL argument");
+  if (row_lo >= row_hi || row_hi > map->size_y)
+    return fail(DPOSE_EINVAL, "row band [%u, %u) is empty or outside the map (%u rows)", row_lo, row_hi, map->size_y);
+  return get_cost_batch_device(pg, map, d_poses, n, d_out, want_jacobian, (cudaStream_t)stream, false, row_lo, row_hi);
+}
+
 // host buffers: H2D / kernel / D2H chunks on three streams, triple-buffered device staging.  The
 // streams, events and staging buffers live in the pose_gradient handle (created on first use, grown
 // on demand), so a call costs no cudaMalloc / cudaFree; concurrent calls on one handle serialise.

@@ -195,11 +195,15 @@ struct BatchSpec {
   // the size of a staging chunk / lattice slab: the cooperative kernel sums a pose's cells in another order, and the
   // bits of a pose must not depend on where a chunk boundary falls (a 131 073-pose call used to run its last pose there)
   size_t call_n = 0;
+  // band of map rows [row_lo, row_hi) the launch is restricted to (row_hi == 0: the whole map): only lethal cells of
+  // these rows count, and only these rows of a volatile map's tile plane are rebuilt in front of the launch — a caller
+  // that shards its poses spatially (a rank's slice of a sweep sorted by map row) shards the map pass with them
+  uint32_t row_lo = 0, row_hi = 0;
 };
 int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream);
 int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses,
                           size_t n, double *d_out, int want_jacobian, cudaStream_t stream,
-                          bool hold_planes = false);
+                          bool hold_planes = false, uint32_t row_lo = 0, uint32_t row_hi = 0);
 // lattice pose of index gi, the same bits as numpy's x0 + dx * ix (one rounded product, one rounded sum)
 __host__ __device__ inline void sweep_pose(const dpose_sweep &sw, size_t gi, double *x, double *y, double *th) {
   const size_t ix = gi % sw.nx, r = gi / sw.nx;
@@ -216,7 +220,7 @@ __host__ __device__ inline void sweep_pose(const dpose_sweep &sw, size_t gi, dou
 }
 // get_cost_batch_tile.cu: the lethal tile plane, the thread-per-pose batch kernel (large batches) and the dispatcher
 std::mutex &map_state_mutex();  // guards the lazily built per-handle state (coefficient images, tile-plane dirty flags)
-int tileplane_ensure(const dpose_map *map, cudaStream_t stream, bool hold_planes);
+int tileplane_ensure(const dpose_map *map, cudaStream_t stream, bool hold_planes, uint32_t row_lo = 0, uint32_t row_hi = 0);
 int coef_abs_ensure(const dpose_pg *pg, cudaStream_t stream);
 int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream);
 // get_cost_batch_coop.cu: G lanes per pose, for batches too small to fill the GPU with one thread per pose; used when

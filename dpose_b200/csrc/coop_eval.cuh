@@ -28,7 +28,8 @@ namespace dpose {
 
 struct CoopCtx {
   TableGeom g;
-  int size_x, size_y;
+  int size_x, size_y;     // size_y: end of the band of map rows that count (BatchSpec::row_hi; the map's height otherwise)
+  int y_lo = 0;           // its start
   const uint32_t *tiles;  // lethal tile plane (common.cuh)
   uint32_t ntx, nty;
   const double *coef_abs;  // 4 doubles per patch: b00, b10, b01, b11 (coef_abs_ensure)
@@ -77,7 +78,7 @@ __device__ __forceinline__ void coop_eval(const CoopCtx &a, double tx, double ty
   constexpr int K = CoopK<G>::value;
   double s, c;
   sincos(th, &s, &c);
-  const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y);
+  const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y, a.y_lo);
   const int W = w.x1 - w.x0 + 1, H = w.y1 - w.y0 + 1;  // <= 0 when empty (also for NaN poses)
   const int cols = a.g.cols;
   const double cx15 = a.g.cx - 1.5, cy15 = a.g.cy - 1.5;

@@ -15,8 +15,10 @@ struct TableGeom {
 // Centre / half-extent form: the box of a rotated rectangle is its rotated centre -+ (|c| hu + |s| hv, |s| hu + |c| hv) —
 // 16 FP64 operations and no floating-point min / max (a double fmin is a compare, two selects and NaN fix-ups on the
 // GPU; the corner form needed twelve of them per pose).  Conversions saturate, the clamps are integer.
+// Rows: the window is clamped to [y_lo, size_y) — callers that restrict a launch to a band of map rows (BatchSpec::row_lo /
+// row_hi) pass the band's end as size_y and its start as y_lo; the clamp constants change, the instruction count does not.
 __host__ __device__ inline WindowRect pose_window(const TableGeom &g, double tx, double ty, double c,
-                                                  double s, int size_x, int size_y) {
+                                                  double s, int size_x, int size_y, int y_lo = 0) {
   const double hu = 0.5 * ((double)g.cols - 3.0), hv = 0.5 * ((double)g.rows - 3.0);  // half extents of the valid region
   const double mu = 0.5 * (double)g.cols - g.cx, mv = 0.5 * (double)g.rows - g.cy;    // its centre relative to C
   const double eps = 1e-7;
@@ -31,13 +33,13 @@ __host__ __device__ inline WindowRect pose_window(const TableGeom &g, double tx,
 #ifdef __CUDA_ARCH__
   // cvt.rpi / cvt.rmi saturate to the int range, so windows far off the map come out empty after the clamps
   w.x0 = max(__double2int_ru(xmin), 0);
-  w.y0 = max(__double2int_ru(ymin), 0);
+  w.y0 = max(__double2int_ru(ymin), y_lo);
   w.x1 = min(__double2int_rd(xmax), size_x - 1);
   w.y1 = min(__double2int_rd(ymax), size_y - 1);
 #else
   // the same values on the host (clamped in floating point, so the int casts cannot overflow)
   w.x0 = (int)ceil(fmin(fmax(xmin, 0.0), 2147483647.0));
-  w.y0 = (int)ceil(fmin(fmax(ymin, 0.0), 2147483647.0));
+  w.y0 = (int)ceil(fmin(fmax(ymin, (double)y_lo), 2147483647.0));
   w.x1 = (int)floor(fmax(fmin(xmax, (double)size_x - 1.0), -2147483648.0));
   w.y1 = (int)floor(fmax(fmin(ymax, (double)size_y - 1.0), -2147483648.0));
 #endif

@@ -107,9 +107,10 @@ int get_cost_batch_coop(const dpose_pg *pg, const dpose_map *map, const BatchSpe
   const int want_jacobian = spec.want_jacobian && !spec.cost_only;
   const int sms = device_info(pg->device).sms;
   DPOSE_TRY(coef_abs_ensure(pg, stream));
-  DPOSE_TRY(tileplane_ensure(map, stream, spec.hold_planes));
+  DPOSE_TRY(tileplane_ensure(map, stream, spec.hold_planes, spec.row_lo, spec.row_hi));
   CoopBatchArgs a;
   a.ctx = coop_ctx(pg, map);
+  if (spec.row_hi) a.ctx.size_y = (int)std::min(spec.row_hi, map->size_y), a.ctx.y_lo = (int)spec.row_lo;  // the band of rows that count
   a.poses = spec.d_poses;
   a.out = spec.d_out;
   a.n = n;

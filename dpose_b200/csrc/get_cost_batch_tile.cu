@@ -210,7 +210,8 @@ struct TileArgs {
   const uint4 *coef_image;  // replicated coefficient image (global)
   uint32_t coef_bytes;      // its size in bytes (multiple of 128)
   TableGeom g;
-  int size_x, size_y;
+  int size_x, size_y;       // size_y: end of the band of map rows that count (the map's height unless BatchSpec::row_hi)
+  int y_lo;                 // its start
   const uint32_t *tiles;
   uint32_t ntx, nty;
   const double *poses;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cost_batch_tile(TileArgs a) {
     const double tx = __ldg(pp), ty = __ldg(pp + 1), th = __ldg(pp + 2);
     double s, c;
     sincos(th, &s, &c);
-    const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y);
+    const WindowRect w = pose_window(a.g, tx, ty, c, s, a.size_x, a.size_y, a.y_lo);
     const int W = w.x1 - w.x0 + 1, H = w.y1 - w.y0 + 1;  // <= 0 when empty
     double ku0, kv0;  // k' at the window origin
     {
@@ -708,12 +709,15 @@ std::mutex &map_state_mutex() {
 }
 
 // caller holds map_state_mutex()
-static int tileplane_build_locked(const dpose_map *map, cudaStream_t stream) {
+static int tileplane_build_locked(const dpose_map *map, cudaStream_t stream, uint32_t row_lo, uint32_t row_hi) {
   if (!map->d_tiles || map->size_x == 0 || map->size_y == 0) return DPOSE_OK;
-  // only the tile rows that cover the dirty map rows (all of them after create / in volatile mode)
+  // only the tile rows that cover the dirty map rows (all of them after create); a volatile map: every row, or the band
+  // of rows the launch behind this rebuild is restricted to (BatchSpec::row_lo / row_hi) — whatever reads the plane of a
+  // volatile map next rebuilds what it needs itself, so the rows outside the band may stay stale
   dpose_map *m = const_cast<dpose_map *>(map);
-  const uint32_t lo = map->is_volatile ? 0u : std::min(map->tiles_dirty_lo, map->size_y);
-  const uint32_t hi = map->is_volatile ? map->size_y : std::min(map->tiles_dirty_hi, map->size_y);
+  const bool band = map->is_volatile && row_hi != 0;
+  const uint32_t lo = band ? std::min(row_lo, map->size_y) : map->is_volatile ? 0u : std::min(map->tiles_dirty_lo, map->size_y);
+  const uint32_t hi = band ? std::min(row_hi, map->size_y) : map->is_volatile ? map->size_y : std::min(map->tiles_dirty_hi, map->size_y);
   m->tiles_dirty_lo = 0xffffffffu;
   m->tiles_dirty_hi = 0;
   if (hi <= lo) return DPOSE_OK;
@@ -729,15 +733,15 @@ static int tileplane_build_locked(const dpose_map *map, cudaStream_t stream) {
 
 // Makes the lethal tile plane of `map` current for work queued on `stream` afterwards: rebuilds the dirty rows (every
 // row of a volatile map unless hold_planes) in front of it, or orders `stream` behind the rebuild another stream did.
-int tileplane_ensure(const dpose_map *map, cudaStream_t stream, bool hold_planes) {
+int tileplane_ensure(const dpose_map *map, cudaStream_t stream, bool hold_planes, uint32_t row_lo, uint32_t row_hi) {
   if (!map->d_tiles) return DPOSE_OK;
   dpose_map *m = const_cast<dpose_map *>(map);
   std::lock_guard<std::mutex> lock(map_state_mutex());
   if (!m->tiles_ready) DPOSE_CUDA(cudaEventCreateWithFlags(&m->tiles_ready, cudaEventDisableTiming));
   if (m->tiles_dirty || (m->is_volatile && !hold_planes)) {
-    DPOSE_TRY(tileplane_build_locked(map, stream));
+    DPOSE_TRY(tileplane_build_locked(map, stream, row_lo, row_hi));
     DPOSE_CUDA(cudaEventRecord(m->tiles_ready, stream));
-    m->tiles_dirty = false;
+    m->tiles_dirty = false;  // (a volatile map is rebuilt in front of every use whatever this flag says)
   } else {
     DPOSE_CUDA(cudaStreamWaitEvent(stream, m->tiles_ready, 0));  // built on another stream?
   }
@@ -849,14 +853,15 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
       p->coef_image_shift = rep_shift;
     }
   }
-  DPOSE_TRY(tileplane_ensure(map, stream, hold_planes));
+  DPOSE_TRY(tileplane_ensure(map, stream, hold_planes, spec.row_lo, spec.row_hi));
 
   TileArgs a;
   a.coef_image = reinterpret_cast<const uint4 *>(p->d_coef_image);
   a.coef_bytes = rep_shift < 0 ? 0u : (uint32_t)(table_bytes << rep_shift);
   a.g = TableGeom{pg->rows, pg->cols, (double)pg->center[0], (double)pg->center[1]};
   a.size_x = (int)map->size_x;
-  a.size_y = (int)map->size_y;
+  a.size_y = (int)(spec.row_hi ? std::min(spec.row_hi, map->size_y) : map->size_y);  // the band of rows that count
+  a.y_lo = (int)spec.row_lo;
   a.tiles = map->d_tiles;
   a.ntx = map->tiles_ntx;
   a.nty = map->tiles_nty;
@@ -881,6 +886,8 @@ int get_cost_batch_tile(const dpose_pg *pg, const dpose_map *map, const BatchSpe
 int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpec &spec, cudaStream_t stream) {
   if (spec.n == 0) return DPOSE_OK;
   if (pg->device != map->device) return fail(DPOSE_EINVAL, "pose_gradient and map live on different devices");
+  if (spec.row_hi != 0 && (spec.row_lo >= spec.row_hi || spec.row_hi > map->size_y))
+    return fail(DPOSE_EINVAL, "row band [%u, %u) is empty or outside the map (%u rows)", spec.row_lo, spec.row_hi, map->size_y);
   DeviceGuard guard(pg->device);
   if (!guard.ok) return fail(DPOSE_ECUDA, "cudaSetDevice(%d) failed", pg->device);
   if (!map->d_tiles || pg->rows < 4 || pg->cols < 4) {  // empty map / no valid patch: every sum is empty
@@ -915,8 +922,10 @@ int get_cost_batch_spec(const dpose_pg *pg, const dpose_map *map, const BatchSpe
 }
 
 int get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, const double *d_poses, size_t n, double *d_out,
-                          int want_jacobian, cudaStream_t stream, bool hold_planes) {
+                          int want_jacobian, cudaStream_t stream, bool hold_planes, uint32_t row_lo, uint32_t row_hi) {
   BatchSpec spec;
+  spec.row_lo = row_lo;
+  spec.row_hi = row_hi;
   spec.d_poses = d_poses;
   spec.n = n;
   spec.d_out = d_out;

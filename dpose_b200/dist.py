@@ -14,6 +14,33 @@ def shard_bounds(n, rank, world):
     return min(n, per * rank), min(n, per * (rank + 1))
 
 
+def row_order(y):
+    """order of a pose set by map row (stable argsort of the y coordinates): what a caller does once, at set-up, so that
+    the contiguous slices of shard_bounds become stripes of the map ("pre-sorted by map tile so each
+    GPU's slice touches a compact region")"""
+    import numpy as np
+    return np.argsort(np.asarray(y, dtype=np.float64), kind="stable")
+
+
+def reach_of_box(box):
+    """dpose_pg_reach from cost_data::get_box() (5 x 2 ring around the centre): the farthest corner of the cost table from
+    its centre, rounded up, + 1 — no cell farther than this from a pose contributes to its cost"""
+    import math
+    import numpy as np
+    b = np.asarray(box, dtype=np.float64).reshape(-1, 2)[:4]
+    return int(math.ceil(math.sqrt(float((b * b).sum(axis=1).max())))) + 1
+
+
+def row_band(y_min, y_max, reach, size_y):
+    """[row_lo, row_hi) of the map rows that can contribute to poses with y in [y_min, y_max]: the stripe grown by the
+    footprint's reach (pose_gradient.reach()), clamped to the map — the band a rank hands to
+    dpose_pg_get_cost_batch_device_rows with its slice of a row-ordered pose set"""
+    import math
+    lo = max(0, int(math.floor(y_min)) - int(reach))
+    hi = min(int(size_y), int(math.ceil(y_max)) + int(reach) + 1)
+    return lo, max(hi, lo + 1)
+
+
 class Ranks:
     """rank / world of this process and the reductions a timed multi-rank run needs"""
 

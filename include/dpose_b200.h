@@ -141,6 +141,20 @@ int dpose_pg_get_cost_batch(const dpose_pg *pg, const dpose_map *map, const doub
 int dpose_pg_get_cost_batch_device(const dpose_pg *pg, const dpose_map *map,
                                    const double *d_poses, size_t n, double *d_out,
                                    int want_jacobian, void *stream);
+/* The same, restricted to the band of map rows [row_lo, row_hi): only lethal cells of these rows count (the batched
+ * form of the reference's search box, dpose_goal_tolerance.cpp:119-141 — there, too, a solve sees only the cells of
+ * lethal_cells_within(map, box)), and only these rows of a VOLATILE map are re-read in front of the launch.  For callers
+ * that shard a pose set spatially ("pre-sorted by map tile so each GPU's slice touches a compact
+ * region"): a rank whose slice of the poses lives in a stripe of the map passes the stripe grown by
+ * dpose_pg_reach() rows and pays for 1/N of the map pass; results are bit-identical to the unrestricted call for every
+ * pose whose kernel window lies inside the band.  DPOSE_EINVAL if the band is empty or exceeds the map. */
+int dpose_pg_get_cost_batch_device_rows(const dpose_pg *pg, const dpose_map *map,
+                                        const double *d_poses, size_t n, double *d_out,
+                                        int want_jacobian, void *stream, uint32_t row_lo,
+                                        uint32_t row_hi);
+/* rows (= columns) around a pose beyond which no cell can contribute to its cost: the largest distance of a corner of
+ * the cost table from its centre, rounded up, + 1.  A pose at y sees lethal cells of rows [y - reach, y + reach] only. */
+int dpose_pg_reach(const dpose_pg *pg, uint32_t *reach);
 /* pose batch sharded contiguously over ndev devices (pgs[i] / maps[i] live on device i's
  * GPU; map and table replicated; no collective), one host thread per device. */
 int dpose_pg_get_cost_batch_multi(dpose_pg *const *pgs, dpose_map *const *maps, int ndev,

@@ -591,6 +591,65 @@ def test_batch_device_pointer_entry(dp):
     assert pg.window_bytes(cm, poses) > 400 * len(poses)
 
 
+@pytest.mark.parametrize("n", [300, 20000])  # cooperative kernel / thread-per-pose kernel
+def test_batch_row_band(dp, n):
+    """dpose_pg_get_cost_batch_device_rows: only lethal cells of the band's rows count — the plain call on a map whose
+    other rows are free (to rounding where the band cuts a pose's window: the kernel coordinates are formed from the
+    window's origin, which the cut moves; bit for bit everywhere else); poses whose reach lies inside the band get the
+    bits of the plain call on the whole map; and of a VOLATILE map only the band's rows are re-read in front of the launch"""
+    torch = pytest.importorskip("torch")
+    from dpose_b200.dist import reach_of_box, row_band
+    m = fx.bernoulli_map(640, 500, 0.10, 21)
+    pg = dp.pose_gradient(fx.RECT)
+    reach = pg.reach()
+    assert reach == reach_of_box(pg.get_data().get_box())
+    poses = fx.random_poses(n, 640, 500, 22, margin=-10.0)
+    d_p = torch.from_numpy(poses).cuda()
+    d_o = torch.empty((n, 4), dtype=torch.float64, device="cuda")
+
+    def run(cm, rows=None):
+        d_o.fill_(-1.0)
+        pg.get_cost_batch_device(cm, d_p.data_ptr(), n, d_o.data_ptr(), rows=rows)
+        torch.cuda.synchronize()
+        return d_o.cpu().numpy()
+    cm = dp.Costmap(m)
+    whole = run(cm)
+    for lo, hi in ((0, 500), (137, 301), (0, 9), (491, 500), (250, 251)):
+        cut = np.zeros_like(m)
+        cut[lo:hi] = m[lo:hi]
+        got, want = run(cm, (lo, hi)), run(dp.Costmap(cut))
+        uncut = (poses[:, 1] - reach >= lo) & (poses[:, 1] + reach <= hi - 1) | (poses[:, 1] + reach < lo) | (poses[:, 1] - reach > hi - 1)
+        assert np.array_equal(got[uncut], want[uncut]), (lo, hi)
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-9), (lo, hi)
+        assert (got[(poses[:, 1] + reach < lo) | (poses[:, 1] - reach > hi - 1)] == 0).all()
+    stripe = (poses[:, 1] >= 200.0) & (poses[:, 1] <= 330.5)
+    band = row_band(200.0, 330.5, reach, 500)
+    assert band == (200 - reach, 332 + reach)
+    assert stripe.sum() > n // 5 and np.array_equal(run(cm, band)[stripe], whole[stripe])
+    for bad in ((5, 5), (7, 3), (0, 501)):
+        with pytest.raises(dp.DposeError):
+            pg.get_cost_batch_device(cm, d_p.data_ptr(), n, d_o.data_ptr(), rows=bad)
+    # a volatile map (a producer on the device rewrites the library's copy behind its back): the band call re-reads the
+    # band's rows, and only them
+    vm = dp.Costmap(m)
+    vm.set_volatile(True)
+    assert np.array_equal(run(vm), whole)
+    m2 = fx.bernoulli_map(640, 500, 0.15, 23)
+    ptr, pitch = vm.device_ptr()
+    assert pitch == 640
+
+    class Raw:  # the library's buffer as a torch tensor (CUDA array interface)
+        __cuda_array_interface__ = {"shape": (500, 640), "typestr": "|u1", "data": (ptr, False), "version": 2, "strides": None}
+    torch.as_tensor(Raw(), device="cuda").copy_(torch.from_numpy(m2))
+    torch.cuda.synchronize()
+    cut = np.zeros_like(m2)
+    cut[band[0]:band[1]] = m2[band[0]:band[1]]
+    got, want = run(vm, band), run(dp.Costmap(cut))
+    assert np.array_equal(got[stripe], want[stripe]) and np.allclose(got, want, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(got[stripe], run(dp.Costmap(m2))[stripe]) and not np.array_equal(got[stripe], whole[stripe])
+    assert np.array_equal(run(vm), run(dp.Costmap(m2)))  # the next plain call re-reads every row
+
+
 def test_batch_multi_gpu_shards(dp):
     """dpose_pg_get_cost_batch_multi: one process, one host buffer, the pose batch sharded contiguously over all GPUs of
     the box.  Bit-equal to the per-device calls on the same shards; for batches whose shards run the thread-per-pose
