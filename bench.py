@@ -13,9 +13,10 @@ Workloads (BASELINE.json `configs`):
                   "1e7-pose sweep sharded across 1/2/4/8 B200"): the 1e7 poses are split contiguously over the ranks;
                   weak: 1e7 poses PER GPU.  On N > 1 the other mode is timed as well and reported under `other_scaling`.
                   Map and table replicated, no collective on the data path.  Strong scaling orders the job's poses by map
-                  row at set-up: a rank's slice is a stripe of the map, the rank passes the stripe's rows to
-                  the call (dpose_pg_get_cost_batch_device_rows) and the per-step rebuild of the volatile map's lethal plane
-                  shards with the poses; `list_order` is the same job unordered through the plain call.
+                  tile at set-up (dpose_order_poses_by_tile): a rank's slice is a stripe of the map, the rank
+                  passes the stripe's rows to the call (dpose_pg_get_cost_batch_device_rows) and the per-step rebuild of the
+                  volatile map's lethal plane shards with the poses; `list_order` is the same job unordered through the
+                  plain call.
   cfg2 / cfg3     1e5 poses on 2000x2000 / 1e6 poses with the 40-vertex footprint (table 35x55), same call.
   cfg4            the goal-tolerance solve: 4096 multi-start offsets from the plugin's sampler, max_iter 20, one
                   dpose_problem_solve_batch per step; value = pose evaluations (solver iterates) per second.
@@ -83,6 +84,10 @@ WORKLOADS = {
              "BASELINE cfg1: dpose_core perf bench (perf/dpose_core.cpp:45-71): arrow footprint pad 3, 10x10 cells, pose 0, "
              "single-pose get_cost with Jacobian"),
 }
+
+
+# order of a strong-scaling job's poses (see run_batch)
+JOB_ORDER = {"cfg5": "tile"}
 
 
 def load_peaks():
@@ -375,26 +380,31 @@ def run_batch(args, ranks, torch, dp, fx):
     cmap.set_volatile(True)
     stream = torch.cuda.current_stream()
 
-    # Strong scaling (BASELINE cfg5: "1e7-pose sweep sharded across 1/2/4/8 B200"): the job is the SAME 1e7 poses at every N,
-    # ordered by map row once at set-up ("pre-sorted by map tile so each GPU's slice touches a compact
-    # region"); a rank's contiguous slice is then a stripe of the map, and with N > 1 it tells the call so
+    # Strong scaling of cfg5 (BASELINE: "1e7-pose sweep sharded across 1/2/4/8 B200"): the job is the SAME 1e7 random poses
+    # at every N, ordered once at set-up by the map tile of their position (dpose_order_poses_by_tile; SURVEY.md 8(e):
+    # "pre-sorted by map tile so each GPU's slice touches a compact region") — what a caller does that evaluates one pose
+    # set against successive versions of a map, which is what the volatile map of this bench stands for.  A rank's
+    # contiguous slice is then a stripe of the map, and with N > 1 it tells the call so
     # (dpose_pg_get_cost_batch_device_rows): the rebuild of the volatile map's lethal plane — the part of the step that
     # did not shard — covers the stripe + the footprint's reach, 1 / N of the map.  `list_order` in the line is the same
-    # leg on the unordered list with the plain call (every rank re-reads the whole map).
+    # job on the unordered list through the plain call (every rank re-reads the whole map).  cfg2 / cfg3 ("a batch of
+    # random poses") stay in list order.
+    job_order = JOB_ORDER.get(args.workload, "list") if scaling == "strong" else "list"
     srank, sworld = (int(v) for v in args.as_rank.split("/")) if args.as_rank else (rank, world)
 
     def job_poses(order):
         full = device_poses(torch, dev, n_total, side, pose_seed)
-        if order == "row":
-            full = full[torch.argsort(full[:, 1], stable=True)].contiguous()
+        if order == "tile":  # the library's set-up helper (host arithmetic): the 32 x 8-cell tiles of the lethal plane, row-major
+            perm = dp.order_poses_by_tile(full.cpu().numpy(), side, side)
+            full = full[torch.from_numpy(perm).to(dev)].contiguous()
         return full
 
-    def make_mode(mode, order="row"):
+    def make_mode(mode, order=job_order):
         band = None
         if mode == "strong":  # n_total poses in all, this rank's contiguous slice
             lo, hi = dp.dist.shard_bounds(n_total, srank, sworld)
             poses = job_poses(order)[lo:hi].contiguous()
-            if sworld > 1 and order == "row":
+            if sworld > 1 and order == "tile":
                 band = dp.dist.row_band(float(poses[:, 1].min()), float(poses[:, 1].max()), pg.reach(), side)
         else:  # weak: n_total poses per GPU, rank-specific
             poses = device_poses(torch, dev, n_total, side, pose_seed + rank)
@@ -402,7 +412,7 @@ def run_batch(args, ranks, torch, dp, fx):
         torch.cuda.empty_cache()
         return poses, out, band
 
-    def device_leg(mode, order="row"):
+    def device_leg(mode, order=job_order):
         poses, out, band = make_mode(mode, order)
         n = poses.shape[0]
 
@@ -433,7 +443,7 @@ def run_batch(args, ranks, torch, dp, fx):
         other = {"scaling": om, "value": leg["value"], "ms_per_step": leg["ms_per_step"], "poses_per_gpu": leg["n"],
                  "host_issue_ms_per_step": leg["host_issue_ms_per_step"]}
         del leg
-    if scaling == "strong":
+    if job_order != "list":
         leg = device_leg("strong", order="list")
         list_order = {"value": leg["value"], "ms_per_step": leg["ms_per_step"],
                       "note": "the same 1e7 poses in list order, contiguous slices, the plain call: every rank's slice spans "
@@ -527,7 +537,7 @@ def run_batch(args, ranks, torch, dp, fx):
         if rank == 0:
             try:
                 host_map = d_map.cpu().numpy()
-                full = job_poses("row") if scaling == "strong" else device_poses(torch, dev, n_total, side, pose_seed)
+                full = job_poses(job_order) if scaling == "strong" else device_poses(torch, dev, n_total, side, pose_seed)
                 hp = torch.empty((n_total, 3), dtype=torch.float64, pin_memory=True)
                 hp.copy_(full)
                 ho = torch.empty((n_total, 4), dtype=torch.float64, pin_memory=True)
@@ -617,11 +627,12 @@ def run_batch(args, ranks, torch, dp, fx):
         "config": {"workload": desc, "poses_per_gpu": n, "poses_total": int(n * world) if scaling == "weak" else n_total,
                    "map": f"{side}x{side} uint8, Bernoulli(0.10)",
                    "parallelism": f"dp{world} (poses sharded contiguously, map + table replicated, no collective)", "l2": l2,
-                   "pose_order": ("ordered by map row at set-up (untimed): a rank's contiguous slice is a stripe of the map"
+                   "pose_order": ("ordered by map tile at set-up (untimed; dpose_order_poses_by_tile): a 32-pose group reads the "
+                                  "same few tiles of the lethal plane, a rank's contiguous slice is a stripe of the map"
                                   + (f"; this rank's call is restricted to map rows [{main['band'][0]}, {main['band'][1]}) = its "
                                      "stripe + the footprint's reach (dpose_pg_get_cost_batch_device_rows), so the per-step "
                                      "rebuild of the volatile map's lethal plane shards with the poses" if main["band"] else
-                                     "; one rank: the plain call on the whole map")) if scaling == "strong" else "list order"},
+                                     "; one rank: the plain call on the whole map")) if job_order != "list" else "list order"},
         "clocks": main["clocks"], "e2e": e2e, "e2e_multi": e2e_multi, "e2e_variants": variants,
         "other_scaling": other, "list_order": list_order, "clean_map": clean, "gpu_launches": int(main["launches"]), "roofline": roofline,
         "cpu_baseline": cpu_baseline, "parity": parity,

@@ -47,6 +47,7 @@ SYMBOLS = {
     "dpose_pg_get_cost_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
     "dpose_pg_get_cost_batch_device": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "dpose_pg_get_cost_batch_device_rows": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, C.c_uint32, C.c_uint32]),
+    "dpose_order_poses_by_tile": (_i, [_vp, _sz, C.c_uint32, C.c_uint32, _vp]),
     "dpose_pg_reach": (_i, [_vp, C.POINTER(C.c_uint32)]),
     "dpose_pg_get_cost_batch_costs": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "dpose_pg_get_cost_sweep": (_i, [_vp, _vp, _vp, _vp, _i, _i]),

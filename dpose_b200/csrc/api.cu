@@ -595,6 +595,36 @@ int dpose_pg_get_cost_batch_device(const dpose_pg *pg, const dpose_map *map, con
   return get_cost_batch_device(pg, map, d_poses, n, d_out, want_jacobian, (cudaStream_t)stream);
 }
 
+int dpose_order_poses_by_tile(const double *poses, size_t n, uint32_t size_x, uint32_t size_y, uint64_t *perm) {
+  if (n && (!poses || !perm)) return fail(DPOSE_EINVAL, "NULL argument");
+  if (size_x == 0 || size_y == 0) return fail(DPOSE_EINVAL, "empty map");
+  try {
+    // a stable counting sort over the tiles of the lethal plane (32 x 8 cells, row-major) + one bucket for NaN positions
+    const uint64_t ntx = ((uint64_t)size_x + 31) / 32, nty = ((uint64_t)size_y + 7) / 8, nb = ntx * nty + 1;
+    auto bucket = [&](size_t i) -> uint64_t {
+      const double x = poses[3 * i], y = poses[3 * i + 1];
+      if (x != x || y != y) return nb - 1;
+      const double cx = std::min(std::max(x, 0.0), (double)size_x - 1.0), cy = std::min(std::max(y, 0.0), (double)size_y - 1.0);
+      return ((uint64_t)cy / 8) * ntx + (uint64_t)cx / 32;
+    };
+    std::vector<uint64_t> start(nb + 1, 0);
+    std::vector<uint32_t> key32;
+    std::vector<uint64_t> key64;
+    const bool narrow = nb <= 0xffffffffull;
+    if (narrow) key32.resize(n); else key64.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      const uint64_t b = bucket(i);
+      if (narrow) key32[i] = (uint32_t)b; else key64[i] = b;
+      ++start[b + 1];
+    }
+    for (uint64_t b = 0; b < nb; ++b) start[b + 1] += start[b];
+    for (size_t i = 0; i < n; ++i) perm[start[narrow ? key32[i] : key64[i]]++] = i;
+    return DPOSE_OK;
+  } catch (const std::exception &e) {
+    return fail(DPOSE_ENOMEM, "dpose_order_poses_by_tile: %s", e.what());
+  }
+}
+
 int dpose_pg_reach(const dpose_pg *pg, uint32_t *reach) {
   if (!pg || !reach) return fail(DPOSE_EINVAL, "NULL argument");
   double r2 = 0.0;  // farthest corner of the table from its centre (the valid region, :181-182, lies 1.5 cells inside)

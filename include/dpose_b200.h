@@ -155,6 +155,15 @@ int dpose_pg_get_cost_batch_device_rows(const dpose_pg *pg, const dpose_map *map
 /* rows (= columns) around a pose beyond which no cell can contribute to its cost: the largest distance of a corner of
  * the cost table from its centre, rounded up, + 1.  A pose at y sees lethal cells of rows [y - reach, y + reach] only. */
 int dpose_pg_reach(const dpose_pg *pg, uint32_t *reach);
+/* Set-up helper for callers that evaluate one pose set against many versions of a map (a sweep lattice, a planner's
+ * candidate set): the order of the poses by the 32 x 8-cell tile of the lethal plane their position falls into (tiles
+ * row-major; stable; positions outside the map go to the nearest border tile, NaN last).  perm[i] = index of the pose that
+ * comes i-th.  In this order a 32-pose group of the batch kernel reads the same few tiles (L1 hits instead of L2
+ * round trips: 1e7 poses on the 10000^2 map 0.948 -> 0.898 ms), and the contiguous slices of
+ * dpose_pg_get_cost_batch_multi / of one rank per GPU are stripes of the map (see
+ * dpose_pg_get_cost_batch_device_rows).  Host arithmetic, O(n + tiles), deterministic. */
+int dpose_order_poses_by_tile(const double *poses /* n x 3 */, size_t n, uint32_t size_x, uint32_t size_y,
+                              uint64_t *perm /* n */);
 /* pose batch sharded contiguously over ndev devices (pgs[i] / maps[i] live on device i's
  * GPU; map and table replicated; no collective), one host thread per device. */
 int dpose_pg_get_cost_batch_multi(dpose_pg *const *pgs, dpose_map *const *maps, int ndev,

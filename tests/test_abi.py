@@ -44,6 +44,32 @@ def test_host_side_functions_match_oracle(built):
     assert np.array_equal(dp.to_rectangle((1, 2), (3, 4)), fx.to_rectangle((1, 2), (3, 4)))
 
 
+def test_order_poses_by_tile(built):
+    """dpose_order_poses_by_tile (host arithmetic: runs without a GPU): the stable order by the 32 x 8-cell tile of the
+    pose's position, positions outside the map at the border tiles, NaN last; contiguous slices of the ordered set are
+    stripes of the map"""
+    import dpose_b200 as dp
+    from dpose_b200.dist import shard_bounds
+    rng = np.random.default_rng(7)
+    for size_x, size_y, n in ((300, 260, 5000), (33, 9, 400), (1, 1, 10), (2000, 2000, 100000)):
+        poses = np.stack([rng.uniform(-20, size_x + 20, n), rng.uniform(-20, size_y + 20, n), rng.uniform(-3, 3, n)], axis=1)
+        if n >= 400:
+            poses[rng.integers(0, n, 7), rng.integers(0, 2, 7)] = np.nan
+        perm = dp.order_poses_by_tile(poses, size_x, size_y)
+        ntx = (size_x + 31) // 32
+        x, y = np.clip(poses[:, 0], 0, size_x - 1), np.clip(poses[:, 1], 0, size_y - 1)
+        key = np.floor(y / 8) * ntx + np.floor(x / 32)
+        key[np.isnan(poses[:, 0]) | np.isnan(poses[:, 1])] = np.inf
+        assert np.array_equal(perm, np.argsort(key, kind="stable"))
+    inside = fx.random_poses(100000, 2000, 2000, 3)
+    ordered = inside[dp.order_poses_by_tile(inside, 2000, 2000)]
+    spans = [ordered[slice(*shard_bounds(len(ordered), r, 8)), 1] for r in range(8)]
+    assert all(s.max() - s.min() < 2000 / 8 + 16 for s in spans)            # each slice: an eighth of the rows (+ a tile row)
+    assert all(a.max() < b.min() + 8 for a, b in zip(spans, spans[1:]))     # in map order
+    with pytest.raises(dp.DposeError):
+        dp.order_poses_by_tile(inside, 0, 5)
+
+
 def test_world_cell_conversions(built):  # dpose_goal_tolerance.cpp:294-330 (Costmap2D::worldToMap / mapToWorld)
     import dpose_b200 as dp
     origin, res, size = (-10.0, 5.0), 0.05, (400, 300)
