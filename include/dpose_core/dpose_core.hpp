@@ -228,6 +228,29 @@ struct pose_gradient {
     detail::check(dpose_pg_get_cost_batch(data_.handle(), _map.handle(), _poses, _n, _out, _jacobian ? 1 : 0));
   }
 
+  /// NEW: the same on DEVICE buffers, asynchronous on _stream (a cudaStream_t), restricted to the map rows
+  /// [_row_lo, _row_hi) — only their lethal cells count, only they are re-read of a volatile map (the batched form of
+  /// the search box, dpose_goal_tolerance.cpp:119-141).  _row_hi == 0: the whole map.  See get_reach().
+  void
+  get_cost_device(const device_costmap& _map, const double* _d_poses, size_t _n, double* _d_out, bool _jacobian = true,
+                  void* _stream = nullptr, uint32_t _row_lo = 0, uint32_t _row_hi = 0) const {
+    if (!data_.handle()) throw std::runtime_error("pose_gradient is not initialised");
+    if (_row_hi == 0)
+      detail::check(dpose_pg_get_cost_batch_device(data_.handle(), _map.handle(), _d_poses, _n, _d_out, _jacobian ? 1 : 0, _stream));
+    else
+      detail::check(dpose_pg_get_cost_batch_device_rows(data_.handle(), _map.handle(), _d_poses, _n, _d_out, _jacobian ? 1 : 0,
+                                                        _stream, _row_lo, _row_hi));
+  }
+
+  /// rows / columns around a pose beyond which no cell contributes to its cost (dpose_pg_reach)
+  uint32_t
+  get_reach() const {
+    if (!data_.handle()) throw std::runtime_error("pose_gradient is not initialised");
+    uint32_t r = 0;
+    detail::check(dpose_pg_reach(data_.handle(), &r));
+    return r;
+  }
+
   /// convenience overload of the batched call on std::vector
   void
   get_cost(const device_costmap& _map, const std::vector<pose>& _poses, std::vector<double>& _costs,

@@ -650,6 +650,38 @@ def test_batch_row_band(dp, n):
     assert np.array_equal(run(vm), run(dp.Costmap(m2)))  # the next plain call re-reads every row
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_tile_ordered_stripes_equal_plain_call(dp, world):
+    """the strong-scaling recipe of bench.py / INTEGRATION.md 4a on one device, rank by rank: order the pose set by map tile
+    (dpose_order_poses_by_tile), cut it into contiguous slices (dist.shard_bounds), evaluate every slice on ITS band of a
+    volatile map (dist.row_band, dpose_pg_get_cost_batch_device_rows), scatter the results back — bit for bit the plain
+    call on the whole list (a pose's result depends neither on its position in the batch nor on rows outside its reach)"""
+    torch = pytest.importorskip("torch")
+    from dpose_b200.dist import row_band, shard_bounds
+    m = fx.bernoulli_map(1500, 1100, 0.10, 31)
+    n = 60000 * world // 2
+    poses = fx.random_poses(n, 1500, 1100, 32, margin=-5.0)  # windows across the border included
+    pg = dp.pose_gradient(fx.RECT)
+    cm = dp.Costmap(m)
+    want = pg.get_cost_batch(cm, poses)
+    cm.set_volatile(True)
+    perm = dp.order_poses_by_tile(poses, 1500, 1100)
+    ordered = np.ascontiguousarray(poses[perm])
+    d_p = torch.from_numpy(ordered).cuda()
+    d_o = torch.full((n, 4), -1.0, dtype=torch.float64, device="cuda")
+    rows_read = 0
+    for r in range(world):
+        lo, hi = shard_bounds(n, r, world)
+        band = row_band(ordered[lo:hi, 1].min(), ordered[lo:hi, 1].max(), pg.reach(), 1100)
+        rows_read += band[1] - band[0]
+        pg.get_cost_batch_device(cm, d_p.data_ptr() + 24 * lo, hi - lo, d_o.data_ptr() + 32 * lo, rows=band)
+    torch.cuda.synchronize()
+    got = np.empty_like(want)
+    got[perm] = d_o.cpu().numpy()
+    assert np.array_equal(got, want)
+    assert rows_read < 1100 + world * (2 * pg.reach() + 10)  # the bands tile the map: all ranks together read it about once
+
+
 def test_batch_multi_gpu_shards(dp):
     """dpose_pg_get_cost_batch_multi: one process, one host buffer, the pose batch sharded contiguously over all GPUs of
     the box.  Bit-equal to the per-device calls on the same shards; for batches whose shards run the thread-per-pose
