@@ -389,7 +389,7 @@ def run_batch(args, ranks, torch, dp, fx):
     # did not shard — covers the stripe + the footprint's reach, 1 / N of the map.  `list_order` in the line is the same
     # job on the unordered list through the plain call (every rank re-reads the whole map).  cfg2 / cfg3 ("a batch of
     # random poses") stay in list order.
-    job_order = JOB_ORDER.get(args.workload, "list") if scaling == "strong" else "list"
+    job_order = (args.job_order or JOB_ORDER.get(args.workload, "list")) if scaling == "strong" else "list"
     srank, sworld = (int(v) for v in args.as_rank.split("/")) if args.as_rank else (rank, world)
 
     def job_poses(order):
@@ -448,14 +448,21 @@ def run_batch(args, ranks, torch, dp, fx):
         list_order = {"value": leg["value"], "ms_per_step": leg["ms_per_step"],
                       "note": "the same 1e7 poses in list order, contiguous slices, the plain call: every rank's slice spans "
                               "the whole map, so every rank rebuilds the whole lethal plane of the volatile map in its step"}
+        e_poses, e_out = leg["poses"], leg["out"]
         del leg
+    else:
+        e_poses, e_out = d_poses, d_out
+    # The end-to-end legs below run on the job AS IT COMES (list order): a caller of the host-buffer call hands over its own
+    # list, the call is bound by the host link, not by the kernel, and ordering buys it nothing — measured, it costs: the
+    # same call on the tile-ordered list takes 8.0 ms instead of 6.7 ms although its kernels are faster
+    # (profiles/r2_e2e_order_ab.txt; the interplay of the two copy directions, not yet explained).
 
     # ---- end to end through the host-buffer C ABI call, this rank's shard --------------------------------------------------
     e2e = e2e_ok = None
     variants = None
     if not args.no_e2e:
         h_poses = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
-        h_poses.copy_(d_poses)
+        h_poses.copy_(e_poses)
         h_out = torch.empty((n, 4), dtype=torch.float64, pin_memory=True)
         np_poses, np_out = h_poses.numpy(), h_out.numpy()
 
@@ -471,7 +478,7 @@ def run_batch(args, ranks, torch, dp, fx):
 
         dt = wall(lambda: pg.get_cost_batch(cmap, np_poses, out=np_out), args.steps)
         e2e_value = ranks.sum(n * args.steps) / ranks.max(dt)
-        e2e_ok = bool(np.array_equal(np_out[:4096], d_out[:4096].cpu().numpy()))
+        e2e_ok = bool(np.array_equal(np_out[:4096], e_out[:4096].cpu().numpy()))
 
         # what the box's host link gives plain pinned copies of the same sizes: each direction alone, and both at once
         def copy_ms(pairs):
@@ -486,10 +493,10 @@ def run_batch(args, ranks, torch, dp, fx):
                 torch.cuda.synchronize()
                 best = min(best, time.perf_counter() - t0)
             return best * 1e3
-        scratch = torch.empty_like(d_out)
-        h2d_ms = copy_ms([(d_poses, h_poses)])
+        scratch = torch.empty_like(e_out)
+        h2d_ms = copy_ms([(e_poses, h_poses)])
         d2h_ms = copy_ms([(h_out, scratch)])
-        bidir_ms = copy_ms([(d_poses, h_poses), (h_out, scratch)])
+        bidir_ms = copy_ms([(e_poses, h_poses), (h_out, scratch)])
         del scratch
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": int(n * 32),
                "ms_per_step": 1e3 * ranks.max(dt) / args.steps,
@@ -498,7 +505,8 @@ def run_batch(args, ranks, torch, dp, fx):
                "frac_of_bidirectional_copy_floor": ranks.max(bidir_ms) / (1e3 * ranks.max(dt) / args.steps),
                "host_threads_bound_to_gpu_numa_node": bool(prev_affinity),
                "timing": "host wall clock around the synchronous C-ABI call (it drives its own streams), max over ranks; "
-                         "bytes are per rank"}
+                         "bytes are per rank",
+               "pose_order": "list order (the job as it comes; `value` runs the tile-ordered job)" if job_order != "list" else "list order"}
         # the entry points that move fewer bytes: cost only (8 B/pose back), lattice sweep (nothing in)
         v_steps = max(3, args.steps // 4)
         h_cost = torch.empty((n,), dtype=torch.float64, pin_memory=True)
@@ -515,7 +523,7 @@ def run_batch(args, ranks, torch, dp, fx):
         # the driver stages every chunk through its own pinned buffers)
         pg_poses, pg_out = np.array(np_poses), np.empty_like(np_out)
         dt_p = wall(lambda: pg.get_cost_batch(cmap, pg_poses, out=pg_out), v_steps)
-        pageable_ok = bool(np.array_equal(pg_out[:4096], d_out[:4096].cpu().numpy()))
+        pageable_ok = bool(np.array_equal(pg_out[:4096], e_out[:4096].cpu().numpy()))
         variants = {
             "pageable_buffers": {"value": ranks.sum(n * v_steps) / ranks.max(dt_p), "unit": UNIT,
                                  "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": int(n * 32),
@@ -537,7 +545,7 @@ def run_batch(args, ranks, torch, dp, fx):
         if rank == 0:
             try:
                 host_map = d_map.cpu().numpy()
-                full = job_poses(job_order) if scaling == "strong" else device_poses(torch, dev, n_total, side, pose_seed)
+                full = job_poses("list") if scaling == "strong" else device_poses(torch, dev, n_total, side, pose_seed)
                 hp = torch.empty((n_total, 3), dtype=torch.float64, pin_memory=True)
                 hp.copy_(full)
                 ho = torch.empty((n_total, 4), dtype=torch.float64, pin_memory=True)
@@ -554,7 +562,7 @@ def run_batch(args, ranks, torch, dp, fx):
                 for _ in range(m_steps):
                     dp.get_cost_batch_multi(pgs, maps, hp.numpy(), out=ho.numpy())
                 dtm = time.perf_counter() - t0
-                same = bool(np.array_equal(ho.numpy()[:4096], d_out[:4096].cpu().numpy())) if scaling == "strong" else None
+                same = bool(np.array_equal(ho.numpy()[:4096], e_out[:4096].cpu().numpy())) if scaling == "strong" else None
                 lo, hi = dp.dist.shard_bounds(n_total, ndev - 1, ndev)  # the last device's shard, once more on device 0
                 single = pg.get_cost_batch(cmap, hp.numpy()[lo:hi])
                 e2e_multi = {"value": n_total * m_steps / dtm, "unit": UNIT, "ms_per_step": 1e3 * dtm / m_steps,
@@ -774,6 +782,8 @@ def main():
                     help="batch workloads on N > 1 GPUs: total work fixed (default, BASELINE cfg5) or per-GPU work fixed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--job-order", default=None, choices=["list", "tile"],
+                    help="order of a strong-scaling job's poses (default: tile for cfg5, list otherwise)")
     ap.add_argument("--as-rank", default=None, metavar="R/W",
                     help="development aid: time, in ONE process on one GPU, the strong-scaling shard rank R of W would own "
                          "(value and ms_per_step are then that shard's, not a job's)")

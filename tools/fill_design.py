@@ -61,8 +61,11 @@ rep["R2_PRECOMPUTE_TABLE"] = "; ".join(
     f"{x['footprint'].split('_')[0]} {x['table'][0]}×{x['table'][1]}: {x['gpu_kernel_us']:.0f} µs device / {x['gpu_call_wall_us']:.0f} µs per call (cv2, one thread: {x['cpu_cv2_us']:.0f} µs)"
     for x in pre)
 d1 = line("r2_bench_cfg5.json")
-rows = ["| GPUs | strong: poses/s (step) | efficiency | clean map | weak: poses/s | e2e per-rank calls | e2e `_multi` (one process) | cost-only / sweep / sweep cost-only e2e |",
-        "|---|---|---|---|---|---|---|---|"]
+lo1 = d1.get("list_order") or {}
+rep["R2_CFG5_LIST_MS"] = f"{lo1['ms_per_step']:.3f}" if lo1 else "?"
+rep["R2_CFG5_LIST_VALUE"] = sci(lo1["value"]) if lo1 else "?"
+rows = ["| GPUs | strong: poses/s (step) | efficiency | the job in list order, plain call (efficiency) | clean map | weak: poses/s | e2e per-rank calls | e2e `_multi` (one process) | cost-only / sweep / sweep cost-only e2e |",
+        "|---|---|---|---|---|---|---|---|---|"]
 v1 = d1["value"]
 v1c = (d1.get("clean_map") or {}).get("value")
 for n, d in ((1, d1),) + tuple((n, line(f"r2_bench_cfg5_n{n}.json")) for n in (2, 8) if os.path.exists(os.path.join(P, f"r2_bench_cfg5_n{n}.json"))):
@@ -72,7 +75,9 @@ for n, d in ((1, d1),) + tuple((n, line(f"r2_bench_cfg5_n{n}.json")) for n in (2
     cm = d.get("clean_map") or {}
     ev = d.get("e2e_variants") or {}
     em = d.get("e2e_multi") or {}
+    lo = d.get("list_order") or {}
     rows.append(f"| {n} | {sci(d['value'])} ({d['ms_per_step']:.3f} ms) | {d['value'] / (n * v1):.2f} | "
+                + (f"{sci(lo['value'])} ({lo['value'] / (n * lo1['value']):.2f})" if lo and lo1 else "—") + " | "
                 + (f"{sci(cm['value'])} ({cm['value'] / (n * v1c):.2f})" if cm and v1c else "—") + " | "
                 + (f"{sci(weak_v)} ({weak_v / (n * v1):.3f})" if weak_v else "—") + " | "
                 + f"{sci(d['e2e']['value'])} | " + (sci(em["value"]) if em.get("value") else "—") + " | "
@@ -81,6 +86,9 @@ rep["R2_SCALING_TABLE"] = "\n\n" + "\n".join(rows) + "\n"
 if os.path.exists(os.path.join(P, "r2_bench_cfg5_n8.json")):
     d8 = line("r2_bench_cfg5_n8.json")
     rep["R2_PACK_SHARE_N8"] = f"{100 * 0.052 / d8['ms_per_step']:.0f} %"
+    rep["R2_N8_VALUE"] = sci(d8["value"])
+    rep["R2_N8_EFF"] = f"{d8['value'] / (8 * v1):.2f}"
+    rep["R2_N8_LIST_EFF"] = f"{(d8.get('list_order') or {}).get('value', 0) / (8 * lo1['value']):.2f}" if lo1 else "?"
 t = json.load(open(os.path.join(P, "traffic.json")))["ncu_cfg5"]
 rep["R2_TILE_COUNTERS"] = (f"ncu of this round's build: {t['kernel_ms']:.3f} ms per launch, issue slots {t['issue_active_pct']:.1f} % busy, "
                            f"{t['warps_active_pct']:.1f} % of the warp slots occupied, "
