@@ -391,6 +391,16 @@ def run_batch(args, ranks, torch, dp, fx):
     # random poses") stay in list order.
     job_order = (args.job_order or JOB_ORDER.get(args.workload, "list")) if scaling == "strong" else "list"
     srank, sworld = (int(v) for v in args.as_rank.split("/")) if args.as_rank else (rank, world)
+    if not args.no_e2e:
+        # the pinned host buffers of the end-to-end legs, allocated FIRST: the set-up below moves hundreds of megabytes
+        # through pageable host memory (the job's poses to the host and back for dpose_order_poses_by_tile), and pinned
+        # buffers allocated after that churn copy 10 - 20 % slower on this pool (7.4 - 8.0 against 6.7 ms per 1e7-pose
+        # call on the same bytes, in either pose order: profiles/r2_e2e_order_ab.txt) — a property of the pages the
+        # host hands out, not of the library or of the pose order
+        n_e2e = n_total if scaling == "weak" else (lambda b: b[1] - b[0])(dp.dist.shard_bounds(n_total, srank, sworld))
+        h_poses = torch.empty((n_e2e, 3), dtype=torch.float64, pin_memory=True)
+        h_out = torch.empty((n_e2e, 4), dtype=torch.float64, pin_memory=True)
+        h_poses.zero_(), h_out.zero_()
 
     def job_poses(order):
         full = device_poses(torch, dev, n_total, side, pose_seed)
@@ -453,17 +463,13 @@ def run_batch(args, ranks, torch, dp, fx):
     else:
         e_poses, e_out = d_poses, d_out
     # The end-to-end legs below run on the job AS IT COMES (list order): a caller of the host-buffer call hands over its own
-    # list, the call is bound by the host link, not by the kernel, and ordering buys it nothing — measured, it costs: the
-    # same call on the tile-ordered list takes 8.0 ms instead of 6.7 ms although its kernels are faster
-    # (profiles/r2_e2e_order_ab.txt; the interplay of the two copy directions, not yet explained).
+    # list, and the call is bound by the host link, not by the kernel — ordering buys it nothing.
 
     # ---- end to end through the host-buffer C ABI call, this rank's shard --------------------------------------------------
     e2e = e2e_ok = None
     variants = None
     if not args.no_e2e:
-        h_poses = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
         h_poses.copy_(e_poses)
-        h_out = torch.empty((n, 4), dtype=torch.float64, pin_memory=True)
         np_poses, np_out = h_poses.numpy(), h_out.numpy()
 
         def wall(fn, steps):

@@ -64,14 +64,14 @@ d1 = line("r2_bench_cfg5.json")
 lo1 = d1.get("list_order") or {}
 rep["R2_CFG5_LIST_MS"] = f"{lo1['ms_per_step']:.3f}" if lo1 else "?"
 rep["R2_CFG5_LIST_VALUE"] = sci(lo1["value"]) if lo1 else "?"
-rows = ["| GPUs | strong: poses/s (step) | efficiency | the job in list order, plain call (efficiency) | clean map | weak: poses/s | e2e per-rank calls | e2e `_multi` (one process) | cost-only / sweep / sweep cost-only e2e |",
+rows = ["| GPUs | strong: poses/s (step) | efficiency | the job in list order, plain call (efficiency) | clean map | weak (list order): poses/s | e2e per-rank calls | e2e `_multi` (one process) | cost-only / sweep / sweep cost-only e2e |",
         "|---|---|---|---|---|---|---|---|---|"]
 v1 = d1["value"]
 v1c = (d1.get("clean_map") or {}).get("value")
 for n, d in ((1, d1),) + tuple((n, line(f"r2_bench_cfg5_n{n}.json")) for n in (2, 8) if os.path.exists(os.path.join(P, f"r2_bench_cfg5_n{n}.json"))):
     strong = d if d["scaling"] == "strong" else None
     other = d.get("other_scaling") or {}
-    weak_v = other.get("value") if n > 1 else d["value"]
+    weak_v = other.get("value") if n > 1 else (lo1.get("value") or d["value"])  # the weak-scaling leg draws its poses per rank: list order
     cm = d.get("clean_map") or {}
     ev = d.get("e2e_variants") or {}
     em = d.get("e2e_multi") or {}
@@ -79,7 +79,7 @@ for n, d in ((1, d1),) + tuple((n, line(f"r2_bench_cfg5_n{n}.json")) for n in (2
     rows.append(f"| {n} | {sci(d['value'])} ({d['ms_per_step']:.3f} ms) | {d['value'] / (n * v1):.2f} | "
                 + (f"{sci(lo['value'])} ({lo['value'] / (n * lo1['value']):.2f})" if lo and lo1 else "—") + " | "
                 + (f"{sci(cm['value'])} ({cm['value'] / (n * v1c):.2f})" if cm and v1c else "—") + " | "
-                + (f"{sci(weak_v)} ({weak_v / (n * v1):.3f})" if weak_v else "—") + " | "
+                + (f"{sci(weak_v)} ({weak_v / (n * (lo1.get('value') or v1)):.3f})" if weak_v else "—") + " | "
                 + f"{sci(d['e2e']['value'])} | " + (sci(em["value"]) if em.get("value") else "—") + " | "
                 + " / ".join(sci(ev[k]["value"]) for k in ("cost_only", "sweep", "sweep_cost_only") if k in ev) + " |")
 rep["R2_SCALING_TABLE"] = "\n\n" + "\n".join(rows) + "\n"
