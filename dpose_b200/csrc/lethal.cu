@@ -578,9 +578,10 @@ int lethal_extract(const dpose_map *map, const int32_t box[10], int2 **d_cells, 
   auto body = [&]() -> int {
     DPOSE_CUDA(cudaMemcpyAsync(ws->d_spans, ws->h_spans, sizeof(RowSpan) * nrows, cudaMemcpyHostToDevice, st));
     DPOSE_CUDA(cudaEventRecord(ws->ev0, st));
-    // the ONE read of the uint8 map: the lethal tile plane, rebuilt for the rows that changed (every row of a volatile
-    // map); a clean plane costs nothing here.  The compaction below reads the 1-bit plane (1/8 of the map's bytes).
-    DPOSE_TRY(tileplane_ensure(map, st, false));
+    // the ONE read of the uint8 map: the lethal tile plane, rebuilt for the rows that changed (of a volatile map: the
+    // rows of this box — a search box on a 10000^2 map does not pay for the whole map's pass); a clean plane costs nothing
+    // here.  The compaction below reads the 1-bit plane (1/8 of the map's bytes).
+    DPOSE_TRY(tileplane_ensure(map, st, false, (uint32_t)y_lo, (uint32_t)y_hi + 1u));
     // capacity of the result buffer: the box itself while that is small, else what the last call on this map needed
     // (+25 %); a first call on a large box reads the total back before the write pass (one more synchronisation)
     unsigned long long cap = box_cells <= kBoxSizedCells ? box_cells : (ws->hint ? ws->hint + ws->hint / 4 + 4096 : 0);

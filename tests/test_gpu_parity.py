@@ -267,6 +267,29 @@ def test_lethal_large_boxes_capacity_estimates(dp, capi):
     assert np.array_equal(dp.lethal_cells_within(cm, full), capi.lethal_cells_within(m2, full))
 
 
+def test_lethal_volatile_map_rereads_the_box_rows(dp, capi):
+    """extraction on a VOLATILE map (a producer on the device rewrites the library's copy behind its back) re-reads the
+    rows of the box it is asked for — and sees the new bytes there; the next full-map extraction sees them everywhere"""
+    torch = pytest.importorskip("torch")
+    m = fx.bernoulli_map(1200, 900, 0.10, 41)
+    cm = dp.Costmap(m)
+    cm.set_volatile(True)
+    full = fx.to_rectangle((0, 0), (1199, 899))
+    assert np.array_equal(dp.lethal_cells_within(cm, full), capi.lethal_cells_within(m, full))
+    m2 = fx.bernoulli_map(1200, 900, 0.20, 42)
+    ptr, pitch = cm.device_ptr()
+
+    class Raw:  # the library's buffer as a torch tensor (CUDA array interface)
+        __cuda_array_interface__ = {"shape": (900, pitch), "typestr": "|u1", "data": (ptr, False), "version": 2, "strides": None}
+    torch.as_tensor(Raw(), device="cuda")[:, :1200].copy_(torch.from_numpy(m2))
+    torch.cuda.synchronize()
+    for ring in (fx.to_rectangle((300, 411), (401, 512)),                                         # the plugin's search box: one launch
+                 fx.rotated_ring(fx.to_rectangle((-500, -300), (500, 300)), (600.0, 450.0, 0.4)),  # count / scan / write
+                 fx.to_rectangle((0, 0), (1199, 0)), full):
+        got, want = dp.lethal_cells_within(cm, ring), capi.lethal_cells_within(m2, ring)
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+
 def test_lethal_perf_bench_workload(dp, capi):  # dpose_core/perf/dpose_core.cpp:73-90
     m = np.zeros((200, 200), np.uint8)
     m.reshape(-1)[::2] = fx.LETHAL
