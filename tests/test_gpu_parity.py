@@ -740,7 +740,9 @@ def test_full_size_properties_cfg5(dp):
       * batch-position independence: a permuted batch gives bit-identical per-pose results
       * additivity over the obstacle set: cost / J over the map = over its even-x cells + over its odd-x cells
       * angle periodicity: theta and theta + 2 pi agree
-      * a random sample agrees with the oracle (shifted-input protocol)"""
+      * the strong-scaling recipe of bench.py: the job ordered by map tile, cut into 8 contiguous slices, every slice
+        evaluated on its band of rows of the (volatile) map — bit-identical to the plain call
+      * EVERY pose agrees with the oracle (shifted-input protocol)"""
     from oracle import capi
     side, n = 10000, 10_000_000
     rng = np.random.default_rng(4)
@@ -774,6 +776,25 @@ def test_full_size_properties_cfg5(dp):
     turned = poses[sub].copy()
     turned[:, 2] += 2.0 * math.pi
     assert np.all(fx.tol_ok(pg.get_cost_batch(cm, turned), out[sub], rel=1e-9, abs_=1e-8))
+    del turned
+    # the job ordered by map tile, 8 contiguous slices, each on its band of the volatile map (device entry point)
+    torch = pytest.importorskip("torch")
+    from dpose_b200.dist import row_band, shard_bounds
+    order = dp.order_poses_by_tile(poses, side, side)
+    ordered = np.ascontiguousarray(poses[order])
+    d_p = torch.from_numpy(ordered).cuda()
+    d_o = torch.full((n, 4), -1.0, dtype=torch.float64, device="cuda")
+    cm.set_volatile(True)
+    rows_read = 0
+    for r in range(8):
+        lo, hi = shard_bounds(n, r, 8)
+        band = row_band(ordered[lo:hi, 1].min(), ordered[lo:hi, 1].max(), pg.reach(), side)
+        rows_read += band[1] - band[0]
+        pg.get_cost_batch_device(cm, d_p.data_ptr() + 24 * lo, hi - lo, d_o.data_ptr() + 32 * lo, rows=band)
+    torch.cuda.synchronize()
+    cm.set_volatile(False)
+    assert np.array_equal(d_o.cpu().numpy(), out[order]) and rows_read < side + 8 * (2 * pg.reach() + 10)
+    del d_p, d_o, ordered, order
     # EVERY pose against the oracle (translated-equivalent inputs): the CPU port does ~5e6 poses/s
     # on the GPU box's cores, so the full batch takes a few seconds
     oc = capi.CostData(fx.RECT, 2)
