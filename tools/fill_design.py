@@ -68,7 +68,7 @@ rows = ["| GPUs | strong: poses/s (step) | efficiency | the job in list order, p
         "|---|---|---|---|---|---|---|---|---|"]
 v1 = d1["value"]
 v1c = (d1.get("clean_map") or {}).get("value")
-for n, d in ((1, d1),) + tuple((n, line(f"r2_bench_cfg5_n{n}.json")) for n in (2, 8) if os.path.exists(os.path.join(P, f"r2_bench_cfg5_n{n}.json"))):
+for n, d in ((1, d1),) + tuple((n, line(f"r2_bench_cfg5_n{n}.json")) for n in (2, 4, 8) if os.path.exists(os.path.join(P, f"r2_bench_cfg5_n{n}.json"))):
     strong = d if d["scaling"] == "strong" else None
     other = d.get("other_scaling") or {}
     weak_v = other.get("value") if n > 1 else (lo1.get("value") or d["value"])  # the weak-scaling leg draws its poses per rank: list order
