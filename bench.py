@@ -402,18 +402,22 @@ def run_batch(args, ranks, torch, dp, fx):
         h_out = torch.empty((n_e2e, 4), dtype=torch.float64, pin_memory=True)
         h_poses.zero_(), h_out.zero_()
 
+    job_cache = {}
+
     def job_poses(order):
-        full = device_poses(torch, dev, n_total, side, pose_seed)
-        if order == "tile":  # the library's set-up helper (host arithmetic): the 32 x 8-cell tiles of the lethal plane, row-major
-            perm = dp.order_poses_by_tile(full.cpu().numpy(), side, side)
-            full = full[torch.from_numpy(perm).to(dev)].contiguous()
-        return full
+        if order not in job_cache:
+            full = device_poses(torch, dev, n_total, side, pose_seed)
+            if order == "tile":  # the library's set-up helper (host arithmetic): the 32 x 8-cell tiles of the lethal plane, row-major
+                perm = dp.order_poses_by_tile(full.cpu().numpy(), side, side)
+                full = full[torch.from_numpy(perm).to(dev)].contiguous()
+            job_cache[order] = full
+        return job_cache[order]
 
     def make_mode(mode, order=job_order):
         band = None
         if mode == "strong":  # n_total poses in all, this rank's contiguous slice
             lo, hi = dp.dist.shard_bounds(n_total, srank, sworld)
-            poses = job_poses(order)[lo:hi].contiguous()
+            poses = job_poses(order)[lo:hi].clone()
             if sworld > 1 and order == "tile":
                 band = dp.dist.row_band(float(poses[:, 1].min()), float(poses[:, 1].max()), pg.reach(), side)
         else:  # weak: n_total poses per GPU, rank-specific
@@ -462,6 +466,13 @@ def run_batch(args, ranks, torch, dp, fx):
         del leg
     else:
         e_poses, e_out = d_poses, d_out
+    tile_order = None
+    if job_order == "list" and scaling == "strong" and not args.as_rank:
+        leg = device_leg("strong", order="tile")
+        tile_order = {"value": leg["value"], "ms_per_step": leg["ms_per_step"],
+                      "note": "for information: the same batch ordered by map tile at set-up (dpose_order_poses_by_tile); `value` "
+                              "is the batch as drawn"}
+        del leg
     # The end-to-end legs below run on the job AS IT COMES (list order): a caller of the host-buffer call hands over its own
     # list, and the call is bound by the host link, not by the kernel — ordering buys it nothing.
 
@@ -648,7 +659,7 @@ def run_batch(args, ranks, torch, dp, fx):
                                      "rebuild of the volatile map's lethal plane shards with the poses" if main["band"] else
                                      "; one rank: the plain call on the whole map")) if job_order != "list" else "list order"},
         "clocks": main["clocks"], "e2e": e2e, "e2e_multi": e2e_multi, "e2e_variants": variants,
-        "other_scaling": other, "list_order": list_order, "clean_map": clean, "gpu_launches": int(main["launches"]), "roofline": roofline,
+        "other_scaling": other, "list_order": list_order, "tile_order": tile_order, "clean_map": clean, "gpu_launches": int(main["launches"]), "roofline": roofline,
         "cpu_baseline": cpu_baseline, "parity": parity,
     }
 

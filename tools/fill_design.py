@@ -36,6 +36,9 @@ for w in ("cfg5", "cfg3", "cfg2"):
         f"; both copies alone, at once: {e['pcie_bidirectional_ms_per_step']:.2f} ms)" if w == "cfg5" else ")")
     cb = d.get("cpu_baseline") or {}
     rep[f"R2_{W}_CPU"] = f"{sci(cb.get('value', 0))}" + (f" (C port {sci(cb['port_value'])})" if cb.get("port_value") else "")
+for w in ("cfg2", "cfg3"):
+    to = line(f"r2_bench_{w}.json").get("tile_order") or {}
+    rep[f"R2_{w.upper()}_TILE_VALUE"] = sci(to["value"]) if to else "?"
 d4 = line("r2_bench_cfg4.json")
 r4 = line("r2_bench_cfg4_reference_arm.json")
 rep["R2_CFG4_EVALS"] = str(d4["config"]["pose_evals_per_solve"])
