@@ -2,7 +2,7 @@
 """parity soak: random footprints (3 - 12 vertices, 3 - 70 cells, convex and not), paddings, map sizes (ragged pitches, tiny
 maps), densities and pose sets — through the precompute, the extraction, the list kernel, BOTH batched kernels, the row-band
 call and the ordered-stripes recipe, each against the CPU oracle.  One JSON line per configuration, a summary at the end.
-usage (under gpurun): python tools/fuzz_parity.py [configs] [seed]"""
+usage (under gpurun): python tools/fuzz_parity.py [configs] [seed] [big]"""
 import json
 import math
 import os
@@ -19,6 +19,7 @@ from dpose_b200.dist import row_band, shard_bounds  # noqa: E402
 from oracle import capi  # noqa: E402
 
 n_cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+BIG = len(sys.argv) > 3 and sys.argv[3] == "big"  # tables of 200 - 480 cells a side (the cap is 512): texture / no-shared-memory modes, Meijster row pass
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2024)
 nt = capi.max_threads()
 TILE_MIN = 148 * 32 + 1
@@ -32,7 +33,7 @@ def check(tag, cond, detail=""):
 
 
 for k in range(n_cfg):
-    radius = float(rng.choice([3, 5, 8, 12, 18, 26, 40, 55, 70]))
+    radius = float(rng.choice([100, 160, 230] if BIG else [3, 5, 8, 12, 18, 26, 40, 55, 70]))
     nv = int(rng.integers(3, 13))
     ang = np.sort(rng.uniform(0, 2 * math.pi, nv))
     if rng.random() < 0.3:
@@ -42,8 +43,8 @@ for k in range(n_cfg):
     if len(np.unique(fp[:, 0])) < 2 or len(np.unique(fp[:, 1])) < 2:
         continue
     pad = int(rng.integers(0, 7))
-    sx, sy = int(rng.integers(40, 1400)), int(rng.integers(40, 1100))
-    dens = float(rng.choice([0.0, 0.01, 0.05, 0.10, 0.3, 1.0]))
+    sx, sy = (int(rng.integers(900, 2400)), int(rng.integers(900, 2000))) if BIG else (int(rng.integers(40, 1400)), int(rng.integers(40, 1100)))
+    dens = float(rng.choice([0.0, 0.01, 0.05, 0.10] if BIG else [0.0, 0.01, 0.05, 0.10, 0.3, 1.0]))
     m = fx.bernoulli_map(sx, sy, dens, int(rng.integers(1 << 30)))
     if rng.random() < 0.3:
         m[rng.random(m.shape) < 0.05] = rng.choice([253, 255, 1, 128])  # non-lethal costs must not count
@@ -63,7 +64,7 @@ for k in range(n_cfg):
     # poses inside (the oracle's per-pose box is clamped at the border) -> both batched kernels against the oracle
     reach = pg.reach()
     if sx > 2 * reach + 4 and sy > 2 * reach + 4:
-        n = int(rng.choice([1, 37, 700, 5000]))
+        n = int(rng.choice([1, 37, 300] if BIG else [1, 37, 700, 5000]))
         poses = fx.random_poses(n, sx, sy, int(rng.integers(1 << 30)), margin=float(reach + 1))
         want = oc.get_cost_batch(m, poses, shift=True, nthreads=nt)
         coop = pg.get_cost_batch(cm, poses) if n < TILE_MIN else None
