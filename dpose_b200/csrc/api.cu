@@ -74,7 +74,10 @@ namespace {
 constexpr int kBuf = 3;
 constexpr int kMaxTableSide = 512;
 // poses per staging chunk of the host-buffer call: 3 MB in / 4 MB out, short pipeline fill and drain.  Measured on
-// B200 (cfg5, 1e7 poses): 2^16 .. 2^21 poses give 7.50 / 6.68 / 6.54 / 6.58 / 6.79 / 7.27 ms per call.
+// B200 (cfg5, 1e7 poses): 2^16 .. 2^21 poses give 7.50 / 6.68 / 6.54 / 6.58 / 6.79 / 7.27 ms per call on one box,
+// 7.54 / 6.68 / 7.03 on another (profiles/r2_ab_tile_walk.txt, run v52): with both copy directions busy 2^17 is the
+// robust choice.  Calls that keep ONE copy direction busy — cost only (8 B per pose back), a lattice sweep (nothing in) —
+// take chunks of twice that: cost-only 1.95e9 -> 2.13e9 poses/s, sweep 1.68e9 -> 1.71e9.
 #ifndef DPOSE_BATCH_CHUNK_LOG2
 #define DPOSE_BATCH_CHUNK_LOG2 17
 #endif
@@ -700,7 +703,7 @@ static int batch_host(const dpose_pg *pg, const dpose_map *map, const HostBatch 
     if (rc != DPOSE_OK) cudaDeviceSynchronize();
     return rc;
   }
-  const size_t chunk = std::min<size_t>(n, kChunkPoses);
+  const size_t chunk = std::min<size_t>(n, hb.cost_only || !hb.poses ? 2 * kChunkPoses : kChunkPoses);
   DPOSE_TRY(ctx->reserve(chunk));
   auto body = [&]() -> int {
     size_t it = 0;
