@@ -401,6 +401,8 @@ def run_batch(args, ranks, torch, dp, fx):
         h_poses = torch.empty((n_e2e, 3), dtype=torch.float64, pin_memory=True)
         h_out = torch.empty((n_e2e, 4), dtype=torch.float64, pin_memory=True)
         h_poses.zero_(), h_out.zero_()
+        # the result buffers of the byte-lean variants too; the lattice sweep's results reuse h_out (it holds <= n_e2e poses)
+        h_cost = torch.zeros((n_e2e,), dtype=torch.float64, pin_memory=True)
 
     job_cache = {}
 
@@ -526,15 +528,13 @@ def run_batch(args, ranks, torch, dp, fx):
                "pose_order": "list order (the job as it comes; `value` runs the tile-ordered job)" if job_order != "list" else "list order"}
         # the entry points that move fewer bytes: cost only (8 B/pose back), lattice sweep (nothing in)
         v_steps = max(3, args.steps // 4)
-        h_cost = torch.empty((n,), dtype=torch.float64, pin_memory=True)
         dt_c = wall(lambda: pg.get_cost_batch_costs(cmap, np_poses, out=h_cost.numpy()), v_steps)
         nt = 8
         nxy = max(1, int(math.isqrt(max(n // nt, 1))))
         ns = nxy * nxy * nt
         xs, ys, ts = (32.0, (side - 64.0) / nxy, nxy), (32.0, (side - 64.0) / nxy, nxy), (-math.pi, 2 * math.pi / nt, nt)
-        h_sw = torch.empty((ns, 4), dtype=torch.float64, pin_memory=True)
+        h_sw, h_swc = h_out[:ns], h_cost[:ns]  # ns <= n: the pinned pages allocated at the start
         dt_s = wall(lambda: pg.get_cost_sweep(cmap, xs, ys, ts, out=h_sw.numpy()), v_steps)
-        h_swc = torch.empty((ns,), dtype=torch.float64, pin_memory=True)
         dt_sc = wall(lambda: pg.get_cost_sweep(cmap, xs, ys, ts, cost_only=True, out=h_swc.numpy()), v_steps)
         # the same full-output call with PAGEABLE host buffers (what a caller that does not use dpose_host_alloc gets:
         # the driver stages every chunk through its own pinned buffers)
@@ -553,7 +553,7 @@ def run_batch(args, ranks, torch, dp, fx):
             "sweep_cost_only": {"value": ranks.sum(ns * v_steps) / ranks.max(dt_sc), "unit": "cost-only pose evals/s",
                                 "poses": ns, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(ns * 8)},
         }
-        del h_cost, h_sw, h_swc, pg_poses, pg_out
+        del h_sw, h_swc, pg_poses, pg_out
 
     # ---- ONE process driving all N GPUs through the in-process multi-GPU entry point (rank 0; the others stay idle) -------
     e2e_multi = None
